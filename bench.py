@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""bench.py -- vertex-moves/sec of the Metropolis-Hastings sweep on synthetic planted bipartite SBMs.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[2]): 1M nodes (5e5+5e5) / 10M edges,
+planted 32+32, Ka=Kb=32, epsilon=1, T=1 constant, 256 batched chains per GPU with randomised
+starts.  One "step" = SWEEPS_PER_STEP full sweeps of every chain (one bisbm_anneal call).
+Chains are sharded over GPUs with the graph replicated (weak scaling: 256 chains per GPU).
+
+value   = attempted single-vertex moves / s, all chains, state resident in HBM.
+e2e     = the same through the C ABI with HOST buffers: every step uploads the chains' labels
+          (pinned host memory), runs the sweeps and reads the labels back.
+roofline= algorithmic HBM bytes per move (16 + 8*(2E/N) + 4*acceptance) x moves
+          / CUDA-event time of the sweep launches, against MEASURED_PEAKS.json hbm_gbs.
+cpu_baseline / --impl reference = the UNMODIFIED reference (oracle/_ref/libref.so, built from
+          /root/reference/src) or, if that build is absent, the oracle port, one chain per host
+          core, anneal() only, on a bounded sample of the same workload.
+"""
+import argparse
+import ctypes
+import importlib
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SWEEPS_PER_STEP = 4
+
+
+def planted(na, nb, ka, kb, n_edges, seed, ratio=10.0):
+    """SURVEY.md 8(d) generator: block of type-a node i = i*ka//na; block pair weight `ratio` on the
+    paired diagonal, 1 elsewhere; uniform node within each block; multi-edges kept."""
+    rng = np.random.default_rng(seed)
+    w = np.ones((ka, kb))
+    for r in range(ka):
+        w[r, r * kb // ka] = ratio
+    p = (w / w.sum()).ravel()
+    pair = rng.choice(ka * kb, size=n_edges, p=p)
+    r, s = pair // kb, pair % kb
+    ba = np.arange(na) * ka // na
+    bb = np.arange(nb) * kb // nb
+    a_start = np.searchsorted(ba, np.arange(ka))
+    a_cnt = np.bincount(ba, minlength=ka)
+    b_start = np.searchsorted(bb, np.arange(kb))
+    b_cnt = np.bincount(bb, minlength=kb)
+    ea = a_start[r] + (rng.random(n_edges) * a_cnt[r]).astype(np.int64)
+    eb = na + b_start[s] + (rng.random(n_edges) * b_cnt[s]).astype(np.int64)
+    return np.stack([ea, eb], 1).astype(np.uint32)
+
+
+def planted_labels(na, nb, ka, kb):
+    return np.concatenate([np.arange(na) * ka // na, ka + np.arange(nb) * kb // nb]).astype(np.uint32)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if not self.proc:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        return out
+
+
+# ------------------------------------------------------------------------------ CPU arm
+_CPU_WORKER = r"""
+import sys, time, numpy as np
+sys.path.insert(0, sys.argv[1])
+kind, path, na, nb, ka, kb, moves, seed = sys.argv[2], sys.argv[3], int(sys.argv[4]), int(sys.argv[5]), int(sys.argv[6]), int(sys.argv[7]), int(sys.argv[8]), int(sys.argv[9])
+edges = np.load(path, mmap_mode="r")
+n = na + nb
+labels = np.concatenate([np.arange(na) * ka // na, ka + np.arange(nb) * kb // nb]).astype(np.uint32)
+if kind == "reference":
+    from oracle import ref as mod
+    c = mod.RefChain(n, na, nb, np.asarray(edges), labels, ka, kb, 1.0, seed, 1000 + seed)
+else:
+    from oracle import port as mod
+    c = mod.PortChain(n, na, nb, np.asarray(edges), labels, ka, kb, 1.0, seed, 1000 + seed)
+c.init(True)
+sweeps = max(1, moves // n)
+print("READY", flush=True)
+sys.stdin.readline()
+t0 = time.perf_counter()
+acc = c.anneal(3, 1.0, 0.0, sweeps * n, 10 ** 18)   # constant T = 1, no early stop; summary() skipped (SURVEY T4)
+dt = time.perf_counter() - t0
+print("DONE %d %.6f %.4f" % (sweeps * n, dt, acc), flush=True)
+"""
+
+
+def cpu_kind():
+    from oracle import ref
+    return "reference" if ref.available() else "port"
+
+
+def run_cpu_sample(edges_path, na, nb, ka, kb, moves_per_proc, procs, kind):
+    """One chain per core: `procs` processes each build the reference state (untimed), then all
+    start anneal() together; returns aggregate moves/s over the slowest process's wall time."""
+    ps = []
+    for i in range(procs):
+        cmd = [sys.executable, "-c", _CPU_WORKER, ROOT, kind, edges_path, str(na), str(nb), str(ka), str(kb),
+               str(moves_per_proc), str(i + 1)]
+        if hasattr(os, "sched_getaffinity"):
+            cores = sorted(os.sched_getaffinity(0))
+            cmd = ["taskset", "-c", str(cores[i % len(cores)])] + cmd
+        ps.append(subprocess.Popen(cmd, stdin=subprocess.PIPE, stdout=subprocess.PIPE, text=True))
+    for p in ps:
+        line = p.stdout.readline()
+        if not line.startswith("READY"):
+            raise RuntimeError("cpu worker failed: " + line)
+    for p in ps:
+        p.stdin.write("go\n"); p.stdin.flush()
+    moves, worst = 0, 0.0
+    for p in ps:
+        line = p.stdout.readline().split()
+        moves += int(line[1]); worst = max(worst, float(line[2]))
+        p.wait()
+    return moves / worst, moves, worst
+
+
+def cpu_procs(per_proc_gb):
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    avail_gb = 16.0
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable"):
+                avail_gb = int(line.split()[1]) / 1e6
+    except Exception:
+        pass
+    return max(1, min(cores, int(avail_gb * 0.5 / per_proc_gb), 64))
+
+
+# ------------------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nodes", type=int, default=1000000)
+    ap.add_argument("--edges", type=int, default=10000000)
+    ap.add_argument("--k", type=int, default=32)
+    ap.add_argument("--chains", type=int, default=256, help="chains per GPU")
+    ap.add_argument("--sweeps-per-step", type=int, default=SWEEPS_PER_STEP)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-moves", type=int, default=2000000, help="CPU sample: moves per process per step")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    na = nb = args.nodes // 2
+    n = na + nb
+    ka = kb = args.k
+    workload = "planted bipartite SBM %d nodes / %d edges, Ka=Kb=%d, %d chains/GPU, T=1, eps=1" % (n, args.edges, ka, args.chains)
+    config = {"workload": workload, "sweeps_per_step": args.sweeps_per_step, "chains_per_gpu": args.chains,
+              "l2": "inputs larger than L2 (labels %.0f MB, CSR %.0f MB per GPU)" % (n * args.chains * 4 / 1e6,
+                                                                                      args.edges * 8 / 1e6),
+              "parallelism": "chains sharded over %d GPU(s), graph replicated" % world}
+
+    # ---------------- reference arm: the reference's own CPU implementation on the host cores
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        edges = planted(na, nb, ka, kb, args.edges, 0)
+        path = os.path.join(tempfile.gettempdir(), "bisbm_bench_edges_%d.npy" % os.getpid())
+        np.save(path, edges)
+        kind = cpu_kind()
+        procs = cpu_procs(3.5 if kind == "reference" else 1.5)
+        vals = []
+        for i in range(args.warmup + args.steps):
+            # every step is a fresh bounded sample (state build untimed, anneal timed)
+            v, moves, worst = run_cpu_sample(path, na, nb, ka, kb, args.cpu_moves, procs, kind)
+            if i >= args.warmup:
+                vals.append((v, moves, worst))
+            if i == 0 and args.warmup > 1:
+                pass
+        os.unlink(path)
+        value = float(np.mean([v for v, _, _ in vals]))
+        ms = float(np.mean([w for _, _, w in vals])) * 1e3
+        sample = "%d processes x %d moves of anneal() (T=1) on the full %d-node / %d-edge graph, state build untimed" % (
+            procs, vals[0][1] // procs, n, args.edges)
+        line = {"impl": "reference", "metric": "vertex-moves/sec", "value": value, "unit": "moves/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64+int32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": value, "unit": "moves/s", "cores": procs, "kind": kind, "sample": sample},
+                "e2e": {"value": value, "unit": "moves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    # ---------------- our arm
+    import torch
+    import torch.distributed as dist
+    pkg = importlib.import_module("bipartitesbm-mcmc_b200")
+    host = pkg.host
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libbisbm has no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    edges = planted(na, nb, ka, kb, args.edges, 0)
+    graph = host.Graph(edges, na, nb, device=local_rank)
+    C = args.chains
+    chain0 = rank * C  # global chain ids of this rank: chain0 .. chain0 + C - 1
+    base = planted_labels(na, nb, ka, kb)
+    labels_host = torch.empty((C, n), dtype=torch.int32).pin_memory()
+    labels_host.numpy().view(np.uint32)[:] = base[None, :]
+    pool = host.ChainPool(graph, labels_host.numpy().view(np.uint32), ka, kb, 1.0)
+    seeds = (np.arange(C, dtype=np.uint64) + np.uint64(chain0))
+    pool.randomize(seeds)
+    duration = args.sweeps_per_step * n
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # -------- value: state resident in HBM
+    for _ in range(args.warmup):
+        pool.anneal("constant", 1.0, 0.0, duration, 10 ** 18, seeds)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    t0 = time.perf_counter()
+    ev_ms, launches, moves, accs = 0.0, 0, 0, []
+    for _ in range(args.steps):
+        acc, _sw = pool.anneal("constant", 1.0, 0.0, duration, 10 ** 18, seeds)
+        ms_, la_, mv_ = pool.last_timing()
+        ev_ms += ms_; launches += la_; moves += mv_; accs.append(float(acc.mean()))
+    if world > 1:
+        # the path's only collective: one all-reduce of the per-node marginal histogram
+        pool.marginals_clear()
+        pool.marginalize(0, 1, 1, seeds)
+        hist = host.marginals_tensor(pool)
+        dist.all_reduce(hist)
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    t = torch.tensor([wall, ev_ms], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(moves)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    wall_max, ev_max = float(t[0]), float(t[1])
+    total_moves = float(tot[0])
+    value = total_moves / wall_max
+    acceptance = float(np.mean(accs))
+
+    # -------- e2e: host buffers in, host buffers out, every step
+    out_host = torch.empty((C, n), dtype=torch.int32).pin_memory()
+    pool.labels(out=out_host.numpy().view(np.uint32))
+    labels_host.copy_(out_host)
+    for _ in range(1):
+        pool.set_labels(labels_host.numpy().view(np.uint32))
+        pool.anneal("constant", 1.0, 0.0, duration, 10 ** 18, seeds)
+        pool.labels(out=out_host.numpy().view(np.uint32))
+    barrier()
+    t1 = time.perf_counter()
+    e2e_moves = 0
+    for _ in range(args.steps):
+        pool.set_labels(labels_host.numpy().view(np.uint32))          # H2D: C*n*4 bytes
+        pool.anneal("constant", 1.0, 0.0, duration, 10 ** 18, seeds)
+        pool.labels(out=out_host.numpy().view(np.uint32))             # D2H: C*n*4 bytes
+        labels_host, out_host = out_host, labels_host
+        e2e_moves += pool.last_timing()[2]
+    barrier()
+    e2e_wall = time.perf_counter() - t1
+    te = torch.tensor([e2e_wall], dtype=torch.float64, device="cuda")
+    me = torch.tensor([float(e2e_moves)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        dist.all_reduce(me, op=dist.ReduceOp.SUM)
+    e2e_value = float(me[0]) / float(te[0])
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
+        bytes_per_move = 16.0 + 8.0 * (2.0 * args.edges / n) + 4.0 * acceptance
+        # dominant kernel = sweep_kernel; per-launch algorithmic bytes / average launch duration
+        sweep_launches = 2 * args.sweeps_per_step * args.steps
+        alg_bytes_per_launch = bytes_per_move * (moves / sweep_launches)
+        achieved = bytes_per_move * moves / (ev_ms * 1e-3) / 1e9
+        line = {"metric": "vertex-moves/sec", "value": value, "unit": "moves/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": wall_max / args.steps * 1e3, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64+int32", "data": "synthetic", "config": config,
+                "acceptance": acceptance,
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": None, "kernel": "sweep_kernel", "bytes_per_move": bytes_per_move,
+                             "alg_bytes_per_launch": alg_bytes_per_launch,
+                             "avg_launch_ms": ev_ms / sweep_launches, "peak_source": peak_src,
+                             "note": "event time spans sweep + logq_refresh + bookkeeping launches of rank 0"},
+                "e2e": {"value": e2e_value, "unit": "moves/s", "h2d_bytes_per_step": C * n * 4, "d2h_bytes_per_step": C * n * 4},
+                "gpu_launches": int(launches), "clocks": clocks}
+        traffic_file = os.path.join(ROOT, "profiles", "sweep_kernel_traffic.json")
+        if os.path.exists(traffic_file):
+            try:
+                line["roofline"]["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
+            except Exception:
+                pass
+        if not args.no_cpu_baseline and world == 1:
+            try:
+                path = os.path.join(tempfile.gettempdir(), "bisbm_bench_edges_%d.npy" % os.getpid())
+                np.save(path, edges)
+                kind = cpu_kind()
+                procs = cpu_procs(3.5 if kind == "reference" else 1.5)
+                v, mv, worst = run_cpu_sample(path, na, nb, ka, kb, args.cpu_moves, procs, kind)
+                os.unlink(path)
+                line["cpu_baseline"] = {"value": v, "unit": "moves/s", "cores": procs, "kind": kind,
+                                        "sample": "%d processes x %d moves of anneal() (T=1) on the full graph, %.1f s, state build untimed" % (
+                                            procs, mv // procs, worst)}
+            except Exception as ex:  # the baseline is a reported number, never a reason to lose the bench line
+                line["cpu_baseline"] = {"value": None, "unit": "moves/s", "cores": 0, "kind": "unavailable", "sample": str(ex)[:200]}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,979 @@
+// capi.cu -- C ABI of libbisbm.so (include/bisbm.h): handle, device state management, launches.
+//
+// Host side of the B200-native Metropolis-Hastings sweep.  Everything that computes runs on
+// the device (kernels in replay.cuh / sweep.cuh); the host builds the exact glibc tables
+// the replay mode needs, owns the device buffers and sequences the launches on one stream.
+// There is no CPU execution path for any compute entry point.
+#include "../../include/bisbm.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "replay.cuh"
+#include "sweep.cuh"
+
+using namespace bisbm;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(BISBM_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+struct ReplaySlot {
+    ReplayState* d_rs = nullptr;
+    uint32_t* d_vlist = nullptr;
+    int32_t* d_kh = nullptr;
+};
+
+}  // namespace
+
+struct bisbm_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int sm_count = 148;
+    // graph
+    uint32_t n = 0, na = 0, nb = 0, W = 0, max_degree = 0;
+    uint64_t n_edges = 0;
+    std::vector<uint32_t> h_row_ptr, h_degvals;
+    uint32_t *d_row_ptr = nullptr, *d_col = nullptr, *d_degidx = nullptr;
+    double ent_base = 0.0;  // label-independent entropy terms
+    // tables
+    double* d_qtab = nullptr;
+    uint32_t qn = 0, qk = 0;
+    double* d_lg = nullptr;
+    uint64_t lg_n = 0;
+    // chains
+    uint32_t n_chains = 0, C = 0, KA = 0, KB = 0;
+    std::vector<uint32_t> h_ka, h_kb;
+    uint32_t *d_ka = nullptr, *d_kb = nullptr;
+    int32_t *d_labels = nullptr, *d_labels_tmp = nullptr, *d_m = nullptr, *d_e = nullptr, *d_nr = nullptr,
+            *d_eta = nullptr;
+    double eps = 1.0;
+    LogqExp* d_lq = nullptr;
+    uint64_t* d_seeds = nullptr;
+    uint8_t* d_active = nullptr;
+    unsigned long long *d_accepted = nullptr, *d_u = nullptr, *d_sweeps = nullptr;
+    double *d_dS = nullptr, *d_entmin = nullptr, *d_ent_out = nullptr;
+    uint32_t* d_nactive = nullptr;
+    uint64_t sweep_epoch = 0;
+    std::map<uint32_t, ReplaySlot> replay;
+    // marginals
+    uint32_t* d_hist = nullptr;
+    uint32_t hist_width = 0;
+    // timing of the last parallel call
+    double last_ms = 0.0;
+    uint64_t last_launches = 0, last_moves = 0;
+};
+
+namespace {
+
+template <typename T>
+void dfree(T*& p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+void free_chains(bisbm_handle* h) {
+    dfree(h->d_ka); dfree(h->d_kb); dfree(h->d_labels); dfree(h->d_labels_tmp);
+    dfree(h->d_m); dfree(h->d_e); dfree(h->d_nr); dfree(h->d_eta); dfree(h->d_lq);
+    dfree(h->d_seeds); dfree(h->d_active); dfree(h->d_accepted); dfree(h->d_u); dfree(h->d_sweeps);
+    dfree(h->d_dS); dfree(h->d_entmin); dfree(h->d_ent_out); dfree(h->d_nactive); dfree(h->d_hist);
+    for (auto& kv : h->replay) { dfree(kv.second.d_rs); dfree(kv.second.d_vlist); dfree(kv.second.d_kh); }
+    h->replay.clear();
+    h->n_chains = 0;
+}
+
+GraphView gview(const bisbm_handle* h) {
+    GraphView g;
+    g.n = h->n; g.na = h->na; g.nb = h->nb; g.n_edges = h->n_edges;
+    g.row_ptr = h->d_row_ptr; g.col = h->d_col; g.degidx = h->d_degidx;
+    g.W = h->W; g.max_degree = h->max_degree;
+    return g;
+}
+
+StateView sview(const bisbm_handle* h) {
+    StateView s;
+    s.C = h->C; s.KA = h->KA; s.KB = h->KB; s.W = h->W;
+    s.labels = h->d_labels; s.m = h->d_m; s.e = h->d_e; s.nr = h->d_nr; s.eta = h->d_eta;
+    s.ka = h->d_ka; s.kb = h->d_kb; s.eps = h->eps;
+    return s;
+}
+
+Tables tview(const bisbm_handle* h, bool with_lgamma) {
+    Tables t;
+    t.lg = with_lgamma ? h->d_lg : nullptr;
+    t.lg_n = with_lgamma ? h->lg_n : 0;
+    t.qtab = h->d_qtab; t.qn = h->qn; t.qk = h->qk;
+    return t;
+}
+
+// exact log q table, the recurrence of init_q_cache in log space (reference
+// src/support/int_part.cc:30-51) restricted to rows n <= qn and columns k <= qk; cells the
+// reference never writes stay -inf.  Host glibc log1p/exp so the values equal the reference's.
+void build_qtab(std::vector<double>& q, uint32_t qn, uint32_t qk) {
+    const size_t W = (size_t)qk + 1;
+    q.assign(((size_t)qn + 1) * W, -INFINITY);
+    auto lsum = [](double a, double b) {
+        double mx = a > b ? a : b;
+        return mx + std::log1p(std::exp(-std::fabs(a - b)));
+    };
+    for (size_t n = 1; n <= qn; ++n) {
+        double* row = q.data() + n * W;
+        row[1] = 0.0;
+        const size_t kend = std::min<size_t>(n, qk);
+        for (size_t k = 2; k <= kend; ++k) {
+            double v = lsum(row[k], row[k - 1]);
+            if (n > k) v = lsum(v, q[(n - k) * W + k]);
+            row[k] = v;
+        }
+    }
+}
+
+int ensure_lgamma_table(bisbm_handle* h) {
+    if (h->d_lg) return BISBM_OK;
+    // lgamma_fast table of init_cache(E): indices 0..2E (reference src/support/cache.cc:64-91);
+    // capped at 2^26 entries, beyond which the device falls back to its own lgamma
+    uint64_t want = 2 * h->n_edges + 2 + h->max_degree;
+    want = std::min<uint64_t>(want, 1ull << 26);
+    std::vector<double> lg(want);
+    lg[0] = INFINITY;
+    for (uint64_t i = 1; i < want; ++i) lg[i] = std::lgamma((double)i);
+    CU(cudaMalloc(&h->d_lg, want * sizeof(double)));
+    CU(cudaMemcpy(h->d_lg, lg.data(), want * sizeof(double), cudaMemcpyHostToDevice));
+    h->lg_n = want;
+    return BISBM_OK;
+}
+
+int finish_graph(bisbm_handle* h, std::vector<uint32_t>& col) {
+    const uint32_t n = h->n;
+    // distinct degrees -> compressed eta columns
+    std::vector<uint32_t> deg(n);
+    h->max_degree = 0;
+    for (uint32_t v = 0; v < n; ++v) {
+        deg[v] = h->h_row_ptr[v + 1] - h->h_row_ptr[v];
+        h->max_degree = std::max(h->max_degree, deg[v]);
+    }
+    h->h_degvals = deg;
+    std::sort(h->h_degvals.begin(), h->h_degvals.end());
+    h->h_degvals.erase(std::unique(h->h_degvals.begin(), h->h_degvals.end()), h->h_degvals.end());
+    h->W = (uint32_t)h->h_degvals.size();
+    std::vector<uint32_t> degidx(n);
+    for (uint32_t v = 0; v < n; ++v)
+        degidx[v] = (uint32_t)(std::lower_bound(h->h_degvals.begin(), h->h_degvals.end(), deg[v]) - h->h_degvals.begin());
+    // label-independent entropy terms (reference src/blockmodel.cc:755-757, 772-779)
+    double base = 0.0;
+    for (uint32_t v = 0; v < n; ++v) base -= std::lgamma((double)deg[v] + 1.0);
+    {
+        std::vector<uint32_t> row;
+        for (uint32_t v = 0; v < n; ++v) {
+            if (deg[v] < 2) continue;
+            row.assign(col.begin() + h->h_row_ptr[v], col.begin() + h->h_row_ptr[v + 1]);
+            std::sort(row.begin(), row.end());
+            size_t i = 0;
+            while (i < row.size()) {
+                size_t j = i;
+                while (j < row.size() && row[j] == row[i]) ++j;
+                if (j - i > 1 && v > row[i]) base += std::lgamma((double)(j - i) + 1.0);
+                i = j;
+            }
+        }
+    }
+    h->ent_base = base;
+    CU(cudaSetDevice(h->device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, h->device));
+    h->sm_count = prop.multiProcessorCount;
+    CU(cudaStreamCreate(&h->stream));
+    CU(cudaEventCreate(&h->ev0));
+    CU(cudaEventCreate(&h->ev1));
+    CU(cudaMalloc(&h->d_row_ptr, ((size_t)n + 1) * sizeof(uint32_t)));
+    CU(cudaMalloc(&h->d_col, std::max<size_t>(col.size(), 1) * sizeof(uint32_t)));
+    CU(cudaMalloc(&h->d_degidx, std::max<size_t>(n, 1) * sizeof(uint32_t)));
+    CU(cudaMemcpy(h->d_row_ptr, h->h_row_ptr.data(), ((size_t)n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    if (!col.empty()) CU(cudaMemcpy(h->d_col, col.data(), col.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    if (n) CU(cudaMemcpy(h->d_degidx, degidx.data(), (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    // exact log q table for every (n, k) this graph can look up below the 10001 threshold
+    h->qn = (uint32_t)std::min<uint64_t>(h->n_edges, 10000);
+    h->qk = std::max<uint32_t>(1, std::min<uint32_t>(std::max(h->na, h->nb), h->qn));
+    {
+        std::vector<double> q;
+        build_qtab(q, h->qn, h->qk);
+        CU(cudaMalloc(&h->d_qtab, q.size() * sizeof(double)));
+        CU(cudaMemcpy(h->d_qtab, q.data(), q.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    return BISBM_OK;
+}
+
+int need_chains(bisbm_handle* h) {
+    if (!h) return fail(BISBM_ERR_ARG, "null handle");
+    if (h->n_chains == 0) return fail(BISBM_ERR_STATE, "no chains: call bisbm_set_chains first");
+    CU(cudaSetDevice(h->device));
+    return BISBM_OK;
+}
+
+int rebuild_counts(bisbm_handle* h) {
+    const size_t KK = (size_t)h->KA + h->KB;
+    CU(cudaMemsetAsync(h->d_m, 0, (size_t)h->C * h->KA * h->KB * sizeof(int32_t), h->stream));
+    CU(cudaMemsetAsync(h->d_e, 0, (size_t)h->C * KK * sizeof(int32_t), h->stream));
+    CU(cudaMemsetAsync(h->d_nr, 0, (size_t)h->C * KK * sizeof(int32_t), h->stream));
+    CU(cudaMemsetAsync(h->d_eta, 0, (size_t)h->C * KK * h->W * sizeof(int32_t), h->stream));
+    const uint32_t wpc = 8;
+    const uint64_t warps = (uint64_t)h->n * (h->C / 32);
+    if (warps) {
+        const uint64_t blocks = (warps + wpc - 1) / wpc;
+        if (blocks > 0x7fffffffull) return fail(BISBM_ERR_ARG, "n * chains too large for one launch");
+        build_counts_kernel<<<(unsigned)blocks, wpc * 32, 0, h->stream>>>(gview(h), sview(h), h->n_chains);
+    }
+    const uint32_t tot = h->n_chains * (uint32_t)KK;
+    build_e_kernel<<<(tot + 255) / 256, 256, 0, h->stream>>>(sview(h), h->n_chains);
+    CU(cudaGetLastError());
+    return BISBM_OK;
+}
+
+ReplayCtx rctx(bisbm_handle* h, uint32_t chain, const ReplaySlot& sl) {
+    ReplayCtx x;
+    x.g = gview(h);
+    StateView s = sview(h);
+    // chain_ref reads ka/kb through device pointers; build it from the host copies instead
+    ChainRef r;
+    r.labels = s.labels + chain;
+    r.C = s.C;
+    r.m = s.m + (size_t)chain * s.KA * s.KB;
+    r.e = s.e + (size_t)chain * (s.KA + s.KB);
+    r.nr = s.nr + (size_t)chain * (s.KA + s.KB);
+    r.eta = s.eta + (size_t)chain * (s.KA + s.KB) * s.W;
+    r.ka = h->h_ka[chain]; r.kb = h->h_kb[chain];
+    r.KA = s.KA; r.KB = s.KB; r.W = s.W;
+    x.c = r;
+    x.tb = tview(h, true);
+    x.rs = sl.d_rs;
+    x.vlist = sl.d_vlist;
+    x.kh = sl.d_kh;
+    x.eps = h->eps;
+    return x;
+}
+
+int need_replay(bisbm_handle* h, uint32_t chain, ReplaySlot** out) {
+    int rc = need_chains(h);
+    if (rc) return rc;
+    if (chain >= h->n_chains) return fail(BISBM_ERR_ARG, "chain %u out of range", chain);
+    auto it = h->replay.find(chain);
+    if (it == h->replay.end()) return fail(BISBM_ERR_STATE, "chain %u: call bisbm_replay_init first", chain);
+    *out = &it->second;
+    return BISBM_OK;
+}
+
+// host-side reference schedules (glibc pow / log), for the replay temperature arrays and
+// the cold-step bookkeeping; same expressions as reference src/metropolis_hasting.cc:10-37
+double host_schedule(int schedule, float p0, float p1, uint64_t t) {
+    switch (schedule) {
+        case BISBM_EXPONENTIAL: return (double)p0 * std::pow((double)p1, (double)t);
+        case BISBM_LINEAR: { volatile float pr = p1 * (float)t; volatile float r = p0 - pr; return (double)r; }
+        case BISBM_LOGARITHMIC: {
+            float x = (float)t + p1;
+            uint64_t i = (uint64_t)x;
+            double l = (i == 0) ? 0.0 : std::log((double)i);
+            return (double)p0 / l;
+        }
+        case BISBM_CONSTANT: return (double)p0;
+        default: return ((float)t < p0) ? 1.0 : 0.0;
+    }
+}
+
+// number of steps t in [t0, t1) with T(t) < 1; every schedule is non-increasing in t
+uint64_t cold_steps(int schedule, float p0, float p1, uint64_t t0, uint64_t t1) {
+    if (t1 <= t0) return 0;
+    if (host_schedule(schedule, p0, p1, t0) < 1.0) return t1 - t0;
+    if (!(host_schedule(schedule, p0, p1, t1 - 1) < 1.0)) return 0;
+    uint64_t lo = t0, hi = t1 - 1;  // T(lo) >= 1, T(hi) < 1
+    while (hi - lo > 1) {
+        uint64_t mid = lo + (hi - lo) / 2;
+        if (host_schedule(schedule, p0, p1, mid) < 1.0) hi = mid; else lo = mid;
+    }
+    return t1 - hi;
+}
+
+struct LaunchPlan {
+    uint32_t wpc, tiles, ctas_per_group;
+    size_t smem;
+    bool wide_hist;
+};
+
+int plan_sweep(bisbm_handle* h, uint32_t type, uint32_t max_inflight, LaunchPlan* lp) {
+    const uint32_t kopp_max = type ? h->KA : h->KB;
+    const uint32_t nv = type ? h->nb : h->na;
+    lp->wide_hist = h->max_degree >= 65535u;
+    const size_t per_warp = (size_t)kopp_max * 32 * (lp->wide_hist ? 4 : 2);
+    uint32_t wpc = 16;
+    while (wpc > 1 && per_warp * wpc > 200 * 1024) wpc >>= 1;
+    if (per_warp * wpc > 200 * 1024) return fail(BISBM_ERR_ARG, "K too large for the shared-memory histogram");
+    const uint32_t n_groups = h->C / 32;
+    // fill the GPU: ~48 resident warps per SM
+    uint64_t resident = (uint64_t)h->sm_count * 48;
+    uint32_t tiles = (uint32_t)std::max<uint64_t>(1, resident / n_groups);
+    // keep the in-flight fraction of a half sweep small
+    uint32_t cap = std::max<uint32_t>(1, nv / 64);
+    if (max_inflight) cap = max_inflight;
+    tiles = std::min(tiles, cap);
+    tiles = std::max<uint32_t>(1, std::min<uint32_t>(tiles, std::max<uint32_t>(nv, 1)));
+    if (tiles < wpc) wpc = 1u << (31 - __builtin_clz(tiles));  // largest power of two <= tiles
+    lp->wpc = wpc;
+    lp->tiles = tiles;
+    lp->ctas_per_group = (tiles + wpc - 1) / wpc;
+    lp->smem = per_warp * wpc;
+    return BISBM_OK;
+}
+
+template <typename HistT>
+int launch_sweep_t(bisbm_handle* h, const SweepParams& P, const LaunchPlan& lp) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        CU(cudaFuncSetAttribute(sweep_kernel<HistT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    const unsigned grid = P.n_groups * lp.ctas_per_group;
+    sweep_kernel<HistT><<<grid, lp.wpc * 32, lp.smem, h->stream>>>(P);
+    CU(cudaGetLastError());
+    return BISBM_OK;
+}
+
+// one full sweep = type-a half sweep + type-b half sweep (each preceded by the log q refresh
+// of the blocks that half sweep changes)
+int launch_full_sweep(bisbm_handle* h, int schedule, float p0, float p1, uint64_t sweep_in_call, uint32_t max_inflight) {
+    for (uint32_t type = 0; type < 2; ++type) {
+        const uint32_t nv = type ? h->nb : h->na;
+        if (nv == 0) continue;
+        LaunchPlan lp;
+        int rc = plan_sweep(h, type, max_inflight, &lp);
+        if (rc) return rc;
+        const uint32_t kmax = type ? h->KB : h->KA;
+        const uint32_t tot = h->n_chains * kmax;
+        logq_refresh_kernel<<<(tot + 127) / 128, 128, 0, h->stream>>>(sview(h), tview(h, false), h->d_lq, h->n_chains, type);
+        SweepParams P;
+        P.g = gview(h); P.s = sview(h); P.tb = tview(h, false);
+        P.seeds = h->d_seeds; P.active = h->d_active; P.accepted = h->d_accepted; P.dS_accum = h->d_dS;
+        P.lq = h->d_lq;
+        P.n_chains = h->n_chains; P.type = type; P.tiles = lp.tiles; P.n_groups = h->C / 32;
+        P.half_bits = feistel_half_bits(nv);
+        P.hist_stride = type ? h->KA : h->KB;
+        P.sweep = h->sweep_epoch;
+        P.step_base = sweep_in_call * (uint64_t)h->n + (type ? h->na : 0);
+        P.schedule = schedule; P.p0 = p0; P.p1 = p1;
+        rc = lp.wide_hist ? launch_sweep_t<uint32_t>(h, P, lp) : launch_sweep_t<uint16_t>(h, P, lp);
+        if (rc) return rc;
+        h->last_launches += 2;
+    }
+    h->sweep_epoch++;
+    h->last_moves += (uint64_t)h->n * h->n_chains;
+    return BISBM_OK;
+}
+
+int upload_seeds(bisbm_handle* h, const uint64_t* seeds) {
+    std::vector<uint64_t> s(h->C, 0);
+    for (uint32_t c = 0; c < h->n_chains; ++c) s[c] = seeds ? seeds[c] : (0x5851F42D4C957F2Dull * (c + 1));
+    CU(cudaMemcpyAsync(h->d_seeds, s.data(), h->C * sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return BISBM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* bisbm_last_error(void) { return g_err.c_str(); }
+const char* bisbm_version(void) { return "bisbm-b200 0.1 (sm_100a)"; }
+
+int bisbm_create_csr(uint32_t na, uint32_t nb, const uint32_t* row_ptr, const uint32_t* col_idx, int device,
+                     bisbm_handle** out) {
+    if (!out || !row_ptr) return fail(BISBM_ERR_ARG, "null argument");
+    *out = nullptr;
+    const uint64_t n64 = (uint64_t)na + nb;
+    if (n64 == 0 || n64 > 0xfffffff0ull) return fail(BISBM_ERR_ARG, "bad node count");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(BISBM_ERR_CUDA, "no CUDA device (libbisbm has no CPU path)");
+    if (device < 0 || device >= ndev) return fail(BISBM_ERR_ARG, "device %d out of range (%d devices)", device, ndev);
+    std::unique_ptr<bisbm_handle> h(new bisbm_handle());
+    h->device = device;
+    h->n = (uint32_t)n64; h->na = na; h->nb = nb;
+    h->h_row_ptr.assign(row_ptr, row_ptr + n64 + 1);
+    const uint64_t nnz = row_ptr[n64];
+    if (nnz & 1) return fail(BISBM_ERR_ARG, "odd number of adjacency entries");
+    h->n_edges = nnz / 2;
+    if (nnz && !col_idx) return fail(BISBM_ERR_ARG, "null col_idx");
+    std::vector<uint32_t> col(col_idx, col_idx + nnz);
+    for (uint32_t v = 0; v < h->n; ++v) {
+        if (row_ptr[v + 1] < row_ptr[v]) return fail(BISBM_ERR_ARG, "row_ptr not monotone");
+        const bool va = v < na;
+        for (uint32_t e = row_ptr[v]; e < row_ptr[v + 1]; ++e) {
+            if (col[e] >= h->n) return fail(BISBM_ERR_ARG, "neighbour id out of range");
+            if ((col[e] < na) == va) return fail(BISBM_ERR_ARG, "edge %u-%u joins two nodes of the same type", v, col[e]);
+        }
+    }
+    int rc = finish_graph(h.get(), col);
+    if (rc) { bisbm_destroy(h.release()); return rc; }
+    *out = h.release();
+    return BISBM_OK;
+}
+
+int bisbm_create(uint32_t na, uint32_t nb, uint64_t n_edges, const uint32_t* ea, const uint32_t* eb, int device,
+                 bisbm_handle** out) {
+    if (!out) return fail(BISBM_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (n_edges && (!ea || !eb)) return fail(BISBM_ERR_ARG, "null edge arrays");
+    const uint64_t n = (uint64_t)na + nb;
+    if (2 * n_edges >= 0xffffffffull) return fail(BISBM_ERR_ARG, "too many edges for 32-bit row offsets");
+    // edge_to_adj: push both directions, file order, multi-edges kept (reference
+    // src/graph_utilities.cc:36-49)
+    std::vector<uint32_t> row_ptr(n + 1, 0);
+    for (uint64_t i = 0; i < n_edges; ++i) {
+        if (ea[i] >= n || eb[i] >= n) return fail(BISBM_ERR_ARG, "edge %llu: node id out of range", (unsigned long long)i);
+        row_ptr[ea[i] + 1]++; row_ptr[eb[i] + 1]++;
+    }
+    for (uint64_t v = 0; v < n; ++v) row_ptr[v + 1] += row_ptr[v];
+    std::vector<uint32_t> fill(row_ptr.begin(), row_ptr.end() - 1), col(2 * n_edges);
+    for (uint64_t i = 0; i < n_edges; ++i) { col[fill[ea[i]]++] = eb[i]; col[fill[eb[i]]++] = ea[i]; }
+    return bisbm_create_csr(na, nb, row_ptr.data(), col.data(), device, out);
+}
+
+int bisbm_destroy(bisbm_handle* h) {
+    if (!h) return BISBM_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    free_chains(h);
+    dfree(h->d_row_ptr); dfree(h->d_col); dfree(h->d_degidx); dfree(h->d_qtab); dfree(h->d_lg);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return BISBM_OK;
+}
+
+int bisbm_set_chains(bisbm_handle* h, uint32_t n_chains, const uint32_t* ka, const uint32_t* kb,
+                     const uint32_t* labels, double eps) {
+    if (!h || !ka || !kb || !labels) return fail(BISBM_ERR_ARG, "null argument");
+    if (n_chains == 0) return fail(BISBM_ERR_ARG, "n_chains must be > 0");
+    if (!(eps > 0.0)) return fail(BISBM_ERR_ARG, "epsilon must be > 0");
+    CU(cudaSetDevice(h->device));
+    uint32_t KA = 0, KB = 0;
+    for (uint32_t c = 0; c < n_chains; ++c) {
+        if (ka[c] == 0 || kb[c] == 0) return fail(BISBM_ERR_ARG, "chain %u: ka and kb must be >= 1", c);
+        KA = std::max(KA, ka[c]); KB = std::max(KB, kb[c]);
+    }
+    const uint32_t C = (n_chains + 31) / 32 * 32;
+    const uint32_t n = h->n;
+    const size_t KK = (size_t)KA + KB;
+    const bool reuse = h->n_chains == n_chains && h->C == C && h->KA == KA && h->KB == KB && h->d_labels;
+    if (!reuse) {
+        free_chains(h);
+        h->n_chains = n_chains; h->C = C; h->KA = KA; h->KB = KB;
+        CU(cudaMalloc(&h->d_ka, C * sizeof(uint32_t)));
+        CU(cudaMalloc(&h->d_kb, C * sizeof(uint32_t)));
+        CU(cudaMalloc(&h->d_labels, (size_t)n * C * sizeof(int32_t)));
+        CU(cudaMalloc(&h->d_labels_tmp, (size_t)n * C * sizeof(int32_t)));
+        CU(cudaMalloc(&h->d_m, (size_t)C * KA * KB * sizeof(int32_t)));
+        CU(cudaMalloc(&h->d_e, (size_t)C * KK * sizeof(int32_t)));
+        CU(cudaMalloc(&h->d_nr, (size_t)C * KK * sizeof(int32_t)));
+        CU(cudaMalloc(&h->d_eta, (size_t)C * KK * h->W * sizeof(int32_t)));
+        CU(cudaMalloc(&h->d_lq, (size_t)C * KK * sizeof(LogqExp)));
+        CU(cudaMalloc(&h->d_seeds, C * sizeof(uint64_t)));
+        CU(cudaMalloc(&h->d_active, C));
+        CU(cudaMalloc(&h->d_accepted, C * sizeof(unsigned long long)));
+        CU(cudaMalloc(&h->d_u, C * sizeof(unsigned long long)));
+        CU(cudaMalloc(&h->d_sweeps, C * sizeof(unsigned long long)));
+        CU(cudaMalloc(&h->d_dS, C * sizeof(double)));
+        CU(cudaMalloc(&h->d_entmin, C * sizeof(double)));
+        CU(cudaMalloc(&h->d_ent_out, C * sizeof(double)));
+        CU(cudaMalloc(&h->d_nactive, sizeof(uint32_t)));
+    } else {
+        // same shapes: keep the device buffers, drop per-chain replay state
+        for (auto& kv : h->replay) { dfree(kv.second.d_rs); dfree(kv.second.d_vlist); dfree(kv.second.d_kh); }
+        h->replay.clear();
+    }
+    h->eps = eps;
+    h->h_ka.assign(C, 1); h->h_kb.assign(C, 1);
+    std::copy(ka, ka + n_chains, h->h_ka.begin());
+    std::copy(kb, kb + n_chains, h->h_kb.begin());
+    CU(cudaMemsetAsync(h->d_lq, 0, (size_t)C * KK * sizeof(LogqExp), h->stream));
+    CU(cudaMemsetAsync(h->d_dS, 0, C * sizeof(double), h->stream));
+    CU(cudaMemcpyAsync(h->d_ka, h->h_ka.data(), C * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_kb, h->h_kb.data(), C * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+    // host labels [chain][node], global ids  ->  chain-minor, type-local (device transpose)
+    {
+        uint32_t* stage = reinterpret_cast<uint32_t*>(h->d_labels_tmp);
+        CU(cudaMemcpyAsync(stage, labels, (size_t)n_chains * n * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+        unsigned long long* d_bad = reinterpret_cast<unsigned long long*>(h->d_accepted);
+        CU(cudaMemsetAsync(d_bad, 0xff, sizeof(unsigned long long), h->stream));
+        dim3 grid((n + 31) / 32, C / 32), block(32, 8);
+        import_labels_kernel<<<grid, block, 0, h->stream>>>(stage, h->d_labels, n, h->na, n_chains, C, h->d_ka, h->d_kb, d_bad);
+        CU(cudaGetLastError());
+        unsigned long long bad = 0;
+        CU(cudaMemcpyAsync(&bad, d_bad, sizeof bad, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        if (bad != ~0ull) {
+            const unsigned long long idx = bad - 1;
+            const uint32_t c = (uint32_t)(idx / n), v = (uint32_t)(idx % n);
+            const uint32_t g = labels[idx];
+            free_chains(h);
+            return fail(BISBM_ERR_ARG, "chain %u node %u: block %u is not a type-%c block (ka=%u kb=%u)", c, v, g,
+                        v < h->na ? 'a' : 'b', ka[c], kb[c]);
+        }
+    }
+    int rc = rebuild_counts(h);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(h->stream));
+    return BISBM_OK;
+}
+
+int bisbm_randomize(bisbm_handle* h, const uint64_t* seeds) {
+    int rc = need_chains(h);
+    if (rc) return rc;
+    rc = upload_seeds(h, seeds);
+    if (rc) return rc;
+    if (!h->d_labels_tmp) CU(cudaMalloc(&h->d_labels_tmp, (size_t)h->n * h->C * sizeof(int32_t)));
+    const uint64_t tot = (uint64_t)h->n * h->C;
+    randomize_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(
+        gview(h), h->d_labels, h->d_labels_tmp, h->C, h->n_chains, h->d_seeds, feistel_half_bits(h->na),
+        feistel_half_bits(h->nb));
+    CU(cudaGetLastError());
+    std::swap(h->d_labels, h->d_labels_tmp);
+    rc = rebuild_counts(h);
+    if (rc) return rc;
+    CU(cudaMemsetAsync(h->d_dS, 0, h->C * sizeof(double), h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return BISBM_OK;
+}
+
+// ---------------------------------------------------------------- replay mode
+int bisbm_replay_init(bisbm_handle* h, uint32_t chain, uint32_t engine_seed, uint32_t gen_seed, int randomize) {
+    int rc = need_chains(h);
+    if (rc) return rc;
+    if (chain >= h->n_chains) return fail(BISBM_ERR_ARG, "chain %u out of range", chain);
+    rc = ensure_lgamma_table(h);
+    if (rc) return rc;
+    ReplaySlot& sl = h->replay[chain];
+    if (!sl.d_rs) {
+        CU(cudaMalloc(&sl.d_rs, sizeof(ReplayState)));
+        CU(cudaMalloc(&sl.d_vlist, (size_t)h->n * sizeof(uint32_t)));
+        CU(cudaMalloc(&sl.d_kh, (size_t)std::max(h->KA, h->KB) * sizeof(int32_t)));
+    }
+    replay_init_kernel<<<1, 32, 0, h->stream>>>(rctx(h, chain, sl), engine_seed, gen_seed, randomize);
+    CU(cudaGetLastError());
+    if (randomize) {  // compute_n_r / k / m / m_r / eta_rk after the shuffle
+        rc = rebuild_counts(h);
+        if (rc) return rc;
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    return BISBM_OK;
+}
+
+int bisbm_replay_anneal(bisbm_handle* h, uint32_t chain, int schedule, float p0, float p1, uint64_t duration,
+                        uint64_t steps_await, double* accept_ratio, uint64_t* sweeps_done) {
+    ReplaySlot* sl;
+    int rc = need_replay(h, chain, &sl);
+    if (rc) return rc;
+    if (schedule < 0 || schedule > 4) return fail(BISBM_ERR_ARG, "unknown cooling schedule %d", schedule);
+    const uint64_t N = h->n;
+    const uint64_t all_sweeps = duration / N;
+    // anneal() resets entropy_min_, the accepted counter and u on entry
+    // (reference src/metropolis_hasting.cc:71-75)
+    ReplayState hs;
+    CU(cudaMemcpy(&hs, sl->d_rs, sizeof hs, cudaMemcpyDeviceToHost));
+    hs.entropy_min = INFINITY; hs.accepted = 0; hs.u = 0; hs.sweeps_done = 0; hs.stopped = 0;
+    CU(cudaMemcpy(sl->d_rs, &hs, sizeof hs, cudaMemcpyHostToDevice));
+    const bool host_temps = (schedule == BISBM_EXPONENTIAL || schedule == BISBM_LOGARITHMIC);
+    const uint64_t chunk = std::max<uint64_t>(1, (1ull << 20) / std::max<uint64_t>(N, 1));
+    double* d_temps = nullptr;
+    std::vector<double> temps;
+    if (host_temps) CU(cudaMalloc(&d_temps, chunk * N * sizeof(double)));
+    uint64_t done = 0;
+    uint32_t stopped = 0;
+    while (done < all_sweeps && !stopped) {
+        const uint64_t ns = std::min(chunk, all_sweeps - done);
+        if (host_temps) {
+            temps.resize(ns * N);
+            for (uint64_t i = 0; i < ns * N; ++i) temps[i] = host_schedule(schedule, p0, p1, done * N + i);
+            CU(cudaMemcpyAsync(d_temps, temps.data(), ns * N * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        }
+        replay_anneal_kernel<<<1, 32, 0, h->stream>>>(rctx(h, chain, *sl), schedule, p0, p1, d_temps, done, ns, steps_await);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(h->stream));
+        CU(cudaMemcpy(&hs, sl->d_rs, sizeof hs, cudaMemcpyDeviceToHost));
+        stopped = hs.stopped;
+        done += ns;
+    }
+    if (d_temps) cudaFree(d_temps);
+    if (accept_ratio) {
+        if (hs.stopped) *accept_ratio = (double)hs.accepted / (double)(hs.sweeps_done * N);
+        else *accept_ratio = (double)hs.accepted / (double)duration;
+    }
+    if (sweeps_done) *sweeps_done = hs.sweeps_done;
+    return BISBM_OK;
+}
+
+int bisbm_replay_step(bisbm_handle* h, uint32_t chain, uint32_t v, double T, int* accepted) {
+    ReplaySlot* sl;
+    int rc = need_replay(h, chain, &sl);
+    if (rc) return rc;
+    if (v >= h->n) return fail(BISBM_ERR_ARG, "vertex out of range");
+    replay_step_kernel<<<1, 32, 0, h->stream>>>(rctx(h, chain, *sl), v, T);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(h->stream));
+    ReplayState hs;
+    CU(cudaMemcpy(&hs, sl->d_rs, sizeof hs, cudaMemcpyDeviceToHost));
+    if (accepted) *accepted = hs.last_accept;
+    return BISBM_OK;
+}
+
+int bisbm_replay_transition(bisbm_handle* h, uint32_t chain, uint32_t v, uint32_t s, double* dS, double* accu_r) {
+    ReplaySlot* sl;
+    int rc = need_replay(h, chain, &sl);
+    if (rc) return rc;
+    if (v >= h->n || s >= h->h_ka[chain] + h->h_kb[chain]) return fail(BISBM_ERR_ARG, "vertex or block out of range");
+    replay_transition_kernel<<<1, 32, 0, h->stream>>>(rctx(h, chain, *sl), v, s);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(h->stream));
+    ReplayState hs;
+    CU(cudaMemcpy(&hs, sl->d_rs, sizeof hs, cudaMemcpyDeviceToHost));
+    if (dS) *dS = hs.last_dS;
+    if (accu_r) *accu_r = hs.accu_r;
+    return BISBM_OK;
+}
+
+int bisbm_replay_get_vlist(bisbm_handle* h, uint32_t chain, uint32_t* vlist) {
+    ReplaySlot* sl;
+    int rc = need_replay(h, chain, &sl);
+    if (rc) return rc;
+    CU(cudaMemcpy(vlist, sl->d_vlist, (size_t)h->n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    return BISBM_OK;
+}
+
+int bisbm_replay_rng_words(bisbm_handle* h, uint32_t chain, uint64_t* engine_words, uint64_t* gen_words) {
+    ReplaySlot* sl;
+    int rc = need_replay(h, chain, &sl);
+    if (rc) return rc;
+    ReplayState hs;
+    CU(cudaMemcpy(&hs, sl->d_rs, sizeof hs, cudaMemcpyDeviceToHost));
+    if (engine_words) *engine_words = ((uint64_t)hs.engine[626] << 32) | hs.engine[625];
+    if (gen_words) *gen_words = ((uint64_t)hs.gen[626] << 32) | hs.gen[625];
+    return BISBM_OK;
+}
+
+// ---------------------------------------------------------------- parallel mode
+int bisbm_anneal(bisbm_handle* h, int schedule, float p0, float p1, uint64_t duration, uint64_t steps_await,
+                 const uint64_t* seeds, uint32_t max_inflight, double* accept_ratio, uint64_t* sweeps_done) {
+    int rc = need_chains(h);
+    if (rc) return rc;
+    if (schedule < 0 || schedule > 4) return fail(BISBM_ERR_ARG, "unknown cooling schedule %d", schedule);
+    rc = upload_seeds(h, seeds);
+    if (rc) return rc;
+    const uint64_t N = h->n;
+    const uint64_t all_sweeps = duration / N;
+    const uint32_t C = h->C;
+    {
+        std::vector<uint8_t> act(C, 0);
+        std::fill(act.begin(), act.begin() + h->n_chains, 1);
+        std::vector<double> inf(C, INFINITY);
+        CU(cudaMemcpyAsync(h->d_active, act.data(), C, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemcpyAsync(h->d_entmin, inf.data(), C * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemsetAsync(h->d_accepted, 0, C * sizeof(unsigned long long), h->stream));
+        CU(cudaMemsetAsync(h->d_u, 0, C * sizeof(unsigned long long), h->stream));
+        CU(cudaMemsetAsync(h->d_sweeps, 0, C * sizeof(unsigned long long), h->stream));
+        uint32_t na_ = h->n_chains;
+        CU(cudaMemcpyAsync(h->d_nactive, &na_, sizeof na_, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+    }
+    h->last_launches = 0; h->last_moves = 0; h->last_ms = 0.0;
+    CU(cudaEventRecord(h->ev0, h->stream));
+    uint64_t sweep = 0;
+    uint32_t n_active = h->n_chains;
+    // early stop can only trigger once enough cold steps exist; poll the device counter
+    // every `poll` sweeps (each poll is a stream sync)
+    const bool can_stop = steps_await < duration;
+    for (; sweep < all_sweeps && n_active; ++sweep) {
+        rc = launch_full_sweep(h, schedule, p0, p1, sweep, max_inflight);
+        if (rc) return rc;
+        const uint64_t cold = cold_steps(schedule, p0, p1, sweep * N, (sweep + 1) * N);
+        bookkeep_kernel<<<(h->n_chains + 127) / 128, 128, 0, h->stream>>>(
+            h->n_chains, h->d_active, h->d_dS, h->d_entmin, h->d_u, h->d_sweeps, sweep, cold, steps_await, h->d_nactive);
+        h->last_launches += 1;
+        if (can_stop && cold) {
+            CU(cudaMemcpyAsync(&n_active, h->d_nactive, sizeof n_active, cudaMemcpyDeviceToHost, h->stream));
+            CU(cudaStreamSynchronize(h->stream));
+        }
+    }
+    CU(cudaEventRecord(h->ev1, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->last_ms = ms;
+    std::vector<unsigned long long> acc(C), sw(C);
+    std::vector<uint8_t> act(C);
+    CU(cudaMemcpy(acc.data(), h->d_accepted, C * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(sw.data(), h->d_sweeps, C * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(act.data(), h->d_active, C, cudaMemcpyDeviceToHost));
+    for (uint32_t c = 0; c < h->n_chains; ++c) {
+        // reference: accepted / ((sweep+1)*N) on early stop, accepted / duration otherwise
+        if (accept_ratio) {
+            if (!act[c]) accept_ratio[c] = (double)acc[c] / (double)(sw[c] * N);
+            else accept_ratio[c] = duration ? (double)acc[c] / (double)duration : 0.0;
+        }
+        if (sweeps_done) sweeps_done[c] = sw[c];
+    }
+    return BISBM_OK;
+}
+
+int bisbm_marginals_clear(bisbm_handle* h) {
+    int rc = need_chains(h);
+    if (rc) return rc;
+    uint32_t width = 0;
+    for (uint32_t c = 0; c < h->n_chains; ++c) width = std::max(width, h->h_ka[c] + h->h_kb[c]);
+    if (!h->d_hist || h->hist_width != width) {
+        dfree(h->d_hist);
+        CU(cudaMalloc(&h->d_hist, (size_t)h->n * width * sizeof(uint32_t)));
+        h->hist_width = width;
+    }
+    CU(cudaMemsetAsync(h->d_hist, 0, (size_t)h->n * width * sizeof(uint32_t), h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return BISBM_OK;
+}
+
+int bisbm_marginalize(bisbm_handle* h, uint64_t burn_in, uint64_t sweeps, uint64_t every, const uint64_t* seeds,
+                      uint32_t max_inflight) {
+    int rc = need_chains(h);
+    if (rc) return rc;
+    if (every == 0) return fail(BISBM_ERR_ARG, "sampling interval must be >= 1");
+    if (!h->d_hist) { rc = bisbm_marginals_clear(h); if (rc) return rc; }
+    rc = upload_seeds(h, seeds);
+    if (rc) return rc;
+    {
+        std::vector<uint8_t> act(h->C, 0);
+        std::fill(act.begin(), act.begin() + h->n_chains, 1);
+        CU(cudaMemcpyAsync(h->d_active, act.data(), h->C, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemsetAsync(h->d_accepted, 0, h->C * sizeof(unsigned long long), h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+    }
+    h->last_launches = 0; h->last_moves = 0; h->last_ms = 0.0;
+    CU(cudaEventRecord(h->ev0, h->stream));
+    const uint64_t tot = (uint64_t)h->n * h->C;
+    for (uint64_t sw = 0; sw < burn_in + sweeps; ++sw) {
+        rc = launch_full_sweep(h, BISBM_CONSTANT, 1.0f, 0.0f, sw, max_inflight);
+        if (rc) return rc;
+        if (sw >= burn_in && ((sw - burn_in + 1) % every) == 0) {
+            marginal_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(gview(h), sview(h), h->n_chains,
+                                                                                 h->d_hist, h->hist_width);
+            h->last_launches += 1;
+        }
+    }
+    CU(cudaEventRecord(h->ev1, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->last_ms = ms;
+    return BISBM_OK;
+}
+
+int bisbm_marginals_device(bisbm_handle* h, void** dev_ptr, uint64_t* n_elems, uint32_t* width) {
+    int rc = need_chains(h);
+    if (rc) return rc;
+    if (!h->d_hist) return fail(BISBM_ERR_STATE, "no marginal histogram yet");
+    if (dev_ptr) *dev_ptr = h->d_hist;
+    if (n_elems) *n_elems = (uint64_t)h->n * h->hist_width;
+    if (width) *width = h->hist_width;
+    return BISBM_OK;
+}
+
+int bisbm_get_marginals(bisbm_handle* h, uint32_t* hist) {
+    int rc = need_chains(h);
+    if (rc) return rc;
+    if (!h->d_hist) return fail(BISBM_ERR_STATE, "no marginal histogram yet");
+    CU(cudaMemcpy(hist, h->d_hist, (size_t)h->n * h->hist_width * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    return BISBM_OK;
+}
+
+int bisbm_marginal_argmax(bisbm_handle* h, uint32_t* labels) {
+    int rc = need_chains(h);
+    if (rc) return rc;
+    if (!h->d_hist) return fail(BISBM_ERR_STATE, "no marginal histogram yet");
+    uint32_t* d_out = nullptr;
+    CU(cudaMalloc(&d_out, (size_t)h->n * sizeof(uint32_t)));
+    marginal_argmax_kernel<<<(h->n + 255) / 256, 256, 0, h->stream>>>(h->n, h->d_hist, h->hist_width, d_out);
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    if (e == cudaSuccess) e = cudaMemcpy(labels, d_out, (size_t)h->n * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return fail(BISBM_ERR_CUDA, "marginal_argmax: %s", cudaGetErrorString(e));
+    return BISBM_OK;
+}
+
+int bisbm_last_timing(bisbm_handle* h, double* sweep_ms, uint64_t* launches, uint64_t* moves) {
+    if (!h) return fail(BISBM_ERR_ARG, "null handle");
+    if (sweep_ms) *sweep_ms = h->last_ms;
+    if (launches) *launches = h->last_launches;
+    if (moves) *moves = h->last_moves;
+    return BISBM_OK;
+}
+
+int bisbm_stream(bisbm_handle* h, void** stream) {
+    if (!h || !stream) return fail(BISBM_ERR_ARG, "null argument");
+    *stream = (void*)h->stream;
+    return BISBM_OK;
+}
+
+// ---------------------------------------------------------------- read-back
+int bisbm_info(bisbm_handle* h, uint32_t* n, uint64_t* n_edges, uint32_t* max_degree, uint32_t* n_chains) {
+    if (!h) return fail(BISBM_ERR_ARG, "null handle");
+    if (n) *n = h->n;
+    if (n_edges) *n_edges = h->n_edges;
+    if (max_degree) *max_degree = h->max_degree;
+    if (n_chains) *n_chains = h->n_chains;
+    return BISBM_OK;
+}
+
+int bisbm_get_all_labels(bisbm_handle* h, uint32_t* labels) {
+    int rc = need_chains(h);
+    if (rc) return rc;
+    const uint32_t n = h->n, C = h->C;
+    if (!h->d_labels_tmp) CU(cudaMalloc(&h->d_labels_tmp, (size_t)n * C * sizeof(int32_t)));
+    uint32_t* stage = reinterpret_cast<uint32_t*>(h->d_labels_tmp);
+    dim3 grid((n + 31) / 32, C / 32), block(32, 8);
+    export_labels_kernel<<<grid, block, 0, h->stream>>>(h->d_labels, stage, n, h->na, h->n_chains, C, h->d_ka);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(labels, stage, (size_t)h->n_chains * n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return BISBM_OK;
+}
+
+int bisbm_get_labels(bisbm_handle* h, uint32_t chain, uint32_t* labels) {
+    int rc = need_chains(h);
+    if (rc) return rc;
+    if (chain >= h->n_chains) return fail(BISBM_ERR_ARG, "chain %u out of range", chain);
+    const uint32_t n = h->n;
+    std::vector<int32_t> lab(n);
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaMemcpy2D(lab.data(), sizeof(int32_t), h->d_labels + chain, (size_t)h->C * sizeof(int32_t), sizeof(int32_t),
+                    n, cudaMemcpyDeviceToHost));
+    const uint32_t ka = h->h_ka[chain];
+    for (uint32_t v = 0; v < n; ++v) labels[v] = v < h->na ? (uint32_t)lab[v] : ka + (uint32_t)lab[v];
+    return BISBM_OK;
+}
+
+int bisbm_get_m(bisbm_handle* h, uint32_t chain, int32_t* m) {
+    int rc = need_chains(h);
+    if (rc) return rc;
+    if (chain >= h->n_chains) return fail(BISBM_ERR_ARG, "chain %u out of range", chain);
+    std::vector<int32_t> M((size_t)h->KA * h->KB);
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaMemcpy(M.data(), h->d_m + (size_t)chain * h->KA * h->KB, M.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    const uint32_t ka = h->h_ka[chain], kb = h->h_kb[chain], K = ka + kb;
+    std::fill(m, m + (size_t)K * K, 0);
+    for (uint32_t a = 0; a < ka; ++a)
+        for (uint32_t b = 0; b < kb; ++b) {
+            const int32_t x = M[(size_t)a * h->KB + b];
+            m[(size_t)a * K + ka + b] = x;
+            m[(size_t)(ka + b) * K + a] = x;
+        }
+    return BISBM_OK;
+}
+
+static int get_slots(bisbm_handle* h, uint32_t chain, const int32_t* d_src, int32_t* out) {
+    int rc = need_chains(h);
+    if (rc) return rc;
+    if (chain >= h->n_chains) return fail(BISBM_ERR_ARG, "chain %u out of range", chain);
+    const size_t KK = (size_t)h->KA + h->KB;
+    std::vector<int32_t> tmp(KK);
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaMemcpy(tmp.data(), d_src + (size_t)chain * KK, KK * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    const uint32_t ka = h->h_ka[chain], kb = h->h_kb[chain];
+    for (uint32_t a = 0; a < ka; ++a) out[a] = tmp[a];
+    for (uint32_t b = 0; b < kb; ++b) out[ka + b] = tmp[h->KA + b];
+    return BISBM_OK;
+}
+
+int bisbm_get_m_r(bisbm_handle* h, uint32_t chain, int32_t* e_r) { return get_slots(h, chain, h ? h->d_e : nullptr, e_r); }
+int bisbm_get_n_r(bisbm_handle* h, uint32_t chain, int32_t* n_r) { return get_slots(h, chain, h ? h->d_nr : nullptr, n_r); }
+
+int bisbm_get_eta(bisbm_handle* h, uint32_t chain, uint32_t* eta) {
+    int rc = need_chains(h);
+    if (rc) return rc;
+    if (chain >= h->n_chains) return fail(BISBM_ERR_ARG, "chain %u out of range", chain);
+    const size_t KK = (size_t)h->KA + h->KB;
+    std::vector<int32_t> tmp(KK * h->W);
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaMemcpy(tmp.data(), h->d_eta + (size_t)chain * KK * h->W, tmp.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    const uint32_t ka = h->h_ka[chain], kb = h->h_kb[chain];
+    const size_t Wf = (size_t)h->max_degree + 1;
+    std::fill(eta, eta + (size_t)(ka + kb) * Wf, 0u);
+    for (uint32_t q = 0; q < ka + kb; ++q) {
+        const size_t slot = q < ka ? q : h->KA + (q - ka);
+        for (uint32_t w = 0; w < h->W; ++w) eta[q * Wf + h->h_degvals[w]] = (uint32_t)tmp[slot * h->W + w];
+    }
+    return BISBM_OK;
+}
+
+int bisbm_entropy_all(bisbm_handle* h, double* entropy) {
+    int rc = need_chains(h);
+    if (rc) return rc;
+    entropy_kernel<<<h->n_chains, 256, 0, h->stream>>>(gview(h), sview(h), tview(h, false), h->ent_base, h->n_chains,
+                                                       h->d_ent_out);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaMemcpy(entropy, h->d_ent_out, h->n_chains * sizeof(double), cudaMemcpyDeviceToHost));
+    return BISBM_OK;
+}
+
+int bisbm_entropy(bisbm_handle* h, uint32_t chain, double* entropy) {
+    int rc = need_chains(h);
+    if (rc) return rc;
+    if (chain >= h->n_chains) return fail(BISBM_ERR_ARG, "chain %u out of range", chain);
+    std::vector<double> all(h->n_chains);
+    rc = bisbm_entropy_all(h, all.data());
+    if (rc) return rc;
+    *entropy = all[chain];
+    return BISBM_OK;
+}
+
+int bisbm_entropy_accum(bisbm_handle* h, uint32_t chain, double* entropy_accum) {
+    int rc = need_chains(h);
+    if (rc) return rc;
+    if (chain >= h->n_chains) return fail(BISBM_ERR_ARG, "chain %u out of range", chain);
+    auto it = h->replay.find(chain);
+    CU(cudaStreamSynchronize(h->stream));
+    if (it != h->replay.end()) {
+        ReplayState hs;
+        CU(cudaMemcpy(&hs, it->second.d_rs, sizeof hs, cudaMemcpyDeviceToHost));
+        *entropy_accum = hs.entropy_accum;
+    } else {
+        CU(cudaMemcpy(entropy_accum, h->d_dS + chain, sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    return BISBM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,135 @@
+/* include/bisbm.h -- C ABI of libbisbm.so: the B200-native Metropolis-Hastings sweep of the
+ * degree-corrected bipartite SBM.
+ *
+ * This is the drop-in boundary for ONE path of junipertcy/bipartiteSBM-MCMC: the simulated
+ * annealing / sampling loop  metropolis_hasting::anneal -> step -> {single_vertex_change,
+ * transition_ratio, apply_mcmc_moves}.  The reference exposes no FFI; the entry points
+ * below are what a binding for that path would bind, each citing the reference interface
+ * it replaces (paths under the reference tree).  Plain C types only; the caller owns
+ * every host buffer, the handle owns all device memory; every call returns 0 on success
+ * and a non-zero code otherwise (bisbm_last_error() gives the message); nothing aborts.
+ * There is no CPU fallback: without a CUDA device every compute call fails with
+ * BISBM_ERR_CUDA.
+ *
+ * Two execution modes over the same device-resident state:
+ *   replay   -- one chain, strictly sequential, consuming the reference's two mt19937
+ *               streams (`engine`, `gen`) through libstdc++-exact distribution transforms;
+ *               reproduces the reference's label trajectory, m_rs, e_r, n_r bit for bit.
+ *   parallel -- many independent chains per launch (lane = chain, chain-minor labels),
+ *               counter-based RNG, type-alternating half sweeps; statistically
+ *               equivalent, not draw-for-draw identical.
+ */
+#ifndef BISBM_H
+#define BISBM_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bisbm_handle bisbm_handle;
+
+enum {
+    BISBM_OK = 0,
+    BISBM_ERR_ARG = 1,    /* invalid argument / inconsistent sizes */
+    BISBM_ERR_CUDA = 2,   /* CUDA runtime error (incl. no device) */
+    BISBM_ERR_STATE = 3,  /* call out of order (e.g. anneal before set_chains) */
+    BISBM_ERR_ALLOC = 4
+};
+
+/* cooling schedules, reference src/metropolis_hasting.cc:10-37 and src/mcmc_main.cc:463-482 */
+enum {
+    BISBM_EXPONENTIAL = 0, /* p0 * pow(p1, t)                    */
+    BISBM_LINEAR = 1,      /* p0 - p1 * t            (float)     */
+    BISBM_LOGARITHMIC = 2, /* p0 / log(trunc(t + p1))            */
+    BISBM_CONSTANT = 3,    /* p0                                 */
+    BISBM_ABRUPT_COOL = 4  /* t < p0 ? 1 : 0                     */
+};
+
+const char* bisbm_last_error(void);
+/* library version string; also proves the library loaded */
+const char* bisbm_version(void);
+
+/* ---- graph -------------------------------------------------------------------------
+ * Replaces edge_to_adj + the adjacency part of the blockmodel_t constructor
+ * (src/graph_utilities.cc:36-49, src/blockmodel.cc:15-75).  Node ids 0..na-1 are type a,
+ * na..na+nb-1 type b (src/mcmc_main.cc:121-130).  Edges are (ea[i], eb[i]) in FILE ORDER;
+ * the adjacency keeps that order and multi-edges, as the reference does. */
+int bisbm_create(uint32_t na, uint32_t nb, uint64_t n_edges, const uint32_t* ea, const uint32_t* eb,
+                 int device, bisbm_handle** out);
+/* Same, from a ready CSR (row_ptr[n+1], col_idx[2E]) whose rows are already in the
+ * reference's adjacency order. */
+int bisbm_create_csr(uint32_t na, uint32_t nb, const uint32_t* row_ptr, const uint32_t* col_idx,
+                     int device, bisbm_handle** out);
+int bisbm_destroy(bisbm_handle* h);
+
+/* ---- chains ------------------------------------------------------------------------
+ * Replaces the blockmodel_t state + init_bisbm (src/blockmodel.hh:92-143,
+ * src/blockmodel.cc:681-746).  labels[c*n + v] is chain c's GLOBAL block id of node v
+ * (type-a blocks 0..ka[c]-1, type-b blocks ka[c]..ka[c]+kb[c]-1).  Builds n_r, e_r, m_rs,
+ * eta_rk on the device.  eps is the reference's epsilon (-E). */
+int bisbm_set_chains(bisbm_handle* h, uint32_t n_chains, const uint32_t* ka, const uint32_t* kb,
+                     const uint32_t* labels, double eps);
+/* Parallel-mode --randomize: permutes each chain's labels within type a and within
+ * type b with a counter-based RNG keyed by seeds[c] (same block sizes as shuffle_bisbm,
+ * src/blockmodel.cc:672-679, different stream), then rebuilds the counts. */
+int bisbm_randomize(bisbm_handle* h, const uint64_t* seeds);
+
+/* ---- replay mode (one chain, bit-exact) ----------------------------------------------
+ * Seeds the two engines of the reference: `engine` (src/mcmc_main.cc:242) and `gen`
+ * (src/blockmodel.hh:17-18), resets vlist to identity (src/blockmodel.cc:41) and, if
+ * randomize != 0, runs shuffle_bisbm with `engine` (src/blockmodel.cc:672-679). */
+int bisbm_replay_init(bisbm_handle* h, uint32_t chain, uint32_t engine_seed, uint32_t gen_seed, int randomize);
+/* metropolis_hasting::anneal (src/metropolis_hasting.cc:64-101) with the reference's
+ * float-typed schedule parameters; duration is in single-vertex steps. */
+int bisbm_replay_anneal(bisbm_handle* h, uint32_t chain, int schedule, float p0, float p1, uint64_t duration,
+                        uint64_t steps_await, double* accept_ratio, uint64_t* sweeps_done);
+/* metropolis_hasting::step on one vertex at temperature T (src/metropolis_hasting.cc:42-62) */
+int bisbm_replay_step(bisbm_handle* h, uint32_t chain, uint32_t v, double T, int* accepted);
+/* metropolis_hasting::transition_ratio for moving v to global block s
+ * (src/metropolis_hasting.cc:103-192); accu_r is the member left by the call. */
+int bisbm_replay_transition(bisbm_handle* h, uint32_t chain, uint32_t v, uint32_t s, double* dS, double* accu_r);
+int bisbm_replay_get_vlist(bisbm_handle* h, uint32_t chain, uint32_t* vlist);
+int bisbm_replay_rng_words(bisbm_handle* h, uint32_t chain, uint64_t* engine_words, uint64_t* gen_words);
+
+/* ---- parallel mode (all chains per launch) -------------------------------------------
+ * anneal for every chain at once.  duration / steps_await as in the reference (steps);
+ * seeds[c] keys chain c's counter-based RNG.  max_inflight bounds how many moves of ONE
+ * chain may be evaluated concurrently against slightly stale block counts (0 = let the
+ * library fill the GPU; 1 = strictly sequential chains).  Outputs per chain. */
+int bisbm_anneal(bisbm_handle* h, int schedule, float p0, float p1, uint64_t duration, uint64_t steps_await,
+                 const uint64_t* seeds, uint32_t max_inflight, double* accept_ratio, uint64_t* sweeps_done);
+/* Marginalisation (README "marginalization" mode; no code in the reference snapshot):
+ * burn_in sweeps at T=1, then `sweeps` sweeps sampling every `every` sweeps into the
+ * device-resident per-node label histogram uint32[n][hist_width] (summed over chains). */
+int bisbm_marginalize(bisbm_handle* h, uint64_t burn_in, uint64_t sweeps, uint64_t every, const uint64_t* seeds,
+                      uint32_t max_inflight);
+int bisbm_marginals_clear(bisbm_handle* h);
+/* device pointer + element count of the histogram, for an in-place NCCL all-reduce */
+int bisbm_marginals_device(bisbm_handle* h, void** dev_ptr, uint64_t* n_elems, uint32_t* width);
+int bisbm_get_marginals(bisbm_handle* h, uint32_t* hist);          /* [n][width], global block ids */
+int bisbm_marginal_argmax(bisbm_handle* h, uint32_t* labels);      /* [n] */
+/* device-side sweep timing of the last parallel call: total kernel ms (CUDA events on the
+ * handle's stream), kernel launches, and single-vertex moves attempted */
+int bisbm_last_timing(bisbm_handle* h, double* sweep_ms, uint64_t* launches, uint64_t* moves);
+/* stream the handle launches on (cudaStream_t as void*) */
+int bisbm_stream(bisbm_handle* h, void** stream);
+
+/* ---- state read-back (getters of blockmodel_t, src/blockmodel.hh:35-53) ---------------- */
+int bisbm_info(bisbm_handle* h, uint32_t* n, uint64_t* n_edges, uint32_t* max_degree, uint32_t* n_chains);
+int bisbm_get_labels(bisbm_handle* h, uint32_t chain, uint32_t* labels);          /* [n] global ids */
+int bisbm_get_all_labels(bisbm_handle* h, uint32_t* labels);                     /* [n_chains][n] */
+int bisbm_get_m(bisbm_handle* h, uint32_t chain, int32_t* m);                    /* [K][K] symmetric */
+int bisbm_get_m_r(bisbm_handle* h, uint32_t chain, int32_t* e_r);                /* [K] */
+int bisbm_get_n_r(bisbm_handle* h, uint32_t chain, int32_t* n_r);                /* [K] */
+int bisbm_get_eta(bisbm_handle* h, uint32_t chain, uint32_t* eta);               /* [K][max_degree+1] */
+/* blockmodel_t::entropy (src/blockmodel.cc:753-787), evaluated on the device */
+int bisbm_entropy(bisbm_handle* h, uint32_t chain, double* entropy);
+int bisbm_entropy_all(bisbm_handle* h, double* entropy);                         /* [n_chains] */
+/* blockmodel_t::get_entropy: running sum of accepted dS (src/blockmodel.hh:100) */
+int bisbm_entropy_accum(bisbm_handle* h, uint32_t chain, double* entropy_accum);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

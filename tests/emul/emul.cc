@@ -1,0 +1,225 @@
+// tests/emul/emul.cc -- HOST compilation of the device headers, for debugging only.
+//
+// The container that authors this code has no GPU.  The replay logic (replay.cuh) and the
+// per-move arithmetic of the parallel kernel (sweep.cuh: lgamma_diff, logq_delta) are plain
+// BISBM_HD functions, so g++ can compile the very same text and a CPU test can compare it
+// with the oracle before any GPU time is spent.  TEST INFRASTRUCTURE: built only by
+// tests/test_emul.py into tests/emul/libemul.so; libbisbm.so never contains or calls it.
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../bipartitesbm-mcmc_b200/csrc/replay.cuh"
+#include "../../bipartitesbm-mcmc_b200/csrc/sweep.cuh"
+
+using namespace bisbm;
+
+struct Emul {
+    uint32_t n, na, nb, ka, kb, C, chain, W, maxdeg;
+    uint64_t E;
+    std::vector<uint32_t> row_ptr, col, degidx, degvals, vlist;
+    std::vector<int32_t> labels, m, e, nr, eta, kh;
+    std::vector<double> lg, qtab;
+    uint32_t qn, qk;
+    ReplayState rs;
+    double eps;
+};
+
+static void build_qtab(std::vector<double>& q, uint32_t qn, uint32_t qk) {
+    const size_t W = (size_t)qk + 1;
+    q.assign(((size_t)qn + 1) * W, -INFINITY);
+    for (size_t n = 1; n <= qn; ++n) {
+        double* row = q.data() + n * W;
+        row[1] = 0.0;
+        size_t kend = n < qk ? n : qk;
+        for (size_t k = 2; k <= kend; ++k) {
+            auto lsum = [](double a, double b) { double mx = a > b ? a : b; return mx + log1p(exp(-fabs(a - b))); };
+            double v = lsum(row[k], row[k - 1]);
+            if (n > k) v = lsum(v, q[(n - k) * W + k]);
+            row[k] = v;
+        }
+    }
+}
+
+static void rebuild(Emul* s) {
+    const uint32_t KA = s->ka, KB = s->kb;
+    std::fill(s->m.begin(), s->m.end(), 0); std::fill(s->e.begin(), s->e.end(), 0);
+    std::fill(s->nr.begin(), s->nr.end(), 0); std::fill(s->eta.begin(), s->eta.end(), 0);
+    for (uint32_t v = 0; v < s->n; ++v) {
+        uint32_t b = s->labels[(size_t)v * s->C + s->chain];
+        uint32_t slot = v < s->na ? b : KA + b;
+        s->nr[slot]++;
+        s->eta[(size_t)slot * s->W + s->degidx[v]]++;
+        if (v < s->na)
+            for (uint32_t x = s->row_ptr[v]; x < s->row_ptr[v + 1]; ++x)
+                s->m[(size_t)b * KB + s->labels[(size_t)s->col[x] * s->C + s->chain]]++;
+    }
+    for (uint32_t a = 0; a < KA; ++a) for (uint32_t b = 0; b < KB; ++b) {
+        s->e[a] += s->m[(size_t)a * KB + b]; s->e[KA + b] += s->m[(size_t)a * KB + b];
+    }
+}
+
+static ReplayCtx ctx(Emul* s) {
+    ReplayCtx x;
+    x.g.n = s->n; x.g.na = s->na; x.g.nb = s->nb; x.g.n_edges = s->E;
+    x.g.row_ptr = s->row_ptr.data(); x.g.col = s->col.data(); x.g.degidx = s->degidx.data();
+    x.g.W = s->W; x.g.max_degree = s->maxdeg;
+    x.c.labels = s->labels.data() + s->chain; x.c.C = s->C;
+    x.c.m = s->m.data(); x.c.e = s->e.data(); x.c.nr = s->nr.data(); x.c.eta = s->eta.data();
+    x.c.ka = s->ka; x.c.kb = s->kb; x.c.KA = s->ka; x.c.KB = s->kb; x.c.W = s->W;
+    x.tb.lg = s->lg.data(); x.tb.lg_n = s->lg.size(); x.tb.qtab = s->qtab.data(); x.tb.qn = s->qn; x.tb.qk = s->qk;
+    x.rs = &s->rs; x.vlist = s->vlist.data(); x.kh = s->kh.data(); x.eps = s->eps;
+    return x;
+}
+
+extern "C" {
+
+void* emul_create(uint32_t na, uint32_t nb, uint64_t E, const uint32_t* ea, const uint32_t* eb, const uint32_t* labels,
+                  uint32_t ka, uint32_t kb, double eps, uint32_t engine_seed, uint32_t gen_seed, int randomize) {
+    Emul* s = new Emul();
+    s->n = na + nb; s->na = na; s->nb = nb; s->ka = ka; s->kb = kb; s->E = E; s->eps = eps;
+    s->C = 32; s->chain = 3;
+    s->row_ptr.assign(s->n + 1, 0);
+    for (uint64_t i = 0; i < E; ++i) { s->row_ptr[ea[i] + 1]++; s->row_ptr[eb[i] + 1]++; }
+    for (uint32_t v = 0; v < s->n; ++v) s->row_ptr[v + 1] += s->row_ptr[v];
+    std::vector<uint32_t> fill(s->row_ptr.begin(), s->row_ptr.end() - 1);
+    s->col.resize(2 * E);
+    for (uint64_t i = 0; i < E; ++i) { s->col[fill[ea[i]]++] = eb[i]; s->col[fill[eb[i]]++] = ea[i]; }
+    std::vector<uint32_t> deg(s->n);
+    s->maxdeg = 0;
+    for (uint32_t v = 0; v < s->n; ++v) { deg[v] = s->row_ptr[v + 1] - s->row_ptr[v]; if (deg[v] > s->maxdeg) s->maxdeg = deg[v]; }
+    s->degvals = deg;
+    std::sort(s->degvals.begin(), s->degvals.end());
+    s->degvals.erase(std::unique(s->degvals.begin(), s->degvals.end()), s->degvals.end());
+    s->W = s->degvals.size();
+    s->degidx.resize(s->n);
+    for (uint32_t v = 0; v < s->n; ++v) s->degidx[v] = std::lower_bound(s->degvals.begin(), s->degvals.end(), deg[v]) - s->degvals.begin();
+    s->labels.assign((size_t)s->n * s->C, 0);
+    for (uint32_t v = 0; v < s->n; ++v) s->labels[(size_t)v * s->C + s->chain] = v < na ? labels[v] : labels[v] - ka;
+    s->m.assign((size_t)ka * kb, 0); s->e.assign(ka + kb, 0); s->nr.assign(ka + kb, 0);
+    s->eta.assign((size_t)(ka + kb) * s->W, 0); s->kh.assign(std::max(ka, kb), 0);
+    s->vlist.resize(s->n);
+    for (uint32_t v = 0; v < s->n; ++v) s->vlist[v] = v;
+    s->lg.resize(2 * E + 2 + s->maxdeg);
+    s->lg[0] = INFINITY;
+    for (size_t i = 1; i < s->lg.size(); ++i) s->lg[i] = lgamma((double)i);
+    s->qn = E < 10000 ? E : 10000;
+    uint32_t kmax = na > nb ? na : nb;
+    s->qk = kmax < s->qn ? kmax : s->qn;
+    if (s->qk < 1) s->qk = 1;
+    build_qtab(s->qtab, s->qn, s->qk);
+    mt_seed(s->rs.engine, engine_seed); mt_seed(s->rs.gen, gen_seed);
+    s->rs.entropy_accum = 0; s->rs.entropy_min = INFINITY; s->rs.accu_r = 0;
+    s->rs.accepted = 0; s->rs.u = 0; s->rs.sweeps_done = 0; s->rs.stopped = 0;
+    if (randomize) rp_shuffle_labels(ctx(s));
+    rebuild(s);
+    return s;
+}
+
+void emul_destroy(void* p) { delete (Emul*)p; }
+
+double emul_anneal(void* p, int schedule, float p0, float p1, const double* temps, uint64_t duration, uint64_t steps_await) {
+    Emul* s = (Emul*)p;
+    s->rs.entropy_min = INFINITY; s->rs.accepted = 0; s->rs.u = 0; s->rs.sweeps_done = 0; s->rs.stopped = 0;
+    uint64_t sweeps = duration / s->n;
+    rp_anneal_sweeps(ctx(s), schedule, p0, p1, temps, 0, sweeps, steps_await);
+    if (s->rs.stopped) return (double)s->rs.accepted / (double)(s->rs.sweeps_done * s->n);
+    return (double)s->rs.accepted / (double)duration;
+}
+
+void emul_transition(void* p, uint32_t v, uint32_t sg, double* dS, double* accu) {
+    Emul* s = (Emul*)p;
+    ReplayCtx x = ctx(s);
+    rp_hist(x, v);
+    *dS = rp_transition(x, v, rp_label(x, v), sg);
+    *accu = s->rs.accu_r;
+}
+
+// the parallel kernel's arithmetic for the same move: dS via log-products / Stirling / logq_delta
+void emul_par_dS(void* p, uint32_t v, uint32_t sg, int use_taylor, double* dS, double* accu) {
+    Emul* s = (Emul*)p;
+    ReplayCtx x = ctx(s);
+    rp_hist(x, v);
+    const bool va = v < s->na;
+    const uint32_t r = s->labels[(size_t)v * s->C + s->chain];
+    const uint32_t sl = va ? sg : sg - s->ka;
+    const uint32_t kopp = va ? s->kb : s->ka, KB = s->kb, KA = s->ka;
+    const uint32_t own_off = va ? 0 : KA, opp_off = va ? KA : 0;
+    const uint32_t sx = va ? KB : 1, st = va ? 1 : KB;
+    const int32_t* Mr = s->m.data() + (size_t)r * sx; const int32_t* Ms = s->m.data() + (size_t)sl * sx;
+    const double eps = s->eps, epsK = eps * (double)(KA + KB);
+    const uint32_t d = s->row_ptr[v + 1] - s->row_ptr[v];
+    double a0 = 0, a1 = 0, ratio = 1, logacc = 0;
+    for (uint32_t t = 0; t < kopp; ++t) {
+        int kk = s->kh[t];
+        if (!kk) continue;
+        int m_r = Mr[(size_t)t * st], m_s = Ms[(size_t)t * st];
+        double inv = 1.0 / ((double)s->e[opp_off + t] + epsK);
+        a0 += (double)kk * ((double)m_s + eps) * inv;
+        a1 += (double)kk * ((double)(m_r - kk) + eps) * inv;
+        if (kk <= 8) {
+            double num = 1, den = 1;
+            for (int q = 0; q < kk; ++q) { num *= (double)(m_r - q); den *= (double)(m_s + 1 + q); }
+            ratio *= num / den;
+            if (ratio > 1e100 || ratio < 1e-100) { logacc += log(ratio); ratio = 1.0; }
+        } else {
+            logacc += lgamma_diff((double)(m_r - kk + 1), (double)kk) - lgamma_diff((double)(m_s + 1), (double)kk);
+        }
+    }
+    int e_r = s->e[own_off + r], e_s = s->e[own_off + sl], n_r = s->nr[own_off + r], n_s = s->nr[own_off + sl];
+    uint32_t didx = s->degidx[v];
+    int eta_r = s->eta[(size_t)(own_off + r) * s->W + didx], eta_s = s->eta[(size_t)(own_off + sl) * s->W + didx];
+    ratio *= (double)(eta_r > 0 ? eta_r : 1) / (double)(eta_s + 1);
+    double out = logacc + log(ratio);
+    out += lgamma_diff((double)(e_s + 1), (double)d) - lgamma_diff((double)(e_r - (int)d + 1), (double)d);
+    Tables tb = x.tb; tb.lg = nullptr; tb.lg_n = 0;
+    LogqExp qr, qs;
+    memset(&qr, 0, sizeof qr); memset(&qs, 0, sizeof qs);
+    if (use_taylor) {
+        auto mk = [&](int e0, int n0) {
+            LogqExp q; memset(&q, 0, sizeof q); q.e0 = e0; q.n0 = n0;
+            if (e0 >= 16384 && n0 >= 1024 && 2 * (int64_t)n0 <= (int64_t)e0) {
+                int he = e0 >> 10, hn = n0 >> 8;
+                double f00 = log_q_approx(tb, e0, n0);
+                double fp0 = log_q_approx(tb, e0 + he, n0), fm0 = log_q_approx(tb, e0 - he, n0);
+                double f0p = log_q_approx(tb, e0, n0 + hn), f0m = log_q_approx(tb, e0, n0 - hn);
+                double fpp = log_q_approx(tb, e0 + he, n0 + hn), fpm = log_q_approx(tb, e0 + he, n0 - hn);
+                double fmp = log_q_approx(tb, e0 - he, n0 + hn), fmm = log_q_approx(tb, e0 - he, n0 - hn);
+                double He = he, Hn = hn;
+                q.fe = (float)((fp0 - fm0) / (2 * He)); q.fn = (float)((f0p - f0m) / (2 * Hn));
+                q.fee = (float)((fp0 - 2 * f00 + fm0) / (He * He)); q.fnn = (float)((f0p - 2 * f00 + f0m) / (Hn * Hn));
+                q.fen = (float)((fpp - fpm - fmp + fmm) / (4 * He * Hn)); q.valid = 1;
+            }
+            return q;
+        };
+        // expansion point deliberately off the current point, to exercise the drift terms
+        qr = mk(e_r + e_r / 40, n_r - n_r / 50); qs = mk(e_s - e_s / 40, n_s + n_s / 50);
+    }
+    out += logq_delta(tb, qr, e_r, n_r, -(int)d, -1);
+    out += logq_delta(tb, qs, e_s, n_s, (int)d, 1);
+    *dS = out;
+    *accu = d == 0 ? 1.0 : a1 / a0;
+}
+
+double emul_entropy_accum(void* p) { return ((Emul*)p)->rs.entropy_accum; }
+void emul_get_labels(void* p, uint32_t* out) {
+    Emul* s = (Emul*)p;
+    for (uint32_t v = 0; v < s->n; ++v) { uint32_t l = s->labels[(size_t)v * s->C + s->chain]; out[v] = v < s->na ? l : s->ka + l; }
+}
+void emul_get_counts(void* p, int32_t* m, int32_t* e, int32_t* nr) {
+    Emul* s = (Emul*)p;
+    memcpy(m, s->m.data(), s->m.size() * 4); memcpy(e, s->e.data(), s->e.size() * 4); memcpy(nr, s->nr.data(), s->nr.size() * 4);
+}
+void emul_words(void* p, uint64_t* ew, uint64_t* gw) {
+    Emul* s = (Emul*)p;
+    *ew = ((uint64_t)s->rs.engine[626] << 32) | s->rs.engine[625];
+    *gw = ((uint64_t)s->rs.gen[626] << 32) | s->rs.gen[625];
+}
+double emul_lgamma_diff(double x, double d) { return lgamma_diff(x, d); }
+double emul_log_q_approx(uint64_t n, uint64_t k) { Tables tb; memset(&tb, 0, sizeof tb); return log_q_approx(tb, n, k); }
+uint32_t emul_feistel(uint32_t i, uint32_t n, uint64_t key) { return feistel_perm(i, n, feistel_half_bits(n), key); }
+
+}  // extern "C"

@@ -1,0 +1,145 @@
+"""Host compilation of the DEVICE headers (csrc/replay.cuh, sweep.cuh, devmath.cuh) checked
+against the golden fixtures.  This is a debugging aid for a container without a GPU: it
+proves the text of the replay routine and of the parallel kernel's per-move arithmetic is
+right before GPU time is spent.  It is not a product path: libbisbm.so has no host
+execution route (see test_capi_cpu.py)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, TRAJECTORIES, load_golden
+from oracle import port
+
+EMUL_DIR = os.path.join(ROOT, "tests", "emul")
+LIB = os.path.join(EMUL_DIR, "libemul.so")
+pu = C.POINTER(C.c_uint32)
+
+
+@pytest.fixture(scope="module")
+def emul():
+    src = os.path.join(EMUL_DIR, "emul.cc")
+    deps = [src] + [os.path.join(ROOT, "bipartitesbm-mcmc_b200", "csrc", f) for f in
+                    ("devmath.cuh", "state.cuh", "replay.cuh", "sweep.cuh")]
+    if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-x", "c++",
+                               "-o", LIB, src, "-lm"])
+    L = C.CDLL(LIB)
+    L.emul_create.restype = C.c_void_p
+    L.emul_create.argtypes = [C.c_uint32, C.c_uint32, C.c_uint64, pu, pu, pu, C.c_uint32, C.c_uint32, C.c_double,
+                              C.c_uint32, C.c_uint32, C.c_int]
+    L.emul_destroy.argtypes = [C.c_void_p]
+    L.emul_anneal.restype = C.c_double
+    L.emul_anneal.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_uint64, C.c_uint64]
+    L.emul_entropy_accum.restype = C.c_double
+    L.emul_entropy_accum.argtypes = [C.c_void_p]
+    L.emul_get_labels.argtypes = [C.c_void_p, pu]
+    L.emul_get_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.emul_words.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.emul_transition.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.emul_par_dS.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.emul_lgamma_diff.restype = C.c_double
+    L.emul_lgamma_diff.argtypes = [C.c_double, C.c_double]
+    L.emul_log_q_approx.restype = C.c_double
+    L.emul_log_q_approx.argtypes = [C.c_uint64, C.c_uint64]
+    L.emul_feistel.restype = C.c_uint32
+    L.emul_feistel.argtypes = [C.c_uint32, C.c_uint32, C.c_uint64]
+    return L
+
+
+def _create(L, g, randomize=None):
+    ea = np.ascontiguousarray(g["edges"][:, 0], dtype=np.uint32)
+    eb = np.ascontiguousarray(g["edges"][:, 1], dtype=np.uint32)
+    lab = np.ascontiguousarray(g["labels0"], dtype=np.uint32)
+    rnd = int(g["randomize"]) if randomize is None else int(randomize)
+    return L.emul_create(g["na"], g["nb"], len(ea), ea.ctypes.data_as(pu), eb.ctypes.data_as(pu), lab.ctypes.data_as(pu),
+                         g["ka"], g["kb"], g["eps"], g["seed"], g["gen_seed"], rnd)
+
+
+@pytest.mark.parametrize("name", TRAJECTORIES)
+def test_replay_text_is_bit_exact_on_host(emul, name):
+    g = load_golden(name)
+    n = g["na"] + g["nb"]
+    h = _create(emul, g)
+    K = g["ka"] + g["kb"]
+    for v, s, dS, ar in zip(g["kat_v"], g["kat_s"], g["kat_dS"], g["kat_accu"]):
+        d, a = C.c_double(), C.c_double()
+        emul.emul_transition(h, int(v), int(s), C.byref(d), C.byref(a))
+        assert d.value == dS or (np.isinf(d.value) and np.isinf(dS))
+        if not np.isinf(dS):
+            assert a.value == ar
+    sched = int(g["schedule"])
+    temps = None
+    if sched in (0, 2):
+        sweeps = int(g["duration"]) // n
+        t = np.array([port.schedule(sched, float(g["p0"]), float(g["p1"]), i) for i in range(sweeps * n)])
+        temps = t.ctypes.data_as(C.c_void_p)
+    acc = emul.emul_anneal(h, sched, float(g["p0"]), float(g["p1"]), temps, int(g["duration"]), int(g["steps_await"]))
+    assert acc == g["accept"]
+    out = np.empty(n, dtype=np.uint32)
+    emul.emul_get_labels(h, out.ctypes.data_as(pu))
+    assert (out == g["labels"]).all()
+    assert emul.emul_entropy_accum(h) == g["entropy_accum"]
+    m = np.zeros((g["ka"], g["kb"]), dtype=np.int32)
+    e = np.zeros(K, dtype=np.int32)
+    nr = np.zeros(K, dtype=np.int32)
+    emul.emul_get_counts(h, m.ctypes.data, e.ctypes.data, nr.ctypes.data)
+    assert (m == g["m"][:g["ka"], g["ka"]:]).all() and (e == g["m_r"]).all() and (nr == g["n_r"]).all()
+    a, b = C.c_uint64(), C.c_uint64()
+    emul.emul_words(h, C.byref(a), C.byref(b))
+    assert (a.value, b.value) == tuple(int(x) for x in g["rng_words"])
+    emul.emul_destroy(h)
+
+
+@pytest.mark.parametrize("name,taylor,tol", [("c1_seed1", 0, 1e-9), ("c2_abrupt", 0, 1e-9), ("c2_const_k46", 0, 1e-9),
+                                             ("big_blocks", 0, 1e-9), ("big_blocks", 1, 2e-6), ("isolated", 0, 1e-9)])
+def test_parallel_move_arithmetic_matches_reference(emul, name, taylor, tol):
+    """dS / accu_r as the parallel kernel computes them (log-products, Stirling differences,
+    log q expansion) vs the reference's transition_ratio known answers.  Tolerance: 1e-9
+    relative (north-star) on the exact paths; 2e-6 ABSOLUTE for the second-order log q
+    expansion evaluated 2.5% away from its expansion point."""
+    g = load_golden(name)
+    h = _create(emul, g)
+    checked = 0
+    for v, s, dS, ar in zip(g["kat_v"], g["kat_s"], g["kat_dS"], g["kat_accu"]):
+        r = g["init_labels"][v]
+        if np.isinf(dS) or r == s:
+            continue
+        d, a = C.c_double(), C.c_double()
+        emul.emul_par_dS(h, int(v), int(s), taylor, C.byref(d), C.byref(a))
+        if taylor:
+            assert abs(d.value - dS) < tol
+        else:
+            assert abs(d.value - dS) <= tol * max(1.0, abs(dS))
+        assert abs(a.value - ar) <= 1e-12 * abs(ar)
+        checked += 1
+    assert checked > 0
+    emul.emul_destroy(h)
+
+
+def test_lgamma_diff(emul):
+    from math import lgamma
+    for x in [1, 2, 5, 31, 32, 33, 100, 12345, 10 ** 6, 3 * 10 ** 8]:
+        for d in [0, 1, 2, 7, 20, 57, 500]:
+            want = lgamma(x + d) - lgamma(x)
+            got = emul.emul_lgamma_diff(float(x), float(d))
+            # the direct difference itself loses ~1e-16 * lgamma(x) to cancellation
+            assert abs(got - want) <= 1e-11 * max(1.0, abs(want)) + 4e-16 * abs(lgamma(x + d))
+
+
+def test_log_q_approx_device_text(emul):
+    m = load_golden("math")
+    for n, k, v in zip(m["a_n"], m["a_k"], m["a_v"]):
+        assert emul.emul_log_q_approx(int(n), int(k)) == v
+
+
+def test_feistel_is_a_permutation(emul):
+    for n in (1, 2, 3, 18, 500, 4097, 100000):
+        for key in (0, 1, 0xDEADBEEFCAFE):
+            p = np.array([emul.emul_feistel(i, n, key) for i in range(n)])
+            assert (np.sort(p) == np.arange(n)).all()
+    a = np.array([emul.emul_feistel(i, 1000, 1) for i in range(1000)])
+    b = np.array([emul.emul_feistel(i, 1000, 2) for i in range(1000)])
+    assert (a != b).mean() > 0.9
