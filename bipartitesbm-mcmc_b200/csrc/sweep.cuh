@@ -167,20 +167,21 @@ __global__ void __launch_bounds__(512) sweep_kernel(SweepParams P) {
     double ds_sum = 0.0;
 
     for (uint32_t i = tile; i < nv; i += P.tiles) {
+        // The trip count is warp-uniform: reconverge all 32 lanes (= chains) at every vertex so
+        // the neighbour gathers below stay coalesced 128-byte loads.
+        __syncwarp();
         const uint32_t v = v0 + feistel_perm(i, nv, P.half_bits, pkey);
         const uint32_t row = G.row_ptr[v];
         const uint32_t d = G.row_ptr[v + 1] - row;
-        if (!live) continue;
-        const uint32_t r = (uint32_t)LAB[(size_t)v * C];
+        const double T = par_temperature(P.schedule, P.p0, P.p1, P.step_base + i);
+        const uint32_t r = live ? (uint32_t)LAB[(size_t)v * C] : 0u;
 
         // ---- proposal (single_vertex_change) ----
         u32x4 ctr; ctr.x = v; ctr.y = (uint32_t)P.sweep; ctr.z = (uint32_t)(P.sweep >> 32); ctr.w = 0;
         const u32x4 ra = philox4x32(ctr, key0, key1);
-        uint32_t s;            // own-type local index of the target block
+        uint32_t s = r;        // own-type local index of the target block
         bool cross = false;    // proposal fell on a block of the other type
-        if (kown == 1) {
-            s = r;
-        } else {
+        if (live && kown != 1) {
             bool uniform_pick = (d == 0);
             uint32_t t = 0;
             int e_t = 0;
@@ -202,92 +203,107 @@ __global__ void __launch_bounds__(512) sweep_kernel(SweepParams P) {
                 uint64_t cum = 0;
                 s = kown - 1;
                 const int32_t* col_t = M + (size_t)t * st;
-                for (uint32_t x = 0; x < kown; ++x) {
+                bool found = false;
+                for (uint32_t x = 0; x < kown; ++x) {   // no early exit: keeps the lanes in step
                     cum += (uint32_t)ldc(&col_t[(size_t)x * sx]);
-                    if (cum > z) { s = x; break; }
+                    if (!found && cum > z) { s = x; found = true; }
                 }
             }
         }
-        if (cross) continue;  // dS = +inf: rejected
-        if (s == r) {         // dS = 0, accu_r = 1: accepted unless the block would empty
-            if (ldc(&NR[own_off + r]) != 1) ++n_acc;
-            continue;
+        // dS = +inf for a cross-type target (rejected); dS = 0, accu_r = 1 for s == r: at T > 0
+        // accepted unless the block would empty, at T == 0 the reference requires dS < 0
+        // (src/metropolis_hasting.cc:47-52)
+        const bool eval = live && !cross && (s != r);
+        if (live && !cross && s == r) {
+            if (T != 0.0 && ldc(&NR[own_off + r]) != 1) ++n_acc;
         }
+        __syncwarp();
+        if (!__any_sync(0xffffffffu, eval)) continue;
 
         // ---- neighbour-block histogram (exact: neighbours are frozen in this half sweep) ----
-        for (uint32_t t = 0; t < kopp; ++t) hist[t * 32] = 0;
+        if (eval) {
+            for (uint32_t t = 0; t < kopp; ++t) hist[t * 32] = 0;
 #pragma unroll 4
-        for (uint32_t e = 0; e < d; ++e) {
-            const uint32_t nb = G.col[row + e];
-            const uint32_t t = (uint32_t)LAB[(size_t)nb * C];
-            hist[t * 32] += 1;
+            for (uint32_t e = 0; e < d; ++e) {
+                const uint32_t nb = G.col[row + e];
+                const uint32_t t = (uint32_t)LAB[(size_t)nb * C];
+                hist[t * 32] += 1;
+            }
         }
+        __syncwarp();
 
         // ---- dS and Hastings factor (transition_ratio) ----
-        const int32_t* Mr = M + (size_t)r * sx;
-        const int32_t* Ms = M + (size_t)s * sx;
-        double a0 = 0.0, a1 = 0.0, ratio = 1.0, logacc = 0.0;
-        for (uint32_t t = 0; t < kopp; ++t) {
-            const int kk = (int)hist[t * 32];
-            if (kk == 0) continue;
-            const int m_r = ldc(&Mr[(size_t)t * st]), m_s = ldc(&Ms[(size_t)t * st]);
-            const double inv = 1.0 / ((double)ldc(&E[opp_off + t]) + epsK);
-            a0 += (double)kk * ((double)m_s + eps) * inv;
-            a1 += (double)kk * ((double)(m_r - kk) + eps) * inv;
-            if (kk <= 8) {
-                double num = 1.0, den = 1.0;
-                for (int q = 0; q < kk; ++q) { num *= (double)(m_r - q); den *= (double)(m_s + 1 + q); }
-                ratio *= num / den;
-                if (ratio > 1e100 || ratio < 1e-100) { logacc += log(ratio); ratio = 1.0; }
-            } else {
-                logacc += lgamma_diff((double)(m_r - kk + 1), (double)kk) - lgamma_diff((double)(m_s + 1), (double)kk);
-            }
-        }
-        const int e_r = ldc(&E[own_off + r]), e_s = ldc(&E[own_off + s]);
-        const int n_r = ldc(&NR[own_off + r]), n_s = ldc(&NR[own_off + s]);
+        bool go = false;
+        double dS = 0.0;
         const uint32_t didx = G.degidx[v];
-        const int eta_r = ldc(&ETA[(size_t)(own_off + r) * W + didx]), eta_s = ldc(&ETA[(size_t)(own_off + s) * W + didx]);
-        ratio *= (double)(eta_r > 0 ? eta_r : 1) / (double)(eta_s + 1);
-        double dS = logacc + log(ratio);
-        dS += lgamma_diff((double)(e_s + 1), (double)d) - lgamma_diff((double)(e_r - (int)d + 1), (double)d);
-        dS += logq_delta(P.tb, LQ[own_off + r], e_r, n_r, -(int)d, -1);
-        dS += logq_delta(P.tb, LQ[own_off + s], e_s, n_s, (int)d, 1);
+        if (eval) {
+            const int32_t* Mr = M + (size_t)r * sx;
+            const int32_t* Ms = M + (size_t)s * sx;
+            double a0 = 0.0, a1 = 0.0, ratio = 1.0, logacc = 0.0;
+            for (uint32_t t = 0; t < kopp; ++t) {
+                const int kk = (int)hist[t * 32];
+                if (kk == 0) continue;
+                const int m_r = ldc(&Mr[(size_t)t * st]), m_s = ldc(&Ms[(size_t)t * st]);
+                const double inv = 1.0 / ((double)ldc(&E[opp_off + t]) + epsK);
+                a0 += (double)kk * ((double)m_s + eps) * inv;
+                a1 += (double)kk * ((double)(m_r - kk) + eps) * inv;
+                if (kk <= 8) {
+                    double num = 1.0, den = 1.0;
+                    for (int q = 0; q < kk; ++q) { num *= (double)(m_r - q); den *= (double)(m_s + 1 + q); }
+                    ratio *= num / den;
+                    if (ratio > 1e100 || ratio < 1e-100) { logacc += log(ratio); ratio = 1.0; }
+                } else {
+                    logacc += lgamma_diff((double)(m_r - kk + 1), (double)kk) - lgamma_diff((double)(m_s + 1), (double)kk);
+                }
+            }
+            const int e_r = ldc(&E[own_off + r]), e_s = ldc(&E[own_off + s]);
+            const int n_r = ldc(&NR[own_off + r]), n_s = ldc(&NR[own_off + s]);
+            const int eta_r = ldc(&ETA[(size_t)(own_off + r) * W + didx]), eta_s = ldc(&ETA[(size_t)(own_off + s) * W + didx]);
+            ratio *= (double)(eta_r > 0 ? eta_r : 1) / (double)(eta_s + 1);
+            dS = logacc + log(ratio);
+            dS += lgamma_diff((double)(e_s + 1), (double)d) - lgamma_diff((double)(e_r - (int)d + 1), (double)d);
+            dS += logq_delta(P.tb, LQ[own_off + r], e_r, n_r, -(int)d, -1);
+            dS += logq_delta(P.tb, LQ[own_off + s], e_s, n_s, (int)d, 1);
 
-        // ---- accept (step) ----
-        const double T = par_temperature(P.schedule, P.p0, P.p1, P.step_base + i);
-        bool go;
-        if (T == 0.0) {
-            go = dS < 0.0;
-        } else {
-            const double a = -dS / T + ((d == 0) ? 0.0 : log(a1 / a0));
-            if (a > 0.0) go = true;
-            else {
-                ctr.w = 1;
-                const u32x4 rb = philox4x32(ctr, key0, key1);
-                go = u53(rb.x, rb.y) < exp(a);
+            // ---- accept (step) ----
+            if (T == 0.0) {
+                go = dS < 0.0;
+            } else {
+                const double a = -dS / T + ((d == 0) ? 0.0 : log(a1 / a0));
+                if (a > 0.0) go = true;
+                else {
+                    ctr.w = 1;
+                    const u32x4 rb = philox4x32(ctr, key0, key1);
+                    go = u53(rb.x, rb.y) < exp(a);
+                }
             }
         }
-        if (!go) continue;
+        __syncwarp();
 
         // ---- commit (apply_mcmc_moves) ----
-        const int old = atomicSub(&NR[own_off + r], 1);
-        if (old <= 1) { atomicAdd(&NR[own_off + r], 1); continue; }  // would empty block r
-        atomicAdd(&NR[own_off + s], 1);
-        atomicSub(&ETA[(size_t)(own_off + r) * W + didx], 1);
-        atomicAdd(&ETA[(size_t)(own_off + s) * W + didx], 1);
-        int32_t* Mrw = M + (size_t)r * sx;
-        int32_t* Msw = M + (size_t)s * sx;
-        for (uint32_t t = 0; t < kopp; ++t) {
-            const int kk = (int)hist[t * 32];
-            if (kk == 0) continue;
-            atomicSub(&Mrw[(size_t)t * st], kk);
-            atomicAdd(&Msw[(size_t)t * st], kk);
+        if (go) {
+            const int old = atomicSub(&NR[own_off + r], 1);
+            if (old <= 1) {
+                atomicAdd(&NR[own_off + r], 1);  // would empty block r: vetoed
+            } else {
+                atomicAdd(&NR[own_off + s], 1);
+                atomicSub(&ETA[(size_t)(own_off + r) * W + didx], 1);
+                atomicAdd(&ETA[(size_t)(own_off + s) * W + didx], 1);
+                int32_t* Mrw = M + (size_t)r * sx;
+                int32_t* Msw = M + (size_t)s * sx;
+                for (uint32_t t = 0; t < kopp; ++t) {
+                    const int kk = (int)hist[t * 32];
+                    if (kk == 0) continue;
+                    atomicSub(&Mrw[(size_t)t * st], kk);
+                    atomicAdd(&Msw[(size_t)t * st], kk);
+                }
+                atomicSub(&E[own_off + r], (int)d);
+                atomicAdd(&E[own_off + s], (int)d);
+                LAB[(size_t)v * C] = (int32_t)s;
+                ++n_acc;
+                ds_sum += dS;
+            }
         }
-        atomicSub(&E[own_off + r], (int)d);
-        atomicAdd(&E[own_off + s], (int)d);
-        LAB[(size_t)v * C] = (int32_t)s;
-        ++n_acc;
-        ds_sum += dS;
     }
     if (live) {
         if (n_acc) atomicAdd(&P.accepted[c], n_acc);

@@ -164,7 +164,7 @@ def test_large_graph_invariants_and_logq_expansion(host):
     # stale reads make the accumulated dS approximate, but it must track the true change closely
     for c in (0, 63):
         d_true, d_acc = e2[c] - e1[c], pool.entropy_accum(c)
-        assert abs(d_true - d_acc) <= 0.02 * abs(d_true) + 5.0
+        assert abs(d_true - d_acc) <= 0.10 * abs(d_true) + 10.0
     # sequential chains: exact
     pool2 = host.ChainPool(graph, np.tile(planted_labels(na, nb, ka, kb), (C, 1)), ka, kb, 1.0)
     pool2.randomize(seeds)
