@@ -16,9 +16,11 @@
 #ifdef __CUDACC__
 #define BISBM_HD __host__ __device__ __forceinline__
 #define BISBM_D __device__ __forceinline__
+#define BISBM_NOINLINE_HD __host__ __device__ __noinline__
 #else
 #define BISBM_HD inline
 #define BISBM_D inline
+#define BISBM_NOINLINE_HD
 #endif
 
 namespace bisbm {

@@ -52,7 +52,7 @@ struct SweepParams {
 
 // temperature of global step t (same five schedules as src/metropolis_hasting.cc:10-37,
 // device libm for pow / log)
-BISBM_HD double par_temperature(int schedule, float p0, float p1, uint64_t t) {
+BISBM_NOINLINE_HD static double par_temperature(int schedule, float p0, float p1, uint64_t t) {
     switch (schedule) {
         case 0: return (double)p0 * pow((double)p1, (double)t);
         case 1: return (double)(p0 - p1 * (float)t);
@@ -67,8 +67,9 @@ BISBM_HD double par_temperature(int schedule, float p0, float p1, uint64_t t) {
 }
 
 // lgamma(x + d) - lgamma(x) for integers x >= 1, d >= 0, without the 2E-entry table:
-// Stirling difference with log1p for large x, direct lgamma for small x.
-BISBM_HD double lgamma_diff(double x, double d) {
+// Stirling difference with log1p for large x, direct lgamma for small x.  Kept out of line:
+// the sweep kernel must stay small enough for the instruction cache.
+BISBM_NOINLINE_HD static double lgamma_diff(double x, double d) {
     if (d == 0.0) return 0.0;
     if (x < 32.0) return lgamma(x + d) - lgamma(x);
     double y = x + d;
@@ -76,6 +77,11 @@ BISBM_HD double lgamma_diff(double x, double d) {
     double ser = (iy - ix) * (1.0 / 12.0) - (iy * iy * iy - ix * ix * ix) * (1.0 / 360.0) +
                  (iy * iy * iy * iy * iy - ix * ix * ix * ix * ix) * (1.0 / 1260.0);
     return (x - 0.5) * log1p(d * ix) + d * (log(y) - 1.0) + ser;
+}
+
+// exact (table / full asymptotic formula) difference: the rare slow path, out of line
+BISBM_NOINLINE_HD static double logq_delta_exact(const Tables& tb, int e, int n, int de, int dn) {
+    return log_q(tb, e + de, n + dn) - log_q(tb, e, n);
 }
 
 // log q difference f(e+de, n+dn) - f(e, n) for one block
@@ -87,7 +93,7 @@ BISBM_HD double logq_delta(const Tables& tb, const LogqExp& q, int e, int n, int
         return (double)q.fe * De + (double)q.fn * Dn + 0.5 * (double)q.fee * (De * De + 2.0 * dx * De) +
                (double)q.fen * (dx * Dn + dy * De + De * Dn) + 0.5 * (double)q.fnn * (Dn * Dn + 2.0 * dy * Dn);
     }
-    return log_q(tb, e + de, n + dn) - log_q(tb, e, n);
+    return logq_delta_exact(tb, e, n, de, dn);
 }
 
 #ifdef __CUDACC__
@@ -173,7 +179,7 @@ __global__ void __launch_bounds__(512) sweep_kernel(SweepParams P) {
         const uint32_t v = v0 + feistel_perm(i, nv, P.half_bits, pkey);
         const uint32_t row = G.row_ptr[v];
         const uint32_t d = G.row_ptr[v + 1] - row;
-        const double T = par_temperature(P.schedule, P.p0, P.p1, P.step_base + i);
+        const double T = (P.schedule == 3) ? (double)P.p0 : par_temperature(P.schedule, P.p0, P.p1, P.step_base + i);
         const uint32_t r = live ? (uint32_t)LAB[(size_t)v * C] : 0u;
 
         // ---- proposal (single_vertex_change) ----
