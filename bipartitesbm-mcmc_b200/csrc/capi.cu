@@ -19,7 +19,7 @@
 #include <vector>
 
 #include "replay.cuh"
-#include "sweep.cuh"
+#include "sweep_aux.cuh"
 
 using namespace bisbm;
 
@@ -74,6 +74,7 @@ struct bisbm_handle {
     uint32_t *d_ka = nullptr, *d_kb = nullptr;
     int32_t *d_labels = nullptr, *d_labels_tmp = nullptr, *d_m = nullptr, *d_e = nullptr, *d_nr = nullptr,
             *d_eta = nullptr;
+    int32_t *d_m2 = nullptr, *d_e2 = nullptr;  // "next" count buffers of the sliced shared-memory sweep
     double eps = 1.0;
     LogqExp* d_lq = nullptr;
     uint64_t* d_seeds = nullptr;
@@ -101,7 +102,7 @@ void dfree(T*& p) {
 
 void free_chains(bisbm_handle* h) {
     dfree(h->d_ka); dfree(h->d_kb); dfree(h->d_labels); dfree(h->d_labels_tmp);
-    dfree(h->d_m); dfree(h->d_e); dfree(h->d_nr); dfree(h->d_eta); dfree(h->d_lq);
+    dfree(h->d_m); dfree(h->d_e); dfree(h->d_nr); dfree(h->d_eta); dfree(h->d_lq); dfree(h->d_m2); dfree(h->d_e2);
     dfree(h->d_seeds); dfree(h->d_active); dfree(h->d_accepted); dfree(h->d_u); dfree(h->d_sweeps);
     dfree(h->d_dS); dfree(h->d_entmin); dfree(h->d_ent_out); dfree(h->d_nactive); dfree(h->d_hist);
     for (auto& kv : h->replay) { dfree(kv.second.d_rs); dfree(kv.second.d_vlist); dfree(kv.second.d_kh); }
@@ -259,18 +260,7 @@ int rebuild_counts(bisbm_handle* h) {
 ReplayCtx rctx(bisbm_handle* h, uint32_t chain, const ReplaySlot& sl) {
     ReplayCtx x;
     x.g = gview(h);
-    StateView s = sview(h);
-    // chain_ref reads ka/kb through device pointers; build it from the host copies instead
-    ChainRef r;
-    r.labels = s.labels + chain;
-    r.C = s.C;
-    r.m = s.m + (size_t)chain * s.KA * s.KB;
-    r.e = s.e + (size_t)chain * (s.KA + s.KB);
-    r.nr = s.nr + (size_t)chain * (s.KA + s.KB);
-    r.eta = s.eta + (size_t)chain * (s.KA + s.KB) * s.W;
-    r.ka = h->h_ka[chain]; r.kb = h->h_kb[chain];
-    r.KA = s.KA; r.KB = s.KB; r.W = s.W;
-    x.c = r;
+    x.c = chain_ref(sview(h), chain, h->h_ka[chain], h->h_kb[chain]);
     x.tb = tview(h, true);
     x.rs = sl.d_rs;
     x.vlist = sl.d_vlist;
@@ -320,45 +310,55 @@ uint64_t cold_steps(int schedule, float p0, float p1, uint64_t t0, uint64_t t1) 
 }
 
 struct LaunchPlan {
-    uint32_t wpc, tiles, ctas_per_group;
-    size_t smem;
-    bool wide_hist;
+    bool smem, wide_hist;
+    uint32_t wpc;             // warps per CTA (blockDim / 32)
+    uint32_t warps_used;      // of which take vertices
+    uint32_t ctas_per_group;
+    uint32_t slice;           // positions of the visiting order per launch
+    size_t smem_bytes;
 };
 
+// How one half sweep is cut into launches.  `max_inflight` bounds the number of moves of one
+// chain that may be evaluated against counts that do not yet include each other:
+//   one CTA per chain group  -> warps_used concurrent moves (shared-memory counts are exact)
+//   several CTAs per group   -> one slice of the visiting order per launch (a CTA sees the other
+//                               CTAs' moves of the same slice only in the next launch)
 int plan_sweep(bisbm_handle* h, uint32_t type, uint32_t max_inflight, LaunchPlan* lp) {
     const uint32_t kopp_max = type ? h->KA : h->KB;
     const uint32_t nv = type ? h->nb : h->na;
-    lp->wide_hist = h->max_degree >= 65535u;
-    const size_t per_warp = (size_t)kopp_max * 32 * (lp->wide_hist ? 4 : 2);
-    uint32_t wpc = 16;
-    while (wpc > 1 && per_warp * wpc > 200 * 1024) wpc >>= 1;
-    if (per_warp * wpc > 200 * 1024) return fail(BISBM_ERR_ARG, "K too large for the shared-memory histogram");
     const uint32_t n_groups = h->C / 32;
-    // fill the GPU: ~48 resident warps per SM
-    uint64_t resident = (uint64_t)h->sm_count * 48;
-    uint32_t tiles = (uint32_t)std::max<uint64_t>(1, resident / n_groups);
-    // keep the in-flight fraction of a half sweep small
-    uint32_t cap = std::max<uint32_t>(1, nv / 64);
-    if (max_inflight) cap = max_inflight;
-    tiles = std::min(tiles, cap);
-    tiles = std::max<uint32_t>(1, std::min<uint32_t>(tiles, std::max<uint32_t>(nv, 1)));
-    if (tiles < wpc) wpc = 1u << (31 - __builtin_clz(tiles));  // largest power of two <= tiles
+    lp->wide_hist = h->max_degree >= 65535u;
+    const uint32_t hb = lp->wide_hist ? 4 : 2;
+    const size_t budget = 200 * 1024;
+    uint32_t wpc = 16;
+    lp->smem = sweep_smem_bytes(true, h->KA, h->KB, type, 4, hb) <= budget;
+    while (wpc > 1 && sweep_smem_bytes(lp->smem, h->KA, h->KB, type, wpc, hb) > budget) wpc >>= 1;
+    if (sweep_smem_bytes(lp->smem, h->KA, h->KB, type, wpc, hb) > budget)
+        return fail(BISBM_ERR_ARG, "K too large for the shared-memory histogram");
+    const uint32_t inflight = max_inflight ? max_inflight : std::max<uint32_t>(wpc, nv / 64);
+    // CTAs per group: fill the SMs, but never more warps than the in-flight bound or the work allows
+    uint32_t cpg = std::max<uint32_t>(1, (uint32_t)h->sm_count / n_groups);
+    if (!lp->smem) cpg = std::max<uint32_t>(1, ((uint32_t)h->sm_count * 3) / n_groups);  // 3 resident CTAs per SM
+    cpg = std::min<uint32_t>(cpg, std::max<uint32_t>(1, inflight / wpc));
+    cpg = std::min<uint32_t>(cpg, std::max<uint32_t>(1, nv / (wpc * 4)));
+    lp->ctas_per_group = cpg;
     lp->wpc = wpc;
-    lp->tiles = tiles;
-    lp->ctas_per_group = (tiles + wpc - 1) / wpc;
-    lp->smem = per_warp * wpc;
+    lp->warps_used = (cpg == 1) ? std::max<uint32_t>(1, std::min<uint32_t>(wpc, std::min<uint32_t>(inflight, std::max<uint32_t>(nv, 1)))) : wpc;
+    if (lp->smem && cpg > 1) lp->slice = std::max<uint32_t>(cpg * wpc, std::min<uint32_t>(inflight, nv));
+    else lp->slice = std::max<uint32_t>(nv, 1);
+    lp->smem_bytes = sweep_smem_bytes(lp->smem, h->KA, h->KB, type, wpc, hb);
     return BISBM_OK;
 }
 
-template <typename HistT>
+template <bool SMEM, typename HistT>
 int launch_sweep_t(bisbm_handle* h, const SweepParams& P, const LaunchPlan& lp) {
     static bool attr_set = false;
     if (!attr_set) {
-        CU(cudaFuncSetAttribute(sweep_kernel<HistT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CU(cudaFuncSetAttribute(sweep_kernel<SMEM, HistT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = true;
     }
     const unsigned grid = P.n_groups * lp.ctas_per_group;
-    sweep_kernel<HistT><<<grid, lp.wpc * 32, lp.smem, h->stream>>>(P);
+    sweep_kernel<SMEM, HistT><<<grid, lp.wpc * 32, lp.smem_bytes, h->stream>>>(P);
     CU(cudaGetLastError());
     return BISBM_OK;
 }
@@ -375,19 +375,35 @@ int launch_full_sweep(bisbm_handle* h, int schedule, float p0, float p1, uint64_
         const uint32_t kmax = type ? h->KB : h->KA;
         const uint32_t tot = h->n_chains * kmax;
         logq_refresh_kernel<<<(tot + 127) / 128, 128, 0, h->stream>>>(sview(h), tview(h, false), h->d_lq, h->n_chains, type);
-        SweepParams P;
-        P.g = gview(h); P.s = sview(h); P.tb = tview(h, false);
-        P.seeds = h->d_seeds; P.active = h->d_active; P.accepted = h->d_accepted; P.dS_accum = h->d_dS;
-        P.lq = h->d_lq;
-        P.n_chains = h->n_chains; P.type = type; P.tiles = lp.tiles; P.n_groups = h->C / 32;
-        P.half_bits = feistel_half_bits(nv);
-        P.hist_stride = type ? h->KA : h->KB;
-        P.sweep = h->sweep_epoch;
-        P.step_base = sweep_in_call * (uint64_t)h->n + (type ? h->na : 0);
-        P.schedule = schedule; P.p0 = p0; P.p1 = p1;
-        rc = lp.wide_hist ? launch_sweep_t<uint32_t>(h, P, lp) : launch_sweep_t<uint16_t>(h, P, lp);
-        if (rc) return rc;
-        h->last_launches += 2;
+        h->last_launches += 1;
+        const size_t m_bytes = (size_t)h->C * h->KA * h->KB * sizeof(int32_t);
+        const size_t e_bytes = (size_t)h->C * (h->KA + h->KB) * sizeof(int32_t);
+        const bool sliced = lp.smem && lp.ctas_per_group > 1;
+        for (uint32_t pos = 0; pos < nv; pos += lp.slice) {
+            if (sliced) {  // next := base; the launch adds each CTA's (staged - base) into next
+                CU(cudaMemcpyAsync(h->d_m2, h->d_m, m_bytes, cudaMemcpyDeviceToDevice, h->stream));
+                CU(cudaMemcpyAsync(h->d_e2, h->d_e, e_bytes, cudaMemcpyDeviceToDevice, h->stream));
+            }
+            SweepParams P;
+            P.g = gview(h); P.s = sview(h); P.tb = tview(h, false);
+            P.m_next = h->d_m2; P.e_next = h->d_e2;
+            P.seeds = h->d_seeds; P.active = h->d_active; P.accepted = h->d_accepted; P.dS_accum = h->d_dS;
+            P.lq = h->d_lq;
+            P.n_chains = h->n_chains; P.type = type; P.n_groups = h->C / 32;
+            P.ctas_per_group = lp.ctas_per_group; P.warps_used = lp.warps_used;
+            P.pos_begin = pos; P.pos_end = std::min<uint64_t>(nv, (uint64_t)pos + lp.slice);
+            P.half_bits = feistel_half_bits(nv);
+            P.kopp_max = type ? h->KA : h->KB;
+            P.exclusive = sliced ? 0 : 1;
+            P.sweep = h->sweep_epoch;
+            P.step_base = sweep_in_call * (uint64_t)h->n + (type ? h->na : 0);
+            P.schedule = schedule; P.p0 = p0; P.p1 = p1;
+            if (lp.smem) rc = lp.wide_hist ? launch_sweep_t<true, uint32_t>(h, P, lp) : launch_sweep_t<true, uint16_t>(h, P, lp);
+            else rc = lp.wide_hist ? launch_sweep_t<false, uint32_t>(h, P, lp) : launch_sweep_t<false, uint16_t>(h, P, lp);
+            if (rc) return rc;
+            h->last_launches += 1;
+            if (sliced) { std::swap(h->d_m, h->d_m2); std::swap(h->d_e, h->d_e2); }
+        }
     }
     h->sweep_epoch++;
     h->last_moves += (uint64_t)h->n * h->n_chains;
@@ -499,6 +515,8 @@ int bisbm_set_chains(bisbm_handle* h, uint32_t n_chains, const uint32_t* ka, con
         CU(cudaMalloc(&h->d_labels_tmp, (size_t)n * C * sizeof(int32_t)));
         CU(cudaMalloc(&h->d_m, (size_t)C * KA * KB * sizeof(int32_t)));
         CU(cudaMalloc(&h->d_e, (size_t)C * KK * sizeof(int32_t)));
+        CU(cudaMalloc(&h->d_m2, (size_t)C * KA * KB * sizeof(int32_t)));
+        CU(cudaMalloc(&h->d_e2, (size_t)C * KK * sizeof(int32_t)));
         CU(cudaMalloc(&h->d_nr, (size_t)C * KK * sizeof(int32_t)));
         CU(cudaMalloc(&h->d_eta, (size_t)C * KK * h->W * sizeof(int32_t)));
         CU(cudaMalloc(&h->d_lq, (size_t)C * KK * sizeof(LogqExp)));
@@ -885,13 +903,22 @@ int bisbm_get_labels(bisbm_handle* h, uint32_t chain, uint32_t* labels) {
     return BISBM_OK;
 }
 
+// copy entries [first, first+count) of chain `chain` out of a group-interleaved count array
+static int fetch_counts(bisbm_handle* h, const int32_t* d_src, size_t per_chain, uint32_t chain, std::vector<int32_t>& out) {
+    out.resize(per_chain);
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaMemcpy2D(out.data(), sizeof(int32_t), d_src + cnt_base(chain, per_chain), GROUP * sizeof(int32_t),
+                    sizeof(int32_t), per_chain, cudaMemcpyDeviceToHost));
+    return BISBM_OK;
+}
+
 int bisbm_get_m(bisbm_handle* h, uint32_t chain, int32_t* m) {
     int rc = need_chains(h);
     if (rc) return rc;
     if (chain >= h->n_chains) return fail(BISBM_ERR_ARG, "chain %u out of range", chain);
-    std::vector<int32_t> M((size_t)h->KA * h->KB);
-    CU(cudaStreamSynchronize(h->stream));
-    CU(cudaMemcpy(M.data(), h->d_m + (size_t)chain * h->KA * h->KB, M.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    std::vector<int32_t> M;
+    rc = fetch_counts(h, h->d_m, (size_t)h->KA * h->KB, chain, M);
+    if (rc) return rc;
     const uint32_t ka = h->h_ka[chain], kb = h->h_kb[chain], K = ka + kb;
     std::fill(m, m + (size_t)K * K, 0);
     for (uint32_t a = 0; a < ka; ++a)
@@ -907,10 +934,9 @@ static int get_slots(bisbm_handle* h, uint32_t chain, const int32_t* d_src, int3
     int rc = need_chains(h);
     if (rc) return rc;
     if (chain >= h->n_chains) return fail(BISBM_ERR_ARG, "chain %u out of range", chain);
-    const size_t KK = (size_t)h->KA + h->KB;
-    std::vector<int32_t> tmp(KK);
-    CU(cudaStreamSynchronize(h->stream));
-    CU(cudaMemcpy(tmp.data(), d_src + (size_t)chain * KK, KK * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    std::vector<int32_t> tmp;
+    rc = fetch_counts(h, d_src, (size_t)h->KA + h->KB, chain, tmp);
+    if (rc) return rc;
     const uint32_t ka = h->h_ka[chain], kb = h->h_kb[chain];
     for (uint32_t a = 0; a < ka; ++a) out[a] = tmp[a];
     for (uint32_t b = 0; b < kb; ++b) out[ka + b] = tmp[h->KA + b];
@@ -924,10 +950,9 @@ int bisbm_get_eta(bisbm_handle* h, uint32_t chain, uint32_t* eta) {
     int rc = need_chains(h);
     if (rc) return rc;
     if (chain >= h->n_chains) return fail(BISBM_ERR_ARG, "chain %u out of range", chain);
-    const size_t KK = (size_t)h->KA + h->KB;
-    std::vector<int32_t> tmp(KK * h->W);
-    CU(cudaStreamSynchronize(h->stream));
-    CU(cudaMemcpy(tmp.data(), h->d_eta + (size_t)chain * KK * h->W, tmp.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    std::vector<int32_t> tmp;
+    rc = fetch_counts(h, h->d_eta, ((size_t)h->KA + h->KB) * h->W, chain, tmp);
+    if (rc) return rc;
     const uint32_t ka = h->h_ka[chain], kb = h->h_kb[chain];
     const size_t Wf = (size_t)h->max_degree + 1;
     std::fill(eta, eta + (size_t)(ka + kb) * Wf, 0u);

@@ -65,9 +65,9 @@ BISBM_HD double rp_transition(const ReplayCtx& x, uint32_t v, uint32_t r, uint32
     int deg = (int)(x.g.row_ptr[v + 1] - x.g.row_ptr[v]);
     uint32_t didx = x.g.degidx[v];
     uint32_t sr = slot_of(c, r), ss = slot_of(c, s);
-    int n_rr = c.nr[sr], n_rs = c.nr[ss];
-    int eta_r = c.eta[(size_t)sr * c.W + didx], eta_s = c.eta[(size_t)ss * c.W + didx];
-    int e0r = c.e[sr], e1r = e0r - deg, e0s = c.e[ss], e1s = e0s + deg;
+    int n_rr = nr_ref(c, sr), n_rs = nr_ref(c, ss);
+    int eta_r = eta_ref(c, sr, didx), eta_s = eta_ref(c, ss, didx);
+    int e0r = e_ref(c, sr), e1r = e0r - deg, e0s = e_ref(c, ss), e1s = e0s + deg;
     double a0 = 0.0, a1 = 0.0, S0 = 0.0, S1 = 0.0;
     bool va = r < ka;
     uint32_t kopp = va ? c.kb : c.ka;
@@ -76,7 +76,7 @@ BISBM_HD double rp_transition(const ReplayCtx& x, uint32_t v, uint32_t r, uint32
         if (kk == 0) continue;
         uint32_t gi = va ? ka + t : t;
         int m_r = m_at(c, r, gi), m_s = m_at(c, s, gi);
-        int e_i = c.e[slot_of(c, gi)];
+        int e_i = e_ref(c, slot_of(c, gi));
         double den = dadd((double)e_i, dmul(eps, Kd));
         a0 = dadd(a0, ddiv(ddiv(dmul((double)kk, dadd((double)m_s, eps)), den), (double)deg));
         a1 = dadd(a1, ddiv(ddiv(dmul((double)kk, dadd((double)(m_r - kk), eps)), den), (double)deg));
@@ -132,7 +132,7 @@ BISBM_HD uint32_t rp_propose(const ReplayCtx& x, uint32_t v, uint32_t r) {
     uint32_t j = x.g.col[row + which];
     uint32_t t = rp_label(x, j);
     double eK = dmul(x.eps, (double)K);
-    double R = ddiv(eK, dadd((double)c.e[slot_of(c, t)], eK));
+    double R = ddiv(eK, dadd((double)e_ref(c, slot_of(c, t)), eK));
     if (mt_canon(x.rs->engine) < R) return (uint32_t)(uint64_t)dmul(mt_canon(x.rs->engine), (double)K);
     return rp_categorical(x, t);
 }
@@ -141,12 +141,12 @@ BISBM_HD uint32_t rp_propose(const ReplayCtx& x, uint32_t v, uint32_t r) {
 BISBM_HD bool rp_apply(const ReplayCtx& x, uint32_t v, uint32_t r, uint32_t s, double dS) {
     const ChainRef& c = x.c;
     uint32_t sr = slot_of(c, r), ss = slot_of(c, s);
-    if (c.nr[sr] - 1 == 0) return false;  // would empty block r
+    if (nr_ref(c, sr) - 1 == 0) return false;  // would empty block r
     if (r != s) {
-        c.nr[sr]--; c.nr[ss]++;
+        nr_ref(c, sr)--; nr_ref(c, ss)++;
         uint32_t didx = x.g.degidx[v];
-        c.eta[(size_t)sr * c.W + didx]--;
-        c.eta[(size_t)ss * c.W + didx]++;
+        eta_ref(c, sr, didx)--;
+        eta_ref(c, ss, didx)++;
         bool va = r < c.ka;
         uint32_t kopp = va ? c.kb : c.ka;
         for (uint32_t t = 0; t < kopp; ++t) {
@@ -157,8 +157,8 @@ BISBM_HD bool rp_apply(const ReplayCtx& x, uint32_t v, uint32_t r, uint32_t s, d
             *m_ptr(c, s, gi) += kk;
         }
         int deg = (int)(x.g.row_ptr[v + 1] - x.g.row_ptr[v]);
-        c.e[sr] -= deg;
-        c.e[ss] += deg;
+        e_ref(c, sr) -= deg;
+        e_ref(c, ss) += deg;
         c.labels[(size_t)v * c.C] = (int32_t)(va ? s : s - c.ka);
     }
     x.rs->entropy_accum = dadd(x.rs->entropy_accum, dS);

@@ -1,0 +1,212 @@
+// sweep_aux.cuh -- the small kernels around the sweep: state construction (init_bisbm), label
+// import / export / randomisation, per-sweep bookkeeping, marginal histograms, entropy().
+// Count arrays are group-interleaved (see state.cuh): entry j of chain c is at
+// [(c/32 * per_chain + j) * 32 + c%32].
+#pragma once
+#include "sweep.cuh"
+
+namespace bisbm {
+
+#ifdef __CUDACC__
+
+// ---- state construction (init_bisbm: compute_n_r / compute_m / compute_m_r / compute_eta_rk,
+//      reference src/blockmodel.cc:681-746).  lane = chain, one warp per vertex. ----
+__global__ void build_counts_kernel(GraphView G, StateView S, uint32_t n_chains) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t wpc = blockDim.x >> 5;
+    const uint32_t n_groups = S.C / 32;
+    const uint64_t gw = (uint64_t)blockIdx.x * wpc + (threadIdx.x >> 5);
+    const uint32_t group = gw % n_groups;
+    const uint64_t v64 = gw / n_groups;
+    if (v64 >= G.n) return;
+    const uint32_t v = (uint32_t)v64;
+    const uint32_t c = group * 32 + lane;
+    if (c >= n_chains) return;
+    const uint32_t KA = S.KA, KB = S.KB, W = S.W, KK = KA + KB;
+    const bool tb = v >= G.na;
+    const uint32_t b = (uint32_t)S.labels[(size_t)v * S.C + c];
+    const uint32_t slot = (tb ? KA : 0) + b;
+    atomicAdd(&S.nr[((size_t)group * KK + slot) * GROUP + lane], 1);
+    atomicAdd(&S.eta[(((size_t)group * KK + slot) * W + G.degidx[v]) * GROUP + lane], 1);
+    if (!tb) {
+        int32_t* M = S.m + (((size_t)group * KA + b) * KB) * GROUP + lane;
+        for (uint32_t e = G.row_ptr[v]; e < G.row_ptr[v + 1]; ++e) {
+            const uint32_t t = (uint32_t)S.labels[(size_t)G.col[e] * S.C + c];
+            atomicAdd(&M[(size_t)t * GROUP], 1);
+        }
+    }
+}
+
+__global__ void build_e_kernel(StateView S, uint32_t n_chains) {  // compute_m_r
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t KA = S.KA, KB = S.KB;
+    if (idx >= n_chains * (KA + KB)) return;
+    const uint32_t slot = idx / n_chains, c = idx % n_chains;  // consecutive threads = consecutive chains
+    const int32_t* M = S.m + cnt_base(c, (size_t)KA * KB);
+    int64_t sum = 0;
+    if (slot < KA) for (uint32_t b = 0; b < KB; ++b) sum += M[((size_t)slot * KB + b) * GROUP];
+    else for (uint32_t a = 0; a < KA; ++a) sum += M[((size_t)a * KB + (slot - KA)) * GROUP];
+    S.e[cnt_base(c, (size_t)KA + KB) + (size_t)slot * GROUP] = (int32_t)sum;
+}
+
+// parallel-mode --randomize: per chain, permute the labels of each type with a keyed
+// Feistel permutation (keeps block sizes, like shuffle_bisbm)
+__global__ void randomize_kernel(GraphView G, const int32_t* in, int32_t* out, uint32_t C, uint32_t n_chains,
+                                 const uint64_t* seeds, uint32_t hb_a, uint32_t hb_b) {
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (uint64_t)G.n * C) return;
+    const uint32_t v = (uint32_t)(idx / C), c = (uint32_t)(idx % C);
+    if (c >= n_chains) { out[idx] = in[idx]; return; }
+    const bool tb = v >= G.na;
+    const uint32_t v0 = tb ? G.na : 0, nv = tb ? G.nb : G.na;
+    const uint64_t key = seeds[c] * 0x9E3779B97F4A7C15ull + (tb ? 0x632BE59BD9B4E019ull : 0x2545F4914F6CDD1Dull);
+    const uint32_t src = v0 + feistel_perm(v - v0, nv, tb ? hb_b : hb_a, key);
+    out[idx] = in[(size_t)src * C + c];
+}
+
+
+// ---- label import / export: host layout [chain][node] with GLOBAL block ids  <->  device
+//      layout [node][C] chain-minor, type-local.  32x32 tiles through shared memory so both
+//      sides are coalesced.  `bad` receives 1 + (chain * n + node) of the first invalid label. ----
+__global__ void import_labels_kernel(const uint32_t* __restrict__ in, int32_t* __restrict__ out, uint32_t n,
+                                     uint32_t na, uint32_t n_chains, uint32_t C, const uint32_t* __restrict__ ka,
+                                     const uint32_t* __restrict__ kb, unsigned long long* bad) {
+    __shared__ uint32_t tile[32][33];
+    const uint32_t v0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (uint32_t j = threadIdx.y; j < 32; j += blockDim.y) {
+        const uint32_t c = c0 + j, v = v0 + threadIdx.x;
+        tile[j][threadIdx.x] = (c < n_chains && v < n) ? in[(size_t)c * n + v] : 0u;
+    }
+    __syncthreads();
+    for (uint32_t j = threadIdx.y; j < 32; j += blockDim.y) {
+        const uint32_t v = v0 + j, c = c0 + threadIdx.x;
+        if (v >= n) continue;
+        int32_t l = 0;
+        if (c < n_chains) {
+            const uint32_t g = tile[threadIdx.x][j];
+            const uint32_t kac = ka[c], kbc = kb[c];
+            bool ok;
+            if (v < na) { ok = g < kac; l = (int32_t)g; }
+            else { ok = (g >= kac) && (g < kac + kbc); l = (int32_t)(g - kac); }
+            if (!ok) { atomicMin(bad, 1ull + (unsigned long long)c * n + v); l = 0; }
+        }
+        out[(size_t)v * C + c] = l;
+    }
+}
+
+__global__ void export_labels_kernel(const int32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t n,
+                                     uint32_t na, uint32_t n_chains, uint32_t C, const uint32_t* __restrict__ ka) {
+    __shared__ uint32_t tile[32][33];
+    const uint32_t v0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (uint32_t j = threadIdx.y; j < 32; j += blockDim.y) {
+        const uint32_t v = v0 + j, c = c0 + threadIdx.x;
+        uint32_t g = 0;
+        if (v < n && c < n_chains) {
+            const uint32_t l = (uint32_t)in[(size_t)v * C + c];
+            g = v < na ? l : ka[c] + l;
+        }
+        tile[j][threadIdx.x] = g;
+    }
+    __syncthreads();
+    for (uint32_t j = threadIdx.y; j < 32; j += blockDim.y) {
+        const uint32_t c = c0 + j, v = v0 + threadIdx.x;
+        if (c < n_chains && v < n) out[(size_t)c * n + v] = tile[threadIdx.x][j];
+    }
+}
+
+// per-sweep bookkeeping of anneal (src/metropolis_hasting.cc:86-98) at sweep granularity
+__global__ void bookkeep_kernel(uint32_t n_chains, uint8_t* active, const double* dS_accum, double* ent_min,
+                                unsigned long long* u, unsigned long long* sweeps_done, uint64_t sweep,
+                                uint64_t cold_steps, uint64_t steps_await, uint32_t* n_active) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_chains || !active[c]) return;
+    const double ent = dS_accum[c];
+    if (ent < ent_min[c]) { ent_min[c] = ent; u[c] = 0; }
+    else u[c] += cold_steps;
+    sweeps_done[c] = sweep + 1;
+    if (u[c] >= steps_await) { active[c] = 0; atomicSub(n_active, 1u); }
+}
+
+// marginal accumulation: hist[v][g] += #chains with global label g at v
+__global__ void marginal_kernel(GraphView G, StateView S, uint32_t n_chains, uint32_t* hist, uint32_t width) {
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (uint64_t)G.n * S.C) return;
+    const uint32_t v = (uint32_t)(idx / S.C), c = (uint32_t)(idx % S.C);
+    if (c >= n_chains) return;
+    const uint32_t l = (uint32_t)S.labels[idx];
+    const uint32_t g = v < G.na ? l : S.ka[c] + l;
+    atomicAdd(&hist[(size_t)v * width + g], 1u);
+}
+
+__global__ void marginal_argmax_kernel(uint32_t n, const uint32_t* hist, uint32_t width, uint32_t* out) {
+    const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    uint32_t best = 0, bc = 0;
+    for (uint32_t g = 0; g < width; ++g) {
+        const uint32_t x = hist[(size_t)v * width + g];
+        if (x > bc) { bc = x; best = g; }
+    }
+    out[v] = best;
+}
+
+// blockmodel_t::entropy (src/blockmodel.cc:753-787) for every chain: one CTA per chain,
+// fixed-order block reduction.  `base` holds the label-independent terms
+// -sum_v lgamma(d_v+1) + sum_{i>j, A_ij>1} lgamma(A_ij+1), computed once per graph.
+__global__ void entropy_kernel(GraphView G, StateView S, Tables tb, double base, uint32_t n_chains, double* out) {
+    const uint32_t c = blockIdx.x;
+    if (c >= n_chains) return;
+    const uint32_t KA = S.KA, KB = S.KB, W = S.W;
+    const uint32_t ka = S.ka[c], kb = S.kb[c];
+    const int32_t* M = S.m + cnt_base(c, (size_t)KA * KB);           // entry j at [j * GROUP]
+    const int32_t* E = S.e + cnt_base(c, (size_t)KA + KB);
+    const int32_t* NR = S.nr + cnt_base(c, (size_t)KA + KB);
+    const int32_t* ETA = S.eta + cnt_base(c, ((size_t)KA + KB) * W);
+    double acc = 0.0;
+    for (uint32_t i = threadIdx.x; i < ka * kb; i += blockDim.x) {
+        const uint32_t a = i / kb, b = i % kb;
+        acc -= lgamma((double)M[((size_t)a * KB + b) * GROUP] + 1.0);
+    }
+    for (uint32_t i = threadIdx.x; i < (ka + kb) * W; i += blockDim.x) {
+        const uint32_t q = i / W, w = i % W;
+        const uint32_t slot = q < ka ? q : KA + (q - ka);
+        acc -= lgamma((double)ETA[((size_t)slot * W + w) * GROUP] + 1.0);
+    }
+    for (uint32_t q = threadIdx.x; q < ka + kb; q += blockDim.x) {
+        const uint32_t slot = q < ka ? q : KA + (q - ka);
+        acc += lgamma((double)E[(size_t)slot * GROUP] + 1.0);
+        acc += log_q(tb, E[(size_t)slot * GROUP], NR[(size_t)slot * GROUP]);
+    }
+    __shared__ double red[256];
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (uint32_t s = blockDim.x / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        double ent = base + red[0];
+        const double Ed = (double)G.n_edges, na = (double)G.na, nb = (double)G.nb;
+        const double kab = (double)ka * (double)kb;
+        // lbinom_fast(N, k) = lgamma(N+1) - lgamma(k+1) - lgamma(N-k+1), 0 if N==0, k==0 or k>N
+        {
+            const double N = kab + Ed - 1.0, k = Ed;
+            if (!(N == 0.0 || k == 0.0 || k > N)) ent += lgamma(N + 1.0) - lgamma(k + 1.0) - lgamma(N - k + 1.0);
+        }
+        {
+            const double N = na - 1.0, k = (double)ka - 1.0;
+            if (!(N == 0.0 || k == 0.0 || k > N)) ent += lgamma(N + 1.0) - lgamma(k + 1.0) - lgamma(N - k + 1.0);
+        }
+        {
+            const double N = nb - 1.0, k = (double)kb - 1.0;
+            if (!(N == 0.0 || k == 0.0 || k > N)) ent += lgamma(N + 1.0) - lgamma(k + 1.0) - lgamma(N - k + 1.0);
+        }
+        ent += (na * nb == 0.0) ? 0.0 : log(na * nb);
+        ent += lgamma(na + 1.0);
+        ent += lgamma(nb + 1.0);
+        out[c] = ent;
+    }
+}
+
+#endif  // __CUDACC__
+
+}  // namespace bisbm

@@ -69,7 +69,7 @@ static ReplayCtx ctx(Emul* s) {
     x.g.W = s->W; x.g.max_degree = s->maxdeg;
     x.c.labels = s->labels.data() + s->chain; x.c.C = s->C;
     x.c.m = s->m.data(); x.c.e = s->e.data(); x.c.nr = s->nr.data(); x.c.eta = s->eta.data();
-    x.c.ka = s->ka; x.c.kb = s->kb; x.c.KA = s->ka; x.c.KB = s->kb; x.c.W = s->W;
+    x.c.ka = s->ka; x.c.kb = s->kb; x.c.KA = s->ka; x.c.KB = s->kb; x.c.W = s->W; x.c.cs = 1;
     x.tb.lg = s->lg.data(); x.tb.lg_n = s->lg.size(); x.tb.qtab = s->qtab.data(); x.tb.qn = s->qn; x.tb.qk = s->qk;
     x.rs = &s->rs; x.vlist = s->vlist.data(); x.kh = s->kh.data(); x.eps = s->eps;
     return x;
@@ -152,29 +152,24 @@ void emul_par_dS(void* p, uint32_t v, uint32_t sg, int use_taylor, double* dS, d
     const int32_t* Mr = s->m.data() + (size_t)r * sx; const int32_t* Ms = s->m.data() + (size_t)sl * sx;
     const double eps = s->eps, epsK = eps * (double)(KA + KB);
     const uint32_t d = s->row_ptr[v + 1] - s->row_ptr[v];
-    double a0 = 0, a1 = 0, ratio = 1, logacc = 0;
-    for (uint32_t t = 0; t < kopp; ++t) {
-        int kk = s->kh[t];
-        if (!kk) continue;
-        int m_r = Mr[(size_t)t * st], m_s = Ms[(size_t)t * st];
+    // the kernel's one pass over v's neighbours (sweep.cuh: acc_edge / acc_guard)
+    MoveAcc A; acc_init(A);
+    std::vector<int> cnt(kopp, 0);
+    for (uint32_t e = 0; e < d; ++e) {
+        uint32_t nb = s->col[s->row_ptr[v] + e];
+        uint32_t t = s->labels[(size_t)nb * s->C + s->chain];
+        int c = cnt[t]++;
         double inv = 1.0 / ((double)s->e[opp_off + t] + epsK);
-        a0 += (double)kk * ((double)m_s + eps) * inv;
-        a1 += (double)kk * ((double)(m_r - kk) + eps) * inv;
-        if (kk <= 8) {
-            double num = 1, den = 1;
-            for (int q = 0; q < kk; ++q) { num *= (double)(m_r - q); den *= (double)(m_s + 1 + q); }
-            ratio *= num / den;
-            if (ratio > 1e100 || ratio < 1e-100) { logacc += log(ratio); ratio = 1.0; }
-        } else {
-            logacc += lgamma_diff((double)(m_r - kk + 1), (double)kk) - lgamma_diff((double)(m_s + 1), (double)kk);
-        }
+        acc_edge(A, Mr[(size_t)t * st], Ms[(size_t)t * st], c, inv, eps);
+        if ((e & 7u) == 7u) acc_guard(A);
     }
     int e_r = s->e[own_off + r], e_s = s->e[own_off + sl], n_r = s->nr[own_off + r], n_s = s->nr[own_off + sl];
     uint32_t didx = s->degidx[v];
     int eta_r = s->eta[(size_t)(own_off + r) * s->W + didx], eta_s = s->eta[(size_t)(own_off + sl) * s->W + didx];
-    ratio *= (double)(eta_r > 0 ? eta_r : 1) / (double)(eta_s + 1);
-    double out = logacc + log(ratio);
-    out += lgamma_diff((double)(e_s + 1), (double)d) - lgamma_diff((double)(e_r - (int)d + 1), (double)d);
+    double eta_ratio = (double)(eta_r > 0 ? eta_r : 1) / (double)(eta_s + 1);
+    double out = A.logacc + log(A.num / A.den * eta_ratio);
+    out += block_degree_delta(e_r, e_s, (int)d);
+    double a0 = A.a0, a1 = A.a1;
     Tables tb = x.tb; tb.lg = nullptr; tb.lg_n = 0;
     LogqExp qr, qs;
     memset(&qr, 0, sizeof qr); memset(&qs, 0, sizeof qs);
@@ -219,6 +214,7 @@ void emul_words(void* p, uint64_t* ew, uint64_t* gw) {
     *gw = ((uint64_t)s->rs.gen[626] << 32) | s->rs.gen[625];
 }
 double emul_lgamma_diff(double x, double d) { return lgamma_diff(x, d); }
+double emul_block_degree_delta(int e_r, int e_s, int d) { return block_degree_delta(e_r, e_s, d); }
 double emul_log_q_approx(uint64_t n, uint64_t k) { Tables tb; memset(&tb, 0, sizeof tb); return log_q_approx(tb, n, k); }
 uint32_t emul_feistel(uint32_t i, uint32_t n, uint64_t key) { return feistel_perm(i, n, feistel_half_bits(n), key); }
 

@@ -42,6 +42,8 @@ def emul():
     L.emul_par_dS.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.emul_lgamma_diff.restype = C.c_double
     L.emul_lgamma_diff.argtypes = [C.c_double, C.c_double]
+    L.emul_block_degree_delta.restype = C.c_double
+    L.emul_block_degree_delta.argtypes = [C.c_int, C.c_int, C.c_int]
     L.emul_log_q_approx.restype = C.c_double
     L.emul_log_q_approx.argtypes = [C.c_uint64, C.c_uint64]
     L.emul_feistel.restype = C.c_uint32
@@ -127,6 +129,20 @@ def test_lgamma_diff(emul):
             got = emul.emul_lgamma_diff(float(x), float(d))
             # the direct difference itself loses ~1e-16 * lgamma(x) to cancellation
             assert abs(got - want) <= 1e-11 * max(1.0, abs(want)) + 4e-16 * abs(lgamma(x + d))
+
+
+def test_block_degree_delta(emul):
+    """Euler-Maclaurin midpoint form of the e_r terms vs lgamma, across the switch at c = 32 d."""
+    from math import lgamma
+    for e_r in [60, 100, 640, 641, 2000, 10 ** 5, 312500, 2 * 10 ** 9 - 100]:
+        for e_s in [0, 5, 639, 640, 5000, 312500, 2 * 10 ** 9 - 100]:
+            for d in [0, 1, 2, 7, 20, 57]:
+                if d > e_r or e_s + d > 2 ** 31 - 2:
+                    continue
+                want = (lgamma(e_s + d + 1) - lgamma(e_s + 1)) - (lgamma(e_r + 1) - lgamma(e_r - d + 1))
+                got = emul.emul_block_degree_delta(e_r, e_s, d)
+                slack = 4e-16 * (abs(lgamma(e_s + d + 1)) + abs(lgamma(e_r + 1)))  # cancellation in `want` itself
+                assert abs(got - want) <= 2e-10 * max(1.0, abs(want)) + slack, (e_r, e_s, d, got, want)
 
 
 def test_log_q_approx_device_text(emul):
