@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -310,8 +311,9 @@ uint64_t cold_steps(int schedule, float p0, float p1, uint64_t t0, uint64_t t1) 
 }
 
 struct LaunchPlan {
-    bool smem, wide_hist;
-    uint32_t wpc;             // warps per CTA (blockDim / 32)
+    bool smem;
+    int hist_bytes;           // 1, 2 or 4
+    uint32_t wpc;             // warps per CTA (blockDim / 32): 32 or 16 (fewer only when shared memory is short)
     uint32_t warps_used;      // of which take vertices
     uint32_t ctas_per_group;
     uint32_t slice;           // positions of the visiting order per launch
@@ -324,43 +326,56 @@ struct LaunchPlan {
 //   several CTAs per group   -> one slice of the visiting order per launch (a CTA sees the other
 //                               CTAs' moves of the same slice only in the next launch)
 int plan_sweep(bisbm_handle* h, uint32_t type, uint32_t max_inflight, LaunchPlan* lp) {
-    const uint32_t kopp_max = type ? h->KA : h->KB;
     const uint32_t nv = type ? h->nb : h->na;
     const uint32_t n_groups = h->C / 32;
-    lp->wide_hist = h->max_degree >= 65535u;
-    const uint32_t hb = lp->wide_hist ? 4 : 2;
-    const size_t budget = 200 * 1024;
-    uint32_t wpc = 16;
-    lp->smem = sweep_smem_bytes(true, h->KA, h->KB, type, 4, hb) <= budget;
-    while (wpc > 1 && sweep_smem_bytes(lp->smem, h->KA, h->KB, type, wpc, hb) > budget) wpc >>= 1;
+    const uint32_t hb = h->max_degree <= 255u ? 1 : (h->max_degree <= 65535u ? 2 : 4);
+    lp->hist_bytes = (int)hb;
+    const size_t budget = 220 * 1024;
+    lp->smem = sweep_smem_bytes(true, h->KA, h->KB, type, 16, hb) <= budget;
+    uint32_t wpc = 32;
+    if (const char* e = getenv("BISBM_WPC")) wpc = (atoi(e) == 16) ? 16 : 32;  // tuning knob: warps per CTA
+    if (sweep_smem_bytes(lp->smem, h->KA, h->KB, type, wpc, hb) > budget) wpc = 16;
     if (sweep_smem_bytes(lp->smem, h->KA, h->KB, type, wpc, hb) > budget)
         return fail(BISBM_ERR_ARG, "K too large for the shared-memory histogram");
-    const uint32_t inflight = max_inflight ? max_inflight : std::max<uint32_t>(wpc, nv / 64);
+    uint32_t inflight_div = 64;
+    if (const char* e = getenv("BISBM_INFLIGHT_DIV")) inflight_div = std::max(1, atoi(e));  // tuning knob
+    const uint32_t inflight = max_inflight ? max_inflight : std::max<uint32_t>(wpc, nv / inflight_div);
     // CTAs per group: fill the SMs, but never more warps than the in-flight bound or the work allows
     uint32_t cpg = std::max<uint32_t>(1, (uint32_t)h->sm_count / n_groups);
-    if (!lp->smem) cpg = std::max<uint32_t>(1, ((uint32_t)h->sm_count * 3) / n_groups);  // 3 resident CTAs per SM
     cpg = std::min<uint32_t>(cpg, std::max<uint32_t>(1, inflight / wpc));
     cpg = std::min<uint32_t>(cpg, std::max<uint32_t>(1, nv / (wpc * 4)));
     lp->ctas_per_group = cpg;
     lp->wpc = wpc;
     lp->warps_used = (cpg == 1) ? std::max<uint32_t>(1, std::min<uint32_t>(wpc, std::min<uint32_t>(inflight, std::max<uint32_t>(nv, 1)))) : wpc;
-    if (lp->smem && cpg > 1) lp->slice = std::max<uint32_t>(cpg * wpc, std::min<uint32_t>(inflight, nv));
+    if (cpg > 1) lp->slice = std::max<uint32_t>(cpg * wpc, std::min<uint32_t>(inflight, nv));
     else lp->slice = std::max<uint32_t>(nv, 1);
     lp->smem_bytes = sweep_smem_bytes(lp->smem, h->KA, h->KB, type, wpc, hb);
     return BISBM_OK;
 }
 
-template <bool SMEM, typename HistT>
+template <bool SMEM, typename HistT, int NT>
 int launch_sweep_t(bisbm_handle* h, const SweepParams& P, const LaunchPlan& lp) {
     static bool attr_set = false;
     if (!attr_set) {
-        CU(cudaFuncSetAttribute(sweep_kernel<SMEM, HistT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CU(cudaFuncSetAttribute(sweep_kernel<SMEM, HistT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         attr_set = true;
     }
     const unsigned grid = P.n_groups * lp.ctas_per_group;
-    sweep_kernel<SMEM, HistT><<<grid, lp.wpc * 32, lp.smem_bytes, h->stream>>>(P);
+    sweep_kernel<SMEM, HistT, NT><<<grid, NT, lp.smem_bytes, h->stream>>>(P);
     CU(cudaGetLastError());
     return BISBM_OK;
+}
+
+template <bool SMEM, typename HistT>
+int launch_sweep_nt(bisbm_handle* h, const SweepParams& P, const LaunchPlan& lp) {
+    return lp.wpc == 32 ? launch_sweep_t<SMEM, HistT, 1024>(h, P, lp) : launch_sweep_t<SMEM, HistT, 512>(h, P, lp);
+}
+
+template <bool SMEM>
+int launch_sweep_h(bisbm_handle* h, const SweepParams& P, const LaunchPlan& lp) {
+    if (lp.hist_bytes == 1) return launch_sweep_nt<SMEM, uint8_t>(h, P, lp);
+    if (lp.hist_bytes == 2) return launch_sweep_nt<SMEM, uint16_t>(h, P, lp);
+    return launch_sweep_nt<SMEM, uint32_t>(h, P, lp);
 }
 
 // one full sweep = type-a half sweep + type-b half sweep (each preceded by the log q refresh
@@ -398,8 +413,7 @@ int launch_full_sweep(bisbm_handle* h, int schedule, float p0, float p1, uint64_
             P.sweep = h->sweep_epoch;
             P.step_base = sweep_in_call * (uint64_t)h->n + (type ? h->na : 0);
             P.schedule = schedule; P.p0 = p0; P.p1 = p1;
-            if (lp.smem) rc = lp.wide_hist ? launch_sweep_t<true, uint32_t>(h, P, lp) : launch_sweep_t<true, uint16_t>(h, P, lp);
-            else rc = lp.wide_hist ? launch_sweep_t<false, uint32_t>(h, P, lp) : launch_sweep_t<false, uint16_t>(h, P, lp);
+            rc = lp.smem ? launch_sweep_h<true>(h, P, lp) : launch_sweep_h<false>(h, P, lp);
             if (rc) return rc;
             h->last_launches += 1;
             if (sliced) { std::swap(h->d_m, h->d_m2); std::swap(h->d_e, h->d_e2); }

@@ -215,8 +215,15 @@ __host__ __device__ inline size_t sweep_smem_bytes(bool smem, uint32_t KA, uint3
     return b;
 }
 
-template <bool SMEM, typename HistT>
-__global__ void __launch_bounds__(512) sweep_kernel(SweepParams P) {
+// 16-byte staged copy (all staged arrays are multiples of 128 bytes)
+__device__ __forceinline__ void copy_i4(int32_t* dst, const int32_t* src, uint32_t n_int) {
+    const int4* s4 = reinterpret_cast<const int4*>(src);
+    int4* d4 = reinterpret_cast<int4*>(dst);
+    for (uint32_t i = threadIdx.x; i < n_int / 4; i += blockDim.x) d4[i] = s4[i];
+}
+
+template <bool SMEM, typename HistT, int NT>
+__global__ void __launch_bounds__(NT, 1) sweep_kernel(SweepParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
     const GraphView& G = P.g;
@@ -238,40 +245,40 @@ __global__ void __launch_bounds__(512) sweep_kernel(SweepParams P) {
     const bool live = (c < P.n_chains) && P.active[c];
     const uint32_t cc = (c < P.s.C) ? c : 0;
     const uint32_t ka = P.s.ka[cc], kb = P.s.kb[cc], K = ka + kb;
-    const uint32_t kown = type ? kb : ka;
+    const uint32_t kown = type ? kb : ka, kopp = type ? ka : kb;
     const double eps = P.s.eps, epsK = eps * (double)K;
 
     // ---- stage the group's counts ----
     int32_t* sM; int32_t* sEo; int32_t* sEp; double* sInv; HistT* hist_all;
     if (SMEM) {
         sM = reinterpret_cast<int32_t*>(smem_raw);
-        sEo = sM + (size_t)KA * KB * 32;
-        sEp = sEo + (size_t)kown_max * 32;
-        sInv = reinterpret_cast<double*>(sEp + (size_t)kopp_max * 32);
-        hist_all = reinterpret_cast<HistT*>(sInv + (size_t)kopp_max * 32);
-        for (uint32_t i = threadIdx.x; i < KA * KB * 32; i += blockDim.x) sM[i] = gM[i];
-        for (uint32_t i = threadIdx.x; i < kown_max * 32; i += blockDim.x) sEo[i] = gE[(size_t)own_off * 32 + i];
+        sEo = sM + KA * KB * 32;
+        sEp = sEo + kown_max * 32;
+        sInv = reinterpret_cast<double*>(sEp + kopp_max * 32);
+        hist_all = reinterpret_cast<HistT*>(sInv + kopp_max * 32);
+        copy_i4(sM, gM, KA * KB * 32);
+        copy_i4(sEo, gE + own_off * 32, kown_max * 32);
         for (uint32_t i = threadIdx.x; i < kopp_max * 32; i += blockDim.x) {
-            const int e = gE[(size_t)opp_off * 32 + i];
+            const int e = gE[opp_off * 32 + i];
             const uint32_t ci = group * 32 + (i & 31);
             const double Kc = (double)(P.s.ka[ci] + P.s.kb[ci]);
             sEp[i] = e;
             sInv[i] = 1.0 / ((double)e + eps * Kc);
         }
     } else {
-        sM = gM; sEo = gE + (size_t)own_off * 32; sEp = gE + (size_t)opp_off * 32; sInv = nullptr;
+        sM = gM; sEo = gE + own_off * 32; sEp = gE + opp_off * 32; sInv = nullptr;
         hist_all = reinterpret_cast<HistT*>(smem_raw);
     }
     for (uint32_t i = threadIdx.x; i < wpc * kopp_max * 32; i += blockDim.x) hist_all[i] = 0;
     __syncthreads();
 
-    HistT* const hist = hist_all + (size_t)warp * kopp_max * 32 + lane;
+    HistT* const hist = hist_all + warp * kopp_max * 32 + lane;
     // lane-private views: entry j of this chain is at [j*32]
     int32_t* const M = sM + lane;
     int32_t* const Eo = sEo + lane;
     const int32_t* const Ep = sEp + lane;
     const double* const Inv = SMEM ? sInv + lane : nullptr;
-    // m(x_own, t_opp) = M[x*sx + t*st]
+    // m(x_own, t_opp) = M[x*sx + t*st]   (32-bit index arithmetic throughout)
     const uint32_t sx = (type ? 1u : KB) * 32u, st = (type ? KB : 1u) * 32u;
     int32_t* const LAB = P.s.labels + cc;
     const uint64_t seed = P.seeds[cc];
@@ -284,13 +291,27 @@ __global__ void __launch_bounds__(512) sweep_kernel(SweepParams P) {
 
     if (warp < P.warps_used) {
         const uint32_t stride = P.ctas_per_group * P.warps_used;
-        for (uint32_t i = P.pos_begin + cta_in_group * P.warps_used + warp; i < P.pos_end; i += stride) {
+        uint32_t i = P.pos_begin + cta_in_group * P.warps_used + warp;
+        // software prefetch of the NEXT vertex's CSR row: row offset, degree and the first 32
+        // neighbour ids (one coalesced load, lane e holds neighbour e; broadcast by shuffle)
+        uint32_t v_n = 0, row_n = 0, d_n = 0, nbr_n = 0;
+        if (i < P.pos_end) {
+            v_n = v0 + feistel_perm(i, nv, P.half_bits, pkey);
+            row_n = G.row_ptr[v_n];
+            d_n = G.row_ptr[v_n + 1] - row_n;
+            nbr_n = (lane < d_n) ? G.col[row_n + lane] : 0u;
+        }
+        for (; i < P.pos_end; i += stride) {
             // warp-uniform trip count: reconverge the 32 lanes (= chains) at every vertex so the
             // neighbour gathers stay coalesced 128-byte loads
             __syncwarp();
-            const uint32_t v = v0 + feistel_perm(i, nv, P.half_bits, pkey);
-            const uint32_t row = G.row_ptr[v];
-            const uint32_t d = G.row_ptr[v + 1] - row;
+            const uint32_t v = v_n, row = row_n, d = d_n, nbr0 = nbr_n;
+            if (i + stride < P.pos_end) {
+                v_n = v0 + feistel_perm(i + stride, nv, P.half_bits, pkey);
+                row_n = G.row_ptr[v_n];
+                d_n = G.row_ptr[v_n + 1] - row_n;
+                nbr_n = (lane < d_n) ? G.col[row_n + lane] : 0u;
+            }
             const double T = (P.schedule == 3) ? (double)P.p0 : par_temperature(P.schedule, P.p0, P.p1, P.step_base + i);
             const uint32_t r = live ? (uint32_t)LAB[(size_t)v * C] : 0u;
 
@@ -304,7 +325,8 @@ __global__ void __launch_bounds__(512) sweep_kernel(SweepParams P) {
                 uint32_t t = 0;
                 int e_t = 0;
                 if (d != 0) {
-                    const uint32_t j = G.col[row + mulhi32(ra.x, d)];
+                    const uint32_t jpos = mulhi32(ra.x, d);   // differs per lane: plain gather
+                    const uint32_t j = G.col[row + jpos];
                     t = (uint32_t)LAB[(size_t)j * C];
                     e_t = cnt_ld<SMEM>(&Ep[t * 32]);
                     const double R = epsK / ((double)e_t + epsK);
@@ -320,10 +342,10 @@ __global__ void __launch_bounds__(512) sweep_kernel(SweepParams P) {
                     const uint32_t z = mulhi32(ra.z, (uint32_t)e_t);
                     uint32_t cum = 0;
                     s = kown - 1;
-                    const int32_t* col_t = M + (size_t)t * st;
+                    const int32_t* col_t = M + t * st;
                     bool found = false;
                     for (uint32_t x = 0; x < kown; ++x) {   // no early exit: keeps the lanes in step
-                        cum += (uint32_t)cnt_ld<SMEM>(&col_t[(size_t)x * sx]);
+                        cum += (uint32_t)cnt_ld<SMEM>(&col_t[x * sx]);
                         if (!found && cum > z) { s = x; found = true; }
                     }
                 }
@@ -342,25 +364,37 @@ __global__ void __launch_bounds__(512) sweep_kernel(SweepParams P) {
             const uint32_t didx = G.degidx[v];
             int n_r = 0, n_s = 0, eta_r = 1, eta_s = 0;
             MoveAcc A; acc_init(A);
-            const int32_t* const Mr = M + (size_t)r * sx;
-            const int32_t* const Ms = M + (size_t)s * sx;
+            const int32_t* const Mr = M + r * sx;
+            const int32_t* const Ms = M + s * sx;
             if (eval) {  // issue the global (L2) loads early; they are consumed after the pass
                 n_r = ldc(&gNR[(own_off + r) * 32]); n_s = ldc(&gNR[(own_off + s) * 32]);
-                eta_r = ldc(&gETA[((size_t)(own_off + r) * W + didx) * 32]);
-                eta_s = ldc(&gETA[((size_t)(own_off + s) * W + didx) * 32]);
+                eta_r = ldc(&gETA[((own_off + r) * W + didx) * 32]);
+                eta_s = ldc(&gETA[((own_off + s) * W + didx) * 32]);
             }
-#pragma unroll 4
-            for (uint32_t e = 0; e < d; ++e) {
-                const uint32_t nb = G.col[row + e];
-                if (eval) {
-                    const uint32_t t = (uint32_t)LAB[(size_t)nb * C];
-                    const int cnt = (int)hist[t * 32];
-                    hist[t * 32] = (HistT)(cnt + 1);
-                    const int m_r = cnt_ld<SMEM>(&Mr[(size_t)t * st]), m_s = cnt_ld<SMEM>(&Ms[(size_t)t * st]);
-                    const double inv = SMEM ? Inv[t * 32] : 1.0 / ((double)ldc(&Ep[t * 32]) + epsK);
-                    acc_edge(A, m_r, m_s, cnt, inv, eps);
+            uint32_t nbr = nbr0;  // lane e holds neighbour (base & ~31) + e
+            for (uint32_t base = 0; base < d; base += 8) {
+                // gather 8 neighbour labels (independent 128-byte loads in flight), then consume them
+                if (base != 0 && (base & 31u) == 0) nbr = (base + lane < d) ? G.col[row + base + lane] : 0u;
+                uint32_t tt[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const uint32_t nb = __shfl_sync(0xffffffffu, nbr, (base + k) & 31);
+                    tt[k] = (eval && base + k < d) ? (uint32_t)LAB[(size_t)nb * C] : 0u;
                 }
-                if ((e & 7u) == 7u) acc_guard(A);
+                if (eval) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        if (base + k < d) {
+                            const uint32_t t = tt[k];
+                            const int cnt = (int)hist[t * 32];
+                            hist[t * 32] = (HistT)(cnt + 1);
+                            const int m_r = cnt_ld<SMEM>(&Mr[t * st]), m_s = cnt_ld<SMEM>(&Ms[t * st]);
+                            const double inv = SMEM ? Inv[t * 32] : 1.0 / ((double)ldc(&Ep[t * 32]) + epsK);
+                            acc_edge(A, m_r, m_s, cnt, inv, eps);
+                        }
+                    }
+                    acc_guard(A);
+                }
             }
             __syncwarp();
 
@@ -387,30 +421,30 @@ __global__ void __launch_bounds__(512) sweep_kernel(SweepParams P) {
             }
             __syncwarp();
 
-            // ---- second pass: clear the histogram and commit (apply_mcmc_moves) ----
-            int32_t* const Mrw = M + (size_t)r * sx;
-            int32_t* const Msw = M + (size_t)s * sx;
-#pragma unroll 4
-            for (uint32_t e = 0; e < d; ++e) {
-                const uint32_t nb = G.col[row + e];
-                if (eval) {
-                    const uint32_t t = (uint32_t)LAB[(size_t)nb * C];
-                    hist[t * 32] = 0;
-                    if (go) {
-                        atomicSub(&Mrw[(size_t)t * st], 1);
-                        atomicAdd(&Msw[(size_t)t * st], 1);
+            // ---- clear the histogram and commit (apply_mcmc_moves): k_t is the histogram ----
+            if (eval) {
+                int32_t* const Mrw = M + r * sx;
+                int32_t* const Msw = M + s * sx;
+                for (uint32_t t = 0; t < kopp; ++t) {
+                    const int kk = (int)hist[t * 32];
+                    if (kk != 0) {
+                        hist[t * 32] = 0;
+                        if (go) {
+                            atomicSub(&Mrw[t * st], kk);
+                            atomicAdd(&Msw[t * st], kk);
+                        }
                     }
                 }
-            }
-            if (go) {
-                atomicSub(&Eo[r * 32], (int)d);
-                atomicAdd(&Eo[s * 32], (int)d);
-                atomicAdd(&gNR[(own_off + s) * 32], 1);
-                atomicSub(&gETA[((size_t)(own_off + r) * W + didx) * 32], 1);
-                atomicAdd(&gETA[((size_t)(own_off + s) * W + didx) * 32], 1);
-                LAB[(size_t)v * C] = (int32_t)s;
-                ++n_acc;
-                ds_sum += dS;
+                if (go) {
+                    atomicSub(&Eo[r * 32], (int)d);
+                    atomicAdd(&Eo[s * 32], (int)d);
+                    atomicAdd(&gNR[(own_off + s) * 32], 1);
+                    atomicSub(&gETA[((own_off + r) * W + didx) * 32], 1);
+                    atomicAdd(&gETA[((own_off + s) * W + didx) * 32], 1);
+                    LAB[(size_t)v * C] = (int32_t)s;
+                    ++n_acc;
+                    ds_sum += dS;
+                }
             }
         }
         if (live) {
@@ -423,17 +457,17 @@ __global__ void __launch_bounds__(512) sweep_kernel(SweepParams P) {
     if (SMEM) {
         __syncthreads();
         if (P.exclusive) {
-            for (uint32_t i = threadIdx.x; i < KA * KB * 32; i += blockDim.x) gM[i] = sM[i];
-            for (uint32_t i = threadIdx.x; i < kown_max * 32; i += blockDim.x) gE[(size_t)own_off * 32 + i] = sEo[i];
+            copy_i4(gM, sM, KA * KB * 32);
+            copy_i4(gE + own_off * 32, sEo, kown_max * 32);
         } else {
             int32_t* const nM = P.m_next + (size_t)group * KA * KB * GROUP;
-            int32_t* const nE = P.e_next + (size_t)group * KK * GROUP + (size_t)own_off * 32;
+            int32_t* const nE = P.e_next + (size_t)group * KK * GROUP + own_off * 32;
             for (uint32_t i = threadIdx.x; i < KA * KB * 32; i += blockDim.x) {
                 const int dlt = sM[i] - gM[i];
                 if (dlt) atomicAdd(&nM[i], dlt);
             }
             for (uint32_t i = threadIdx.x; i < kown_max * 32; i += blockDim.x) {
-                const int dlt = sEo[i] - gE[(size_t)own_off * 32 + i];
+                const int dlt = sEo[i] - gE[own_off * 32 + i];
                 if (dlt) atomicAdd(&nE[i], dlt);
             }
         }
