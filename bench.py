@@ -252,12 +252,12 @@ def main():
     edges = planted(na, nb, ka, kb, args.edges, 0)
     graph = host.Graph(edges, na, nb, device=local_rank)
     C = args.chains
-    chain0 = rank * C  # global chain ids of this rank: chain0 .. chain0 + C - 1
+    chain_ids = pkg.dist.shard_chains(C * world, rank, world)  # round-robin global chain ids of this rank
     base = planted_labels(na, nb, ka, kb)
     labels_host = torch.empty((C, n), dtype=torch.int32).pin_memory()
     labels_host.numpy().view(np.uint32)[:] = base[None, :]
     pool = host.ChainPool(graph, labels_host.numpy().view(np.uint32), ka, kb, 1.0)
-    seeds = (np.arange(C, dtype=np.uint64) + np.uint64(chain0))
+    seeds = pkg.dist.chain_seeds(0, chain_ids)
     pool.randomize(seeds)
     duration = args.sweeps_per_step * n
 
@@ -284,7 +284,7 @@ def main():
         pool.marginals_clear()
         pool.marginalize(0, 1, 1, seeds)
         hist = host.marginals_tensor(pool)
-        dist.all_reduce(hist)
+        pkg.dist.allreduce_marginals(hist)
     barrier()
     wall = time.perf_counter() - t0
     clocks = sampler.stop()

@@ -1,0 +1,68 @@
+"""world_size-2 gloo test of the multi-GPU host logic: chain sharding, seeds that depend only on the
+global chain id, the single all-reduce of marginal histograms and the gather of the best partition.
+The per-rank "chains" here are synthetic label arrays (no GPU in this test); the reduced histogram
+must equal the histogram of all chains computed in one process."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _labels(n_chains, n, K):
+    rng = np.random.default_rng(42)
+    return rng.integers(0, K, size=(n_chains, n))
+
+
+def _worker(rank, world, port, n_chains, n, K, out_dir):
+    import importlib
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    pkg = importlib.import_module("bipartitesbm-mcmc_b200")
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ids = pkg.dist.shard_chains(n_chains, rank, world)
+    lab = _labels(n_chains, n, K)[ids]
+    hist = np.zeros((n, K), dtype=np.int32)
+    for row in lab:
+        np.add.at(hist, (np.arange(n), row), 1)
+    t = torch.from_numpy(hist)
+    pkg.dist.allreduce_marginals(t)
+    ent = -ids.astype(np.float64)  # the chain with the largest global id is "best"
+    best, best_lab, owner = pkg.dist.gather_best(ent, lab)
+    seeds = pkg.dist.chain_seeds(7, ids)
+    np.savez(os.path.join(out_dir, "r%d.npz" % rank), hist=t.numpy(), best=best, best_lab=best_lab, owner=owner, ids=ids,
+             seeds=seeds)
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharding_and_allreduce(tmp_path):
+    world, n_chains, n, K = 2, 11, 50, 6
+    mp.spawn(_worker, args=(world, _free_port(), n_chains, n, K, str(tmp_path)), nprocs=world, join=True)
+    lab = _labels(n_chains, n, K)
+    want = np.zeros((n, K), dtype=np.int32)
+    for row in lab:
+        np.add.at(want, (np.arange(n), row), 1)
+    r = [np.load(os.path.join(str(tmp_path), "r%d.npz" % k)) for k in range(world)]
+    assert sorted(np.concatenate([r[0]["ids"], r[1]["ids"]]).tolist()) == list(range(n_chains))
+    for k in range(world):
+        assert (r[k]["hist"] == want).all()
+        assert r[k]["best"] == -(n_chains - 1) and (r[k]["best_lab"] == lab[n_chains - 1]).all()
+        assert int(r[k]["owner"]) == (n_chains - 1) % world
+    # seeds depend only on the global chain id
+    import importlib
+    pkg = importlib.import_module("bipartitesbm-mcmc_b200")
+    allseeds = pkg.dist.chain_seeds(7, np.arange(n_chains))
+    for k in range(world):
+        assert (r[k]["seeds"] == allseeds[r[k]["ids"]]).all()
