@@ -334,7 +334,8 @@ def main():
         peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
         bytes_per_move = 16.0 + 8.0 * (2.0 * args.edges / n) + 4.0 * acceptance
         # dominant kernel = sweep_kernel; per-launch algorithmic bytes / average launch duration
-        sweep_launches = 2 * args.sweeps_per_step * args.steps
+        # launches per sweep: 2 logq_refresh + 1 bookkeep + the sweep_kernel slice launches
+        sweep_launches = max(1, launches - 3 * args.sweeps_per_step * args.steps)
         alg_bytes_per_launch = bytes_per_move * (moves / sweep_launches)
         achieved = bytes_per_move * moves / (ev_ms * 1e-3) / 1e9
         line = {"metric": "vertex-moves/sec", "value": value, "unit": "moves/s", "n_gpus": world, "steps": args.steps,
@@ -345,7 +346,8 @@ def main():
                              "traffic": None, "kernel": "sweep_kernel", "bytes_per_move": bytes_per_move,
                              "alg_bytes_per_launch": alg_bytes_per_launch,
                              "avg_launch_ms": ev_ms / sweep_launches, "peak_source": peak_src,
-                             "note": "event time spans sweep + logq_refresh + bookkeeping launches of rank 0"},
+                             "sweep_kernel_launches": int(sweep_launches),
+                             "note": "CUDA events on libbisbm's stream around each step; they also span the logq_refresh / bookkeep launches and the 1 MB count copies between slices (<1% of device time, profiles/r01_launch_shares.txt)"},
                 "e2e": {"value": e2e_value, "unit": "moves/s", "h2d_bytes_per_step": C * n * 4, "d2h_bytes_per_step": C * n * 4},
                 "gpu_launches": int(launches), "clocks": clocks}
         traffic_file = os.path.join(ROOT, "profiles", "sweep_kernel_traffic.json")
