@@ -333,7 +333,7 @@ int plan_sweep(bisbm_handle* h, uint32_t type, uint32_t max_inflight, LaunchPlan
     const size_t budget = 220 * 1024;
     lp->smem = sweep_smem_bytes(true, h->KA, h->KB, type, 16, hb) <= budget;
     uint32_t wpc = 32;
-    if (const char* e = getenv("BISBM_WPC")) wpc = (atoi(e) == 16) ? 16 : 32;  // tuning knob: warps per CTA
+    if (const char* e = getenv("BISBM_WPC")) { int w = atoi(e); wpc = (w == 16 || w == 24) ? (uint32_t)w : 32; }  // tuning knob
     if (sweep_smem_bytes(lp->smem, h->KA, h->KB, type, wpc, hb) > budget) wpc = 16;
     if (sweep_smem_bytes(lp->smem, h->KA, h->KB, type, wpc, hb) > budget)
         return fail(BISBM_ERR_ARG, "K too large for the shared-memory histogram");
@@ -368,7 +368,9 @@ int launch_sweep_t(bisbm_handle* h, const SweepParams& P, const LaunchPlan& lp) 
 
 template <bool SMEM, typename HistT>
 int launch_sweep_nt(bisbm_handle* h, const SweepParams& P, const LaunchPlan& lp) {
-    return lp.wpc == 32 ? launch_sweep_t<SMEM, HistT, 1024>(h, P, lp) : launch_sweep_t<SMEM, HistT, 512>(h, P, lp);
+    if (lp.wpc == 32) return launch_sweep_t<SMEM, HistT, 1024>(h, P, lp);
+    if (lp.wpc == 24) return launch_sweep_t<SMEM, HistT, 768>(h, P, lp);
+    return launch_sweep_t<SMEM, HistT, 512>(h, P, lp);
 }
 
 template <bool SMEM>

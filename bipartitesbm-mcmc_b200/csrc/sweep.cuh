@@ -222,6 +222,41 @@ __device__ __forceinline__ void copy_i4(int32_t* dst, const int32_t* src, uint32
     for (uint32_t i = threadIdx.x; i < n_int / 4; i += blockDim.x) d4[i] = s4[i];
 }
 
+// ---- explicit shared-space accesses on 32-bit shared addresses (ld/st/red.shared): the
+//      staged counts are only ever touched through these, so no generic-address LD/ATOM and no
+//      64-bit index arithmetic is left in the move loop ----
+// (count / inverse loads are plain asm so the compiler may schedule them early; a value that is a
+//  few instructions stale is harmless -- other warps update the same entries concurrently anyway)
+__device__ __forceinline__ int sh_ld(uint32_t a) { int v; asm("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ double sh_ld_f64(uint32_t a) { double v; asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sh_red_add(uint32_t a, int v) { asm volatile("red.shared.add.s32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+template <typename T> struct ShHist;
+template <> struct ShHist<uint8_t> {
+    static __device__ __forceinline__ uint32_t ld(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+    static __device__ __forceinline__ void st(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+};
+template <> struct ShHist<uint16_t> {
+    static __device__ __forceinline__ uint32_t ld(uint32_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+    static __device__ __forceinline__ void st(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+};
+template <> struct ShHist<uint32_t> {
+    static __device__ __forceinline__ uint32_t ld(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+    static __device__ __forceinline__ void st(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+};
+
+// one lane's view of a count array: entry j of this chain is element [j*32] (elements of 4 bytes)
+template <bool SMEM> struct Cnt;
+template <> struct Cnt<true> {   // staged in shared memory
+    uint32_t base;               // shared byte address of entry 0 for this lane
+    __device__ __forceinline__ int ld(uint32_t idx32) const { return sh_ld(base + idx32 * 4u); }
+    __device__ __forceinline__ void add(uint32_t idx32, int v) const { sh_red_add(base + idx32 * 4u, v); }
+};
+template <> struct Cnt<false> {  // in global memory: L2 loads, global reductions
+    int32_t* p;
+    __device__ __forceinline__ int ld(uint32_t idx32) const { return __ldcg(p + idx32); }
+    __device__ __forceinline__ void add(uint32_t idx32, int v) const { atomicAdd(p + idx32, v); }
+};
+
 template <bool SMEM, typename HistT, int NT>
 __global__ void __launch_bounds__(NT, 1) sweep_kernel(SweepParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -237,9 +272,9 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(SweepParams P) {
     // global (group-interleaved) count arrays of this group
     int32_t* const gM = P.s.m + (size_t)group * KA * KB * GROUP;
     int32_t* const gE = P.s.e + (size_t)group * KK * GROUP;
-    int32_t* const gNR = P.s.nr + (size_t)group * KK * GROUP + lane;
-    int32_t* const gETA = P.s.eta + (size_t)group * KK * W * GROUP + lane;
-    const LogqExp* const gLQ = P.lq + (size_t)group * KK * GROUP + lane;
+    int32_t* const gNR = P.s.nr + (size_t)group * KK * GROUP + (size_t)own_off * 32 + lane;         // own-type slots
+    int32_t* const gETA = P.s.eta + (size_t)group * KK * W * GROUP + (size_t)own_off * W * 32 + lane;
+    const LogqExp* const gLQ = P.lq + (size_t)group * KK * GROUP + (size_t)own_off * 32 + lane;
 
     const uint32_t c = group * 32 + lane;
     const bool live = (c < P.n_chains) && P.active[c];
@@ -249,7 +284,7 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(SweepParams P) {
     const double eps = P.s.eps, epsK = eps * (double)K;
 
     // ---- stage the group's counts ----
-    int32_t* sM; int32_t* sEo; int32_t* sEp; double* sInv; HistT* hist_all;
+    int32_t* sM = nullptr; int32_t* sEo = nullptr; int32_t* sEp; double* sInv; HistT* hist_all;
     if (SMEM) {
         sM = reinterpret_cast<int32_t*>(smem_raw);
         sEo = sM + KA * KB * 32;
@@ -266,69 +301,98 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(SweepParams P) {
             sInv[i] = 1.0 / ((double)e + eps * Kc);
         }
     } else {
-        sM = gM; sEo = gE + own_off * 32; sEp = gE + opp_off * 32; sInv = nullptr;
+        sEp = nullptr; sInv = nullptr;
         hist_all = reinterpret_cast<HistT*>(smem_raw);
     }
     for (uint32_t i = threadIdx.x; i < wpc * kopp_max * 32; i += blockDim.x) hist_all[i] = 0;
     __syncthreads();
 
-    HistT* const hist = hist_all + warp * kopp_max * 32 + lane;
-    // lane-private views: entry j of this chain is at [j*32]
-    int32_t* const M = sM + lane;
-    int32_t* const Eo = sEo + lane;
-    const int32_t* const Ep = sEp + lane;
-    const double* const Inv = SMEM ? sInv + lane : nullptr;
-    // m(x_own, t_opp) = M[x*sx + t*st]   (32-bit index arithmetic throughout)
+    // lane-private accessors (entry j of this chain at element j*32)
+    Cnt<SMEM> M, Eo, Ep;
+    uint32_t inv_base = 0;
+    if constexpr (SMEM) {
+        M.base = (uint32_t)__cvta_generic_to_shared(sM) + lane * 4u;
+        Eo.base = (uint32_t)__cvta_generic_to_shared(sEo) + lane * 4u;
+        Ep.base = (uint32_t)__cvta_generic_to_shared(sEp) + lane * 4u;
+        inv_base = (uint32_t)__cvta_generic_to_shared(sInv) + lane * 8u;
+    } else {
+        M.p = gM + lane; Eo.p = gE + own_off * 32 + lane; Ep.p = gE + opp_off * 32 + lane;
+    }
+    const uint32_t hist_base = (uint32_t)__cvta_generic_to_shared(hist_all) + (warp * kopp_max * 32 + lane) * (uint32_t)sizeof(HistT);
+    constexpr uint32_t HS = 32u * (uint32_t)sizeof(HistT);   // byte stride between histogram bins
+    // m(x_own, t_opp) = M[x*sx + t*st]   (element indices, already multiplied by the 32-chain interleave)
     const uint32_t sx = (type ? 1u : KB) * 32u, st = (type ? KB : 1u) * 32u;
     int32_t* const LAB = P.s.labels + cc;
     const uint64_t seed = P.seeds[cc];
     const uint32_t key0 = (uint32_t)seed, key1 = (uint32_t)(seed >> 32);
     const uint32_t nv = type ? G.nb : G.na, v0 = type ? G.na : 0;
     const uint64_t pkey = (P.sweep * 2 + type) * 0x9E3779B97F4A7C15ull + (uint64_t)group * 0xD1B54A32D192ED03ull;
+    const bool const_T = (P.schedule == 3);
+    const double T_const = (double)P.p0, beta_const = 1.0 / (double)P.p0;
 
     unsigned long long n_acc = 0;
     double ds_sum = 0.0;
 
     if (warp < P.warps_used) {
         const uint32_t stride = P.ctas_per_group * P.warps_used;
-        uint32_t i = P.pos_begin + cta_in_group * P.warps_used + warp;
-        // software prefetch of the NEXT vertex's CSR row: row offset, degree and the first 32
-        // neighbour ids (one coalesced load, lane e holds neighbour e; broadcast by shuffle)
-        uint32_t v_n = 0, row_n = 0, d_n = 0, nbr_n = 0;
-        if (i < P.pos_end) {
-            v_n = v0 + feistel_perm(i, nv, P.half_bits, pkey);
-            row_n = G.row_ptr[v_n];
-            d_n = G.row_ptr[v_n + 1] - row_n;
-            nbr_n = (lane < d_n) ? G.col[row_n + lane] : 0u;
-        }
-        for (; i < P.pos_end; i += stride) {
-            // warp-uniform trip count: reconverge the 32 lanes (= chains) at every vertex so the
-            // neighbour gathers stay coalesced 128-byte loads
-            __syncwarp();
-            const uint32_t v = v_n, row = row_n, d = d_n, nbr0 = nbr_n;
-            if (i + stride < P.pos_end) {
-                v_n = v0 + feistel_perm(i + stride, nv, P.half_bits, pkey);
-                row_n = G.row_ptr[v_n];
-                d_n = G.row_ptr[v_n + 1] - row_n;
-                nbr_n = (lane < d_n) ? G.col[row_n + lane] : 0u;
+        const uint32_t i_first = P.pos_begin + cta_in_group * P.warps_used + warp;
+        // Vertices are taken in batches of 32: lane l prepares the l-th vertex of the batch (its
+        // place in the permuted order, CSR row offset and degree) -- the Feistel permutation and
+        // the dependent row_ptr loads cost one lane-parallel step per 32 vertices instead of one
+        // warp-uniform step per vertex.  The first 32 neighbour ids of the NEXT vertex are
+        // prefetched with one coalesced load (lane e holds neighbour e; broadcast by shuffle).
+        uint32_t bv = 0, brow = 0, bdeg = 0;      // this lane's vertex of the current batch
+        // software pipeline, one vertex ahead: everything below with suffix _n belongs to the NEXT
+        // vertex and is loaded while the current one is evaluated (own label, Philox draw, the
+        // proposal's random neighbour id and -- one stage later -- that neighbour's label)
+        uint32_t v_n = 0, row_n = 0, d_n = 0, nbr_n = 0, r_n = 0, j_n = 0, t_n = 0;
+        u32x4 ra_n; ra_n.x = ra_n.y = ra_n.z = ra_n.w = 0;
+        auto refill = [&](uint32_t pos0) {        // lane l prepares the vertex at position pos0 + l*stride
+            const uint64_t il = (uint64_t)pos0 + (uint64_t)lane * stride;
+            bv = 0; brow = 0; bdeg = 0;
+            if (il < P.pos_end) {
+                bv = v0 + feistel_perm((uint32_t)il, nv, P.half_bits, pkey);
+                brow = G.row_ptr[bv];
+                bdeg = G.row_ptr[bv + 1] - brow;
             }
-            const double T = (P.schedule == 3) ? (double)P.p0 : par_temperature(P.schedule, P.p0, P.p1, P.step_base + i);
-            const uint32_t r = live ? (uint32_t)LAB[(size_t)v * C] : 0u;
+        };
+        auto prefetch = [&](uint32_t slot) {      // stage 1 of the pipeline for the vertex in batch slot `slot`
+            v_n = __shfl_sync(0xffffffffu, bv, slot);
+            row_n = __shfl_sync(0xffffffffu, brow, slot);
+            d_n = __shfl_sync(0xffffffffu, bdeg, slot);
+            nbr_n = (lane < d_n) ? G.col[row_n + lane] : 0u;
+            r_n = live ? (uint32_t)LAB[(size_t)v_n * C] : 0u;
+            u32x4 ctr; ctr.x = v_n; ctr.y = (uint32_t)P.sweep; ctr.z = (uint32_t)(P.sweep >> 32); ctr.w = 0;
+            ra_n = philox4x32(ctr, key0, key1);
+            j_n = (live && d_n != 0) ? G.col[row_n + mulhi32(ra_n.x, d_n)] : 0u;   // differs per lane: plain gather
+        };
+        if (i_first < P.pos_end) {
+            refill(i_first);
+            prefetch(0);
+            t_n = (live && d_n != 0) ? (uint32_t)LAB[(size_t)j_n * C] : 0u;
+        }
+        for (uint32_t ib = i_first, k = 0; ib < P.pos_end; ib += stride, ++k) {
+            // warp-uniform trip count: all 32 lanes (= chains) reconverge at every vertex
+            __syncwarp();
+            const uint32_t v = v_n, row = row_n, d = d_n, nbr0 = nbr_n, r = r_n, t_prop = t_n;
+            const u32x4 ra = ra_n;
+            const bool has_next = (ib + stride < P.pos_end);
+            if (has_next) {
+                if (((k + 1) & 31u) == 0) refill(ib + stride);
+                prefetch((k + 1) & 31u);
+            }
+            const uint32_t i = ib;
+            const double T = const_T ? T_const : par_temperature(P.schedule, P.p0, P.p1, P.step_base + i);
 
             // ---- proposal (single_vertex_change) ----
-            u32x4 ctr; ctr.x = v; ctr.y = (uint32_t)P.sweep; ctr.z = (uint32_t)(P.sweep >> 32); ctr.w = 0;
-            const u32x4 ra = philox4x32(ctr, key0, key1);
             uint32_t s = r;        // own-type local index of the target block
             bool cross = false;    // the proposal fell on a block of the other type
             if (live && kown != 1) {
                 bool uniform_pick = (d == 0);
-                uint32_t t = 0;
+                const uint32_t t = t_prop;
                 int e_t = 0;
                 if (d != 0) {
-                    const uint32_t jpos = mulhi32(ra.x, d);   // differs per lane: plain gather
-                    const uint32_t j = G.col[row + jpos];
-                    t = (uint32_t)LAB[(size_t)j * C];
-                    e_t = cnt_ld<SMEM>(&Ep[t * 32]);
+                    e_t = Ep.ld(t * 32u);
                     const double R = epsK / ((double)e_t + epsK);
                     uniform_pick = ((double)ra.y * (1.0 / 4294967296.0)) < R;
                 }
@@ -338,24 +402,28 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(SweepParams P) {
                     cross = (sg_a != (type == 0));
                     s = sg_a ? sg : sg - ka;
                 } else {
-                    // categorical over row m[t][.]: block x of the own type w.p. m(x,t)/e_t
+                    // categorical over row m[t][.]: block x of the own type w.p. m(x,t)/e_t.
+                    // s = #{x : cum_x <= z} (cum is non-decreasing); no early exit keeps lanes in step
                     const uint32_t z = mulhi32(ra.z, (uint32_t)e_t);
-                    uint32_t cum = 0;
-                    s = kown - 1;
-                    const int32_t* col_t = M + t * st;
-                    bool found = false;
-                    for (uint32_t x = 0; x < kown; ++x) {   // no early exit: keeps the lanes in step
-                        cum += (uint32_t)cnt_ld<SMEM>(&col_t[x * sx]);
-                        if (!found && cum > z) { s = x; found = true; }
+                    uint32_t cum = 0, cnt_le = 0;
+                    uint32_t idx = t * st;
+#pragma unroll 8
+                    for (uint32_t x = 0; x < kown_max; ++x, idx += sx) {   // uniform bound; blocks >= kown hold 0
+                        cum += (uint32_t)M.ld(idx);
+                        cnt_le += (cum <= z) ? 1u : 0u;
                     }
+                    s = cnt_le < kown ? cnt_le : kown - 1;
                 }
             }
+            // stage 2 of the pipeline: the label of the next vertex's proposal neighbour (its id has
+            // arrived by now)
+            if (has_next) t_n = (live && d_n != 0) ? (uint32_t)LAB[(size_t)j_n * C] : 0u;
             // dS = +inf for a cross-type target (rejected); dS = 0, accu_r = 1 for s == r: at T > 0
             // accepted unless the block would empty, at T == 0 the reference requires dS < 0
             // (src/metropolis_hasting.cc:47-52)
             const bool eval = live && !cross && (s != r);
             if (live && !cross && s == r) {
-                if (T != 0.0 && ldc(&gNR[(own_off + r) * 32]) != 1) ++n_acc;
+                if (T != 0.0 && ldc(&gNR[r * 32]) != 1) ++n_acc;
             }
             __syncwarp();
             if (!__any_sync(0xffffffffu, eval)) continue;
@@ -364,12 +432,11 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(SweepParams P) {
             const uint32_t didx = G.degidx[v];
             int n_r = 0, n_s = 0, eta_r = 1, eta_s = 0;
             MoveAcc A; acc_init(A);
-            const int32_t* const Mr = M + r * sx;
-            const int32_t* const Ms = M + s * sx;
+            const uint32_t ir = r * sx, is = s * sx;
             if (eval) {  // issue the global (L2) loads early; they are consumed after the pass
-                n_r = ldc(&gNR[(own_off + r) * 32]); n_s = ldc(&gNR[(own_off + s) * 32]);
-                eta_r = ldc(&gETA[((own_off + r) * W + didx) * 32]);
-                eta_s = ldc(&gETA[((own_off + s) * W + didx) * 32]);
+                n_r = ldc(&gNR[r * 32]); n_s = ldc(&gNR[s * 32]);
+                eta_r = ldc(&gETA[(r * W + didx) * 32]);
+                eta_s = ldc(&gETA[(s * W + didx) * 32]);
             }
             uint32_t nbr = nbr0;  // lane e holds neighbour (base & ~31) + e
             for (uint32_t base = 0; base < d; base += 8) {
@@ -377,19 +444,23 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(SweepParams P) {
                 if (base != 0 && (base & 31u) == 0) nbr = (base + lane < d) ? G.col[row + base + lane] : 0u;
                 uint32_t tt[8];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const uint32_t nb = __shfl_sync(0xffffffffu, nbr, (base + k) & 31);
-                    tt[k] = (eval && base + k < d) ? (uint32_t)LAB[(size_t)nb * C] : 0u;
+                for (int q = 0; q < 8; ++q) {
+                    const uint32_t nb = __shfl_sync(0xffffffffu, nbr, (base + q) & 31);
+                    tt[q] = (eval && base + q < d) ? (uint32_t)LAB[(size_t)nb * C] : 0u;
                 }
                 if (eval) {
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        if (base + k < d) {
-                            const uint32_t t = tt[k];
-                            const int cnt = (int)hist[t * 32];
-                            hist[t * 32] = (HistT)(cnt + 1);
-                            const int m_r = cnt_ld<SMEM>(&Mr[t * st]), m_s = cnt_ld<SMEM>(&Ms[t * st]);
-                            const double inv = SMEM ? Inv[t * 32] : 1.0 / ((double)ldc(&Ep[t * 32]) + epsK);
+                    for (int q = 0; q < 8; ++q) {
+                        if (base + q < d) {
+                            const uint32_t t = tt[q];
+                            const uint32_t ha = hist_base + t * HS;
+                            const int cnt = (int)ShHist<HistT>::ld(ha);
+                            ShHist<HistT>::st(ha, (uint32_t)(cnt + 1));
+                            const uint32_t it = t * st;
+                            const int m_r = M.ld(ir + it), m_s = M.ld(is + it);
+                            double inv;
+                            if constexpr (SMEM) inv = sh_ld_f64(inv_base + t * 256u);
+                            else inv = 1.0 / ((double)Ep.ld(t * 32u) + epsK);
                             acc_edge(A, m_r, m_s, cnt, inv, eps);
                         }
                     }
@@ -401,46 +472,47 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(SweepParams P) {
             bool go = false;
             double dS = 0.0;
             if (eval) {
-                const int e_r = cnt_ld<SMEM>(&Eo[r * 32]), e_s = cnt_ld<SMEM>(&Eo[s * 32]);
-                const double eta_ratio = (double)(eta_r > 0 ? eta_r : 1) / (double)(eta_s + 1);
-                dS = A.logacc + log(A.num / A.den * eta_ratio);
+                const int e_r = Eo.ld(r * 32u), e_s = Eo.ld(s * 32u);
+                // log( prod (m_rt-c)/(m_st+1+c) * eta_r/(eta_s+1) ) with a single division
+                dS = A.logacc + log((A.num * (double)(eta_r > 0 ? eta_r : 1)) / (A.den * (double)(eta_s + 1)));
                 dS += block_degree_delta(e_r, e_s, (int)d);
-                dS += logq_delta(P.tb, gLQ[(own_off + r) * 32], e_r, n_r, -(int)d, -1);
-                dS += logq_delta(P.tb, gLQ[(own_off + s) * 32], e_s, n_s, (int)d, 1);
+                dS += logq_delta(P.tb, gLQ[r * 32], e_r, n_r, -(int)d, -1);
+                dS += logq_delta(P.tb, gLQ[s * 32], e_s, n_s, (int)d, 1);
                 // ---- accept (step) ----
                 if (T == 0.0) {
                     go = dS < 0.0;
                 } else {
-                    const double a = -dS / T + ((d == 0) ? 0.0 : log(A.a1 / A.a0));
+                    const double beta = const_T ? beta_const : 1.0 / T;
+                    const double a = ((d == 0) ? 0.0 : log(A.a1 / A.a0)) - dS * beta;
                     go = (a > 0.0) || (((double)ra.w + 0.5) * (1.0 / 4294967296.0) < exp(a));
                 }
                 if (go) {  // the exact "would empty block r" veto of apply_mcmc_moves
-                    const int old = atomicSub(&gNR[(own_off + r) * 32], 1);
-                    if (old <= 1) { atomicAdd(&gNR[(own_off + r) * 32], 1); go = false; }
+                    const int old = atomicSub(&gNR[r * 32], 1);
+                    if (old <= 1) { atomicAdd(&gNR[r * 32], 1); go = false; }
                 }
             }
             __syncwarp();
 
             // ---- clear the histogram and commit (apply_mcmc_moves): k_t is the histogram ----
             if (eval) {
-                int32_t* const Mrw = M + r * sx;
-                int32_t* const Msw = M + s * sx;
-                for (uint32_t t = 0; t < kopp; ++t) {
-                    const int kk = (int)hist[t * 32];
+                uint32_t ha = hist_base, it = 0;
+#pragma unroll 4
+                for (uint32_t t = 0; t < kopp_max; ++t, ha += HS, it += st) {   // uniform bound; bins >= kopp stay 0
+                    const int kk = (int)ShHist<HistT>::ld(ha);
                     if (kk != 0) {
-                        hist[t * 32] = 0;
+                        ShHist<HistT>::st(ha, 0u);
                         if (go) {
-                            atomicSub(&Mrw[t * st], kk);
-                            atomicAdd(&Msw[t * st], kk);
+                            M.add(ir + it, -kk);
+                            M.add(is + it, kk);
                         }
                     }
                 }
                 if (go) {
-                    atomicSub(&Eo[r * 32], (int)d);
-                    atomicAdd(&Eo[s * 32], (int)d);
-                    atomicAdd(&gNR[(own_off + s) * 32], 1);
-                    atomicSub(&gETA[((own_off + r) * W + didx) * 32], 1);
-                    atomicAdd(&gETA[((own_off + s) * W + didx) * 32], 1);
+                    Eo.add(r * 32u, -(int)d);
+                    Eo.add(s * 32u, (int)d);
+                    atomicAdd(&gNR[s * 32], 1);
+                    atomicSub(&gETA[(r * W + didx) * 32], 1);
+                    atomicAdd(&gETA[(s * W + didx) * 32], 1);
                     LAB[(size_t)v * C] = (int32_t)s;
                     ++n_acc;
                     ds_sum += dS;

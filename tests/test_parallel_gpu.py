@@ -173,3 +173,55 @@ def test_large_graph_invariants_and_logq_expansion(host):
     f2 = pool2.entropy()
     for c in (0, 63):
         assert abs((f2[c] - f1[c]) - pool2.entropy_accum(c)) <= 1e-6 * abs(f1[c])
+
+
+def test_large_k_uses_global_counts_path(host):
+    """K too large for shared-memory staging (KA*KB*128 B > 220 KB): counts stay in L2, commits are
+    global atomics.  Same invariants; sequential chains are exact."""
+    na = nb = 3000
+    ka = kb = 48
+    edges = planted(na, nb, 8, 8, 60000, 11)
+    graph = host.Graph(edges, na, nb)
+    C = 33
+    lab0 = np.concatenate([np.arange(na) % ka, ka + np.arange(nb) % kb]).astype(np.uint32)
+    pool = host.ChainPool(graph, np.tile(lab0, (C, 1)), ka, kb, 1.0)
+    seeds = np.arange(C, dtype=np.uint64) + 31
+    pool.randomize(seeds)
+    e1 = pool.entropy()
+    pool.anneal("constant", 1.0, 0.0, 4 * (na + nb), 10 ** 9, seeds)
+    check_invariants(pool, edges, na, nb, [0, 31, 32])
+    pool.anneal("abrupt_cool", 2.0 * (na + nb), 0.0, 6 * (na + nb), 10 ** 9, seeds, max_inflight=1)
+    check_invariants(pool, edges, na, nb, [0, 32])
+    e2 = pool.entropy()
+    assert (e2 < e1).all()
+    pool2 = host.ChainPool(graph, np.tile(lab0, (C, 1)), ka, kb, 1.0)
+    pool2.randomize(seeds)
+    f1 = pool2.entropy()
+    pool2.anneal("constant", 1.0, 0.0, 2 * (na + nb), 10 ** 9, seeds, max_inflight=1)
+    f2 = pool2.entropy()
+    for c in (0, 32):
+        assert abs((f2[c] - f1[c]) - pool2.entropy_accum(c)) <= 1e-6 * abs(f1[c])
+
+
+def test_ka_kb_grid_of_chains(host):
+    """BASELINE configs[3] in miniature: a det_k_bisbm-style (Ka, Kb) grid x restarts in ONE pool
+    (heterogeneous K per chain), abrupt_cool annealing; the description length must be lowest near
+    the planted (4, 6)."""
+    g = load_golden("c2_const_k46")
+    na, nb, edges = g["na"], g["nb"], g["edges"]
+    grid = [(a, b) for a in (2, 3, 4, 6, 8) for b in (2, 4, 6, 8, 12)]
+    restarts = 2
+    kas = np.array([a for a, b in grid for _ in range(restarts)], dtype=np.uint32)
+    kbs = np.array([b for a, b in grid for _ in range(restarts)], dtype=np.uint32)
+    labs = np.stack([np.concatenate([np.arange(na) * a // na, a + np.arange(nb) * b // nb]) for a, b in zip(kas, kbs)]).astype(np.uint32)
+    graph = host.Graph(edges, na, nb)
+    pool = host.ChainPool(graph, labs, kas, kbs, 1.0)
+    seeds = np.arange(len(kas), dtype=np.uint64) + 1
+    pool.randomize(seeds)
+    n = na + nb
+    pool.anneal("abrupt_cool", 60.0 * n, 0.0, 120 * n, 10 ** 9, seeds)
+    check_invariants(pool, edges, na, nb, [0, 13, len(kas) - 1])
+    ent = pool.entropy().reshape(len(grid), restarts).min(1)
+    best = grid[int(np.argmin(ent))]
+    print("grid minimum at", best, "entropy", ent.min())
+    assert abs(best[0] - 4) <= 2 and abs(best[1] - 6) <= 2
