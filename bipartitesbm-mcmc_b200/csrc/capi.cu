@@ -76,6 +76,7 @@ struct bisbm_handle {
     int32_t *d_labels = nullptr, *d_labels_tmp = nullptr, *d_m = nullptr, *d_e = nullptr, *d_nr = nullptr,
             *d_eta = nullptr;
     int32_t *d_m2 = nullptr, *d_e2 = nullptr;  // "next" count buffers of the sliced shared-memory sweep
+    uint8_t* d_lab8 = nullptr;                 // u8 shadow of the labels for the shared-memory sweep
     double eps = 1.0;
     LogqExp* d_lq = nullptr;
     uint64_t* d_seeds = nullptr;
@@ -103,7 +104,7 @@ void dfree(T*& p) {
 
 void free_chains(bisbm_handle* h) {
     dfree(h->d_ka); dfree(h->d_kb); dfree(h->d_labels); dfree(h->d_labels_tmp);
-    dfree(h->d_m); dfree(h->d_e); dfree(h->d_nr); dfree(h->d_eta); dfree(h->d_lq); dfree(h->d_m2); dfree(h->d_e2);
+    dfree(h->d_m); dfree(h->d_e); dfree(h->d_nr); dfree(h->d_eta); dfree(h->d_lq); dfree(h->d_m2); dfree(h->d_e2); dfree(h->d_lab8);
     dfree(h->d_seeds); dfree(h->d_active); dfree(h->d_accepted); dfree(h->d_u); dfree(h->d_sweeps);
     dfree(h->d_dS); dfree(h->d_entmin); dfree(h->d_ent_out); dfree(h->d_nactive); dfree(h->d_hist);
     for (auto& kv : h->replay) { dfree(kv.second.d_rs); dfree(kv.second.d_vlist); dfree(kv.second.d_kh); }
@@ -331,7 +332,7 @@ int plan_sweep(bisbm_handle* h, uint32_t type, uint32_t max_inflight, LaunchPlan
     const uint32_t hb = h->max_degree <= 255u ? 1 : (h->max_degree <= 65535u ? 2 : 4);
     lp->hist_bytes = (int)hb;
     const size_t budget = 220 * 1024;
-    lp->smem = sweep_smem_bytes(true, h->KA, h->KB, type, 16, hb) <= budget;
+    lp->smem = sweep_smem_bytes(true, h->KA, h->KB, type, 16, hb) <= budget && h->KA <= 256 && h->KB <= 256;
     uint32_t wpc = 32;
     if (const char* e = getenv("BISBM_WPC")) { int w = atoi(e); wpc = (w == 16 || w == 24) ? (uint32_t)w : 32; }  // tuning knob
     if (sweep_smem_bytes(lp->smem, h->KA, h->KB, type, wpc, hb) > budget) wpc = 16;
@@ -403,7 +404,7 @@ int launch_full_sweep(bisbm_handle* h, int schedule, float p0, float p1, uint64_
             }
             SweepParams P;
             P.g = gview(h); P.s = sview(h); P.tb = tview(h, false);
-            P.m_next = h->d_m2; P.e_next = h->d_e2;
+            P.lab8 = h->d_lab8; P.m_next = h->d_m2; P.e_next = h->d_e2;
             P.seeds = h->d_seeds; P.active = h->d_active; P.accepted = h->d_accepted; P.dS_accum = h->d_dS;
             P.lq = h->d_lq;
             P.n_chains = h->n_chains; P.type = type; P.n_groups = h->C / 32;
@@ -423,6 +424,16 @@ int launch_full_sweep(bisbm_handle* h, int schedule, float p0, float p1, uint64_
     }
     h->sweep_epoch++;
     h->last_moves += (uint64_t)h->n * h->n_chains;
+    return BISBM_OK;
+}
+
+// refresh the u8 label shadow from the canonical i32 labels (start of every parallel call: replay
+// moves, set_chains and randomize only write the canonical array)
+int sync_labels8(bisbm_handle* h) {
+    const uint64_t total = (uint64_t)h->n * h->C;
+    const uint64_t threads = (total + 3) / 4;
+    labels8_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, h->stream>>>(h->d_labels, h->d_lab8, total);
+    CU(cudaGetLastError());
     return BISBM_OK;
 }
 
@@ -533,6 +544,7 @@ int bisbm_set_chains(bisbm_handle* h, uint32_t n_chains, const uint32_t* ka, con
         CU(cudaMalloc(&h->d_e, (size_t)C * KK * sizeof(int32_t)));
         CU(cudaMalloc(&h->d_m2, (size_t)C * KA * KB * sizeof(int32_t)));
         CU(cudaMalloc(&h->d_e2, (size_t)C * KK * sizeof(int32_t)));
+        CU(cudaMalloc(&h->d_lab8, (size_t)n * C));
         CU(cudaMalloc(&h->d_nr, (size_t)C * KK * sizeof(int32_t)));
         CU(cudaMalloc(&h->d_eta, (size_t)C * KK * h->W * sizeof(int32_t)));
         CU(cudaMalloc(&h->d_lq, (size_t)C * KK * sizeof(LogqExp)));
@@ -727,6 +739,8 @@ int bisbm_anneal(bisbm_handle* h, int schedule, float p0, float p1, uint64_t dur
     if (schedule < 0 || schedule > 4) return fail(BISBM_ERR_ARG, "unknown cooling schedule %d", schedule);
     rc = upload_seeds(h, seeds);
     if (rc) return rc;
+    rc = sync_labels8(h);
+    if (rc) return rc;
     const uint64_t N = h->n;
     const uint64_t all_sweeps = duration / N;
     const uint32_t C = h->C;
@@ -806,6 +820,8 @@ int bisbm_marginalize(bisbm_handle* h, uint64_t burn_in, uint64_t sweeps, uint64
     if (every == 0) return fail(BISBM_ERR_ARG, "sampling interval must be >= 1");
     if (!h->d_hist) { rc = bisbm_marginals_clear(h); if (rc) return rc; }
     rc = upload_seeds(h, seeds);
+    if (rc) return rc;
+    rc = sync_labels8(h);
     if (rc) return rc;
     {
         std::vector<uint8_t> act(h->C, 0);

@@ -50,6 +50,7 @@ struct SweepParams {
     GraphView g;
     StateView s;                     // s.m / s.e = BASE counts of this launch
     Tables tb;
+    uint8_t* lab8;                   // SMEM variant: u8 shadow of the labels (chain-minor), 4x less gather traffic
     int32_t* m_next;                 // SMEM variant with shared groups: where deltas are added
     int32_t* e_next;
     const uint64_t* seeds;           // [C]
@@ -323,6 +324,11 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(SweepParams P) {
     // m(x_own, t_opp) = M[x*sx + t*st]   (element indices, already multiplied by the 32-chain interleave)
     const uint32_t sx = (type ? 1u : KB) * 32u, st = (type ? KB : 1u) * 32u;
     int32_t* const LAB = P.s.labels + cc;
+    uint8_t* const LAB8 = SMEM ? P.lab8 + cc : nullptr;
+    auto label_of = [&](uint32_t vtx) -> uint32_t {
+        if constexpr (SMEM) return (uint32_t)LAB8[(size_t)vtx * C];
+        else return (uint32_t)LAB[(size_t)vtx * C];
+    };
     const uint64_t seed = P.seeds[cc];
     const uint32_t key0 = (uint32_t)seed, key1 = (uint32_t)(seed >> 32);
     const uint32_t nv = type ? G.nb : G.na, v0 = type ? G.na : 0;
@@ -361,7 +367,7 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(SweepParams P) {
             row_n = __shfl_sync(0xffffffffu, brow, slot);
             d_n = __shfl_sync(0xffffffffu, bdeg, slot);
             nbr_n = (lane < d_n) ? G.col[row_n + lane] : 0u;
-            r_n = live ? (uint32_t)LAB[(size_t)v_n * C] : 0u;
+            r_n = live ? label_of(v_n) : 0u;
             u32x4 ctr; ctr.x = v_n; ctr.y = (uint32_t)P.sweep; ctr.z = (uint32_t)(P.sweep >> 32); ctr.w = 0;
             ra_n = philox4x32(ctr, key0, key1);
             j_n = (live && d_n != 0) ? G.col[row_n + mulhi32(ra_n.x, d_n)] : 0u;   // differs per lane: plain gather
@@ -369,7 +375,7 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(SweepParams P) {
         if (i_first < P.pos_end) {
             refill(i_first);
             prefetch(0);
-            t_n = (live && d_n != 0) ? (uint32_t)LAB[(size_t)j_n * C] : 0u;
+            t_n = (live && d_n != 0) ? label_of(j_n) : 0u;
         }
         for (uint32_t ib = i_first, k = 0; ib < P.pos_end; ib += stride, ++k) {
             // warp-uniform trip count: all 32 lanes (= chains) reconverge at every vertex
@@ -417,7 +423,7 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(SweepParams P) {
             }
             // stage 2 of the pipeline: the label of the next vertex's proposal neighbour (its id has
             // arrived by now)
-            if (has_next) t_n = (live && d_n != 0) ? (uint32_t)LAB[(size_t)j_n * C] : 0u;
+            if (has_next) t_n = (live && d_n != 0) ? label_of(j_n) : 0u;
             // dS = +inf for a cross-type target (rejected); dS = 0, accu_r = 1 for s == r: at T > 0
             // accepted unless the block would empty, at T == 0 the reference requires dS < 0
             // (src/metropolis_hasting.cc:47-52)
@@ -446,7 +452,7 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(SweepParams P) {
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     const uint32_t nb = __shfl_sync(0xffffffffu, nbr, (base + q) & 31);
-                    tt[q] = (eval && base + q < d) ? (uint32_t)LAB[(size_t)nb * C] : 0u;
+                    tt[q] = (eval && base + q < d) ? label_of(nb) : 0u;
                 }
                 if (eval) {
 #pragma unroll
@@ -514,6 +520,7 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(SweepParams P) {
                     atomicSub(&gETA[(r * W + didx) * 32], 1);
                     atomicAdd(&gETA[(s * W + didx) * 32], 1);
                     LAB[(size_t)v * C] = (int32_t)s;
+                    if constexpr (SMEM) LAB8[(size_t)v * C] = (uint8_t)s;
                     ++n_acc;
                     ds_sum += dS;
                 }

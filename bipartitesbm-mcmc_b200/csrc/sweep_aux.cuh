@@ -114,6 +114,18 @@ __global__ void export_labels_kernel(const int32_t* __restrict__ in, uint32_t* _
     }
 }
 
+// u8 shadow of the chain-minor labels for the shared-memory sweep (blocks per type <= 256)
+__global__ void labels8_kernel(const int32_t* __restrict__ in, uint8_t* __restrict__ out, uint64_t total) {
+    const uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i + 3 < total) {
+        const int4 v = *reinterpret_cast<const int4*>(in + i);
+        uchar4 o; o.x = (uint8_t)v.x; o.y = (uint8_t)v.y; o.z = (uint8_t)v.z; o.w = (uint8_t)v.w;
+        *reinterpret_cast<uchar4*>(out + i) = o;
+    } else {
+        for (uint64_t j = i; j < total; ++j) out[j] = (uint8_t)in[j];
+    }
+}
+
 // per-sweep bookkeeping of anneal (src/metropolis_hasting.cc:86-98) at sweep granularity
 __global__ void bookkeep_kernel(uint32_t n_chains, uint8_t* active, const double* dS_accum, double* ent_min,
                                 unsigned long long* u, unsigned long long* sweeps_done, uint64_t sweep,
