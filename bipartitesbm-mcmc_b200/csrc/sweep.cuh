@@ -444,34 +444,43 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(SweepParams P) {
                 eta_r = ldc(&gETA[(r * W + didx) * 32]);
                 eta_s = ldc(&gETA[(s * W + didx) * 32]);
             }
+            // Every lane runs the pass, also lanes whose proposal needs no evaluation (s == r, cross-type,
+            // padding chains): masked lanes cost the same issue slots anyway, and dropping the per-lane
+            // predicates removes the divergence bookkeeping from the loop.  Their result is ignored.
             uint32_t nbr = nbr0;  // lane e holds neighbour (base & ~31) + e
-            for (uint32_t base = 0; base < d; base += 8) {
+            auto consume = [&](uint32_t t) {
+                const uint32_t ha = hist_base + t * HS;
+                const int cnt = (int)ShHist<HistT>::ld(ha);
+                ShHist<HistT>::st(ha, (uint32_t)(cnt + 1));
+                const uint32_t it = t * st;
+                const int m_r = M.ld(ir + it), m_s = M.ld(is + it);
+                double inv;
+                if constexpr (SMEM) inv = sh_ld_f64(inv_base + t * 256u);
+                else inv = 1.0 / ((double)Ep.ld(t * 32u) + epsK);
+                acc_edge(A, m_r, m_s, cnt, inv, eps);
+            };
+            uint32_t base = 0;
+            for (; base + 8 <= d; base += 8) {
                 // gather 8 neighbour labels (independent 128-byte loads in flight), then consume them
+                if (base != 0 && (base & 31u) == 0) nbr = (base + lane < d) ? G.col[row + base + lane] : 0u;
+                uint32_t tt[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) tt[q] = label_of(__shfl_sync(0xffffffffu, nbr, (base + q) & 31));
+#pragma unroll
+                for (int q = 0; q < 8; ++q) consume(tt[q]);
+                acc_guard(A);
+            }
+            if (base < d) {   // tail of < 8 neighbours
                 if (base != 0 && (base & 31u) == 0) nbr = (base + lane < d) ? G.col[row + base + lane] : 0u;
                 uint32_t tt[8];
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     const uint32_t nb = __shfl_sync(0xffffffffu, nbr, (base + q) & 31);
-                    tt[q] = (eval && base + q < d) ? label_of(nb) : 0u;
+                    tt[q] = (base + q < d) ? label_of(nb) : 0u;
                 }
-                if (eval) {
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        if (base + q < d) {
-                            const uint32_t t = tt[q];
-                            const uint32_t ha = hist_base + t * HS;
-                            const int cnt = (int)ShHist<HistT>::ld(ha);
-                            ShHist<HistT>::st(ha, (uint32_t)(cnt + 1));
-                            const uint32_t it = t * st;
-                            const int m_r = M.ld(ir + it), m_s = M.ld(is + it);
-                            double inv;
-                            if constexpr (SMEM) inv = sh_ld_f64(inv_base + t * 256u);
-                            else inv = 1.0 / ((double)Ep.ld(t * 32u) + epsK);
-                            acc_edge(A, m_r, m_s, cnt, inv, eps);
-                        }
-                    }
-                    acc_guard(A);
-                }
+                for (int q = 0; q < 8; ++q) if (base + q < d) consume(tt[q]);
+                acc_guard(A);
             }
             __syncwarp();
 
@@ -500,17 +509,15 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(SweepParams P) {
             __syncwarp();
 
             // ---- clear the histogram and commit (apply_mcmc_moves): k_t is the histogram ----
-            if (eval) {
+            {
                 uint32_t ha = hist_base, it = 0;
 #pragma unroll 4
                 for (uint32_t t = 0; t < kopp_max; ++t, ha += HS, it += st) {   // uniform bound; bins >= kopp stay 0
                     const int kk = (int)ShHist<HistT>::ld(ha);
-                    if (kk != 0) {
-                        ShHist<HistT>::st(ha, 0u);
-                        if (go) {
-                            M.add(ir + it, -kk);
-                            M.add(is + it, kk);
-                        }
+                    ShHist<HistT>::st(ha, 0u);
+                    if (go && kk != 0) {
+                        M.add(ir + it, -kk);
+                        M.add(is + it, kk);
                     }
                 }
                 if (go) {
