@@ -212,7 +212,7 @@ __host__ __device__ inline size_t sweep_smem_bytes(bool smem, uint32_t KA, uint3
     const uint32_t kown = type ? KB : KA, kopp = type ? KA : KB;
     size_t b = 0;
     if (smem) b += (size_t)KA * KB * 128 + (size_t)kown * 128 + (size_t)kopp * 128 + (size_t)kopp * 256;
-    b += (size_t)warps * kopp * 32 * hist_bytes;
+    b += (size_t)warps * ((kopp * hist_bytes + 3) / 4) * 128;   // lane-major 32-bit words
     return b;
 }
 
@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(SweepParams P) {
     const bool live = (c < P.n_chains) && P.active[c];
     const uint32_t cc = (c < P.s.C) ? c : 0;
     const uint32_t ka = P.s.ka[cc], kb = P.s.kb[cc], K = ka + kb;
-    const uint32_t kown = type ? kb : ka, kopp = type ? ka : kb;
+    const uint32_t kown = type ? kb : ka;
     const double eps = P.s.eps, epsK = eps * (double)K;
 
     // ---- stage the group's counts ----
@@ -305,7 +305,11 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(SweepParams P) {
         sEp = nullptr; sInv = nullptr;
         hist_all = reinterpret_cast<HistT*>(smem_raw);
     }
-    for (uint32_t i = threadIdx.x; i < wpc * kopp_max * 32; i += blockDim.x) hist_all[i] = 0;
+    {
+        uint32_t* hw = reinterpret_cast<uint32_t*>(hist_all);
+        const uint32_t words = wpc * (((kopp_max * (uint32_t)sizeof(HistT) + 3u) / 4u)) * 32u;
+        for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) hw[i] = 0u;
+    }
     __syncthreads();
 
     // lane-private accessors (entry j of this chain at element j*32)
@@ -319,8 +323,15 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(SweepParams P) {
     } else {
         M.p = gM + lane; Eo.p = gE + own_off * 32 + lane; Ep.p = gE + opp_off * 32 + lane;
     }
-    const uint32_t hist_base = (uint32_t)__cvta_generic_to_shared(hist_all) + (warp * kopp_max * 32 + lane) * (uint32_t)sizeof(HistT);
-    constexpr uint32_t HS = 32u * (uint32_t)sizeof(HistT);   // byte stride between histogram bins
+    // histogram bins are packed BPW per 32-bit word and the words are LANE-MAJOR ([t / BPW][lane]), so
+    // lane l only ever touches bank l: bin t of this lane is at hist_base + (t / BPW) * 128 + (t % BPW) * sizeof(HistT)
+    constexpr uint32_t BPW = 4u / (uint32_t)sizeof(HistT);
+    const uint32_t hist_words = (kopp_max + BPW - 1) / BPW;
+    const uint32_t hist_base = (uint32_t)__cvta_generic_to_shared(hist_all) + warp * hist_words * 128u + lane * 4u;
+    auto hist_addr = [&](uint32_t t) -> uint32_t {
+        if constexpr (BPW == 1) return hist_base + t * 128u;
+        else return hist_base + (t / BPW) * 128u + (t % BPW) * (uint32_t)sizeof(HistT);
+    };
     // m(x_own, t_opp) = M[x*sx + t*st]   (element indices, already multiplied by the 32-chain interleave)
     const uint32_t sx = (type ? 1u : KB) * 32u, st = (type ? KB : 1u) * 32u;
     int32_t* const LAB = P.s.labels + cc;
@@ -390,37 +401,30 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(SweepParams P) {
             const uint32_t i = ib;
             const double T = const_T ? T_const : par_temperature(P.schedule, P.p0, P.p1, P.step_base + i);
 
-            // ---- proposal (single_vertex_change) ----
-            uint32_t s = r;        // own-type local index of the target block
-            bool cross = false;    // the proposal fell on a block of the other type
-            if (live && kown != 1) {
-                bool uniform_pick = (d == 0);
-                const uint32_t t = t_prop;
-                int e_t = 0;
-                if (d != 0) {
-                    e_t = Ep.ld(t * 32u);
-                    const double R = epsK / ((double)e_t + epsK);
-                    uniform_pick = ((double)ra.y * (1.0 / 4294967296.0)) < R;
-                }
-                if (uniform_pick) {
-                    const uint32_t sg = mulhi32(ra.z, K);  // uniform over ALL K blocks (either type)
-                    const bool sg_a = sg < ka;
-                    cross = (sg_a != (type == 0));
-                    s = sg_a ? sg : sg - ka;
-                } else {
-                    // categorical over row m[t][.]: block x of the own type w.p. m(x,t)/e_t.
-                    // s = #{x : cum_x <= z} (cum is non-decreasing); no early exit keeps lanes in step
-                    const uint32_t z = mulhi32(ra.z, (uint32_t)e_t);
-                    uint32_t cum = 0, cnt_le = 0;
-                    uint32_t idx = t * st;
+            // ---- proposal (single_vertex_change), branch-free: every lane computes both the uniform
+            //      and the categorical candidate and selects ----
+            const uint32_t tq = t_prop;
+            const int e_t = Ep.ld(tq * 32u);
+            const bool uniform_pick = (d == 0) || (((double)ra.y * (1.0 / 4294967296.0)) < epsK / ((double)e_t + epsK));
+            const uint32_t sg = mulhi32(ra.z, K);      // uniform over ALL K blocks (either type)
+            const bool sg_a = sg < ka;
+            const uint32_t s_uni = sg_a ? sg : sg - ka;
+            // categorical over row m[t][.]: block x of the own type w.p. m(x,t)/e_t;
+            // s = #{x : cum_x <= z} (cum is non-decreasing), no early exit
+            const uint32_t z = mulhi32(ra.z, (uint32_t)e_t);
+            uint32_t cum = 0, cnt_le = 0;
+            {
+                uint32_t idx = tq * st;
 #pragma unroll 8
-                    for (uint32_t x = 0; x < kown_max; ++x, idx += sx) {   // uniform bound; blocks >= kown hold 0
-                        cum += (uint32_t)M.ld(idx);
-                        cnt_le += (cum <= z) ? 1u : 0u;
-                    }
-                    s = cnt_le < kown ? cnt_le : kown - 1;
+                for (uint32_t x = 0; x < kown_max; ++x, idx += sx) {   // uniform bound; blocks >= kown hold 0
+                    cum += (uint32_t)M.ld(idx);
+                    cnt_le += (cum <= z) ? 1u : 0u;
                 }
             }
+            const uint32_t s_cat = cnt_le < kown ? cnt_le : kown - 1;
+            const bool movable = live && (kown != 1);
+            const uint32_t s = movable ? (uniform_pick ? s_uni : s_cat) : r;   // own-type local index of the target
+            const bool cross = movable && uniform_pick && (sg_a != (type == 0));  // fell on a block of the other type
             // stage 2 of the pipeline: the label of the next vertex's proposal neighbour (its id has
             // arrived by now)
             if (has_next) t_n = (live && d_n != 0) ? label_of(j_n) : 0u;
@@ -439,17 +443,16 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(SweepParams P) {
             int n_r = 0, n_s = 0, eta_r = 1, eta_s = 0;
             MoveAcc A; acc_init(A);
             const uint32_t ir = r * sx, is = s * sx;
-            if (eval) {  // issue the global (L2) loads early; they are consumed after the pass
-                n_r = ldc(&gNR[r * 32]); n_s = ldc(&gNR[s * 32]);
-                eta_r = ldc(&gETA[(r * W + didx) * 32]);
-                eta_s = ldc(&gETA[(s * W + didx) * 32]);
-            }
+            // issue the global (L2) loads early; they are consumed after the pass
+            n_r = ldc(&gNR[r * 32]); n_s = ldc(&gNR[s * 32]);
+            eta_r = ldc(&gETA[(r * W + didx) * 32]);
+            eta_s = ldc(&gETA[(s * W + didx) * 32]);
             // Every lane runs the pass, also lanes whose proposal needs no evaluation (s == r, cross-type,
             // padding chains): masked lanes cost the same issue slots anyway, and dropping the per-lane
             // predicates removes the divergence bookkeeping from the loop.  Their result is ignored.
             uint32_t nbr = nbr0;  // lane e holds neighbour (base & ~31) + e
             auto consume = [&](uint32_t t) {
-                const uint32_t ha = hist_base + t * HS;
+                const uint32_t ha = hist_addr(t);
                 const int cnt = (int)ShHist<HistT>::ld(ha);
                 ShHist<HistT>::st(ha, (uint32_t)(cnt + 1));
                 const uint32_t it = t * st;
@@ -484,9 +487,11 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(SweepParams P) {
             }
             __syncwarp();
 
-            bool go = false;
-            double dS = 0.0;
-            if (eval) {
+            // dS and the accept test are evaluated by every lane (masked lanes cost the same issue
+            // slots); only `eval` lanes may commit
+            bool go;
+            double dS;
+            {
                 const int e_r = Eo.ld(r * 32u), e_s = Eo.ld(s * 32u);
                 // log( prod (m_rt-c)/(m_st+1+c) * eta_r/(eta_s+1) ) with a single division
                 dS = A.logacc + log((A.num * (double)(eta_r > 0 ? eta_r : 1)) / (A.den * (double)(eta_s + 1)));
@@ -494,13 +499,10 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(SweepParams P) {
                 dS += logq_delta(P.tb, gLQ[r * 32], e_r, n_r, -(int)d, -1);
                 dS += logq_delta(P.tb, gLQ[s * 32], e_s, n_s, (int)d, 1);
                 // ---- accept (step) ----
-                if (T == 0.0) {
-                    go = dS < 0.0;
-                } else {
-                    const double beta = const_T ? beta_const : 1.0 / T;
-                    const double a = ((d == 0) ? 0.0 : log(A.a1 / A.a0)) - dS * beta;
-                    go = (a > 0.0) || (((double)ra.w + 0.5) * (1.0 / 4294967296.0) < exp(a));
-                }
+                const double beta = const_T ? beta_const : 1.0 / T;
+                const double a = ((d == 0) ? 0.0 : log(A.a1 / A.a0)) - dS * beta;
+                const bool go_hot = (a > 0.0) || (((double)ra.w + 0.5) * (1.0 / 4294967296.0) < exp(a));
+                go = eval && ((T == 0.0) ? (dS < 0.0) : go_hot);
                 if (go) {  // the exact "would empty block r" veto of apply_mcmc_moves
                     const int old = atomicSub(&gNR[r * 32], 1);
                     if (old <= 1) { atomicAdd(&gNR[r * 32], 1); go = false; }
@@ -510,14 +512,21 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(SweepParams P) {
 
             // ---- clear the histogram and commit (apply_mcmc_moves): k_t is the histogram ----
             {
+                // one 32-bit word holds BPW bins: read and clear them together
                 uint32_t ha = hist_base, it = 0;
-#pragma unroll 4
-                for (uint32_t t = 0; t < kopp_max; ++t, ha += HS, it += st) {   // uniform bound; bins >= kopp stay 0
-                    const int kk = (int)ShHist<HistT>::ld(ha);
-                    ShHist<HistT>::st(ha, 0u);
-                    if (go && kk != 0) {
-                        M.add(ir + it, -kk);
-                        M.add(is + it, kk);
+#pragma unroll 2
+                for (uint32_t w = 0; w < hist_words; ++w, ha += 128u) {   // uniform bound; bins >= kopp stay 0
+                    const uint32_t word = ShHist<uint32_t>::ld(ha);
+                    ShHist<uint32_t>::st(ha, 0u);
+#pragma unroll
+                    for (uint32_t b = 0; b < BPW; ++b, it += st) {
+                        int kk;
+                        if constexpr (BPW == 1) kk = (int)word;
+                        else kk = (int)((word >> (b * 8u * (uint32_t)sizeof(HistT))) & ((1u << (8u * (uint32_t)sizeof(HistT))) - 1u));
+                        if (go && kk != 0) {
+                            M.add(ir + it, -kk);
+                            M.add(is + it, kk);
+                        }
                     }
                 }
                 if (go) {
