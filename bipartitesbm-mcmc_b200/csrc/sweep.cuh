@@ -261,7 +261,13 @@ template <> struct Cnt<false> {  // in global memory: L2 loads, global reduction
 template <bool SMEM, typename HistT, int NT>
 __global__ void __launch_bounds__(NT, 1) sweep_kernel(SweepParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    // lane / warp ids through volatile asm: the compiler must keep them in registers instead of
+    // re-deriving them from S2R + ALU at every use (it did so ~40 times per vertex under the 64-register cap)
+    uint32_t lane, warp;
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(warp));
+    warp >>= 5;
+    const uint32_t wpc = blockDim.x >> 5;
     const GraphView& G = P.g;
     const uint32_t type = P.type;
     const uint32_t C = P.s.C, KB = P.s.KB, KA = P.s.KA, W = P.s.W, KK = KA + KB;
@@ -273,9 +279,10 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(SweepParams P) {
     // global (group-interleaved) count arrays of this group
     int32_t* const gM = P.s.m + (size_t)group * KA * KB * GROUP;
     int32_t* const gE = P.s.e + (size_t)group * KK * GROUP;
-    int32_t* const gNR = P.s.nr + (size_t)group * KK * GROUP + (size_t)own_off * 32 + lane;         // own-type slots
-    int32_t* const gETA = P.s.eta + (size_t)group * KK * W * GROUP + (size_t)own_off * W * 32 + lane;
-    const LogqExp* const gLQ = P.lq + (size_t)group * KK * GROUP + (size_t)own_off * 32 + lane;
+    // (warp-uniform bases; the lane is added in the 32-bit index so they can live in uniform registers)
+    int32_t* const gNR = P.s.nr + (size_t)group * KK * GROUP + (size_t)own_off * 32;         // own-type slots
+    int32_t* const gETA = P.s.eta + (size_t)group * KK * W * GROUP + (size_t)own_off * W * 32;
+    const LogqExp* const gLQ = P.lq + (size_t)group * KK * GROUP + (size_t)own_off * 32;
 
     const uint32_t c = group * 32 + lane;
     const bool live = (c < P.n_chains) && P.active[c];
@@ -334,11 +341,11 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(SweepParams P) {
     };
     // m(x_own, t_opp) = M[x*sx + t*st]   (element indices, already multiplied by the 32-chain interleave)
     const uint32_t sx = (type ? 1u : KB) * 32u, st = (type ? KB : 1u) * 32u;
-    int32_t* const LAB = P.s.labels + cc;
-    uint8_t* const LAB8 = SMEM ? P.lab8 + cc : nullptr;
+    int32_t* const LAB = P.s.labels;
+    uint8_t* const LAB8 = P.lab8;
     auto label_of = [&](uint32_t vtx) -> uint32_t {
-        if constexpr (SMEM) return (uint32_t)LAB8[(size_t)vtx * C];
-        else return (uint32_t)LAB[(size_t)vtx * C];
+        if constexpr (SMEM) return (uint32_t)LAB8[(size_t)vtx * C + cc];
+        else return (uint32_t)LAB[(size_t)vtx * C + cc];
     };
     const uint64_t seed = P.seeds[cc];
     const uint32_t key0 = (uint32_t)seed, key1 = (uint32_t)(seed >> 32);
@@ -433,7 +440,7 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(SweepParams P) {
             // (src/metropolis_hasting.cc:47-52)
             const bool eval = live && !cross && (s != r);
             if (live && !cross && s == r) {
-                if (T != 0.0 && ldc(&gNR[r * 32]) != 1) ++n_acc;
+                if (T != 0.0 && ldc(&gNR[r * 32 + lane]) != 1) ++n_acc;
             }
             __syncwarp();
             if (!__any_sync(0xffffffffu, eval)) continue;
@@ -444,9 +451,9 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(SweepParams P) {
             MoveAcc A; acc_init(A);
             const uint32_t ir = r * sx, is = s * sx;
             // issue the global (L2) loads early; they are consumed after the pass
-            n_r = ldc(&gNR[r * 32]); n_s = ldc(&gNR[s * 32]);
-            eta_r = ldc(&gETA[(r * W + didx) * 32]);
-            eta_s = ldc(&gETA[(s * W + didx) * 32]);
+            n_r = ldc(&gNR[r * 32 + lane]); n_s = ldc(&gNR[s * 32 + lane]);
+            eta_r = ldc(&gETA[(r * W + didx) * 32 + lane]);
+            eta_s = ldc(&gETA[(s * W + didx) * 32 + lane]);
             // Every lane runs the pass, also lanes whose proposal needs no evaluation (s == r, cross-type,
             // padding chains): masked lanes cost the same issue slots anyway, and dropping the per-lane
             // predicates removes the divergence bookkeeping from the loop.  Their result is ignored.
@@ -496,16 +503,16 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(SweepParams P) {
                 // log( prod (m_rt-c)/(m_st+1+c) * eta_r/(eta_s+1) ) with a single division
                 dS = A.logacc + log((A.num * (double)(eta_r > 0 ? eta_r : 1)) / (A.den * (double)(eta_s + 1)));
                 dS += block_degree_delta(e_r, e_s, (int)d);
-                dS += logq_delta(P.tb, gLQ[r * 32], e_r, n_r, -(int)d, -1);
-                dS += logq_delta(P.tb, gLQ[s * 32], e_s, n_s, (int)d, 1);
+                dS += logq_delta(P.tb, gLQ[r * 32 + lane], e_r, n_r, -(int)d, -1);
+                dS += logq_delta(P.tb, gLQ[s * 32 + lane], e_s, n_s, (int)d, 1);
                 // ---- accept (step) ----
                 const double beta = const_T ? beta_const : 1.0 / T;
                 const double a = ((d == 0) ? 0.0 : log(A.a1 / A.a0)) - dS * beta;
                 const bool go_hot = (a > 0.0) || (((double)ra.w + 0.5) * (1.0 / 4294967296.0) < exp(a));
                 go = eval && ((T == 0.0) ? (dS < 0.0) : go_hot);
                 if (go) {  // the exact "would empty block r" veto of apply_mcmc_moves
-                    const int old = atomicSub(&gNR[r * 32], 1);
-                    if (old <= 1) { atomicAdd(&gNR[r * 32], 1); go = false; }
+                    const int old = atomicSub(&gNR[r * 32 + lane], 1);
+                    if (old <= 1) { atomicAdd(&gNR[r * 32 + lane], 1); go = false; }
                 }
             }
             __syncwarp();
@@ -532,11 +539,11 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(SweepParams P) {
                 if (go) {
                     Eo.add(r * 32u, -(int)d);
                     Eo.add(s * 32u, (int)d);
-                    atomicAdd(&gNR[s * 32], 1);
-                    atomicSub(&gETA[(r * W + didx) * 32], 1);
-                    atomicAdd(&gETA[(s * W + didx) * 32], 1);
-                    LAB[(size_t)v * C] = (int32_t)s;
-                    if constexpr (SMEM) LAB8[(size_t)v * C] = (uint8_t)s;
+                    atomicAdd(&gNR[s * 32 + lane], 1);
+                    atomicSub(&gETA[(r * W + didx) * 32 + lane], 1);
+                    atomicAdd(&gETA[(s * W + didx) * 32 + lane], 1);
+                    LAB[(size_t)v * C + cc] = (int32_t)s;
+                    if constexpr (SMEM) LAB8[(size_t)v * C + cc] = (uint8_t)s;
                     ++n_acc;
                     ds_sum += dS;
                 }
