@@ -225,3 +225,40 @@ def test_ka_kb_grid_of_chains(host):
     best = grid[int(np.argmin(ent))]
     print("grid minimum at", best, "entropy", ent.min())
     assert abs(best[0] - 4) <= 2 and abs(best[1] - 6) <= 2
+
+
+def test_isolated_nodes_hub_vertex_and_many_chain_groups(host):
+    """Edge cases of the parallel kernel: degree-0 vertices (proposal is uniform over all K blocks,
+    accu_r = 1), a hub of degree > 255 (16-bit histogram bins, neighbour ids reloaded every 32), and
+    more chain groups than SMs (one CTA per group, whole half sweep in one launch)."""
+    g = load_golden("isolated")
+    na, nb, edges = g["na"], g["nb"], g["edges"]
+    graph = host.Graph(edges, na, nb)
+    C = 32 * 160 + 7
+    pool = host.ChainPool(graph, np.tile(g["labels0"], (C, 1)), g["ka"], g["kb"], 0.1)
+    seeds = np.arange(C, dtype=np.uint64) + 3
+    pool.randomize(seeds)
+    acc, sw = pool.anneal("constant", 1.0, 0.0, 50 * (na + nb), 10 ** 9, seeds)
+    assert (sw == 50).all() and (acc > 0).all()
+    check_invariants(pool, edges, na, nb, [0, 31, 32, 5000, C - 1])
+    lab = pool.labels()
+    iso = np.setdiff1d(np.arange(na + nb), np.unique(edges))
+    assert len(iso) > 0 and any(len(np.unique(lab[:, v])) > 1 for v in iso)  # isolated nodes do move
+
+    rng = np.random.default_rng(5)
+    na2 = nb2 = 400
+    e = np.stack([rng.integers(0, na2, 3000), na2 + rng.integers(0, nb2, 3000)], 1)
+    hub = np.stack([np.zeros(300, dtype=np.int64), na2 + rng.integers(0, nb2, 300)], 1)   # vertex 0: degree >= 300
+    edges2 = np.concatenate([e, hub]).astype(np.uint32)
+    graph2 = host.Graph(edges2, na2, nb2)
+    assert graph2.max_degree > 255
+    lab0 = np.concatenate([np.arange(na2) % 5, 5 + np.arange(nb2) % 4]).astype(np.uint32)
+    pool2 = host.ChainPool(graph2, np.tile(lab0, (64, 1)), 5, 4, 1.0)
+    s2 = np.arange(64, dtype=np.uint64) + 9
+    pool2.randomize(s2)
+    f1 = pool2.entropy()
+    pool2.anneal("constant", 1.0, 0.0, 20 * (na2 + nb2), 10 ** 9, s2, max_inflight=1)
+    check_invariants(pool2, edges2, na2, nb2, [0, 63])
+    f2 = pool2.entropy()
+    for c in (0, 63):
+        assert abs((f2[c] - f1[c]) - pool2.entropy_accum(c)) <= 1e-6 * abs(f1[c])

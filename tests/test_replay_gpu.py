@@ -121,3 +121,31 @@ def test_argument_errors(host):
     pool = host.ChainPool(g, np.array([0, 1, 2, 3], dtype=np.uint32), 2, 2, 1.0)
     with pytest.raises(host.BisbmError):
         pool.replay_anneal(0, 3, 1.0, 0, 10, 10)  # replay_init not called
+
+
+def test_replay_at_scale_matches_oracle(host):
+    """A graph far beyond the shipped datasets (50k nodes / 500k edges, K = 8 + 8, block degree totals
+    above the 10001 threshold so log q takes the asymptotic branch): two replay sweeps on the GPU vs
+    the oracle.  Labels and all counts bit-exact; accumulated dS to 1e-11 relative (device libm in
+    log_q_approx)."""
+    from helpers import planted, planted_labels
+    na = nb = 25000
+    ka = kb = 8
+    edges = planted(na, nb, ka, kb, 500000, 21)
+    labels = planted_labels(na, nb, ka, kb)
+    n = na + nb
+    o = port.PortChain(n, na, nb, edges, labels, ka, kb, 1.0, 77, 78)
+    o.init(True)
+    acc_o = o.anneal("constant", 1.0, 0, 2 * n, 10 ** 18)
+    graph = host.Graph(edges, na, nb)
+    pool = host.ChainPool(graph, labels, ka, kb, 1.0)
+    pool.replay_init(0, 77, 78, True)
+    acc, sw = pool.replay_anneal(0, "constant", 1.0, 0, 2 * n, 10 ** 18)
+    assert sw == 2
+    assert (pool.labels(0) == o.labels()).all()
+    assert (pool.m(0) == o.m()).all() and (pool.m_r(0) == o.m_r()).all() and (pool.n_r(0) == o.n_r()).all()
+    assert (pool.eta(0) == o.eta()).all() and (pool.replay_vlist(0) == o.vlist()).all()
+    assert acc == acc_o
+    assert pool.replay_rng_words(0) == o.rng_words()
+    assert abs(pool.entropy_accum(0) - o.entropy_accum()) <= 1e-11 * abs(o.entropy_accum())
+    assert abs(pool.entropy(0) - o.entropy()) <= 1e-9 * abs(o.entropy())
