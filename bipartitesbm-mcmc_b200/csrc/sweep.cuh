@@ -351,6 +351,7 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(SweepParams P) {
     const uint32_t key0 = (uint32_t)seed, key1 = (uint32_t)(seed >> 32);
     const uint32_t nv = type ? G.nb : G.na, v0 = type ? G.na : 0;
     const uint64_t pkey = (P.sweep * 2 + type) * 0x9E3779B97F4A7C15ull + (uint64_t)group * 0xD1B54A32D192ED03ull;
+    constexpr int SAFE_NR = 8192;   // > any number of concurrently evaluated moves of one chain (<= 148 SMs * 32 warps)
     const bool const_T = (P.schedule == 3);
     const double T_const = (double)P.p0, beta_const = 1.0 / (double)P.p0;
 
@@ -365,25 +366,27 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(SweepParams P) {
         // the dependent row_ptr loads cost one lane-parallel step per 32 vertices instead of one
         // warp-uniform step per vertex.  The first 32 neighbour ids of the NEXT vertex are
         // prefetched with one coalesced load (lane e holds neighbour e; broadcast by shuffle).
-        uint32_t bv = 0, brow = 0, bdeg = 0;      // this lane's vertex of the current batch
+        uint32_t bv = 0, brow = 0, bdeg = 0, bdidx = 0;      // this lane's vertex of the current batch
         // software pipeline, one vertex ahead: everything below with suffix _n belongs to the NEXT
         // vertex and is loaded while the current one is evaluated (own label, Philox draw, the
         // proposal's random neighbour id and -- one stage later -- that neighbour's label)
-        uint32_t v_n = 0, row_n = 0, d_n = 0, nbr_n = 0, r_n = 0, j_n = 0, t_n = 0;
+        uint32_t v_n = 0, row_n = 0, d_n = 0, nbr_n = 0, r_n = 0, j_n = 0, t_n = 0, didx_n = 0;
         u32x4 ra_n; ra_n.x = ra_n.y = ra_n.z = ra_n.w = 0;
         auto refill = [&](uint32_t pos0) {        // lane l prepares the vertex at position pos0 + l*stride
             const uint64_t il = (uint64_t)pos0 + (uint64_t)lane * stride;
-            bv = 0; brow = 0; bdeg = 0;
+            bv = 0; brow = 0; bdeg = 0; bdidx = 0;
             if (il < P.pos_end) {
                 bv = v0 + feistel_perm((uint32_t)il, nv, P.half_bits, pkey);
                 brow = G.row_ptr[bv];
                 bdeg = G.row_ptr[bv + 1] - brow;
+                bdidx = G.degidx[bv];
             }
         };
         auto prefetch = [&](uint32_t slot) {      // stage 1 of the pipeline for the vertex in batch slot `slot`
             v_n = __shfl_sync(0xffffffffu, bv, slot);
             row_n = __shfl_sync(0xffffffffu, brow, slot);
             d_n = __shfl_sync(0xffffffffu, bdeg, slot);
+            didx_n = __shfl_sync(0xffffffffu, bdidx, slot);
             nbr_n = (lane < d_n) ? G.col[row_n + lane] : 0u;
             r_n = live ? label_of(v_n) : 0u;
             u32x4 ctr; ctr.x = v_n; ctr.y = (uint32_t)P.sweep; ctr.z = (uint32_t)(P.sweep >> 32); ctr.w = 0;
@@ -398,7 +401,7 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(SweepParams P) {
         for (uint32_t ib = i_first, k = 0; ib < P.pos_end; ib += stride, ++k) {
             // warp-uniform trip count: all 32 lanes (= chains) reconverge at every vertex
             __syncwarp();
-            const uint32_t v = v_n, row = row_n, d = d_n, nbr0 = nbr_n, r = r_n, t_prop = t_n;
+            const uint32_t v = v_n, row = row_n, d = d_n, nbr0 = nbr_n, r = r_n, t_prop = t_n, didx = didx_n;
             const u32x4 ra = ra_n;
             const bool has_next = (ib + stride < P.pos_end);
             if (has_next) {
@@ -446,7 +449,6 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(SweepParams P) {
             if (!__any_sync(0xffffffffu, eval)) continue;
 
             // ---- one pass over v's neighbours: dS and the Hastings factor (transition_ratio) ----
-            const uint32_t didx = G.degidx[v];
             int n_r = 0, n_s = 0, eta_r = 1, eta_s = 0;
             MoveAcc A; acc_init(A);
             const uint32_t ir = r * sx, is = s * sx;
@@ -510,9 +512,16 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(SweepParams P) {
                 const double a = ((d == 0) ? 0.0 : log(A.a1 / A.a0)) - dS * beta;
                 const bool go_hot = (a > 0.0) || (((double)ra.w + 0.5) * (1.0 / 4294967296.0) < exp(a));
                 go = eval && ((T == 0.0) ? (dS < 0.0) : go_hot);
-                if (go) {  // the exact "would empty block r" veto of apply_mcmc_moves
-                    const int old = atomicSub(&gNR[r * 32 + lane], 1);
-                    if (old <= 1) { atomicAdd(&gNR[r * 32 + lane], 1); go = false; }
+                if (go) {
+                    // the exact "would empty block r" veto of apply_mcmc_moves.  n_r was read from L2 a moment
+                    // ago; fewer than SAFE_NR moves of this chain can be in flight, so a block that large
+                    // cannot empty and a fire-and-forget reduction is enough (no round trip on the critical path)
+                    if (n_r > SAFE_NR) {
+                        atomicSub(&gNR[r * 32 + lane], 1);
+                    } else {
+                        const int old = atomicSub(&gNR[r * 32 + lane], 1);
+                        if (old <= 1) { atomicAdd(&gNR[r * 32 + lane], 1); go = false; }
+                    }
                 }
             }
             __syncwarp();
