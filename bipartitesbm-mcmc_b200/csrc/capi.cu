@@ -348,7 +348,8 @@ int plan_sweep(bisbm_handle* h, uint32_t type, uint32_t max_inflight, LaunchPlan
     lp->ctas_per_group = cpg;
     lp->wpc = wpc;
     lp->warps_used = (cpg == 1) ? std::max<uint32_t>(1, std::min<uint32_t>(wpc, std::min<uint32_t>(inflight, std::max<uint32_t>(nv, 1)))) : wpc;
-    if (cpg > 1) lp->slice = std::max<uint32_t>(cpg * wpc, std::min<uint32_t>(inflight, nv));
+    // slices only exist for staged counts shared by several CTAs; global counts are live for everybody
+    if (lp->smem && cpg > 1) lp->slice = std::max<uint32_t>(cpg * wpc, std::min<uint32_t>(inflight, nv));
     else lp->slice = std::max<uint32_t>(nv, 1);
     lp->smem_bytes = sweep_smem_bytes(lp->smem, h->KA, h->KB, type, wpc, hb);
     return BISBM_OK;
