@@ -368,6 +368,19 @@ int launch_sweep_t(bisbm_handle* h, const SweepParams& P, const LaunchPlan& lp) 
     return BISBM_OK;
 }
 
+template <bool SMEM, typename HistT, int NT, int KF, int TYPE>
+int launch_sweep_fixed(bisbm_handle* h, const SweepParams& P, const LaunchPlan& lp) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        CU(cudaFuncSetAttribute(sweep_kernel<SMEM, HistT, NT, KF, TYPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        attr_set = true;
+    }
+    const unsigned grid = P.n_groups * lp.ctas_per_group;
+    sweep_kernel<SMEM, HistT, NT, KF, TYPE><<<grid, NT, lp.smem_bytes, h->stream>>>(P);
+    CU(cudaGetLastError());
+    return BISBM_OK;
+}
+
 template <bool SMEM, typename HistT>
 int launch_sweep_nt(bisbm_handle* h, const SweepParams& P, const LaunchPlan& lp) {
     if (lp.wpc == 32) return launch_sweep_t<SMEM, HistT, 1024>(h, P, lp);
@@ -377,6 +390,12 @@ int launch_sweep_nt(bisbm_handle* h, const SweepParams& P, const LaunchPlan& lp)
 
 template <bool SMEM>
 int launch_sweep_h(bisbm_handle* h, const SweepParams& P, const LaunchPlan& lp) {
+    if constexpr (SMEM) {
+        // compile-time strides for the common Ka = Kb = 32 pool (BASELINE configs[2])
+        if (lp.hist_bytes == 1 && lp.wpc == 32 && h->KA == 32 && h->KB == 32 && !getenv("BISBM_GENERIC"))
+            return P.type ? launch_sweep_fixed<true, uint8_t, 1024, 32, 1>(h, P, lp)
+                          : launch_sweep_fixed<true, uint8_t, 1024, 32, 0>(h, P, lp);
+    }
     if (lp.hist_bytes == 1) return launch_sweep_nt<SMEM, uint8_t>(h, P, lp);
     if (lp.hist_bytes == 2) return launch_sweep_nt<SMEM, uint16_t>(h, P, lp);
     return launch_sweep_nt<SMEM, uint32_t>(h, P, lp);

@@ -258,7 +258,9 @@ template <> struct Cnt<false> {  // in global memory: L2 loads, global reduction
     __device__ __forceinline__ void add(uint32_t idx32, int v) const { atomicAdd(p + idx32, v); }
 };
 
-template <bool SMEM, typename HistT, int NT>
+// KF > 0: specialisation for KA == KB == KF with the moving type TYPE fixed at compile time (all strides
+// and loop bounds become constants); KF == 0: generic, everything from SweepParams.
+template <bool SMEM, typename HistT, int NT, int KF = 0, int TYPE = 0>
 __global__ void __launch_bounds__(NT, 1) sweep_kernel(SweepParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // lane / warp ids through volatile asm: the compiler must keep them in registers instead of
@@ -269,9 +271,9 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(SweepParams P) {
     warp >>= 5;
     const uint32_t wpc = blockDim.x >> 5;
     const GraphView& G = P.g;
-    const uint32_t type = P.type;
-    const uint32_t C = P.s.C, KB = P.s.KB, KA = P.s.KA, W = P.s.W, KK = KA + KB;
-    const uint32_t kown_max = type ? KB : KA, kopp_max = P.kopp_max;
+    const uint32_t type = KF ? (uint32_t)TYPE : P.type;
+    const uint32_t C = P.s.C, KB = KF ? (uint32_t)KF : P.s.KB, KA = KF ? (uint32_t)KF : P.s.KA, W = P.s.W, KK = KA + KB;
+    const uint32_t kown_max = type ? KB : KA, kopp_max = KF ? (uint32_t)KF : P.kopp_max;
     const uint32_t group = blockIdx.x % P.n_groups;
     const uint32_t cta_in_group = blockIdx.x / P.n_groups;
     const uint32_t own_off = type ? KA : 0, opp_off = type ? 0 : KA;

@@ -262,3 +262,25 @@ def test_isolated_nodes_hub_vertex_and_many_chain_groups(host):
     f2 = pool2.entropy()
     for c in (0, 63):
         assert abs((f2[c] - f1[c]) - pool2.entropy_accum(c)) <= 1e-6 * abs(f1[c])
+
+
+def test_k32_specialised_kernel(host):
+    """Ka = Kb = 32 takes the compile-time-stride instantiation of the sweep kernel (the bench workload):
+    same invariants, and sequential chains are exact."""
+    na = nb = 6000
+    ka = kb = 32
+    edges = planted(na, nb, ka, kb, 150000, 17)
+    graph = host.Graph(edges, na, nb)
+    C = 96
+    pool = host.ChainPool(graph, np.tile(planted_labels(na, nb, ka, kb), (C, 1)), ka, kb, 1.0)
+    seeds = np.arange(C, dtype=np.uint64) + 41
+    pool.randomize(seeds)
+    pool.anneal("constant", 1.0, 0.0, 5 * (na + nb), 10 ** 9, seeds)
+    check_invariants(pool, edges, na, nb, [0, 50, 95])
+    f1 = pool.entropy()
+    d0 = np.array([pool.entropy_accum(c) for c in (0, 95)])
+    pool.anneal("constant", 1.0, 0.0, 2 * (na + nb), 10 ** 9, seeds + np.uint64(1000), max_inflight=1)
+    f2 = pool.entropy()
+    for k, c in enumerate((0, 95)):
+        assert abs((f2[c] - f1[c]) - (pool.entropy_accum(c) - d0[k])) <= 1e-6 * abs(f1[c])
+    check_invariants(pool, edges, na, nb, [0, 95])
