@@ -21,6 +21,7 @@
 
 #include "replay.cuh"
 #include "sweep_aux.cuh"
+#include "sweep_fast.cuh"
 
 using namespace bisbm;
 
@@ -92,6 +93,9 @@ struct bisbm_handle {
     // timing of the last parallel call
     double last_ms = 0.0;
     uint64_t last_launches = 0, last_moves = 0;
+    // move arithmetic of the parallel sweep: 0 = fp32 kernel where it applies (sweep_fast.cuh), 1 = double everywhere
+    int precision = 0;
+    bool lab32_stale = false;   // the fp32 kernel only writes the u8 label shadow; i32 labels refreshed on demand
 };
 
 namespace {
@@ -312,6 +316,7 @@ uint64_t cold_steps(int schedule, float p0, float p1, uint64_t t0, uint64_t t1) 
 }
 
 struct LaunchPlan {
+    bool fast;                // fp32 kernel (sweep_fast.cuh)
     bool smem;
     int hist_bytes;           // 1, 2 or 4
     uint32_t wpc;             // warps per CTA (blockDim / 32): 32 or 16 (fewer only when shared memory is short)
@@ -333,10 +338,14 @@ int plan_sweep(bisbm_handle* h, uint32_t type, uint32_t max_inflight, LaunchPlan
     lp->hist_bytes = (int)hb;
     const size_t budget = 220 * 1024;
     lp->smem = sweep_smem_bytes(true, h->KA, h->KB, type, 16, hb) <= budget && h->KA <= 256 && h->KB <= 256;
-    uint32_t wpc = 32;
+    // fp32 throughput kernel: staged counts, u8 histogram bins
+    lp->fast = lp->smem && hb == 1 && h->precision == 0 && !getenv("BISBM_PRECISE") &&
+               sweep_fast_smem_bytes(h->KA, h->KB, type, 32) <= budget;
+    // warps per CTA (one CTA per SM): the fp32 kernel measures best with 24 (80 registers per thread)
+    uint32_t wpc = lp->fast ? 24 : 32;
     if (const char* e = getenv("BISBM_WPC")) { int w = atoi(e); wpc = (w == 16 || w == 24) ? (uint32_t)w : 32; }  // tuning knob
-    if (sweep_smem_bytes(lp->smem, h->KA, h->KB, type, wpc, hb) > budget) wpc = 16;
-    if (sweep_smem_bytes(lp->smem, h->KA, h->KB, type, wpc, hb) > budget)
+    if (!lp->fast && sweep_smem_bytes(lp->smem, h->KA, h->KB, type, wpc, hb) > budget) wpc = 16;
+    if (!lp->fast && sweep_smem_bytes(lp->smem, h->KA, h->KB, type, wpc, hb) > budget)
         return fail(BISBM_ERR_ARG, "K too large for the shared-memory histogram");
     uint32_t inflight_div = 64;
     if (const char* e = getenv("BISBM_INFLIGHT_DIV")) inflight_div = std::max(1, atoi(e));  // tuning knob
@@ -351,7 +360,8 @@ int plan_sweep(bisbm_handle* h, uint32_t type, uint32_t max_inflight, LaunchPlan
     // slices only exist for staged counts shared by several CTAs; global counts are live for everybody
     if (lp->smem && cpg > 1) lp->slice = std::max<uint32_t>(cpg * wpc, std::min<uint32_t>(inflight, nv));
     else lp->slice = std::max<uint32_t>(nv, 1);
-    lp->smem_bytes = sweep_smem_bytes(lp->smem, h->KA, h->KB, type, wpc, hb);
+    lp->smem_bytes = lp->fast ? sweep_fast_smem_bytes(h->KA, h->KB, type, wpc)
+                              : sweep_smem_bytes(lp->smem, h->KA, h->KB, type, wpc, hb);
     return BISBM_OK;
 }
 
@@ -381,6 +391,27 @@ int launch_sweep_fixed(bisbm_handle* h, const SweepParams& P, const LaunchPlan& 
     return BISBM_OK;
 }
 
+template <int KF, int TYPE, int NT>
+int launch_sweep_fast_nt(bisbm_handle* h, const SweepParams& P, const LaunchPlan& lp) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        CU(cudaFuncSetAttribute(sweep_fast_kernel<KF, TYPE, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        attr_set = true;
+    }
+    const unsigned grid = P.n_groups * lp.ctas_per_group;
+    sweep_fast_kernel<KF, TYPE, NT><<<grid, NT, lp.smem_bytes, h->stream>>>(P);
+    CU(cudaGetLastError());
+    h->lab32_stale = true;
+    return BISBM_OK;
+}
+
+template <int KF, int TYPE>
+int launch_sweep_fast(bisbm_handle* h, const SweepParams& P, const LaunchPlan& lp) {
+    if (lp.wpc == 32) return launch_sweep_fast_nt<KF, TYPE, 1024>(h, P, lp);
+    if (lp.wpc == 24) return launch_sweep_fast_nt<KF, TYPE, 768>(h, P, lp);
+    return launch_sweep_fast_nt<KF, TYPE, 512>(h, P, lp);
+}
+
 template <bool SMEM, typename HistT>
 int launch_sweep_nt(bisbm_handle* h, const SweepParams& P, const LaunchPlan& lp) {
     if (lp.wpc == 32) return launch_sweep_t<SMEM, HistT, 1024>(h, P, lp);
@@ -391,6 +422,11 @@ int launch_sweep_nt(bisbm_handle* h, const SweepParams& P, const LaunchPlan& lp)
 template <bool SMEM>
 int launch_sweep_h(bisbm_handle* h, const SweepParams& P, const LaunchPlan& lp) {
     if constexpr (SMEM) {
+        if (lp.fast) {
+            if (h->KA == 32 && h->KB == 32 && !getenv("BISBM_GENERIC"))
+                return P.type ? launch_sweep_fast<32, 1>(h, P, lp) : launch_sweep_fast<32, 0>(h, P, lp);
+            return launch_sweep_fast<0, 0>(h, P, lp);
+        }
         // compile-time strides for the common Ka = Kb = 32 pool (BASELINE configs[2])
         if (lp.hist_bytes == 1 && lp.wpc == 32 && h->KA == 32 && h->KB == 32 && !getenv("BISBM_GENERIC"))
             return P.type ? launch_sweep_fixed<true, uint8_t, 1024, 32, 1>(h, P, lp)
@@ -454,6 +490,17 @@ int sync_labels8(bisbm_handle* h) {
     const uint64_t threads = (total + 3) / 4;
     labels8_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, h->stream>>>(h->d_labels, h->d_lab8, total);
     CU(cudaGetLastError());
+    return BISBM_OK;
+}
+
+// refresh the canonical i32 labels from the u8 shadow (the fp32 kernel only writes the shadow)
+int sync_labels32(bisbm_handle* h) {
+    if (!h->lab32_stale) return BISBM_OK;
+    const uint64_t total = (uint64_t)h->n * h->C;
+    const uint64_t threads = (total + 3) / 4;
+    labels32_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, h->stream>>>(h->d_lab8, h->d_labels, total);
+    CU(cudaGetLastError());
+    h->lab32_stale = false;
     return BISBM_OK;
 }
 
@@ -796,6 +843,8 @@ int bisbm_anneal(bisbm_handle* h, int schedule, float p0, float p1, uint64_t dur
             CU(cudaStreamSynchronize(h->stream));
         }
     }
+    rc = sync_labels32(h);
+    if (rc) return rc;
     CU(cudaEventRecord(h->ev1, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     CU(cudaGetLastError());
@@ -857,17 +906,28 @@ int bisbm_marginalize(bisbm_handle* h, uint64_t burn_in, uint64_t sweeps, uint64
         rc = launch_full_sweep(h, BISBM_CONSTANT, 1.0f, 0.0f, sw, max_inflight);
         if (rc) return rc;
         if (sw >= burn_in && ((sw - burn_in + 1) % every) == 0) {
+            rc = sync_labels32(h);
+            if (rc) return rc;
             marginal_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(gview(h), sview(h), h->n_chains,
                                                                                  h->d_hist, h->hist_width);
             h->last_launches += 1;
         }
     }
+    rc = sync_labels32(h);
+    if (rc) return rc;
     CU(cudaEventRecord(h->ev1, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     CU(cudaGetLastError());
     float ms = 0.f;
     CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     h->last_ms = ms;
+    return BISBM_OK;
+}
+
+int bisbm_set_precision(bisbm_handle* h, int mode) {
+    if (!h) return fail(BISBM_ERR_ARG, "null handle");
+    if (mode != BISBM_PRECISION_FP32 && mode != BISBM_PRECISION_FP64) return fail(BISBM_ERR_ARG, "unknown precision mode %d", mode);
+    h->precision = mode;
     return BISBM_OK;
 }
 

@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(SweepParams P) {
 
             // ---- proposal (single_vertex_change), branch-free: every lane computes both the uniform
             //      and the categorical candidate and selects ----
-            const uint32_t tq = t_prop;
+            const uint32_t tq = min(t_prop, kopp_max - 1u);   // (an isolated vertex has no proposal neighbour: any valid slot)
             const int e_t = Ep.ld(tq * 32u);
             const bool uniform_pick = (d == 0) || (((double)ra.y * (1.0 / 4294967296.0)) < epsK / ((double)e_t + epsK));
             const uint32_t sg = mulhi32(ra.z, K);      // uniform over ALL K blocks (either type)
@@ -435,8 +435,8 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(SweepParams P) {
             }
             const uint32_t s_cat = cnt_le < kown ? cnt_le : kown - 1;
             const bool movable = live && (kown != 1);
-            const uint32_t s = movable ? (uniform_pick ? s_uni : s_cat) : r;   // own-type local index of the target
-            const bool cross = movable && uniform_pick && (sg_a != (type == 0));  // fell on a block of the other type
+            const bool cross = movable && uniform_pick && (sg_a != (type == 0));  // fell on a block of the other type: s stays r
+            const uint32_t s = (movable && !cross) ? (uniform_pick ? s_uni : s_cat) : r;   // own-type local index of the target
             // stage 2 of the pipeline: the label of the next vertex's proposal neighbour (its id has
             // arrived by now)
             if (has_next) t_n = (live && d_n != 0) ? label_of(j_n) : 0u;

@@ -126,6 +126,18 @@ __global__ void labels8_kernel(const int32_t* __restrict__ in, uint8_t* __restri
     }
 }
 
+// the reverse: canonical i32 labels from the u8 shadow (after calls that ran the fp32 sweep kernel)
+__global__ void labels32_kernel(const uint8_t* __restrict__ in, int32_t* __restrict__ out, uint64_t total) {
+    const uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i + 3 < total) {
+        const uchar4 v = *reinterpret_cast<const uchar4*>(in + i);
+        int4 o; o.x = v.x; o.y = v.y; o.z = v.z; o.w = v.w;
+        *reinterpret_cast<int4*>(out + i) = o;
+    } else {
+        for (uint64_t j = i; j < total; ++j) out[j] = (int32_t)in[j];
+    }
+}
+
 // per-sweep bookkeeping of anneal (src/metropolis_hasting.cc:86-98) at sweep granularity
 __global__ void bookkeep_kernel(uint32_t n_chains, uint8_t* active, const double* dS_accum, double* ent_min,
                                 unsigned long long* u, unsigned long long* sweeps_done, uint64_t sweep,

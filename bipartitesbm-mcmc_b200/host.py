@@ -64,6 +64,7 @@ SIGNATURES = {
                                _dp, _u64p]),
     "bisbm_marginalize": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, _u64p, C.c_uint32]),
     "bisbm_marginals_clear": (C.c_int, [C.c_void_p]),
+    "bisbm_set_precision": (C.c_int, [C.c_void_p, C.c_int]),
     "bisbm_marginals_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), _u64p, _u32p]),
     "bisbm_get_marginals": (C.c_int, [C.c_void_p, _u32p]),
     "bisbm_marginal_argmax": (C.c_int, [C.c_void_p, _u32p]),
@@ -209,6 +210,10 @@ class ChainPool:
     def marginalize(self, burn_in, sweeps, every, seeds, max_inflight=0):
         seeds = np.ascontiguousarray(seeds, dtype=np.uint64)
         _check(self.L.bisbm_marginalize(self.g.h, burn_in, sweeps, every, _p(seeds, C.c_uint64), max_inflight))
+
+    def set_precision(self, mode):
+        """'fp32' (default: fp32 move arithmetic where the fast kernel applies) or 'fp64'."""
+        _check(self.L.bisbm_set_precision(self.g.h, {"fp32": 0, "fp64": 1}.get(mode, mode)))
 
     def marginals_clear(self):
         _check(self.L.bisbm_marginals_clear(self.g.h))

@@ -105,6 +105,13 @@ int bisbm_anneal(bisbm_handle* h, int schedule, float p0, float p1, uint64_t dur
 int bisbm_marginalize(bisbm_handle* h, uint64_t burn_in, uint64_t sweeps, uint64_t every, const uint64_t* seeds,
                       uint32_t max_inflight);
 int bisbm_marginals_clear(bisbm_handle* h);
+/* Arithmetic of the parallel sweep's per-move evaluation (dS, Hastings factor, accept test).  The reference
+ * computes transition_ratio in double (src/metropolis_hasting.cc:103-192); parallel mode is only statistically
+ * equivalent to it anyway, and by default evaluates the move in fp32 (|error of the log acceptance ratio|
+ * <~ 2e-5) with integer counts and commits exact.  BISBM_PRECISION_FP64 keeps the whole evaluation in double.
+ * Replay mode is always strict double. */
+enum { BISBM_PRECISION_FP32 = 0, BISBM_PRECISION_FP64 = 1 };
+int bisbm_set_precision(bisbm_handle* h, int mode);
 /* device pointer + element count of the histogram, for an in-place NCCL all-reduce */
 int bisbm_marginals_device(bisbm_handle* h, void** dev_ptr, uint64_t* n_elems, uint32_t* width);
 int bisbm_get_marginals(bisbm_handle* h, uint32_t* hist);          /* [n][width], global block ids */

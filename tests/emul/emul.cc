@@ -14,6 +14,7 @@
 
 #include "../../bipartitesbm-mcmc_b200/csrc/replay.cuh"
 #include "../../bipartitesbm-mcmc_b200/csrc/sweep.cuh"
+#include "../../bipartitesbm-mcmc_b200/csrc/sweep_fast.cuh"
 
 using namespace bisbm;
 
@@ -197,6 +198,70 @@ void emul_par_dS(void* p, uint32_t v, uint32_t sg, int use_taylor, double* dS, d
     out += logq_delta(tb, qs, e_s, n_s, (int)d, 1);
     *dS = out;
     *accu = d == 0 ? 1.0 : a1 / a0;
+}
+
+// the fp32 kernel's arithmetic (sweep_fast.cuh: facc_edge / facc_fold / f_block_degree_delta / f_logq_delta)
+// for the same move; *fell_back counts the terms that took the double-precision completion
+void emul_par_dS_f32(void* p, uint32_t v, uint32_t sg, int use_taylor, double* dS, double* log_accu, int* fell_back) {
+    Emul* s = (Emul*)p;
+    ReplayCtx x = ctx(s);
+    const bool va = v < s->na;
+    const uint32_t r = s->labels[(size_t)v * s->C + s->chain];
+    const uint32_t sl = va ? sg : sg - s->ka;
+    const uint32_t kopp = va ? s->kb : s->ka, KB = s->kb, KA = s->ka;
+    const uint32_t own_off = va ? 0 : KA, opp_off = va ? KA : 0;
+    const uint32_t sx = va ? KB : 1, st = va ? 1 : KB;
+    const int32_t* Mr = s->m.data() + (size_t)r * sx; const int32_t* Ms = s->m.data() + (size_t)sl * sx;
+    const float eps = (float)s->eps;
+    const uint32_t d = s->row_ptr[v + 1] - s->row_ptr[v];
+    FAcc A; facc_init(A);
+    std::vector<int> cnt(kopp, 0);
+    for (uint32_t e = 0; e < d; ++e) {
+        uint32_t nb = s->col[s->row_ptr[v] + e];
+        uint32_t t = s->labels[(size_t)nb * s->C + s->chain];
+        int c = cnt[t]++;
+        float inv = (float)(1.0 / ((double)s->e[opp_off + t] + s->eps * (double)(KA + KB)));
+        facc_edge(A, Mr[(size_t)t * st], Ms[(size_t)t * st], c, c + 1, inv);
+        if ((e & 3u) == 3u || e + 1 == d) facc_fold(A);
+    }
+    int e_r = s->e[own_off + r], e_s = s->e[own_off + sl], n_r = s->nr[own_off + r], n_s = s->nr[own_off + sl];
+    uint32_t didx = s->degidx[v];
+    int eta_r = s->eta[(size_t)(own_off + r) * s->W + didx], eta_s = s->eta[(size_t)(own_off + sl) * s->W + didx];
+    Tables tb = x.tb; tb.lg = nullptr; tb.lg_n = 0;
+    LogqExp qr, qs;
+    memset(&qr, 0, sizeof qr); memset(&qs, 0, sizeof qs);
+    if (use_taylor) {
+        auto mk = [&](int e0, int n0) {
+            LogqExp q; memset(&q, 0, sizeof q); q.e0 = e0; q.n0 = n0;
+            if (e0 >= 16384 && n0 >= 1024 && 2 * (int64_t)n0 <= (int64_t)e0) {
+                int he = e0 >> 10, hn = n0 >> 8;
+                double f00 = log_q_approx(tb, e0, n0);
+                double fp0 = log_q_approx(tb, e0 + he, n0), fm0 = log_q_approx(tb, e0 - he, n0);
+                double f0p = log_q_approx(tb, e0, n0 + hn), f0m = log_q_approx(tb, e0, n0 - hn);
+                double fpp = log_q_approx(tb, e0 + he, n0 + hn), fpm = log_q_approx(tb, e0 + he, n0 - hn);
+                double fmp = log_q_approx(tb, e0 - he, n0 + hn), fmm = log_q_approx(tb, e0 - he, n0 - hn);
+                double He = he, Hn = hn;
+                q.fe = (float)((fp0 - fm0) / (2 * He)); q.fn = (float)((f0p - f0m) / (2 * Hn));
+                q.fee = (float)((fp0 - 2 * f00 + fm0) / (He * He)); q.fnn = (float)((f0p - 2 * f00 + f0m) / (Hn * Hn));
+                q.fen = (float)((fpp - fpm - fmp + fmm) / (4 * He * Hn)); q.valid = 1;
+            }
+            return q;
+        };
+        qr = mk(e_r + e_r / 40, n_r - n_r / 50); qs = mk(e_s - e_s / 40, n_s + n_s / 50);
+    }
+    bool ok_b, ok_r, ok_s;
+    float bdd = f_block_degree_delta(e_r, e_s, (int)d, &ok_b);
+    float lqr = f_logq_delta(qr, e_r, n_r, -(int)d, -1, &ok_r);
+    float lqs = f_logq_delta(qs, e_s, n_s, (int)d, 1, &ok_s);
+    *fell_back = (!ok_b) + (!ok_r) + (!ok_s);
+    if (!ok_b) bdd = (float)block_degree_delta(e_r, e_s, (int)d);
+    if (!ok_r) lqr = (float)logq_delta_exact(tb, e_r, n_r, -(int)d, -1);
+    if (!ok_s) lqs = (float)logq_delta_exact(tb, e_s, n_s, (int)d, 1);
+    float out = BISBM_LN2F * (A.lg + f_lg2((float)(eta_r > 0 ? eta_r : 1) * f_rcp((float)(eta_s + 1))));
+    out += ((d == 0) ? 0.f : bdd) + lqr + lqs;
+    const float ew = eps * A.w;
+    *dS = (double)out;
+    *log_accu = d == 0 ? 0.0 : (double)(BISBM_LN2F * f_lg2((A.a1 + ew) * f_rcp(A.a0 + ew)));
 }
 
 double emul_entropy_accum(void* p) { return ((Emul*)p)->rs.entropy_accum; }

@@ -23,13 +23,14 @@ def check_invariants(pool, edges, na, nb, chains):
         assert (pool.eta(c) == eta).all()
 
 
-@pytest.mark.parametrize("inflight", [1, 0])
-def test_invariants_small_graph(host, inflight):
+@pytest.mark.parametrize("inflight,precision", [(1, "fp64"), (1, "fp32"), (0, "fp32"), (0, "fp64")])
+def test_invariants_small_graph(host, inflight, precision):
     g = load_golden("c2_abrupt")
     na, nb = g["na"], g["nb"]
     graph = host.Graph(g["edges"], na, nb)
     C = 40  # not a multiple of 32: exercises the padded lanes
     pool = host.ChainPool(graph, np.tile(g["labels0"], (C, 1)), 10, 10, 1.0)
+    pool.set_precision(precision)
     check_invariants(pool, g["edges"], na, nb, [0, 39])
     e0 = pool.entropy()
     assert abs(e0[0] - g["init_entropy"]) <= 1e-9 * g["init_entropy"]
@@ -44,9 +45,11 @@ def test_invariants_small_graph(host, inflight):
     check_invariants(pool, g["edges"], na, nb, [0, 5, 31, 32, 39])
     e2 = pool.entropy()
     if inflight == 1:
-        # sequential chains: the accumulated dS is the exact entropy difference
+        # sequential chains: the accumulated dS is the entropy difference (to the rounding of the move
+        # arithmetic: double, or fp32 per move summed in double over ~1e4 accepted moves)
+        tol = 1e-7 if precision == "fp64" else 1e-6
         for c in (0, 33, 39):
-            assert abs((e2[c] - e1[c]) - pool.entropy_accum(c)) <= 1e-7 * abs(e1[c])
+            assert abs((e2[c] - e1[c]) - pool.entropy_accum(c)) <= tol * abs(e1[c])
 
 
 def test_heterogeneous_k_and_single_block_types(host):
