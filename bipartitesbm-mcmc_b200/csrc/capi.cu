@@ -343,13 +343,15 @@ int plan_sweep(bisbm_handle* h, uint32_t type, uint32_t max_inflight, LaunchPlan
                sweep_fast_smem_bytes(h->KA, h->KB, type, 32) <= budget;
     // warps per CTA (one CTA per SM): the fp32 kernel measures best with 24 (80 registers per thread)
     uint32_t wpc = lp->fast ? 24 : 32;
-    if (const char* e = getenv("BISBM_WPC")) { int w = atoi(e); wpc = (w == 16 || w == 24) ? (uint32_t)w : 32; }  // tuning knob
+    if (const char* e = getenv("BISBM_WPC")) { int w = atoi(e); wpc = (w == 16 || w == 24 || (w == 20 && lp->fast)) ? (uint32_t)w : 32; }  // tuning knob
     if (!lp->fast && sweep_smem_bytes(lp->smem, h->KA, h->KB, type, wpc, hb) > budget) wpc = 16;
     if (!lp->fast && sweep_smem_bytes(lp->smem, h->KA, h->KB, type, wpc, hb) > budget)
         return fail(BISBM_ERR_ARG, "K too large for the shared-memory histogram");
     uint32_t inflight_div = 64;
     if (const char* e = getenv("BISBM_INFLIGHT_DIV")) inflight_div = std::max(1, atoi(e));  // tuning knob
-    const uint32_t inflight = max_inflight ? max_inflight : std::max<uint32_t>(wpc, nv / inflight_div);
+    // default bound: 1/64 of the half sweep (staleness study) -- also on small graphs, where it means
+    // fewer busy warps rather than a looser bound
+    const uint32_t inflight = max_inflight ? max_inflight : std::max<uint32_t>(1, nv / inflight_div);
     // CTAs per group: fill the SMs, but never more warps than the in-flight bound or the work allows
     uint32_t cpg = std::max<uint32_t>(1, (uint32_t)h->sm_count / n_groups);
     cpg = std::min<uint32_t>(cpg, std::max<uint32_t>(1, inflight / wpc));
@@ -409,6 +411,7 @@ template <int KF, int TYPE>
 int launch_sweep_fast(bisbm_handle* h, const SweepParams& P, const LaunchPlan& lp) {
     if (lp.wpc == 32) return launch_sweep_fast_nt<KF, TYPE, 1024>(h, P, lp);
     if (lp.wpc == 24) return launch_sweep_fast_nt<KF, TYPE, 768>(h, P, lp);
+    if (lp.wpc == 20) return launch_sweep_fast_nt<KF, TYPE, 640>(h, P, lp);
     return launch_sweep_fast_nt<KF, TYPE, 512>(h, P, lp);
 }
 
@@ -472,6 +475,8 @@ int launch_full_sweep(bisbm_handle* h, int schedule, float p0, float p1, uint64_
             P.sweep = h->sweep_epoch;
             P.step_base = sweep_in_call * (uint64_t)h->n + (type ? h->na : 0);
             P.schedule = schedule; P.p0 = p0; P.p1 = p1;
+            P.prefetch = 1;
+            if (const char* e = getenv("BISBM_PREFETCH")) P.prefetch = (uint32_t)atoi(e);  // tuning knob
             rc = lp.smem ? launch_sweep_h<true>(h, P, lp) : launch_sweep_h<false>(h, P, lp);
             if (rc) return rc;
             h->last_launches += 1;

@@ -71,6 +71,7 @@ struct SweepParams {
     uint64_t step_base;              // global step index of position 0 of this half sweep
     int schedule;
     float p0, p1;
+    uint32_t prefetch;               // fp32 kernel: 1 = prefetch the next vertex's label rows into L1, 2 = into L2, 0 = off
 };
 
 // temperature of global step t (same five schedules as src/metropolis_hasting.cc:10-37,

@@ -46,15 +46,22 @@ struct FAcc {
     float a0, a1, w, num, den, lg;
 };
 BISBM_HD void facc_init(FAcc& A) { A.a0 = 0.f; A.a1 = 0.f; A.w = 0.f; A.num = 1.f; A.den = 1.f; A.lg = 0.f; }
-// one edge of v into block t: c earlier edges of v into t (c1 = c + 1), counts m_rt, m_st, inv = 1/(e_t + eps K)
-BISBM_HD void facc_edge(FAcc& A, int m_r, int m_s, int c, int c1, float inv) {
-    const int x1 = m_r - c;          // m_rt - c
-    const int x2 = x1 - c1;          // m_rt - 2c - 1
-    A.a0 = fmaf((float)m_s, inv, A.a0);
-    A.a1 = fmaf((float)x2, inv, A.a1);
+// one edge of v into block t: c earlier edges of v into t (c1 = c + 1 <= 255), counts m_rt, m_st, inv = 1/(e_t + eps K).
+// Two int->float conversions per edge (the XU pipe converts one warp per clock per SM); c + 1 becomes a float by
+// splicing its 8 bits under the exponent of 2^23, and the remaining terms are float additions (exact below 2^24).
+BISBM_HD void facc_edge(FAcc& A, int m_r, int m_s, int c1, float inv) {
+    const float fr = (float)m_r, fs = (float)m_s;
+#ifdef __CUDA_ARCH__
+    const float fc1 = __uint_as_float(0x4B000000u | (uint32_t)c1) - 8388608.0f;
+#else
+    const float fc1 = (float)c1;
+#endif
+    const float x2 = fr - (fc1 + fc1);        // m_rt - 2c - 1 = (m_rt + 1) - 2 (c + 1)
+    A.a0 = fmaf(fs, inv, A.a0);
+    A.a1 = fmaf(x2 + 1.0f, inv, A.a1);
     A.w += inv;
-    A.num *= (float)x1;
-    A.den *= (float)(m_s + c1);
+    A.num *= (fr + 1.0f) - fc1;               // m_rt - c
+    A.den *= fs + fc1;                        // m_st + 1 + c
 }
 // fold the products into the logarithm; called at least every 4 edges (4 factors < 2^31 stay inside fp32 range)
 BISBM_HD void facc_fold(FAcc& A) {
@@ -92,11 +99,11 @@ BISBM_HD float f_logq_delta(const LogqExp& q, int e, int n, int de, int dn, bool
 //   int32  sEo [kown*32]       e_r of the moving type's blocks
 //   int32  sEp [kopp*32]       e_t of the frozen type's blocks
 //   float  sInv[kopp*32]       1 / (e_t + eps K)
-//   uint4  batch[warps][32]    the warp's next 32 vertices: {vertex, CSR row offset, degree, degree index}
+//   uint4  batch[warps][64]    ring of the warp's next vertices: {vertex, CSR row offset, degree, degree index}
 //   u8     hist[warps][ceil(kopp/4)][32 lanes][4]   (bin t of lane l: word t/4, byte t%4 -- lane l only touches bank l)
 __host__ __device__ inline size_t sweep_fast_smem_bytes(uint32_t KA, uint32_t KB, uint32_t type, uint32_t warps) {
     const uint32_t kown = type ? KB : KA, kopp = type ? KA : KB;
-    return (size_t)KA * KB * 128 + (size_t)kown * 128 + (size_t)kopp * 256 + (size_t)warps * 512 +
+    return (size_t)KA * KB * 128 + (size_t)kown * 128 + (size_t)kopp * 256 + (size_t)warps * 1024 +
            (size_t)warps * ((kopp + 3) / 4) * 128;
 }
 
@@ -126,11 +133,11 @@ __device__ __noinline__ static float slow_beta(int schedule, float p0, float p1,
     const double T = par_temperature(schedule, p0, p1, t);
     return (T == 0.0) ? -1.f : (float)(1.0 / T);
 }
-// commit one histogram bin: m(r,t) -= k, m(s,t) += k when k != 0 (predicated, no branch)
+// commit one histogram bin: m(r,t) -= k, m(s,t) += k.  Unconditional: with 32 chains per warp nearly every bin is
+// non-zero in some lane, so a test per bin only adds branches; lanes that do not move pass k = 0.
 __device__ __forceinline__ void commit_bin(uint32_t ar, uint32_t as, int k) {
-    asm volatile("{\n\t.reg .pred p;\n\t.reg .s32 n;\n\tsetp.ne.s32 p, %2, 0;\n\tneg.s32 n, %2;\n\t"
-                 "@p red.shared.add.s32 [%0], n;\n\t@p red.shared.add.s32 [%1], %2;\n\t}"
-                 :: "r"(ar), "r"(as), "r"(k) : "memory");
+    sh_red_add(ar, -k);
+    sh_red_add(as, k);
 }
 
 // KF > 0: Ka == Kb == KF padded strides and the moving type TYPE fixed at compile time; KF == 0: from SweepParams.
@@ -172,7 +179,7 @@ __global__ void __launch_bounds__(NT, 1) sweep_fast_kernel(const __grid_constant
     int32_t* const sEp = sEo + kown_max * 32;
     float* const sInv = reinterpret_cast<float*>(sEp + kopp_max * 32);
     uint32_t* const sBatch = reinterpret_cast<uint32_t*>(sInv + kopp_max * 32);
-    uint32_t* const hist_all = sBatch + wpc * 128;
+    uint32_t* const hist_all = sBatch + wpc * 256;
     const uint32_t hist_words = (kopp_max + 3u) / 4u;
     copy_i4(sM, gM, KA * KB * 32);
     copy_i4(sEo, gE + own_off * 32, kown_max * 32);
@@ -192,7 +199,7 @@ __global__ void __launch_bounds__(NT, 1) sweep_fast_kernel(const __grid_constant
     const uint32_t Eo_base = (uint32_t)__cvta_generic_to_shared(sEo) + lane4;
     const uint32_t Ep_base = (uint32_t)__cvta_generic_to_shared(sEp) + lane4;
     const uint32_t inv_base = (uint32_t)__cvta_generic_to_shared(sInv) + lane4;
-    const uint32_t batch_base = (uint32_t)__cvta_generic_to_shared(sBatch) + warp * 512u;
+    const uint32_t batch_base = (uint32_t)__cvta_generic_to_shared(sBatch) + warp * 1024u;
     const uint32_t hist_base = (uint32_t)__cvta_generic_to_shared(hist_all) + warp * hist_words * 128u + lane4;
     // m(x_own, t_opp) at M_base + x*SX + t*ST  (bytes)
     const uint32_t SX = (type ? 1u : KB) * 128u, ST = (type ? KB : 1u) * 128u;
@@ -220,12 +227,15 @@ __global__ void __launch_bounds__(NT, 1) sweep_fast_kernel(const __grid_constant
     if (warp < P.warps_used) {
         const uint32_t stride = P.ctas_per_group * P.warps_used;
         const uint32_t i_first = P.pos_begin + cta_in_group * P.warps_used + warp;
-        // The warp's vertices are prepared in batches of 32: lane l computes the l-th one (place in the permuted
-        // visiting order, CSR row offset, degree) and parks it in shared memory.  One vertex ahead, the pipeline
-        // holds the next vertex's own label, Philox draw, proposal neighbour and (one stage later) its label.
-        uint32_t v_n = 0, d_n = 0, nbr_n = 0, r_n = 0, jt_n = 0, didx_n = 0, ry_n = 0, rz_n = 0, rw_n = 0;
-        auto refill = [&](uint32_t pos0) {
-            const uint64_t il = (uint64_t)pos0 + (uint64_t)lane * stride;
+        // The warp's vertices are prepared 32 at a time: lane l computes the l-th one (place in the permuted
+        // visiting order, CSR row offset, degree) and parks it in a 64-slot ring in shared memory.
+        // Latency is hidden by PREFETCHING INTO L1 rather than by holding the next vertex's operands in
+        // registers: while vertex k is evaluated the warp loads the neighbour ids of vertex k+2 (one coalesced
+        // load, lane e = neighbour e) and issues one prefetch per lane for the label rows of vertex k+1's
+        // neighbours (lane e -> row of neighbour e; the last lane -> vertex k+1's own label).  When vertex k+1
+        // is evaluated its gathers hit L1.  Pipeline state: two registers (nbr1, nbr2).
+        auto refill = [&](uint32_t k0) {     // slots k0 .. k0+31 of the ring
+            const uint64_t il = (uint64_t)i_first + (uint64_t)(k0 + lane) * stride;
             uint4 b; b.x = 0; b.y = 0; b.z = 0; b.w = 0;
             if (il < P.pos_end) {
                 const uint64_t pkey = (P.sweep * 2 + type) * 0x9E3779B97F4A7C15ull + (uint64_t)group * 0xD1B54A32D192ED03ull;
@@ -235,33 +245,50 @@ __global__ void __launch_bounds__(NT, 1) sweep_fast_kernel(const __grid_constant
                 b.w = G.degidx[b.x];
             }
             __syncwarp();
-            sh_st_v4(batch_base + lane * 16u, b);
+            sh_st_v4(batch_base + ((k0 + lane) & 63u) * 16u, b);
             __syncwarp();
         };
-        auto prefetch = [&](uint32_t slot) {
-            const uint4 b = sh_ld_v4(batch_base + slot * 16u);
-            v_n = b.x; d_n = b.z; didx_n = b.w;
-            nbr_n = (lane < b.z) ? G.col[b.y + lane] : 0u;
-            r_n = lab_ld(b.x);
-            u32x4 ctr; ctr.x = b.x; ctr.y = (uint32_t)P.sweep; ctr.z = (uint32_t)(P.sweep >> 32); ctr.w = 0;
-            const u32x4 ra = philox4x32(ctr, key0, key1);
-            ry_n = ra.y; rz_n = ra.z; rw_n = ra.w;
-            jt_n = (b.z != 0) ? G.col[b.y + mulhi32(ra.x, b.z)] : b.x;   // differs per lane: plain gather
+        auto load_nbr = [&](uint32_t k) -> uint32_t {   // neighbour ids of the vertex in slot k (lane e = neighbour e, 0 past the degree)
+            const uint4 b = sh_ld_v4(batch_base + (k & 63u) * 16u);
+            return (lane < b.z) ? G.col[b.y + lane] : 0u;
         };
+        auto prefetch_rows = [&](uint32_t k, uint32_t nbr) {   // label rows the vertex in slot k will gather
+            const uint4 b = sh_ld_v4(batch_base + (k & 63u) * 16u);
+            const uint32_t vtx = (lane < b.z) ? nbr : b.x;     // lanes past the degree: the vertex's own label
+            if (P.prefetch == 1)
+                asm volatile("{\n\t.reg .u64 a;\n\tmad.wide.u32 a, %0, %1, %2;\n\tprefetch.global.L1 [a];\n\t}" :: "r"(vtx), "r"(C), "l"(LAB8));
+            else if (P.prefetch == 2)
+                asm volatile("{\n\t.reg .u64 a;\n\tmad.wide.u32 a, %0, %1, %2;\n\tprefetch.global.L2 [a];\n\t}" :: "r"(vtx), "r"(C), "l"(LAB8));
+        };
+        uint32_t nbr1 = 0, nbr2 = 0, nbr0 = 0;
         if (i_first < P.pos_end) {
-            refill(i_first);
-            prefetch(0);
-            jt_n = lab_ld(jt_n);
+            refill(0);
+            refill(32);
+            nbr0 = load_nbr(0);
+            nbr1 = load_nbr(1);
+            prefetch_rows(0, nbr0);
         }
-        for (uint32_t ib = i_first, k = 0; ib < P.pos_end; ib += stride, ++k) {
-            __syncwarp();
-            const uint32_t v = v_n, d = d_n, nbr0 = nbr_n, r = r_n, didx = didx_n, ry = ry_n, rz = rz_n, rw = rw_n;
-            const uint32_t tq = min(jt_n, kopp_max - 1u);   // (an isolated vertex has no proposal neighbour: any valid slot)
-            const bool has_next = (ib + stride < P.pos_end);
-            if (has_next) {
-                if (((k + 1) & 31u) == 0) refill(ib + stride);
-                prefetch((k + 1) & 31u);
+        for (uint32_t ib = i_first, k = 0; ib < P.pos_end; ib += stride, ++k, nbr0 = nbr1, nbr1 = nbr2) {
+            if (k >= 32u && (k & 31u) == 0) refill(k + 32u);   // the ring half holding slots k-32 .. k-1 is free
+            const uint4 cur = sh_ld_v4(batch_base + (k & 63u) * 16u);
+            const uint32_t v = cur.x, d = cur.z, didx = cur.w;
+            nbr2 = load_nbr(k + 2);
+            prefetch_rows(k + 1, nbr1);
+            // ---- the draw of this move: Philox4x32-10 ----
+            uint32_t ry, rz, rw, jv;
+            {
+                // counter = (vertex, sweep, chain seed); the key is common to the pool, so the ten round keys are
+                // warp-uniform constants instead of twenty per-lane registers
+                u32x4 ctr; ctr.x = v; ctr.y = (uint32_t)P.sweep; ctr.z = key0; ctr.w = key1;
+                const u32x4 ra = philox4x32(ctr, (uint32_t)(P.sweep >> 32) ^ 0xA4093822u, 0x299F31D0u);
+                ry = ra.y; rz = ra.z; rw = ra.w;
+                const uint32_t e = mulhi32(ra.x, d);       // the proposal's random neighbour (differs per lane)
+                jv = __shfl_sync(0xffffffffu, nbr0, e & 31u);
+                if (d > 32u) jv = G.col[cur.y + e];
+                if (d == 0u) jv = v;                      // isolated vertex: no neighbour, any valid label
             }
+            const uint32_t r = lab_ld(v);
+            const uint32_t tq = min(lab_ld(jv), kopp_max - 1u);
             float beta = 1.0f / P.p0;
             if (!const_T) beta = slow_beta(P.schedule, P.p0, P.p1, P.step_base + ib);
             const bool T_zero = beta < 0.f;
@@ -289,7 +316,6 @@ __global__ void __launch_bounds__(NT, 1) sweep_fast_kernel(const __grid_constant
             // a uniform draw that falls on a block of the other type is rejected (dS = +inf): s stays r for it
             const bool cross = movable_chain && uniform_pick && (sg_a != (type == 0));
             const uint32_t s = (movable_chain && !cross) ? (uniform_pick ? s_uni : s_cat) : r;   // own-type local index
-            if (has_next) jt_n = lab_ld(jt_n);   // pipeline stage 2: label of the next proposal neighbour
             const bool eval = live && (s != r);
             if (!__any_sync(0xffffffffu, eval)) {
                 // s == r (dS = 0, accu_r = 1): accepted at T > 0 unless the block would empty, rejected at T == 0
@@ -318,7 +344,7 @@ __global__ void __launch_bounds__(NT, 1) sweep_fast_kernel(const __grid_constant
                 const uint32_t cnt1 = cnt + 1u;
                 sh_st_u8(ha, cnt1);
                 const int m_r = sh_ld(Mr + t * ST), m_s = sh_ld(Ms + t * ST);
-                facc_edge(A, m_r, m_s, (int)cnt, (int)cnt1, sh_ld_f32(inv_base + t * 128u));
+                facc_edge(A, m_r, m_s, (int)cnt1, sh_ld_f32(inv_base + t * 128u));
             };
             const uint32_t n_ch = (d + 3u) >> 2;
             if (n_ch) gather4(t0, t1, t2, t3);
@@ -327,7 +353,7 @@ __global__ void __launch_bounds__(NT, 1) sweep_fast_kernel(const __grid_constant
                 if (ch + 1 < n_ch) {   // next chunk's labels in flight while this one is consumed
                     if (((ch + 1) & 7u) == 0) {
                         const uint32_t e0 = ch * 4u + 4u;
-                        nbr = (e0 + lane < d) ? G.col[G.row_ptr[v] + e0 + lane] : 0u;
+                        nbr = (e0 + lane < d) ? G.col[cur.y + e0 + lane] : 0u;
                     }
                     gather4(u0, u1, u2, u3);
                 }

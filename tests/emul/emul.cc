@@ -221,7 +221,7 @@ void emul_par_dS_f32(void* p, uint32_t v, uint32_t sg, int use_taylor, double* d
         uint32_t t = s->labels[(size_t)nb * s->C + s->chain];
         int c = cnt[t]++;
         float inv = (float)(1.0 / ((double)s->e[opp_off + t] + s->eps * (double)(KA + KB)));
-        facc_edge(A, Mr[(size_t)t * st], Ms[(size_t)t * st], c, c + 1, inv);
+        facc_edge(A, Mr[(size_t)t * st], Ms[(size_t)t * st], c + 1, inv);
         if ((e & 3u) == 3u || e + 1 == d) facc_fold(A);
     }
     int e_r = s->e[own_off + r], e_s = s->e[own_off + sl], n_r = s->nr[own_off + r], n_s = s->nr[own_off + sl];
