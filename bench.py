@@ -303,6 +303,12 @@ def main():
     total_moves = float(tot[0])
     value = total_moves / wall_max
     acceptance = float(np.mean(accs))
+    kern, wpc_, cpg_, slice_ = pool.sweep_info()
+    kernel_name = {0: "sweep_kernel<double, counts in L2>", 1: "sweep_kernel<double, staged counts>",
+                   2: "sweep_fast_kernel<fp32, staged counts>"}[kern]
+    config["sweep_plan"] = {"kernel": kernel_name, "warps_per_cta": wpc_, "ctas_per_chain_group": cpg_,
+                            "slice_vertices_per_launch": slice_}
+    dtype = "f32+int32 (dS summed in f64)" if kern >= 2 else "f64+int32"
 
     # -------- e2e: host buffers in, host buffers out, every step
     out_host = torch.empty((C, n), dtype=torch.int32).pin_memory()
@@ -346,10 +352,10 @@ def main():
         achieved = bytes_per_move * moves / (ev_ms * 1e-3) / 1e9
         line = {"metric": "vertex-moves/sec", "value": value, "unit": "moves/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": wall_max / args.steps * 1e3, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64+int32", "data": "synthetic", "config": config,
+                "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic", "config": config,
                 "acceptance": acceptance,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": None, "kernel": "sweep_kernel", "bytes_per_move": bytes_per_move,
+                             "traffic": None, "kernel": kernel_name, "bytes_per_move": bytes_per_move,
                              "alg_bytes_per_launch": alg_bytes_per_launch,
                              "avg_launch_ms": ev_ms / sweep_launches, "peak_source": peak_src,
                              "sweep_kernel_launches": int(sweep_launches),

@@ -80,6 +80,7 @@ struct bisbm_handle {
     uint8_t* d_lab8 = nullptr;                 // u8 shadow of the labels for the shared-memory sweep
     double eps = 1.0;
     LogqExp* d_lq = nullptr;
+    uint32_t* d_lq_soa = nullptr;
     uint64_t* d_seeds = nullptr;
     uint8_t* d_active = nullptr;
     unsigned long long *d_accepted = nullptr, *d_u = nullptr, *d_sweeps = nullptr;
@@ -95,6 +96,8 @@ struct bisbm_handle {
     uint64_t last_launches = 0, last_moves = 0;
     // move arithmetic of the parallel sweep: 0 = fp32 kernel where it applies (sweep_fast.cuh), 1 = double everywhere
     int precision = 0;
+    uint32_t last_wpc = 0, last_cpg = 0, last_slice = 0;   // launch plan of the last half sweep
+    int last_kernel = -1;                                   // 0 = double / counts in L2, 1 = double / staged counts, 2 = fp32 / staged counts
     bool lab32_stale = false;   // the fp32 kernel only writes the u8 label shadow; i32 labels refreshed on demand
 };
 
@@ -108,7 +111,7 @@ void dfree(T*& p) {
 
 void free_chains(bisbm_handle* h) {
     dfree(h->d_ka); dfree(h->d_kb); dfree(h->d_labels); dfree(h->d_labels_tmp);
-    dfree(h->d_m); dfree(h->d_e); dfree(h->d_nr); dfree(h->d_eta); dfree(h->d_lq); dfree(h->d_m2); dfree(h->d_e2); dfree(h->d_lab8);
+    dfree(h->d_m); dfree(h->d_e); dfree(h->d_nr); dfree(h->d_eta); dfree(h->d_lq); dfree(h->d_lq_soa); dfree(h->d_m2); dfree(h->d_e2); dfree(h->d_lab8);
     dfree(h->d_seeds); dfree(h->d_active); dfree(h->d_accepted); dfree(h->d_u); dfree(h->d_sweeps);
     dfree(h->d_dS); dfree(h->d_entmin); dfree(h->d_ent_out); dfree(h->d_nactive); dfree(h->d_hist);
     for (auto& kv : h->replay) { dfree(kv.second.d_rs); dfree(kv.second.d_vlist); dfree(kv.second.d_kh); }
@@ -338,12 +341,19 @@ int plan_sweep(bisbm_handle* h, uint32_t type, uint32_t max_inflight, LaunchPlan
     lp->hist_bytes = (int)hb;
     const size_t budget = 220 * 1024;
     lp->smem = sweep_smem_bytes(true, h->KA, h->KB, type, 16, hb) <= budget && h->KA <= 256 && h->KB <= 256;
-    // fp32 throughput kernel: staged counts, u8 histogram bins
-    lp->fast = lp->smem && hb == 1 && h->precision == 0 && !getenv("BISBM_PRECISE") &&
-               sweep_fast_smem_bytes(h->KA, h->KB, type, 32) <= budget;
-    // warps per CTA (one CTA per SM): the fp32 kernel measures best with 24 (80 registers per thread)
-    uint32_t wpc = lp->fast ? 24 : 32;
-    if (const char* e = getenv("BISBM_WPC")) { int w = atoi(e); wpc = (w == 16 || w == 24 || (w == 20 && lp->fast)) ? (uint32_t)w : 32; }  // tuning knob
+    // fp32 throughput kernel: staged counts, u8 histogram bins; warps per CTA (one CTA per SM): 24 measures best
+    // (80 registers per thread), fewer when shared memory is short
+    const size_t budget_fast = 227 * 1024;
+    uint32_t wpc = 32;
+    lp->fast = false;
+    if (lp->smem && hb == 1 && h->precision == 0 && !getenv("BISBM_PRECISE")) {
+        uint32_t want = 24;
+        if (const char* e = getenv("BISBM_WPC")) { int w = atoi(e); if (w == 16 || w == 20 || w == 24 || w == 32) want = (uint32_t)w; }  // tuning knob
+        for (uint32_t w : {want, 20u, 16u})
+            if (w <= want && sweep_fast_smem_bytes(h->KA, h->KB, type, w) <= budget_fast) { lp->fast = true; wpc = w; break; }
+    }
+    if (!lp->fast)
+        if (const char* e = getenv("BISBM_WPC")) { int w = atoi(e); wpc = (w == 16 || w == 24) ? (uint32_t)w : 32; }  // tuning knob
     if (!lp->fast && sweep_smem_bytes(lp->smem, h->KA, h->KB, type, wpc, hb) > budget) wpc = 16;
     if (!lp->fast && sweep_smem_bytes(lp->smem, h->KA, h->KB, type, wpc, hb) > budget)
         return fail(BISBM_ERR_ARG, "K too large for the shared-memory histogram");
@@ -397,7 +407,7 @@ template <int KF, int TYPE, int NT>
 int launch_sweep_fast_nt(bisbm_handle* h, const SweepParams& P, const LaunchPlan& lp) {
     static bool attr_set = false;
     if (!attr_set) {
-        CU(cudaFuncSetAttribute(sweep_fast_kernel<KF, TYPE, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        CU(cudaFuncSetAttribute(sweep_fast_kernel<KF, TYPE, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
     const unsigned grid = P.n_groups * lp.ctas_per_group;
@@ -451,11 +461,13 @@ int launch_full_sweep(bisbm_handle* h, int schedule, float p0, float p1, uint64_
         if (rc) return rc;
         const uint32_t kmax = type ? h->KB : h->KA;
         const uint32_t tot = h->n_chains * kmax;
-        logq_refresh_kernel<<<(tot + 127) / 128, 128, 0, h->stream>>>(sview(h), tview(h, false), h->d_lq, h->n_chains, type);
+        logq_refresh_kernel<<<(tot + 127) / 128, 128, 0, h->stream>>>(sview(h), tview(h, false), h->d_lq, h->d_lq_soa, h->n_chains, type);
         h->last_launches += 1;
         const size_t m_bytes = (size_t)h->C * h->KA * h->KB * sizeof(int32_t);
         const size_t e_bytes = (size_t)h->C * (h->KA + h->KB) * sizeof(int32_t);
         const bool sliced = lp.smem && lp.ctas_per_group > 1;
+        h->last_wpc = lp.wpc; h->last_cpg = lp.ctas_per_group; h->last_slice = lp.slice;
+        h->last_kernel = lp.fast ? 2 : (lp.smem ? 1 : 0);
         for (uint32_t pos = 0; pos < nv; pos += lp.slice) {
             if (sliced) {  // next := base; the launch adds each CTA's (staged - base) into next
                 CU(cudaMemcpyAsync(h->d_m2, h->d_m, m_bytes, cudaMemcpyDeviceToDevice, h->stream));
@@ -465,7 +477,7 @@ int launch_full_sweep(bisbm_handle* h, int schedule, float p0, float p1, uint64_
             P.g = gview(h); P.s = sview(h); P.tb = tview(h, false);
             P.lab8 = h->d_lab8; P.m_next = h->d_m2; P.e_next = h->d_e2;
             P.seeds = h->d_seeds; P.active = h->d_active; P.accepted = h->d_accepted; P.dS_accum = h->d_dS;
-            P.lq = h->d_lq;
+            P.lq = h->d_lq; P.lq_soa = h->d_lq_soa;
             P.n_chains = h->n_chains; P.type = type; P.n_groups = h->C / 32;
             P.ctas_per_group = lp.ctas_per_group; P.warps_used = lp.warps_used;
             P.pos_begin = pos; P.pos_end = std::min<uint64_t>(nv, (uint64_t)pos + lp.slice);
@@ -475,8 +487,6 @@ int launch_full_sweep(bisbm_handle* h, int schedule, float p0, float p1, uint64_
             P.sweep = h->sweep_epoch;
             P.step_base = sweep_in_call * (uint64_t)h->n + (type ? h->na : 0);
             P.schedule = schedule; P.p0 = p0; P.p1 = p1;
-            P.prefetch = 1;
-            if (const char* e = getenv("BISBM_PREFETCH")) P.prefetch = (uint32_t)atoi(e);  // tuning knob
             rc = lp.smem ? launch_sweep_h<true>(h, P, lp) : launch_sweep_h<false>(h, P, lp);
             if (rc) return rc;
             h->last_launches += 1;
@@ -620,6 +630,7 @@ int bisbm_set_chains(bisbm_handle* h, uint32_t n_chains, const uint32_t* ka, con
         CU(cudaMalloc(&h->d_nr, (size_t)C * KK * sizeof(int32_t)));
         CU(cudaMalloc(&h->d_eta, (size_t)C * KK * h->W * sizeof(int32_t)));
         CU(cudaMalloc(&h->d_lq, (size_t)C * KK * sizeof(LogqExp)));
+        CU(cudaMalloc(&h->d_lq_soa, (size_t)C * KK * 8 * sizeof(uint32_t)));
         CU(cudaMalloc(&h->d_seeds, C * sizeof(uint64_t)));
         CU(cudaMalloc(&h->d_active, C));
         CU(cudaMalloc(&h->d_accepted, C * sizeof(unsigned long long)));
@@ -639,6 +650,7 @@ int bisbm_set_chains(bisbm_handle* h, uint32_t n_chains, const uint32_t* ka, con
     std::copy(ka, ka + n_chains, h->h_ka.begin());
     std::copy(kb, kb + n_chains, h->h_kb.begin());
     CU(cudaMemsetAsync(h->d_lq, 0, (size_t)C * KK * sizeof(LogqExp), h->stream));
+    CU(cudaMemsetAsync(h->d_lq_soa, 0, (size_t)C * KK * 8 * sizeof(uint32_t), h->stream));
     CU(cudaMemsetAsync(h->d_dS, 0, C * sizeof(double), h->stream));
     CU(cudaMemcpyAsync(h->d_ka, h->h_ka.data(), C * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(h->d_kb, h->h_kb.data(), C * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
@@ -926,6 +938,16 @@ int bisbm_marginalize(bisbm_handle* h, uint64_t burn_in, uint64_t sweeps, uint64
     float ms = 0.f;
     CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     h->last_ms = ms;
+    return BISBM_OK;
+}
+
+int bisbm_sweep_info(bisbm_handle* h, int* kernel, uint32_t* warps_per_cta, uint32_t* ctas_per_group, uint32_t* slice) {
+    if (!h) return fail(BISBM_ERR_ARG, "null handle");
+    if (h->last_kernel < 0) return fail(BISBM_ERR_STATE, "no parallel sweep has run yet");
+    if (kernel) *kernel = h->last_kernel;
+    if (warps_per_cta) *warps_per_cta = h->last_wpc;
+    if (ctas_per_group) *ctas_per_group = h->last_cpg;
+    if (slice) *slice = h->last_slice;
     return BISBM_OK;
 }
 

@@ -58,6 +58,7 @@ struct SweepParams {
     unsigned long long* accepted;    // [C]
     double* dS_accum;                // [C]
     const LogqExp* lq;               // [C/32][KA+KB][32]
+    const uint32_t* lq_soa;          // the same, field-major for coalesced lane = chain loads: [C/32][KA+KB][8][32]
     uint32_t n_chains;               // real chains (<= C)
     uint32_t type;                   // 0: move type-a vertices, 1: type-b
     uint32_t n_groups;               // C / 32
@@ -71,7 +72,6 @@ struct SweepParams {
     uint64_t step_base;              // global step index of position 0 of this half sweep
     int schedule;
     float p0, p1;
-    uint32_t prefetch;               // fp32 kernel: 1 = prefetch the next vertex's label rows into L1, 2 = into L2, 0 = off
 };
 
 // temperature of global step t (same five schedules as src/metropolis_hasting.cc:10-37,
@@ -167,7 +167,7 @@ __device__ __forceinline__ int cnt_ld(const int32_t* p) {
 
 // Refresh the log q expansions of the blocks of one type (they only change during that
 // type's half sweep).  One thread per (chain, block).
-__global__ void logq_refresh_kernel(StateView s, Tables tb, LogqExp* lq, uint32_t n_chains, uint32_t type) {
+__global__ void logq_refresh_kernel(StateView s, Tables tb, LogqExp* lq, uint32_t* lq_soa, uint32_t n_chains, uint32_t type) {
     uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t kmax = type ? s.KB : s.KA;
     if (idx >= n_chains * kmax) return;
@@ -199,6 +199,15 @@ __global__ void logq_refresh_kernel(StateView s, Tables tb, LogqExp* lq, uint32_
         }
     }
     lq[off] = q;
+    // field-major copy; a block without expansion is stored as e0 = n0 = 0 (never in range)
+    uint32_t* o = lq_soa + ((size_t)(c / GROUP) * ((size_t)s.KA + s.KB) + slot) * 8 * GROUP + (c % GROUP);
+    o[0 * GROUP] = q.valid ? (uint32_t)q.e0 : 0u;
+    o[1 * GROUP] = q.valid ? (uint32_t)q.n0 : 0u;
+    o[2 * GROUP] = __float_as_uint(q.fe);
+    o[3 * GROUP] = __float_as_uint(q.fn);
+    o[4 * GROUP] = __float_as_uint(q.fee);
+    o[5 * GROUP] = __float_as_uint(q.fen);
+    o[6 * GROUP] = __float_as_uint(q.fnn);
 }
 
 // shared memory of the SMEM variant, in this order:

@@ -86,7 +86,7 @@ BISBM_HD float f_logq_delta(const LogqExp& q, int e, int n, int de, int dn, bool
     const int x = e - q.e0, y = n - q.n0;
     const int ax = x < 0 ? -x : x, ay = y < 0 ? -y : y, ad = de < 0 ? -de : de;
     const int re = q.e0 >> 4, rn = q.n0 >> 4;
-    *ok = q.valid && ax <= re && ay <= rn && ad <= re;
+    *ok = (q.valid != 0u) && ax <= re && ay <= rn && ad <= re;
     const float dx = (float)x, dy = (float)y, De = (float)de, Dn = (float)dn;
     return q.fe * De + q.fn * Dn + 0.5f * q.fee * (De * De + 2.0f * dx * De) + q.fen * (dx * Dn + dy * De + De * Dn) +
            0.5f * q.fnn * (Dn * Dn + 2.0f * dy * Dn);
@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(NT, 1) sweep_fast_kernel(const __grid_constant
     int32_t* const gE = P.s.e + (size_t)group * KK * GROUP;
     int32_t* const gNR = P.s.nr + (size_t)group * KK * GROUP + (size_t)own_off * 32;
     int32_t* const gETA = P.s.eta + (size_t)group * KK * W * GROUP + (size_t)own_off * W * 32;
-    const LogqExp* const gLQ = P.lq + (size_t)group * KK * GROUP + (size_t)own_off * 32;
+    const uint32_t* const gLQ = P.lq_soa + ((size_t)group * KK + own_off) * 8 * GROUP;   // [slot][field][lane]
 
     const uint32_t c = group * 32 + lane;
     const bool live = (c < P.n_chains) && P.active[c];
@@ -229,11 +229,11 @@ __global__ void __launch_bounds__(NT, 1) sweep_fast_kernel(const __grid_constant
         const uint32_t i_first = P.pos_begin + cta_in_group * P.warps_used + warp;
         // The warp's vertices are prepared 32 at a time: lane l computes the l-th one (place in the permuted
         // visiting order, CSR row offset, degree) and parks it in a 64-slot ring in shared memory.
-        // Latency is hidden by PREFETCHING INTO L1 rather than by holding the next vertex's operands in
-        // registers: while vertex k is evaluated the warp loads the neighbour ids of vertex k+2 (one coalesced
-        // load, lane e = neighbour e) and issues one prefetch per lane for the label rows of vertex k+1's
-        // neighbours (lane e -> row of neighbour e; the last lane -> vertex k+1's own label).  When vertex k+1
-        // is evaluated its gathers hit L1.  Pipeline state: two registers (nbr1, nbr2).
+        // While vertex k is evaluated the warp loads the neighbour ids of vertex k+2 (one coalesced load, lane e =
+        // neighbour e) and issues one L2 prefetch per lane for the label rows vertex k+1 will gather (lane e -> row
+        // of neighbour e; lanes past the degree -> vertex k+1's own label).  Pipeline state: two registers.
+        // (Prefetching into L1 was measured useless: with 190 KB of shared memory the L1 holds ~500 lines and every
+        // prefetched 32-byte row occupies a whole line.  See DESIGN.md for the other things that were tried.)
         auto refill = [&](uint32_t k0) {     // slots k0 .. k0+31 of the ring
             const uint64_t il = (uint64_t)i_first + (uint64_t)(k0 + lane) * stride;
             uint4 b; b.x = 0; b.y = 0; b.z = 0; b.w = 0;
@@ -255,10 +255,7 @@ __global__ void __launch_bounds__(NT, 1) sweep_fast_kernel(const __grid_constant
         auto prefetch_rows = [&](uint32_t k, uint32_t nbr) {   // label rows the vertex in slot k will gather
             const uint4 b = sh_ld_v4(batch_base + (k & 63u) * 16u);
             const uint32_t vtx = (lane < b.z) ? nbr : b.x;     // lanes past the degree: the vertex's own label
-            if (P.prefetch == 1)
-                asm volatile("{\n\t.reg .u64 a;\n\tmad.wide.u32 a, %0, %1, %2;\n\tprefetch.global.L1 [a];\n\t}" :: "r"(vtx), "r"(C), "l"(LAB8));
-            else if (P.prefetch == 2)
-                asm volatile("{\n\t.reg .u64 a;\n\tmad.wide.u32 a, %0, %1, %2;\n\tprefetch.global.L2 [a];\n\t}" :: "r"(vtx), "r"(C), "l"(LAB8));
+            asm volatile("{\n\t.reg .u64 a;\n\tmad.wide.u32 a, %0, %1, %2;\n\tprefetch.global.L2 [a];\n\t}" :: "r"(vtx), "r"(C), "l"(LAB8));
         };
         uint32_t nbr1 = 0, nbr2 = 0, nbr0 = 0;
         if (i_first < P.pos_end) {
@@ -382,22 +379,18 @@ __global__ void __launch_bounds__(NT, 1) sweep_fast_kernel(const __grid_constant
                 bool ok_b, ok_r, ok_s;
                 float bdd = f_block_degree_delta(e_r, e_s, (int)d, &ok_b);
                 float lqr, lqs;
-                {
-                    const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(&gLQ[r * 32 + lane]));
-                    const uint4 q1 = __ldg(reinterpret_cast<const uint4*>(&gLQ[r * 32 + lane]) + 1);
+                auto load_q = [&](uint32_t slot) -> LogqExp {   // seven coalesced 4-byte loads (constant during the launch)
+                    const uint32_t* p = gLQ + slot * 256u + lane;
                     LogqExp q;
-                    q.e0 = (int)q0.x; q.n0 = (int)q0.y; q.fe = __uint_as_float(q0.z); q.fn = __uint_as_float(q0.w);
-                    q.fee = __uint_as_float(q1.x); q.fen = __uint_as_float(q1.y); q.fnn = __uint_as_float(q1.z); q.valid = q1.w;
-                    lqr = f_logq_delta(q, e_r, n_r, -(int)d, -1, &ok_r);
-                }
-                {
-                    const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(&gLQ[s * 32 + lane]));
-                    const uint4 q1 = __ldg(reinterpret_cast<const uint4*>(&gLQ[s * 32 + lane]) + 1);
-                    LogqExp q;
-                    q.e0 = (int)q0.x; q.n0 = (int)q0.y; q.fe = __uint_as_float(q0.z); q.fn = __uint_as_float(q0.w);
-                    q.fee = __uint_as_float(q1.x); q.fen = __uint_as_float(q1.y); q.fnn = __uint_as_float(q1.z); q.valid = q1.w;
-                    lqs = f_logq_delta(q, e_s, n_s, (int)d, 1, &ok_s);
-                }
+                    q.e0 = (int)__ldg(p); q.n0 = (int)__ldg(p + 32);
+                    q.fe = __uint_as_float(__ldg(p + 64)); q.fn = __uint_as_float(__ldg(p + 96));
+                    q.fee = __uint_as_float(__ldg(p + 128)); q.fen = __uint_as_float(__ldg(p + 160));
+                    q.fnn = __uint_as_float(__ldg(p + 192));
+                    q.valid = (uint32_t)q.e0;     // blocks without expansion are stored with e0 = 0
+                    return q;
+                };
+                lqr = f_logq_delta(load_q(r), e_r, n_r, -(int)d, -1, &ok_r);
+                lqs = f_logq_delta(load_q(s), e_s, n_s, (int)d, 1, &ok_s);
                 if (__any_sync(0xffffffffu, eval && !(ok_b && ok_r && ok_s))) {
                     if (eval && !ok_b) bdd = slow_block_degree_delta(e_r, e_s, (int)d);
                     if (eval && !ok_r) lqr = slow_logq_delta(P.tb.qtab, P.tb.qn, P.tb.qk, e_r, n_r, -(int)d, -1);

@@ -65,6 +65,8 @@ SIGNATURES = {
     "bisbm_marginalize": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, _u64p, C.c_uint32]),
     "bisbm_marginals_clear": (C.c_int, [C.c_void_p]),
     "bisbm_set_precision": (C.c_int, [C.c_void_p, C.c_int]),
+    "bisbm_sweep_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
+                                   C.POINTER(C.c_uint32)]),
     "bisbm_marginals_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), _u64p, _u32p]),
     "bisbm_get_marginals": (C.c_int, [C.c_void_p, _u32p]),
     "bisbm_marginal_argmax": (C.c_int, [C.c_void_p, _u32p]),
@@ -88,7 +90,7 @@ def load_library(path=None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("BISBM_LIB") or LIB_PATH   # BISBM_LIB: developer knob for A/B builds of the library
     if not os.path.exists(p):
         raise BisbmError(-1, "%s not found: build it with `python -m bipartitesbm-mcmc_b200.build` "
                              "or __graft_entry__.build(); there is no CPU fallback" % p)
@@ -214,6 +216,12 @@ class ChainPool:
     def set_precision(self, mode):
         """'fp32' (default: fp32 move arithmetic where the fast kernel applies) or 'fp64'."""
         _check(self.L.bisbm_set_precision(self.g.h, {"fp32": 0, "fp64": 1}.get(mode, mode)))
+
+    def sweep_info(self):
+        """(kernel, warps per CTA, CTAs per chain group, slice) of the last parallel call; kernel 2 = fp32."""
+        k, w, c, sl = C.c_int(), C.c_uint32(), C.c_uint32(), C.c_uint32()
+        _check(self.L.bisbm_sweep_info(self.g.h, C.byref(k), C.byref(w), C.byref(c), C.byref(sl)))
+        return k.value, w.value, c.value, sl.value
 
     def marginals_clear(self):
         _check(self.L.bisbm_marginals_clear(self.g.h))

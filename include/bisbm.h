@@ -112,6 +112,10 @@ int bisbm_marginals_clear(bisbm_handle* h);
  * Replay mode is always strict double. */
 enum { BISBM_PRECISION_FP32 = 0, BISBM_PRECISION_FP64 = 1 };
 int bisbm_set_precision(bisbm_handle* h, int mode);
+/* which sweep kernel the last parallel call launched and how the half sweep was cut:
+ * kernel 0 = double arithmetic, counts in L2; 1 = double, counts staged in shared memory; 2 = fp32, staged counts;
+ * slice = vertices of the visiting order per launch (the staleness bound between CTAs of one chain group) */
+int bisbm_sweep_info(bisbm_handle* h, int* kernel, uint32_t* warps_per_cta, uint32_t* ctas_per_group, uint32_t* slice);
 /* device pointer + element count of the histogram, for an in-place NCCL all-reduce */
 int bisbm_marginals_device(bisbm_handle* h, void** dev_ptr, uint64_t* n_elems, uint32_t* width);
 int bisbm_get_marginals(bisbm_handle* h, uint32_t* hist);          /* [n][width], global block ids */
