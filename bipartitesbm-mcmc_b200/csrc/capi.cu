@@ -411,7 +411,9 @@ int launch_sweep_fast_nt(bisbm_handle* h, const SweepParams& P, const LaunchPlan
         attr_set = true;
     }
     const unsigned grid = P.n_groups * lp.ctas_per_group;
-    sweep_fast_kernel<KF, TYPE, NT><<<grid, NT, lp.smem_bytes, h->stream>>>(P);
+    size_t smem = lp.smem_bytes;
+    if (const char* e = getenv("BISBM_SMEM_PAD")) smem = std::min<size_t>(227 * 1024, smem + (size_t)atoi(e));  // experiment: shrink L1
+    sweep_fast_kernel<KF, TYPE, NT><<<grid, NT, smem, h->stream>>>(P);
     CU(cudaGetLastError());
     h->lab32_stale = true;
     return BISBM_OK;

@@ -98,12 +98,11 @@ BISBM_HD float f_logq_delta(const LogqExp& q, int e, int n, int de, int dn, bool
 //   int32  sM  [KA*KB*32]      m_rs of the group, [a][b][lane]
 //   int32  sEo [kown*32]       e_r of the moving type's blocks
 //   int32  sEp [kopp*32]       e_t of the frozen type's blocks
-//   float  sInv[kopp*32]       1 / (e_t + eps K)
-//   uint4  batch[warps][64]    ring of the warp's next vertices: {vertex, CSR row offset, degree, degree index}
+//   uint4  batch[warps][32]    ring of the warp's next vertices: {vertex, CSR row offset, degree, degree index}
 //   u8     hist[warps][ceil(kopp/4)][32 lanes][4]   (bin t of lane l: word t/4, byte t%4 -- lane l only touches bank l)
 __host__ __device__ inline size_t sweep_fast_smem_bytes(uint32_t KA, uint32_t KB, uint32_t type, uint32_t warps) {
     const uint32_t kown = type ? KB : KA, kopp = type ? KA : KB;
-    return (size_t)KA * KB * 128 + (size_t)kown * 128 + (size_t)kopp * 256 + (size_t)warps * 1024 +
+    return (size_t)KA * KB * 128 + (size_t)kown * 128 + (size_t)kopp * 128 + (size_t)warps * 512 +
            (size_t)warps * ((kopp + 3) / 4) * 128;
 }
 
@@ -177,19 +176,12 @@ __global__ void __launch_bounds__(NT, 1) sweep_fast_kernel(const __grid_constant
     int32_t* const sM = reinterpret_cast<int32_t*>(smem_raw);
     int32_t* const sEo = sM + KA * KB * 32;
     int32_t* const sEp = sEo + kown_max * 32;
-    float* const sInv = reinterpret_cast<float*>(sEp + kopp_max * 32);
-    uint32_t* const sBatch = reinterpret_cast<uint32_t*>(sInv + kopp_max * 32);
-    uint32_t* const hist_all = sBatch + wpc * 256;
+    uint32_t* const sBatch = reinterpret_cast<uint32_t*>(sEp + kopp_max * 32);
+    uint32_t* const hist_all = sBatch + wpc * 128;
     const uint32_t hist_words = (kopp_max + 3u) / 4u;
     copy_i4(sM, gM, KA * KB * 32);
     copy_i4(sEo, gE + own_off * 32, kown_max * 32);
-    for (uint32_t i = threadIdx.x; i < kopp_max * 32; i += blockDim.x) {
-        const int e = gE[opp_off * 32 + i];
-        const uint32_t ci = group * 32 + (i & 31);
-        const double Kc = (double)(P.s.ka[ci] + P.s.kb[ci]);
-        sEp[i] = e;
-        sInv[i] = (float)(1.0 / ((double)e + P.s.eps * Kc));
-    }
+    copy_i4(sEp, gE + opp_off * 32, kopp_max * 32);
     for (uint32_t i = threadIdx.x; i < wpc * hist_words * 32u; i += blockDim.x) hist_all[i] = 0u;
     __syncthreads();
 
@@ -198,8 +190,8 @@ __global__ void __launch_bounds__(NT, 1) sweep_fast_kernel(const __grid_constant
     const uint32_t M_base = (uint32_t)__cvta_generic_to_shared(sM) + lane4;
     const uint32_t Eo_base = (uint32_t)__cvta_generic_to_shared(sEo) + lane4;
     const uint32_t Ep_base = (uint32_t)__cvta_generic_to_shared(sEp) + lane4;
-    const uint32_t inv_base = (uint32_t)__cvta_generic_to_shared(sInv) + lane4;
-    const uint32_t batch_base = (uint32_t)__cvta_generic_to_shared(sBatch) + warp * 1024u;
+    const uint32_t batch_base = (uint32_t)__cvta_generic_to_shared(sBatch) + warp * 512u;
+    const float epsK = (float)(P.s.eps * (double)K);
     const uint32_t hist_base = (uint32_t)__cvta_generic_to_shared(hist_all) + warp * hist_words * 128u + lane4;
     // m(x_own, t_opp) at M_base + x*SX + t*ST  (bytes)
     const uint32_t SX = (type ? 1u : KB) * 128u, ST = (type ? KB : 1u) * 128u;
@@ -208,7 +200,12 @@ __global__ void __launch_bounds__(NT, 1) sweep_fast_kernel(const __grid_constant
     asm volatile("" : "+l"(LAB8));
     auto lab_ld = [&](uint32_t vtx) -> uint32_t {     // label of vertex vtx in this lane's chain
         uint32_t x;
+#ifdef BISBM_X_LAB_CA
         asm("{\n\t.reg .u64 a;\n\tmad.wide.u32 a, %1, %2, %3;\n\tld.global.u8 %0, [a];\n\t}" : "=r"(x) : "r"(vtx), "r"(C), "l"(LAB8));
+#else
+        // .cg: label rows have no reuse in L1; keeping them out leaves the L1 to the log q expansions and the CSR rows
+        asm("{\n\t.reg .u64 a;\n\tmad.wide.u32 a, %1, %2, %3;\n\tld.global.cg.u8 %0, [a];\n\t}" : "=r"(x) : "r"(vtx), "r"(C), "l"(LAB8));
+#endif
         return x;
     };
     auto lab_st = [&](uint32_t vtx, uint32_t x) {
@@ -234,10 +231,10 @@ __global__ void __launch_bounds__(NT, 1) sweep_fast_kernel(const __grid_constant
         // of neighbour e; lanes past the degree -> vertex k+1's own label).  Pipeline state: two registers.
         // (Prefetching into L1 was measured useless: with 190 KB of shared memory the L1 holds ~500 lines and every
         // prefetched 32-byte row occupies a whole line.  See DESIGN.md for the other things that were tried.)
-        auto refill = [&](uint32_t k0) {     // slots k0 .. k0+31 of the ring
+        auto refill = [&](uint32_t k0) {     // slots k0 .. k0+15 of the ring, prepared by lanes 0..15
             const uint64_t il = (uint64_t)i_first + (uint64_t)(k0 + lane) * stride;
             uint4 b; b.x = 0; b.y = 0; b.z = 0; b.w = 0;
-            if (il < P.pos_end) {
+            if (lane < 16u && il < P.pos_end) {
                 const uint64_t pkey = (P.sweep * 2 + type) * 0x9E3779B97F4A7C15ull + (uint64_t)group * 0xD1B54A32D192ED03ull;
                 b.x = v0 + feistel_perm((uint32_t)il, nv, P.half_bits, pkey);
                 b.y = G.row_ptr[b.x];
@@ -245,29 +242,29 @@ __global__ void __launch_bounds__(NT, 1) sweep_fast_kernel(const __grid_constant
                 b.w = G.degidx[b.x];
             }
             __syncwarp();
-            sh_st_v4(batch_base + ((k0 + lane) & 63u) * 16u, b);
+            if (lane < 16u) sh_st_v4(batch_base + ((k0 + lane) & 31u) * 16u, b);
             __syncwarp();
         };
         auto load_nbr = [&](uint32_t k) -> uint32_t {   // neighbour ids of the vertex in slot k (lane e = neighbour e, 0 past the degree)
-            const uint4 b = sh_ld_v4(batch_base + (k & 63u) * 16u);
+            const uint4 b = sh_ld_v4(batch_base + (k & 31u) * 16u);
             return (lane < b.z) ? G.col[b.y + lane] : 0u;
         };
         auto prefetch_rows = [&](uint32_t k, uint32_t nbr) {   // label rows the vertex in slot k will gather
-            const uint4 b = sh_ld_v4(batch_base + (k & 63u) * 16u);
+            const uint4 b = sh_ld_v4(batch_base + (k & 31u) * 16u);
             const uint32_t vtx = (lane < b.z) ? nbr : b.x;     // lanes past the degree: the vertex's own label
             asm volatile("{\n\t.reg .u64 a;\n\tmad.wide.u32 a, %0, %1, %2;\n\tprefetch.global.L2 [a];\n\t}" :: "r"(vtx), "r"(C), "l"(LAB8));
         };
         uint32_t nbr1 = 0, nbr2 = 0, nbr0 = 0;
         if (i_first < P.pos_end) {
             refill(0);
-            refill(32);
+            refill(16);
             nbr0 = load_nbr(0);
             nbr1 = load_nbr(1);
             prefetch_rows(0, nbr0);
         }
         for (uint32_t ib = i_first, k = 0; ib < P.pos_end; ib += stride, ++k, nbr0 = nbr1, nbr1 = nbr2) {
-            if (k >= 32u && (k & 31u) == 0) refill(k + 32u);   // the ring half holding slots k-32 .. k-1 is free
-            const uint4 cur = sh_ld_v4(batch_base + (k & 63u) * 16u);
+            if (k >= 16u && (k & 15u) == 0) refill(k + 16u);   // the ring half holding slots k-16 .. k-1 is free
+            const uint4 cur = sh_ld_v4(batch_base + (k & 31u) * 16u);
             const uint32_t v = cur.x, d = cur.z, didx = cur.w;
             nbr2 = load_nbr(k + 2);
             prefetch_rows(k + 1, nbr1);
@@ -292,7 +289,7 @@ __global__ void __launch_bounds__(NT, 1) sweep_fast_kernel(const __grid_constant
 
             // ---- proposal (single_vertex_change), branch-free ----
             const int e_t = sh_ld(Ep_base + tq * 128u);
-            const float inv_t = sh_ld_f32(inv_base + tq * 128u);
+            const float inv_t = f_rcp((float)e_t + epsK);
             // U < eps K / (e_t + eps K), both sides scaled by 2^32 (the conversion saturates at 2^32 - 1)
             const bool uniform_pick = (d == 0) || (ry < __float2uint_rz(epsK32 * inv_t));
             const uint32_t sg = mulhi32(rz, K);      // uniform over ALL K blocks (either type)
@@ -341,7 +338,7 @@ __global__ void __launch_bounds__(NT, 1) sweep_fast_kernel(const __grid_constant
                 const uint32_t cnt1 = cnt + 1u;
                 sh_st_u8(ha, cnt1);
                 const int m_r = sh_ld(Mr + t * ST), m_s = sh_ld(Ms + t * ST);
-                facc_edge(A, m_r, m_s, (int)cnt1, sh_ld_f32(inv_base + t * 128u));
+                facc_edge(A, m_r, m_s, (int)cnt1, f_rcp((float)sh_ld(Ep_base + t * 128u) + epsK));
             };
             const uint32_t n_ch = (d + 3u) >> 2;
             if (n_ch) gather4(t0, t1, t2, t3);

@@ -287,3 +287,31 @@ def test_k32_specialised_kernel(host):
     for k, c in enumerate((0, 95)):
         assert abs((f2[c] - f1[c]) - (pool.entropy_accum(c) - d0[k])) <= 1e-6 * abs(f1[c])
     check_invariants(pool, edges, na, nb, [0, 95])
+
+
+def test_fp32_kernel_is_selected_and_matches_double_statistically(host):
+    """The default parallel path is the fp32 kernel (sweep_fast.cuh) where it applies; BISBM_PRECISION_FP64 switches
+    the same pool to the double kernel.  The two use different draw streams, so the comparison is statistical:
+    final description length and acceptance of 96 + 96 strictly sequential chains on the oracle-parity workload."""
+    from scipy.stats import ks_2samp
+    g = load_golden("c2_const_k46")
+    na, nb, edges, mb = g["na"], g["nb"], g["edges"], g["labels0"]
+    n = na + nb
+    graph = host.Graph(edges, na, nb)
+    R = 96
+    out = {}
+    for prec, want_kernel in (("fp32", 2), ("fp64", 1)):
+        pool = host.ChainPool(graph, np.tile(mb, (R, 1)), 4, 6, 1.0)
+        pool.set_precision(prec)
+        seeds = np.arange(R, dtype=np.uint64) + 4242
+        pool.randomize(seeds)
+        acc, _ = pool.anneal("abrupt_cool", 1e5, 0.0, 200 * n, 10 ** 9, seeds, max_inflight=1)
+        kern, wpc, cpg, sl = pool.sweep_info()
+        assert kern == want_kernel and cpg == 1
+        check_invariants(pool, edges, na, nb, [0, R - 1])
+        out[prec] = (pool.entropy(), acc)
+    p_ent = ks_2samp(out["fp32"][0], out["fp64"][0]).pvalue
+    p_acc = ks_2samp(out["fp32"][1], out["fp64"][1]).pvalue
+    print("fp32 vs fp64: entropy %.1f / %.1f (KS p=%.3f), acceptance %.4f / %.4f (KS p=%.3f)" % (
+        out["fp32"][0].mean(), out["fp64"][0].mean(), p_ent, out["fp32"][1].mean(), out["fp64"][1].mean(), p_acc))
+    assert p_ent > 0.001 and p_acc > 0.001
