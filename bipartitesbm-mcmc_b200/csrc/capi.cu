@@ -341,16 +341,25 @@ int plan_sweep(bisbm_handle* h, uint32_t type, uint32_t max_inflight, LaunchPlan
     lp->hist_bytes = (int)hb;
     const size_t budget = 220 * 1024;
     lp->smem = sweep_smem_bytes(true, h->KA, h->KB, type, 16, hb) <= budget && h->KA <= 256 && h->KB <= 256;
-    // fp32 throughput kernel: staged counts, u8 histogram bins; warps per CTA (one CTA per SM): 24 measures best
-    // (80 registers per thread), fewer when shared memory is short
-    const size_t budget_fast = 227 * 1024;
+    // fp32 throughput kernel: staged counts, u8 histogram bins.  Warps per CTA (one CTA per SM): what matters most
+    // is the L1 that is left -- the kernel's spill slots and the log q expansions live there -- so take the most
+    // warps (24, 20, 16) whose shared memory still fits the 164 KB carve-out (92 KB of L1); Ka = Kb = 32 gets 16
+    // warps x 128 registers (measured: 1.03e10 moves/s against 9.8e9 with 24 warps and a 60 KB L1).  If nothing
+    // fits 164 KB, the most warps that fit at all.
+    const size_t budget_fast = 227 * 1024, budget_l1 = 163 * 1024;
     uint32_t wpc = 32;
     lp->fast = false;
     if (lp->smem && hb == 1 && h->precision == 0 && !getenv("BISBM_PRECISE")) {
-        uint32_t want = 24;
-        if (const char* e = getenv("BISBM_WPC")) { int w = atoi(e); if (w == 16 || w == 20 || w == 24 || w == 32) want = (uint32_t)w; }  // tuning knob
-        for (uint32_t w : {want, 20u, 16u})
-            if (w <= want && sweep_fast_smem_bytes(h->KA, h->KB, type, w) <= budget_fast) { lp->fast = true; wpc = w; break; }
+        uint32_t pick = 0;
+        for (uint32_t w : {24u, 20u, 16u})
+            if (!pick && sweep_fast_smem_bytes(h->KA, h->KB, type, w) <= budget_l1) pick = w;
+        for (uint32_t w : {24u, 20u, 16u})
+            if (!pick && sweep_fast_smem_bytes(h->KA, h->KB, type, w) <= budget_fast) pick = w;
+        if (const char* e = getenv("BISBM_WPC")) {   // tuning knob
+            const int w = atoi(e);
+            if ((w == 16 || w == 18 || w == 20 || w == 24 || w == 32) && sweep_fast_smem_bytes(h->KA, h->KB, type, (uint32_t)w) <= budget_fast) pick = (uint32_t)w;
+        }
+        if (pick) { lp->fast = true; wpc = pick; }
     }
     if (!lp->fast)
         if (const char* e = getenv("BISBM_WPC")) { int w = atoi(e); wpc = (w == 16 || w == 24) ? (uint32_t)w : 32; }  // tuning knob
@@ -411,9 +420,7 @@ int launch_sweep_fast_nt(bisbm_handle* h, const SweepParams& P, const LaunchPlan
         attr_set = true;
     }
     const unsigned grid = P.n_groups * lp.ctas_per_group;
-    size_t smem = lp.smem_bytes;
-    if (const char* e = getenv("BISBM_SMEM_PAD")) smem = std::min<size_t>(227 * 1024, smem + (size_t)atoi(e));  // experiment: shrink L1
-    sweep_fast_kernel<KF, TYPE, NT><<<grid, NT, smem, h->stream>>>(P);
+    sweep_fast_kernel<KF, TYPE, NT><<<grid, NT, lp.smem_bytes, h->stream>>>(P);
     CU(cudaGetLastError());
     h->lab32_stale = true;
     return BISBM_OK;
@@ -424,6 +431,7 @@ int launch_sweep_fast(bisbm_handle* h, const SweepParams& P, const LaunchPlan& l
     if (lp.wpc == 32) return launch_sweep_fast_nt<KF, TYPE, 1024>(h, P, lp);
     if (lp.wpc == 24) return launch_sweep_fast_nt<KF, TYPE, 768>(h, P, lp);
     if (lp.wpc == 20) return launch_sweep_fast_nt<KF, TYPE, 640>(h, P, lp);
+    if (lp.wpc == 18) return launch_sweep_fast_nt<KF, TYPE, 576>(h, P, lp);
     return launch_sweep_fast_nt<KF, TYPE, 512>(h, P, lp);
 }
 

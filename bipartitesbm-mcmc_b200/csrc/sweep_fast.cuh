@@ -200,12 +200,8 @@ __global__ void __launch_bounds__(NT, 1) sweep_fast_kernel(const __grid_constant
     asm volatile("" : "+l"(LAB8));
     auto lab_ld = [&](uint32_t vtx) -> uint32_t {     // label of vertex vtx in this lane's chain
         uint32_t x;
-#ifdef BISBM_X_LAB_CA
-        asm("{\n\t.reg .u64 a;\n\tmad.wide.u32 a, %1, %2, %3;\n\tld.global.u8 %0, [a];\n\t}" : "=r"(x) : "r"(vtx), "r"(C), "l"(LAB8));
-#else
         // .cg: label rows have no reuse in L1; keeping them out leaves the L1 to the log q expansions and the CSR rows
         asm("{\n\t.reg .u64 a;\n\tmad.wide.u32 a, %1, %2, %3;\n\tld.global.cg.u8 %0, [a];\n\t}" : "=r"(x) : "r"(vtx), "r"(C), "l"(LAB8));
-#endif
         return x;
     };
     auto lab_st = [&](uint32_t vtx, uint32_t x) {
