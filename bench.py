@@ -205,7 +205,7 @@ def main():
     ka = kb = args.k
     workload = "planted bipartite SBM %d nodes / %d edges, Ka=Kb=%d, %d chains/GPU, T=1, eps=1" % (n, args.edges, ka, args.chains)
     config = {"workload": workload, "sweeps_per_step": args.sweeps_per_step, "chains_per_gpu": args.chains,
-              "l2": "inputs larger than L2 (labels %.0f MB, CSR %.0f MB per GPU)" % (n * args.chains * 4 / 1e6,
+              "l2": "inputs larger than L2 (labels %.0f MB as gathered u8, CSR %.0f MB per GPU)" % (n * args.chains / 1e6,
                                                                                       args.edges * 8 / 1e6),
               "parallelism": "chains sharded over %d GPU(s), graph replicated" % world}
 
@@ -359,7 +359,7 @@ def main():
                              "alg_bytes_per_launch": alg_bytes_per_launch,
                              "avg_launch_ms": ev_ms / sweep_launches, "peak_source": peak_src,
                              "sweep_kernel_launches": int(sweep_launches),
-                             "note": "CUDA events on libbisbm's stream around each step; they also span the logq_refresh / bookkeep launches and the 1 MB count copies between slices (<1% of device time, profiles/r01_launch_shares.txt)"},
+                             "note": "CUDA events on libbisbm's stream around each step; they also span the logq_refresh / bookkeep launches and the 1 MB count copies between slices (<1% of device time, profiles/r01c_launch_shares.txt)"},
                 "e2e": {"value": e2e_value, "unit": "moves/s", "h2d_bytes_per_step": C * n * 4, "d2h_bytes_per_step": C * n * 4},
                 "gpu_launches": int(launches), "clocks": clocks}
         traffic_file = os.path.join(ROOT, "profiles", "sweep_kernel_traffic.json")
