@@ -253,6 +253,22 @@ int rebuild_counts(bisbm_handle* h) {
     CU(cudaMemsetAsync(h->d_e, 0, (size_t)h->C * KK * sizeof(int32_t), h->stream));
     CU(cudaMemsetAsync(h->d_nr, 0, (size_t)h->C * KK * sizeof(int32_t), h->stream));
     CU(cudaMemsetAsync(h->d_eta, 0, (size_t)h->C * KK * h->W * sizeof(int32_t), h->stream));
+    const size_t staged_bytes = ((size_t)h->KA * h->KB + KK) * 128;
+    if (staged_bytes <= 200 * 1024 && h->n >= 4096) {
+        // m_rs / n_r accumulated per CTA in shared memory (the 2E * C atomics of compute_m stay on chip)
+        static bool attr_set = false;
+        if (!attr_set) {
+            CU(cudaFuncSetAttribute(build_counts_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr_set = true;
+        }
+        const uint32_t n_groups = h->C / 32;
+        const uint32_t cpg = std::max<uint32_t>(1, (uint32_t)h->sm_count / n_groups);
+        build_counts_staged_kernel<<<n_groups * cpg, 1024, staged_bytes, h->stream>>>(gview(h), sview(h), h->n_chains, cpg);
+        const uint32_t tot = h->n_chains * (uint32_t)KK;
+        build_e_kernel<<<(tot + 255) / 256, 256, 0, h->stream>>>(sview(h), h->n_chains);
+        CU(cudaGetLastError());
+        return BISBM_OK;
+    }
     const uint32_t wpc = 8;
     const uint64_t warps = (uint64_t)h->n * (h->C / 32);
     if (warps) {

@@ -37,6 +37,45 @@ __global__ void build_counts_kernel(GraphView G, StateView S, uint32_t n_chains)
     }
 }
 
+// The same with m_rs and n_r accumulated per CTA in shared memory (one chain group per CTA, [entry][lane] like the
+// sweep kernels) and added to the global counts once at the end: 2E * C global atomics become shared-memory ones.
+// Used when the group's m_rs fits; eta (K x W x 32 per group) still goes straight to global memory.
+// grid = n_groups * ctas_per_group, dynamic shared memory = (KA*KB + KA+KB) * 128 bytes.
+__global__ void __launch_bounds__(1024, 1) build_counts_staged_kernel(GraphView G, StateView S, uint32_t n_chains,
+                                                                      uint32_t ctas_per_group) {
+    extern __shared__ __align__(16) int32_t sm_counts[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    const uint32_t n_groups = S.C / 32;
+    const uint32_t group = blockIdx.x % n_groups, cta = blockIdx.x / n_groups;
+    const uint32_t KA = S.KA, KB = S.KB, W = S.W, KK = KA + KB;
+    int32_t* const sM = sm_counts;
+    int32_t* const sN = sM + KA * KB * 32;
+    for (uint32_t i = threadIdx.x; i < (KA * KB + KK) * 32; i += blockDim.x) sm_counts[i] = 0;
+    __syncthreads();
+    const uint32_t c = group * 32 + lane;
+    const bool live = c < n_chains;
+    int32_t* const gETA = S.eta + (size_t)group * KK * W * GROUP + lane;
+    for (uint32_t v = cta * wpc + warp; v < G.n; v += ctas_per_group * wpc) {
+        if (!live) continue;
+        const bool tb = v >= G.na;
+        const uint32_t b = (uint32_t)S.labels[(size_t)v * S.C + c];
+        const uint32_t slot = (tb ? KA : 0) + b;
+        atomicAdd(&sN[slot * 32 + lane], 1);
+        atomicAdd(&gETA[((size_t)slot * W + G.degidx[v]) * GROUP], 1);
+        if (!tb) {
+            int32_t* const row = sM + (b * KB) * 32 + lane;
+            const uint32_t e1 = G.row_ptr[v + 1];
+            for (uint32_t e = G.row_ptr[v]; e < e1; ++e)
+                atomicAdd(&row[(uint32_t)S.labels[(size_t)G.col[e] * S.C + c] * 32], 1);
+        }
+    }
+    __syncthreads();
+    int32_t* const gM = S.m + (size_t)group * KA * KB * GROUP;
+    int32_t* const gN = S.nr + (size_t)group * KK * GROUP;
+    for (uint32_t i = threadIdx.x; i < KA * KB * 32; i += blockDim.x) if (sM[i]) atomicAdd(&gM[i], sM[i]);
+    for (uint32_t i = threadIdx.x; i < KK * 32; i += blockDim.x) if (sN[i]) atomicAdd(&gN[i], sN[i]);
+}
+
 __global__ void build_e_kernel(StateView S, uint32_t n_chains) {  // compute_m_r
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t KA = S.KA, KB = S.KB;
