@@ -315,3 +315,36 @@ def test_fp32_kernel_is_selected_and_matches_double_statistically(host):
     print("fp32 vs fp64: entropy %.1f / %.1f (KS p=%.3f), acceptance %.4f / %.4f (KS p=%.3f)" % (
         out["fp32"][0].mean(), out["fp64"][0].mean(), p_ent, out["fp32"][1].mean(), out["fp64"][1].mean(), p_acc))
     assert p_ent > 0.001 and p_acc > 0.001
+
+
+def test_full_size_c3_properties(host):
+    """BASELINE configs[2] at FULL size (1M nodes / 10M edges, Ka = Kb = 32, 256 chains on one GPU) through
+    size-independent properties: after sweeps of the default plan (fp32 kernel, 18 CTAs per chain group, slices of
+    n/64) the device counts of any chain equal a from-scratch rebuild from its labels (m_rs, e_r, n_r, eta -- so no
+    delta was lost or applied twice across the 128 slice launches of a sweep), every block stays non-empty, the
+    accumulated dS tracks the true change of the description length, and chains started from different
+    randomisations stay different."""
+    na = nb = 500000
+    ka = kb = 32
+    edges = planted(na, nb, ka, kb, 10_000_000, 0)
+    graph = host.Graph(edges, na, nb)
+    C = 256
+    lab0 = planted_labels(na, nb, ka, kb)
+    pool = host.ChainPool(graph, np.broadcast_to(lab0, (C, na + nb)), ka, kb, 1.0)
+    seeds = np.arange(C, dtype=np.uint64) + 7
+    pool.randomize(seeds)
+    e1 = pool.entropy()
+    acc, sw = pool.anneal("constant", 1.0, 0.0, 2 * (na + nb), 10 ** 18, seeds)
+    kern, wpc, cpg, sl = pool.sweep_info()
+    assert kern == 2 and cpg * (C // 32) <= 148 and sl == na // 64
+    assert (sw == 2).all() and (acc > 0.5).all() and (acc < 1.0).all()
+    check_invariants(pool, edges, na, nb, [0, 131, 255])
+    e2 = pool.entropy()
+    for c in (0, 131, 255):
+        d_true, d_acc = e2[c] - e1[c], pool.entropy_accum(c)
+        assert abs(d_true - d_acc) <= 0.10 * abs(d_true) + 50.0
+    l0, l1 = pool.labels(0), pool.labels(255)
+    assert (l0 != l1).mean() > 0.5
+    ms, launches, moves = pool.last_timing()
+    assert moves == 2 * (na + nb) * C
+    print("C3 full size: %.3e moves/s (device events), acceptance %.4f" % (moves / (ms * 1e-3), acc.mean()))
