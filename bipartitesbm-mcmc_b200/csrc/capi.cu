@@ -395,7 +395,12 @@ int plan_sweep(bisbm_handle* h, uint32_t type, uint32_t max_inflight, LaunchPlan
     lp->wpc = wpc;
     lp->warps_used = (cpg == 1) ? std::max<uint32_t>(1, std::min<uint32_t>(wpc, std::min<uint32_t>(inflight, std::max<uint32_t>(nv, 1)))) : wpc;
     // slices only exist for staged counts shared by several CTAs; global counts are live for everybody
-    if (lp->smem && cpg > 1) lp->slice = std::max<uint32_t>(cpg * wpc, std::min<uint32_t>(inflight, nv));
+    // a whole number of vertices per warp: a slice of 7812 over 288 warps gives 36 warps a 28th vertex and
+    // everybody else 4 % of waiting at the end of every launch
+    if (lp->smem && cpg > 1) {
+        lp->slice = std::max<uint32_t>(cpg * wpc, std::min<uint32_t>(inflight, nv));
+        if (!getenv("BISBM_RAGGED_SLICE")) lp->slice = std::max<uint32_t>(cpg * wpc, lp->slice / (cpg * wpc) * (cpg * wpc));
+    }
     else lp->slice = std::max<uint32_t>(nv, 1);
     lp->smem_bytes = lp->fast ? sweep_fast_smem_bytes(h->KA, h->KB, type, wpc)
                               : sweep_smem_bytes(lp->smem, h->KA, h->KB, type, wpc, hb);

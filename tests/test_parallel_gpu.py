@@ -321,7 +321,7 @@ def test_full_size_c3_properties(host):
     """BASELINE configs[2] at FULL size (1M nodes / 10M edges, Ka = Kb = 32, 256 chains on one GPU) through
     size-independent properties: after sweeps of the default plan (fp32 kernel, 18 CTAs per chain group, slices of
     n/64) the device counts of any chain equal a from-scratch rebuild from its labels (m_rs, e_r, n_r, eta -- so no
-    delta was lost or applied twice across the 128 slice launches of a sweep), every block stays non-empty, the
+    delta was lost or applied twice across the ~130 slice launches of a sweep), every block stays non-empty, the
     accumulated dS tracks the true change of the description length, and chains started from different
     randomisations stay different."""
     na = nb = 500000
@@ -336,7 +336,8 @@ def test_full_size_c3_properties(host):
     e1 = pool.entropy()
     acc, sw = pool.anneal("constant", 1.0, 0.0, 2 * (na + nb), 10 ** 18, seeds)
     kern, wpc, cpg, sl = pool.sweep_info()
-    assert kern == 2 and cpg * (C // 32) <= 148 and sl == na // 64
+    # slices: at most n/64 vertices (the default staleness bound) and a whole number of vertices per warp
+    assert kern == 2 and cpg * (C // 32) <= 148 and na // 64 - cpg * wpc < sl <= na // 64 and sl % (cpg * wpc) == 0
     assert (sw == 2).all() and (acc > 0.5).all() and (acc < 1.0).all()
     check_invariants(pool, edges, na, nb, [0, 131, 255])
     e2 = pool.entropy()
