@@ -349,3 +349,36 @@ def test_full_size_c3_properties(host):
     ms, launches, moves = pool.last_timing()
     assert moves == 2 * (na + nb) * C
     print("C3 full size: %.3e moves/s (device events), acceptance %.4f" % (moves / (ms * 1e-3), acc.mean()))
+
+
+@pytest.mark.parametrize("schedule,p0,p1", [("exponential", 2.0, 0.999), ("linear", 1.5, 0.0003), ("logarithmic", 1.0, 2.0)])
+def test_cooling_schedules_match_oracle_on_southern_women(host, schedule, p0, p1):
+    """BASELINE configs[0] (southernWomen, K = 5 + 5, eps = 1e-3) under the three time-dependent cooling schedules:
+    128 oracle chains vs 128 GPU chains (n = 32, so every GPU chain is strictly sequential), randomised starts,
+    150 sweeps.  Two-sample KS on the final description length and on the acceptance ratio: the temperature of
+    every step, the T -> 0 handling and the fp32 accept test have to agree with the reference's anneal()."""
+    from scipy.stats import ks_2samp
+    g = load_golden("c1_seed1")
+    na, nb, edges, lab0 = g["na"], g["nb"], g["edges"], g["labels0"]
+    n = na + nb
+    ka, kb = int(g["ka"]), int(g["kb"])
+    R, sweeps = 128, 150
+    ent_o, acc_o = [], []
+    for s in range(R):
+        o = port.PortChain(n, na, nb, edges, lab0, ka, kb, 1e-3, 5000 + s, 6000 + s)
+        o.init(True)
+        acc_o.append(o.anneal(schedule, p0, p1, sweeps * n, 10 ** 9))
+        ent_o.append(o.entropy())
+    graph = host.Graph(edges, na, nb)
+    pool = host.ChainPool(graph, np.tile(lab0, (R, 1)), ka, kb, 1e-3)
+    seeds = np.arange(R, dtype=np.uint64) + 99
+    pool.randomize(seeds)
+    acc_g, sw = pool.anneal(schedule, p0, p1, sweeps * n, 10 ** 9, seeds)
+    assert (sw == sweeps).all()
+    check_invariants(pool, edges, na, nb, [0, R - 1])
+    ent_g = pool.entropy()
+    p_ent = ks_2samp(ent_o, ent_g).pvalue
+    p_acc = ks_2samp(acc_o, acc_g).pvalue
+    print("%s: entropy oracle %.2f+-%.2f gpu %.2f+-%.2f p=%.3f | acceptance %.4f %.4f p=%.3f" % (
+        schedule, np.mean(ent_o), np.std(ent_o), np.mean(ent_g), np.std(ent_g), p_ent, np.mean(acc_o), np.mean(acc_g), p_acc))
+    assert p_ent > 0.001 and p_acc > 0.001
