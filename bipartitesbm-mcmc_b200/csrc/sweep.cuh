@@ -230,7 +230,14 @@ __host__ __device__ inline size_t sweep_smem_bytes(bool smem, uint32_t KA, uint3
 __device__ __forceinline__ void copy_i4(int32_t* dst, const int32_t* src, uint32_t n_int) {
     const int4* s4 = reinterpret_cast<const int4*>(src);
     int4* d4 = reinterpret_cast<int4*>(dst);
-    for (uint32_t i = threadIdx.x; i < n_int / 4; i += blockDim.x) d4[i] = s4[i];
+    const uint32_t n4 = n_int / 4;
+    for (uint32_t i0 = threadIdx.x; i0 < n4; i0 += 4 * blockDim.x) {   // four loads in flight per thread
+        int4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const uint32_t i = i0 + u * blockDim.x; if (i < n4) v[u] = s4[i]; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const uint32_t i = i0 + u * blockDim.x; if (i < n4) d4[i] = v[u]; }
+    }
 }
 
 // ---- explicit shared-space accesses on 32-bit shared addresses (ld/st/red.shared): the

@@ -462,11 +462,24 @@ __global__ void __launch_bounds__(NT, 1) sweep_fast_kernel(const __grid_constant
         const int4* const g4 = reinterpret_cast<const int4*>(gM);
         unsigned long long* const n8 = reinterpret_cast<unsigned long long*>(nM);
         const uint32_t n4 = KA * KB * 8;
-        for (uint32_t i = threadIdx.x; i < n4; i += blockDim.x) {
-            const int4 a = g4[i], b = s4[i];
-            const int d0 = b.x - a.x, d1 = b.y - a.y, d2 = b.z - a.z, d3 = b.w - a.w;
-            if (d0 | d1) atomicAdd(&n8[2 * i], (unsigned long long)((long long)d0 + ((long long)d1 << 32)));
-            if (d2 | d3) atomicAdd(&n8[2 * i + 1], (unsigned long long)((long long)d2 + ((long long)d3 << 32)));
+        // four base loads in flight per thread (the loop is a chain of L2 round trips otherwise)
+        for (uint32_t i0 = threadIdx.x; i0 < n4; i0 += 4 * blockDim.x) {
+            int4 a[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t i = i0 + u * blockDim.x;
+                a[u] = (i < n4) ? __ldcg(g4 + i) : make_int4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t i = i0 + u * blockDim.x;
+                if (i < n4) {
+                    const int4 b = s4[i];
+                    const int d0 = b.x - a[u].x, d1 = b.y - a[u].y, d2 = b.z - a[u].z, d3 = b.w - a[u].w;
+                    if (d0 | d1) atomicAdd(&n8[2 * i], (unsigned long long)((long long)d0 + ((long long)d1 << 32)));
+                    if (d2 | d3) atomicAdd(&n8[2 * i + 1], (unsigned long long)((long long)d2 + ((long long)d3 << 32)));
+                }
+            }
         }
         for (uint32_t i = threadIdx.x; i < kown_max * 32; i += blockDim.x) {
             const int dlt = sEo[i] - gE[own_off * 32 + i];
