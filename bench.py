@@ -195,6 +195,10 @@ def main():
     ap.add_argument("--sweeps-per-step", type=int, default=SWEEPS_PER_STEP)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-moves", type=int, default=2000000, help="CPU sample: moves per process per step")
+    ap.add_argument("--precision", default="fp64", choices=["fp64", "fp32"],
+                    help="arithmetic of a move: fp64 like the reference's transition_ratio (headline) or fp32")
+    ap.add_argument("--inflight-div", type=int, default=0, help="in-flight bound = half sweep / this (0: library default)")
+    ap.add_argument("--no-fp32-extra", action="store_true", help="skip the short fp32 run reported under 'extra'")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -229,7 +233,7 @@ def main():
         os.unlink(path)
         value = float(np.mean([v for v, _, _ in vals]))
         ms = float(np.mean([w for _, _, w in vals])) * 1e3
-        sample = "%d processes x %d moves of anneal() (T=1) on the full %d-node / %d-edge graph, state build untimed" % (
+        sample = "%d processes x %d moves of anneal() (T=1) on the full %d-node / %d-edge graph, every step from a fresh randomised start (chain phase: first sweeps, acceptance ~0.93), state build untimed" % (
             procs, vals[0][1] // procs, n, args.edges)
         line = {"impl": "reference", "metric": "vertex-moves/sec", "value": value, "unit": "moves/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
@@ -257,6 +261,9 @@ def main():
     labels_host = torch.empty((C, n), dtype=torch.int32).pin_memory()
     labels_host.numpy().view(np.uint32)[:] = base[None, :]
     pool = host.ChainPool(graph, labels_host.numpy().view(np.uint32), ka, kb, 1.0)
+    pool.set_precision(args.precision)
+    if args.inflight_div:
+        pool.set_option("inflight_div", args.inflight_div)
     seeds = pkg.dist.chain_seeds(0, chain_ids)
     pool.randomize(seeds)
     duration = args.sweeps_per_step * n
@@ -278,17 +285,19 @@ def main():
     barrier()
     sampler.start()
     t0 = time.perf_counter()
-    ev_ms, launches, moves, accs = 0.0, 0, 0, []
+    ev_ms, launches, moves, accs, sweep_launches = 0.0, 0, 0, [], 0
     for _ in range(args.steps):
         acc, _sw = pool.anneal("constant", 1.0, 0.0, duration, 10 ** 18, seeds)
         ms_, la_, mv_ = pool.last_timing()
         ev_ms += ms_; launches += la_; moves += mv_; accs.append(float(acc.mean()))
+        sweep_launches += pool.sweep_launches()
     if world > 1:
         # the path's only collective: one all-reduce of the per-node marginal histogram
         pool.marginals_clear()
         pool.marginalize(0, 1, 1, seeds)          # one more sweep + the histogram accumulation
         ms_, la_, mv_ = pool.last_timing()
         ev_ms += ms_; launches += la_; moves += mv_
+        sweep_launches += pool.sweep_launches()
         hist = host.marginals_tensor(pool)
         pkg.dist.allreduce_marginals(hist)
     barrier()
@@ -304,11 +313,13 @@ def main():
     value = total_moves / wall_max
     acceptance = float(np.mean(accs))
     kern, wpc_, cpg_, slice_ = pool.sweep_info()
-    kernel_name = {0: "sweep_kernel<double, counts in L2>", 1: "sweep_kernel<double, staged counts>",
-                   2: "sweep_fast_kernel<fp32, staged counts>"}[kern]
+    kernel_names = {0: "sweep_kernel<double, counts in L2>", 1: "sweep_kernel<double, staged counts> (round 1)",
+                    2: "sweep2_kernel<float, staged counts>", 3: "sweep2_kernel<double, staged counts>"}
+    kernel_name = kernel_names[kern]
     config["sweep_plan"] = {"kernel": kernel_name, "warps_per_cta": wpc_, "ctas_per_chain_group": cpg_,
-                            "slice_vertices_per_launch": slice_}
-    dtype = "f32+int32 (dS summed in f64)" if kern >= 2 else "f64+int32"
+                            "slice_vertices_per_launch": slice_, "max_inflight": slice_,
+                            "inflight_bound": "half sweep / %d" % (args.inflight_div or 64)}
+    dtype = "f32+int32 (dS summed in f64)" if kern == 2 else "f64+int32"
 
     # -------- e2e: host buffers in, host buffers out, every step
     out_host = torch.empty((C, n), dtype=torch.int32).pin_memory()
@@ -336,6 +347,25 @@ def main():
         dist.all_reduce(me, op=dist.ReduceOp.SUM)
     e2e_value = float(me[0]) / float(te[0])
 
+    # -------- extra: the same pool with fp32 move arithmetic (short run, state resident), for the record
+    extra = {}
+    if not args.no_fp32_extra and args.precision == "fp64":
+        pool.set_precision("fp32")
+        pool.anneal("constant", 1.0, 0.0, duration, 10 ** 18, seeds)
+        ms32, mv32 = 0.0, 0
+        for _ in range(2):
+            pool.anneal("constant", 1.0, 0.0, duration, 10 ** 18, seeds)
+            ms_, _la, mv_ = pool.last_timing()
+            ms32 += ms_; mv32 += mv_
+        pool.set_precision("fp64")
+        t32 = torch.tensor([ms32], dtype=torch.float64, device="cuda")
+        m32 = torch.tensor([float(mv32)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t32, op=dist.ReduceOp.MAX)
+            dist.all_reduce(m32, op=dist.ReduceOp.SUM)
+        extra["fp32_move_arithmetic"] = {"value": float(m32[0]) / (float(t32[0]) * 1e-3), "unit": "moves/s",
+                                         "timing": "CUDA events, 2 steps, state resident", "kernel": kernel_names[2]}
+
     if rank == 0:
         peaks = {}
         try:
@@ -345,9 +375,9 @@ def main():
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
         bytes_per_move = 16.0 + 8.0 * (2.0 * args.edges / n) + 4.0 * acceptance
-        # dominant kernel = sweep_kernel; per-launch algorithmic bytes / average launch duration
-        # launches per sweep: 2 logq_refresh + 1 bookkeep + the sweep_kernel slice launches
-        sweep_launches = max(1, launches - 3 * args.sweeps_per_step * args.steps)
+        # dominant kernel = the sweep kernel; per-launch algorithmic bytes / average launch duration
+        # (the library counts its sweep-kernel launches; the rest are logq_refresh / bookkeep / next-base kernels)
+        sweep_launches = max(1, sweep_launches)
         alg_bytes_per_launch = bytes_per_move * (moves / sweep_launches)
         achieved = bytes_per_move * moves / (ev_ms * 1e-3) / 1e9
         line = {"metric": "vertex-moves/sec", "value": value, "unit": "moves/s", "n_gpus": world, "steps": args.steps,
@@ -359,9 +389,9 @@ def main():
                              "alg_bytes_per_launch": alg_bytes_per_launch,
                              "avg_launch_ms": ev_ms / sweep_launches, "peak_source": peak_src,
                              "sweep_kernel_launches": int(sweep_launches),
-                             "note": "CUDA events on libbisbm's stream around each step; they also span the logq_refresh / bookkeep launches and the 1 MB count copies between slices (<1% of device time, profiles/r01c_launch_shares.txt)"},
+                             "note": "CUDA events on libbisbm's stream around each step; they also span the small kernels between the sweep launches (log q refresh, bookkeeping, next-base initialisation: profiles/r02_launch_shares.txt)"},
                 "e2e": {"value": e2e_value, "unit": "moves/s", "h2d_bytes_per_step": C * n * 4, "d2h_bytes_per_step": C * n * 4},
-                "gpu_launches": int(launches), "clocks": clocks}
+                "gpu_launches": int(launches), "clocks": clocks, "extra": extra}
         traffic_file = os.path.join(ROOT, "profiles", "sweep_kernel_traffic.json")
         if os.path.exists(traffic_file):
             try:
@@ -377,7 +407,7 @@ def main():
                 v, mv, worst = run_cpu_sample(path, na, nb, ka, kb, args.cpu_moves, procs, kind)
                 os.unlink(path)
                 line["cpu_baseline"] = {"value": v, "unit": "moves/s", "cores": procs, "kind": kind,
-                                        "sample": "%d processes x %d moves of anneal() (T=1) on the full graph, %.1f s, state build untimed" % (
+                                        "sample": "%d processes x %d moves of anneal() (T=1) on the full graph from a fresh randomised start (acceptance ~0.93; the GPU arm is timed after its warm-up sweeps, acceptance in 'acceptance'), %.1f s, state build untimed" % (
                                             procs, mv // procs, worst)}
             except Exception as ex:  # the baseline is a reported number, never a reason to lose the bench line
                 line["cpu_baseline"] = {"value": None, "unit": "moves/s", "cores": 0, "kind": "unavailable", "sample": str(ex)[:200]}

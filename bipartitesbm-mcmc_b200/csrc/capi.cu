@@ -15,13 +15,14 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <set>
 #include <memory>
 #include <string>
 #include <vector>
 
 #include "replay.cuh"
 #include "sweep_aux.cuh"
-#include "sweep_fast.cuh"
+#include "sweep2.cuh"
 
 using namespace bisbm;
 
@@ -76,7 +77,9 @@ struct bisbm_handle {
     uint32_t *d_ka = nullptr, *d_kb = nullptr;
     int32_t *d_labels = nullptr, *d_labels_tmp = nullptr, *d_m = nullptr, *d_e = nullptr, *d_nr = nullptr,
             *d_eta = nullptr;
-    int32_t *d_m2 = nullptr, *d_e2 = nullptr;  // "next" count buffers of the sliced shared-memory sweep
+    int32_t *d_m2 = nullptr, *d_e2 = nullptr, *d_nr2 = nullptr;  // "next" count buffers of the sliced shared-memory sweep
+    int32_t* d_nr_live = nullptr;              // exact n_r counters of the blocks that could empty within one sliced launch
+    double* d_kat_out = nullptr;               // {dS, log accu_r} of bisbm_parallel_transition
     uint8_t* d_lab8 = nullptr;                 // u8 shadow of the labels for the shared-memory sweep
     double eps = 1.0;
     LogqExp* d_lq = nullptr;
@@ -94,11 +97,17 @@ struct bisbm_handle {
     // timing of the last parallel call
     double last_ms = 0.0;
     uint64_t last_launches = 0, last_moves = 0;
-    // move arithmetic of the parallel sweep: 0 = fp32 kernel where it applies (sweep_fast.cuh), 1 = double everywhere
-    int precision = 0;
+    // move arithmetic of the parallel sweep: double like the reference (default) or fp32 (sweep2.cuh)
+    int precision = BISBM_PRECISION_FP64;
+    // bisbm_set_option
+    int opt_kernel = -1;               // -1: automatic; KERN_L2 / KERN_STAGED_OLD force the round-1 double kernels
+    uint32_t opt_inflight_div = 64;    // default in-flight bound = half sweep / this
+    int opt_generic = 0;               // 1: never take the Ka = Kb = 32 specialisation
+    std::set<const void*> attr_done;   // kernels whose shared-memory limit is raised on this handle's device
+    uint64_t last_sweep_launches = 0;
     uint32_t last_wpc = 0, last_cpg = 0, last_slice = 0;   // launch plan of the last half sweep
-    int last_kernel = -1;                                   // 0 = double / counts in L2, 1 = double / staged counts, 2 = fp32 / staged counts
-    bool lab32_stale = false;   // the fp32 kernel only writes the u8 label shadow; i32 labels refreshed on demand
+    int last_kernel = -1;                                   // KERN_* of the last parallel call
+    bool lab32_stale = false;   // the staged kernels only write the u8 label shadow; i32 labels refreshed on demand
 };
 
 namespace {
@@ -111,7 +120,7 @@ void dfree(T*& p) {
 
 void free_chains(bisbm_handle* h) {
     dfree(h->d_ka); dfree(h->d_kb); dfree(h->d_labels); dfree(h->d_labels_tmp);
-    dfree(h->d_m); dfree(h->d_e); dfree(h->d_nr); dfree(h->d_eta); dfree(h->d_lq); dfree(h->d_lq_soa); dfree(h->d_m2); dfree(h->d_e2); dfree(h->d_lab8);
+    dfree(h->d_m); dfree(h->d_e); dfree(h->d_nr); dfree(h->d_eta); dfree(h->d_lq); dfree(h->d_lq_soa); dfree(h->d_m2); dfree(h->d_e2); dfree(h->d_nr2); dfree(h->d_nr_live); dfree(h->d_kat_out); dfree(h->d_lab8);
     dfree(h->d_seeds); dfree(h->d_active); dfree(h->d_accepted); dfree(h->d_u); dfree(h->d_sweeps);
     dfree(h->d_dS); dfree(h->d_entmin); dfree(h->d_ent_out); dfree(h->d_nactive); dfree(h->d_hist);
     for (auto& kv : h->replay) { dfree(kv.second.d_rs); dfree(kv.second.d_vlist); dfree(kv.second.d_kh); }
@@ -247,6 +256,15 @@ int need_chains(bisbm_handle* h) {
     return BISBM_OK;
 }
 
+// cudaFuncSetAttribute is per DEVICE and a handle lives on one device: remember per handle which kernels have
+// their dynamic shared memory limit raised
+int ensure_smem_attr(bisbm_handle* h, const void* fn, int bytes) {
+    if (h->attr_done.count(fn)) return BISBM_OK;
+    CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    h->attr_done.insert(fn);
+    return BISBM_OK;
+}
+
 int rebuild_counts(bisbm_handle* h) {
     const size_t KK = (size_t)h->KA + h->KB;
     CU(cudaMemsetAsync(h->d_m, 0, (size_t)h->C * h->KA * h->KB * sizeof(int32_t), h->stream));
@@ -256,11 +274,8 @@ int rebuild_counts(bisbm_handle* h) {
     const size_t staged_bytes = ((size_t)h->KA * h->KB + KK) * 128;
     if (staged_bytes <= 200 * 1024 && h->n >= 4096) {
         // m_rs / n_r accumulated per CTA in shared memory (the 2E * C atomics of compute_m stay on chip)
-        static bool attr_set = false;
-        if (!attr_set) {
-            CU(cudaFuncSetAttribute(build_counts_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            attr_set = true;
-        }
+        int rc = ensure_smem_attr(h, (const void*)build_counts_staged_kernel, 200 * 1024);
+        if (rc) return rc;
         const uint32_t n_groups = h->C / 32;
         const uint32_t cpg = std::max<uint32_t>(1, (uint32_t)h->sm_count / n_groups);
         build_counts_staged_kernel<<<n_groups * cpg, 1024, staged_bytes, h->stream>>>(gview(h), sview(h), h->n_chains, cpg);
@@ -334,59 +349,93 @@ uint64_t cold_steps(int schedule, float p0, float p1, uint64_t t0, uint64_t t1) 
     return t1 - hi;
 }
 
+// The reference validates the schedule parameters in main() (src/mcmc_main.cc:134-218); anneal() itself trusts
+// them.  The library rejects what would make a temperature negative or NaN anywhere in the call (a negative T turns
+// the accept rule of step() upside down and lets cross-type proposals through).
+int validate_schedule(int schedule, float p0, float p1, uint64_t duration) {
+    if (schedule < 0 || schedule > 4) return fail(BISBM_ERR_ARG, "unknown cooling schedule %d", schedule);
+    if (!std::isfinite(p0) || !std::isfinite(p1)) return fail(BISBM_ERR_ARG, "cooling schedule parameters must be finite");
+    const uint64_t last = duration ? duration - 1 : 0;
+    switch (schedule) {
+        case BISBM_EXPONENTIAL:
+            if (p0 < 0.f || p1 < 0.f) return fail(BISBM_ERR_ARG, "exponential schedule: T_0 and alpha must be >= 0");
+            break;
+        case BISBM_LINEAR:
+            if (p1 < 0.f || host_schedule(schedule, p0, p1, last) < 0.0 || p0 < 0.f)
+                return fail(BISBM_ERR_ARG, "linear schedule: T_0 - eta * t must stay >= 0 over the call");
+            break;
+        case BISBM_LOGARITHMIC:
+            if (p0 < 0.f || p1 < 0.f) return fail(BISBM_ERR_ARG, "logarithmic schedule: c and d must be >= 0");
+            break;
+        case BISBM_CONSTANT:
+            if (p0 < 0.f) return fail(BISBM_ERR_ARG, "constant schedule: temperature must be >= 0");
+            break;
+        default: break;
+    }
+    return BISBM_OK;
+}
+
+// kernels of the parallel sweep (bisbm_sweep_info reports which one ran)
+enum { KERN_L2 = 0, KERN_STAGED_OLD = 1, KERN_S2_F32 = 2, KERN_S2_F64 = 3 };
+
 struct LaunchPlan {
-    bool fast;                // fp32 kernel (sweep_fast.cuh)
-    bool smem;
+    int kernel;               // KERN_*
+    bool smem;                // counts staged in shared memory (every kernel except KERN_L2)
     int hist_bytes;           // 1, 2 or 4
-    uint32_t wpc;             // warps per CTA (blockDim / 32): 32 or 16 (fewer only when shared memory is short)
+    uint32_t wpc;             // warps per CTA (blockDim / 32)
     uint32_t warps_used;      // of which take vertices
     uint32_t ctas_per_group;
     uint32_t slice;           // positions of the visiting order per launch
     size_t smem_bytes;
 };
 
+const size_t kSmemMax = 227 * 1024;
+
+// Which kernel a parallel call uses -- decided ONCE for both half sweeps (the kernels keep different label
+// arrays current: the staged ones the u8 shadow, the L2 one the i32 labels), so asymmetric K can never mix them.
+int plan_kernel(const bisbm_handle* h, uint32_t* wpc_out) {
+    const uint32_t hb = h->max_degree <= 255u ? 1 : (h->max_degree <= 65535u ? 2 : 4);
+    *wpc_out = 32;
+    if (h->opt_kernel == KERN_L2) return KERN_L2;
+    const bool k8 = h->KA <= 256 && h->KB <= 256;
+    if (h->opt_kernel == KERN_STAGED_OLD) {
+        for (uint32_t w : {32u, 16u})
+            if (k8 && sweep_smem_bytes(true, h->KA, h->KB, 0, w, hb) <= 220 * 1024 &&
+                sweep_smem_bytes(true, h->KA, h->KB, 1, w, hb) <= 220 * 1024) { *wpc_out = w; return KERN_STAGED_OLD; }
+        return KERN_L2;
+    }
+    if (hb == 1 && k8) {
+        const uint32_t rs = h->precision == BISBM_PRECISION_FP32 ? 4u : 8u;
+        for (uint32_t w : {16u, 8u, 4u})
+            if (sweep2_layout(h->KA, h->KB, 0, w, rs).total <= kSmemMax && sweep2_layout(h->KA, h->KB, 1, w, rs).total <= kSmemMax) {
+                *wpc_out = w;
+                return rs == 4 ? KERN_S2_F32 : KERN_S2_F64;
+            }
+    }
+    return KERN_L2;
+}
+
 // How one half sweep is cut into launches.  `max_inflight` bounds the number of moves of one
 // chain that may be evaluated against counts that do not yet include each other:
 //   one CTA per chain group  -> warps_used concurrent moves (shared-memory counts are exact)
 //   several CTAs per group   -> one slice of the visiting order per launch (a CTA sees the other
 //                               CTAs' moves of the same slice only in the next launch)
-int plan_sweep(bisbm_handle* h, uint32_t type, uint32_t max_inflight, LaunchPlan* lp) {
+int plan_sweep(bisbm_handle* h, uint32_t type, uint32_t max_inflight, int kernel, uint32_t wpc, LaunchPlan* lp) {
     const uint32_t nv = type ? h->nb : h->na;
     const uint32_t n_groups = h->C / 32;
     const uint32_t hb = h->max_degree <= 255u ? 1 : (h->max_degree <= 65535u ? 2 : 4);
     lp->hist_bytes = (int)hb;
-    const size_t budget = 220 * 1024;
-    lp->smem = sweep_smem_bytes(true, h->KA, h->KB, type, 16, hb) <= budget && h->KA <= 256 && h->KB <= 256;
-    // fp32 throughput kernel: staged counts, u8 histogram bins.  Warps per CTA (one CTA per SM): what matters most
-    // is the L1 that is left -- the kernel's spill slots and the log q expansions live there -- so take the most
-    // warps (24, 20, 16) whose shared memory still fits the 164 KB carve-out (92 KB of L1); Ka = Kb = 32 gets 16
-    // warps x 128 registers (measured: 1.03e10 moves/s against 9.8e9 with 24 warps and a 60 KB L1).  If nothing
-    // fits 164 KB, the most warps that fit at all.
-    const size_t budget_fast = 227 * 1024, budget_l1 = 163 * 1024;
-    uint32_t wpc = 32;
-    lp->fast = false;
-    if (lp->smem && hb == 1 && h->precision == 0 && !getenv("BISBM_PRECISE")) {
-        uint32_t pick = 0;
-        for (uint32_t w : {24u, 20u, 16u})
-            if (!pick && sweep_fast_smem_bytes(h->KA, h->KB, type, w) <= budget_l1) pick = w;
-        for (uint32_t w : {24u, 20u, 16u})
-            if (!pick && sweep_fast_smem_bytes(h->KA, h->KB, type, w) <= budget_fast) pick = w;
-        if (const char* e = getenv("BISBM_WPC")) {   // tuning knob
-            const int w = atoi(e);
-            if ((w == 16 || w == 18 || w == 20 || w == 24 || w == 32) && sweep_fast_smem_bytes(h->KA, h->KB, type, (uint32_t)w) <= budget_fast) pick = (uint32_t)w;
-        }
-        if (pick) { lp->fast = true; wpc = pick; }
+    lp->kernel = kernel;
+    lp->smem = kernel != KERN_L2;
+    if (kernel == KERN_L2) {
+        wpc = 32;
+        if (sweep_smem_bytes(false, h->KA, h->KB, type, wpc, hb) > 220 * 1024) wpc = 16;
+        if (sweep_smem_bytes(false, h->KA, h->KB, type, wpc, hb) > 220 * 1024)
+            return fail(BISBM_ERR_ARG, "K too large for the shared-memory histogram");
     }
-    if (!lp->fast)
-        if (const char* e = getenv("BISBM_WPC")) { int w = atoi(e); wpc = (w == 16 || w == 24) ? (uint32_t)w : 32; }  // tuning knob
-    if (!lp->fast && sweep_smem_bytes(lp->smem, h->KA, h->KB, type, wpc, hb) > budget) wpc = 16;
-    if (!lp->fast && sweep_smem_bytes(lp->smem, h->KA, h->KB, type, wpc, hb) > budget)
-        return fail(BISBM_ERR_ARG, "K too large for the shared-memory histogram");
-    uint32_t inflight_div = 64;
-    if (const char* e = getenv("BISBM_INFLIGHT_DIV")) inflight_div = std::max(1, atoi(e));  // tuning knob
-    // default bound: 1/64 of the half sweep (staleness study) -- also on small graphs, where it means
+    // default bound: 1/inflight_div of the half sweep -- also on small graphs, where it means
     // fewer busy warps rather than a looser bound
-    const uint32_t inflight = max_inflight ? max_inflight : std::max<uint32_t>(1, nv / inflight_div);
+    const uint32_t inflight = max_inflight ? max_inflight : std::max<uint32_t>(1, nv / std::max<uint32_t>(1, h->opt_inflight_div));
     // CTAs per group: fill the SMs, but never more warps than the in-flight bound or the work allows
     uint32_t cpg = std::max<uint32_t>(1, (uint32_t)h->sm_count / n_groups);
     cpg = std::min<uint32_t>(cpg, std::max<uint32_t>(1, inflight / wpc));
@@ -394,134 +443,124 @@ int plan_sweep(bisbm_handle* h, uint32_t type, uint32_t max_inflight, LaunchPlan
     lp->ctas_per_group = cpg;
     lp->wpc = wpc;
     lp->warps_used = (cpg == 1) ? std::max<uint32_t>(1, std::min<uint32_t>(wpc, std::min<uint32_t>(inflight, std::max<uint32_t>(nv, 1)))) : wpc;
-    // slices only exist for staged counts shared by several CTAs; global counts are live for everybody
-    // a whole number of vertices per warp: a slice of 7812 over 288 warps gives 36 warps a 28th vertex and
-    // everybody else 4 % of waiting at the end of every launch
+    // slices only exist for staged counts shared by several CTAs; global counts are live for everybody.
+    // A whole number of vertices per warp keeps the CTAs' shares equal.
     if (lp->smem && cpg > 1) {
         lp->slice = std::max<uint32_t>(cpg * wpc, std::min<uint32_t>(inflight, nv));
-        if (!getenv("BISBM_RAGGED_SLICE")) lp->slice = std::max<uint32_t>(cpg * wpc, lp->slice / (cpg * wpc) * (cpg * wpc));
+        lp->slice = std::max<uint32_t>(cpg * wpc, lp->slice / (cpg * wpc) * (cpg * wpc));
     }
     else lp->slice = std::max<uint32_t>(nv, 1);
-    lp->smem_bytes = lp->fast ? sweep_fast_smem_bytes(h->KA, h->KB, type, wpc)
-                              : sweep_smem_bytes(lp->smem, h->KA, h->KB, type, wpc, hb);
+    if (kernel == KERN_S2_F32 || kernel == KERN_S2_F64)
+        lp->smem_bytes = sweep2_layout(h->KA, h->KB, type, wpc, kernel == KERN_S2_F32 ? 4u : 8u).total;
+    else
+        lp->smem_bytes = sweep_smem_bytes(lp->smem, h->KA, h->KB, type, wpc, hb);
     return BISBM_OK;
 }
 
 template <bool SMEM, typename HistT, int NT>
 int launch_sweep_t(bisbm_handle* h, const SweepParams& P, const LaunchPlan& lp) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        CU(cudaFuncSetAttribute(sweep_kernel<SMEM, HistT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        attr_set = true;
-    }
+    int rc = ensure_smem_attr(h, (const void*)sweep_kernel<SMEM, HistT, NT>, 220 * 1024);
+    if (rc) return rc;
     const unsigned grid = P.n_groups * lp.ctas_per_group;
     sweep_kernel<SMEM, HistT, NT><<<grid, NT, lp.smem_bytes, h->stream>>>(P);
     CU(cudaGetLastError());
     return BISBM_OK;
 }
 
-template <bool SMEM, typename HistT, int NT, int KF, int TYPE>
-int launch_sweep_fixed(bisbm_handle* h, const SweepParams& P, const LaunchPlan& lp) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        CU(cudaFuncSetAttribute(sweep_kernel<SMEM, HistT, NT, KF, TYPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        attr_set = true;
-    }
-    const unsigned grid = P.n_groups * lp.ctas_per_group;
-    sweep_kernel<SMEM, HistT, NT, KF, TYPE><<<grid, NT, lp.smem_bytes, h->stream>>>(P);
-    CU(cudaGetLastError());
-    return BISBM_OK;
-}
-
-template <int KF, int TYPE, int NT>
-int launch_sweep_fast_nt(bisbm_handle* h, const SweepParams& P, const LaunchPlan& lp) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        CU(cudaFuncSetAttribute(sweep_fast_kernel<KF, TYPE, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
-    }
-    const unsigned grid = P.n_groups * lp.ctas_per_group;
-    sweep_fast_kernel<KF, TYPE, NT><<<grid, NT, lp.smem_bytes, h->stream>>>(P);
-    CU(cudaGetLastError());
-    h->lab32_stale = true;
-    return BISBM_OK;
-}
-
-template <int KF, int TYPE>
-int launch_sweep_fast(bisbm_handle* h, const SweepParams& P, const LaunchPlan& lp) {
-    if (lp.wpc == 32) return launch_sweep_fast_nt<KF, TYPE, 1024>(h, P, lp);
-    if (lp.wpc == 24) return launch_sweep_fast_nt<KF, TYPE, 768>(h, P, lp);
-    if (lp.wpc == 20) return launch_sweep_fast_nt<KF, TYPE, 640>(h, P, lp);
-    if (lp.wpc == 18) return launch_sweep_fast_nt<KF, TYPE, 576>(h, P, lp);
-    return launch_sweep_fast_nt<KF, TYPE, 512>(h, P, lp);
-}
-
 template <bool SMEM, typename HistT>
 int launch_sweep_nt(bisbm_handle* h, const SweepParams& P, const LaunchPlan& lp) {
     if (lp.wpc == 32) return launch_sweep_t<SMEM, HistT, 1024>(h, P, lp);
-    if (lp.wpc == 24) return launch_sweep_t<SMEM, HistT, 768>(h, P, lp);
     return launch_sweep_t<SMEM, HistT, 512>(h, P, lp);
 }
 
 template <bool SMEM>
 int launch_sweep_h(bisbm_handle* h, const SweepParams& P, const LaunchPlan& lp) {
-    if constexpr (SMEM) {
-        if (lp.fast) {
-            if (h->KA == 32 && h->KB == 32 && !getenv("BISBM_GENERIC"))
-                return P.type ? launch_sweep_fast<32, 1>(h, P, lp) : launch_sweep_fast<32, 0>(h, P, lp);
-            return launch_sweep_fast<0, 0>(h, P, lp);
-        }
-        // compile-time strides for the common Ka = Kb = 32 pool (BASELINE configs[2])
-        if (lp.hist_bytes == 1 && lp.wpc == 32 && h->KA == 32 && h->KB == 32 && !getenv("BISBM_GENERIC"))
-            return P.type ? launch_sweep_fixed<true, uint8_t, 1024, 32, 1>(h, P, lp)
-                          : launch_sweep_fixed<true, uint8_t, 1024, 32, 0>(h, P, lp);
-    }
     if (lp.hist_bytes == 1) return launch_sweep_nt<SMEM, uint8_t>(h, P, lp);
     if (lp.hist_bytes == 2) return launch_sweep_nt<SMEM, uint16_t>(h, P, lp);
     return launch_sweep_nt<SMEM, uint32_t>(h, P, lp);
 }
 
+template <typename R, int KF, int TYPE>
+int launch_sweep2_t(bisbm_handle* h, const SweepParams& P, const LaunchPlan& lp, unsigned grid) {
+    int rc = ensure_smem_attr(h, (const void*)sweep2_kernel<R, KF, TYPE>, (int)kSmemMax);
+    if (rc) return rc;
+    sweep2_kernel<R, KF, TYPE><<<grid, lp.wpc * 32, lp.smem_bytes, h->stream>>>(P);
+    CU(cudaGetLastError());
+    h->lab32_stale = true;    // the staged kernels only write the u8 label shadow
+    return BISBM_OK;
+}
+
+template <typename R>
+int launch_sweep2(bisbm_handle* h, const SweepParams& P, const LaunchPlan& lp, unsigned grid) {
+    // compile-time strides for the common Ka = Kb = 32 pool (BASELINE configs[2])
+    if (h->KA == 32 && h->KB == 32 && !h->opt_generic)
+        return P.type ? launch_sweep2_t<R, 32, 1>(h, P, lp, grid) : launch_sweep2_t<R, 32, 0>(h, P, lp, grid);
+    return launch_sweep2_t<R, 0, 0>(h, P, lp, grid);
+}
+
+SweepParams base_params(bisbm_handle* h, uint32_t type) {
+    SweepParams P;
+    memset(&P, 0, sizeof P);
+    P.g = gview(h); P.s = sview(h); P.tb = tview(h, false);
+    P.lab8 = h->d_lab8; P.m_next = h->d_m2; P.e_next = h->d_e2; P.nr_next = h->d_nr2; P.nr_live = h->d_nr_live;
+    P.seeds = h->d_seeds; P.active = h->d_active; P.accepted = h->d_accepted; P.dS_accum = h->d_dS;
+    P.lq = h->d_lq; P.lq_soa = h->d_lq_soa;
+    P.n_chains = h->n_chains; P.type = type; P.n_groups = h->C / 32;
+    P.kopp_max = type ? h->KA : h->KB;
+    P.half_bits = feistel_half_bits(type ? h->nb : h->na);
+    P.kat_out = h->d_kat_out;
+    return P;
+}
+
 // one full sweep = type-a half sweep + type-b half sweep (each preceded by the log q refresh
 // of the blocks that half sweep changes)
 int launch_full_sweep(bisbm_handle* h, int schedule, float p0, float p1, uint64_t sweep_in_call, uint32_t max_inflight) {
+    uint32_t wpc = 32;
+    const int kernel = plan_kernel(h, &wpc);
     for (uint32_t type = 0; type < 2; ++type) {
         const uint32_t nv = type ? h->nb : h->na;
         if (nv == 0) continue;
         LaunchPlan lp;
-        int rc = plan_sweep(h, type, max_inflight, &lp);
+        int rc = plan_sweep(h, type, max_inflight, kernel, wpc, &lp);
         if (rc) return rc;
         const uint32_t kmax = type ? h->KB : h->KA;
         const uint32_t tot = h->n_chains * kmax;
         logq_refresh_kernel<<<(tot + 127) / 128, 128, 0, h->stream>>>(sview(h), tview(h, false), h->d_lq, h->d_lq_soa, h->n_chains, type);
         h->last_launches += 1;
-        const size_t m_bytes = (size_t)h->C * h->KA * h->KB * sizeof(int32_t);
-        const size_t e_bytes = (size_t)h->C * (h->KA + h->KB) * sizeof(int32_t);
+        const uint32_t n_m = h->C * h->KA * h->KB, n_e = h->C * (h->KA + h->KB);
         const bool sliced = lp.smem && lp.ctas_per_group > 1;
+        const bool s2 = kernel == KERN_S2_F32 || kernel == KERN_S2_F64;
         h->last_wpc = lp.wpc; h->last_cpg = lp.ctas_per_group; h->last_slice = lp.slice;
-        h->last_kernel = lp.fast ? 2 : (lp.smem ? 1 : 0);
+        h->last_kernel = kernel;
         for (uint32_t pos = 0; pos < nv; pos += lp.slice) {
-            if (sliced) {  // next := base; the launch adds each CTA's (staged - base) into next
-                CU(cudaMemcpyAsync(h->d_m2, h->d_m, m_bytes, cudaMemcpyDeviceToDevice, h->stream));
-                CU(cudaMemcpyAsync(h->d_e2, h->d_e, e_bytes, cudaMemcpyDeviceToDevice, h->stream));
+            if (sliced && s2) {
+                // next := -(ctas_per_group - 1) * base: every CTA adds its whole staged copy (sweep2.cuh)
+                const uint32_t nmax = std::max(n_m, n_e);
+                sweep2_preinit_kernel<<<(nmax + 255) / 256, 256, 0, h->stream>>>(h->d_m, h->d_e, h->d_nr, h->d_m2, h->d_e2, h->d_nr2,
+                                                                                 h->d_nr_live, n_m, n_e, h->KA, h->KB, type, lp.ctas_per_group - 1);
+                h->last_launches += 1;
+            } else if (sliced) {  // next := base; the launch adds each CTA's (staged - base) into next
+                CU(cudaMemcpyAsync(h->d_m2, h->d_m, (size_t)n_m * sizeof(int32_t), cudaMemcpyDeviceToDevice, h->stream));
+                CU(cudaMemcpyAsync(h->d_e2, h->d_e, (size_t)n_e * sizeof(int32_t), cudaMemcpyDeviceToDevice, h->stream));
             }
-            SweepParams P;
-            P.g = gview(h); P.s = sview(h); P.tb = tview(h, false);
-            P.lab8 = h->d_lab8; P.m_next = h->d_m2; P.e_next = h->d_e2;
-            P.seeds = h->d_seeds; P.active = h->d_active; P.accepted = h->d_accepted; P.dS_accum = h->d_dS;
-            P.lq = h->d_lq; P.lq_soa = h->d_lq_soa;
-            P.n_chains = h->n_chains; P.type = type; P.n_groups = h->C / 32;
+            SweepParams P = base_params(h, type);
             P.ctas_per_group = lp.ctas_per_group; P.warps_used = lp.warps_used;
-            P.pos_begin = pos; P.pos_end = std::min<uint64_t>(nv, (uint64_t)pos + lp.slice);
-            P.half_bits = feistel_half_bits(nv);
-            P.kopp_max = type ? h->KA : h->KB;
+            P.pos_begin = pos; P.pos_end = (uint32_t)std::min<uint64_t>(nv, (uint64_t)pos + lp.slice);
             P.exclusive = sliced ? 0 : 1;
             P.sweep = h->sweep_epoch;
             P.step_base = sweep_in_call * (uint64_t)h->n + (type ? h->na : 0);
             P.schedule = schedule; P.p0 = p0; P.p1 = p1;
-            rc = lp.smem ? launch_sweep_h<true>(h, P, lp) : launch_sweep_h<false>(h, P, lp);
+            const unsigned grid = P.n_groups * lp.ctas_per_group;
+            if (kernel == KERN_S2_F64) rc = launch_sweep2<double>(h, P, lp, grid);
+            else if (kernel == KERN_S2_F32) rc = launch_sweep2<float>(h, P, lp, grid);
+            else rc = lp.smem ? launch_sweep_h<true>(h, P, lp) : launch_sweep_h<false>(h, P, lp);
             if (rc) return rc;
             h->last_launches += 1;
-            if (sliced) { std::swap(h->d_m, h->d_m2); std::swap(h->d_e, h->d_e2); }
+            h->last_sweep_launches += 1;
+            if (sliced) {
+                std::swap(h->d_m, h->d_m2); std::swap(h->d_e, h->d_e2);
+                if (s2) std::swap(h->d_nr, h->d_nr2);
+            }
         }
     }
     h->sweep_epoch++;
@@ -659,6 +698,9 @@ int bisbm_set_chains(bisbm_handle* h, uint32_t n_chains, const uint32_t* ka, con
         CU(cudaMalloc(&h->d_e2, (size_t)C * KK * sizeof(int32_t)));
         CU(cudaMalloc(&h->d_lab8, (size_t)n * C));
         CU(cudaMalloc(&h->d_nr, (size_t)C * KK * sizeof(int32_t)));
+        CU(cudaMalloc(&h->d_nr2, (size_t)C * KK * sizeof(int32_t)));
+        CU(cudaMalloc(&h->d_nr_live, (size_t)C * KK * sizeof(int32_t)));
+        CU(cudaMalloc(&h->d_kat_out, 2 * sizeof(double)));
         CU(cudaMalloc(&h->d_eta, (size_t)C * KK * h->W * sizeof(int32_t)));
         CU(cudaMalloc(&h->d_lq, (size_t)C * KK * sizeof(LogqExp)));
         CU(cudaMalloc(&h->d_lq_soa, (size_t)C * KK * 8 * sizeof(uint32_t)));
@@ -683,6 +725,8 @@ int bisbm_set_chains(bisbm_handle* h, uint32_t n_chains, const uint32_t* ka, con
     CU(cudaMemsetAsync(h->d_lq, 0, (size_t)C * KK * sizeof(LogqExp), h->stream));
     CU(cudaMemsetAsync(h->d_lq_soa, 0, (size_t)C * KK * 8 * sizeof(uint32_t), h->stream));
     CU(cudaMemsetAsync(h->d_dS, 0, C * sizeof(double), h->stream));
+    CU(cudaMemsetAsync(h->d_active, 0, C, h->stream));
+    CU(cudaMemsetAsync(h->d_active, 1, n_chains, h->stream));
     CU(cudaMemcpyAsync(h->d_ka, h->h_ka.data(), C * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(h->d_kb, h->h_kb.data(), C * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
     // host labels [chain][node], global ids  ->  chain-minor, type-local (device transpose)
@@ -759,7 +803,8 @@ int bisbm_replay_anneal(bisbm_handle* h, uint32_t chain, int schedule, float p0,
     ReplaySlot* sl;
     int rc = need_replay(h, chain, &sl);
     if (rc) return rc;
-    if (schedule < 0 || schedule > 4) return fail(BISBM_ERR_ARG, "unknown cooling schedule %d", schedule);
+    rc = validate_schedule(schedule, p0, p1, duration);
+    if (rc) return rc;
     const uint64_t N = h->n;
     const uint64_t all_sweeps = duration / N;
     // anneal() resets entropy_min_, the accepted counter and u on entry
@@ -851,7 +896,8 @@ int bisbm_anneal(bisbm_handle* h, int schedule, float p0, float p1, uint64_t dur
                  const uint64_t* seeds, uint32_t max_inflight, double* accept_ratio, uint64_t* sweeps_done) {
     int rc = need_chains(h);
     if (rc) return rc;
-    if (schedule < 0 || schedule > 4) return fail(BISBM_ERR_ARG, "unknown cooling schedule %d", schedule);
+    rc = validate_schedule(schedule, p0, p1, duration);
+    if (rc) return rc;
     rc = upload_seeds(h, seeds);
     if (rc) return rc;
     rc = sync_labels8(h);
@@ -872,7 +918,7 @@ int bisbm_anneal(bisbm_handle* h, int schedule, float p0, float p1, uint64_t dur
         CU(cudaMemcpyAsync(h->d_nactive, &na_, sizeof na_, cudaMemcpyHostToDevice, h->stream));
         CU(cudaStreamSynchronize(h->stream));
     }
-    h->last_launches = 0; h->last_moves = 0; h->last_ms = 0.0;
+    h->last_launches = 0; h->last_sweep_launches = 0; h->last_moves = 0; h->last_ms = 0.0;
     CU(cudaEventRecord(h->ev0, h->stream));
     uint64_t sweep = 0;
     uint32_t n_active = h->n_chains;
@@ -947,7 +993,7 @@ int bisbm_marginalize(bisbm_handle* h, uint64_t burn_in, uint64_t sweeps, uint64
         CU(cudaMemsetAsync(h->d_accepted, 0, h->C * sizeof(unsigned long long), h->stream));
         CU(cudaStreamSynchronize(h->stream));
     }
-    h->last_launches = 0; h->last_moves = 0; h->last_ms = 0.0;
+    h->last_launches = 0; h->last_sweep_launches = 0; h->last_moves = 0; h->last_ms = 0.0;
     CU(cudaEventRecord(h->ev0, h->stream));
     const uint64_t tot = (uint64_t)h->n * h->C;
     for (uint64_t sw = 0; sw < burn_in + sweeps; ++sw) {
@@ -989,6 +1035,69 @@ int bisbm_set_precision(bisbm_handle* h, int mode) {
     return BISBM_OK;
 }
 
+int bisbm_set_option(bisbm_handle* h, const char* name, int64_t value) {
+    if (!h || !name) return fail(BISBM_ERR_ARG, "null argument");
+    const std::string k(name);
+    if (k == "kernel") {
+        if (value < -1 || value > KERN_STAGED_OLD) return fail(BISBM_ERR_ARG, "kernel: -1 (automatic), 0 (counts in L2) or 1 (round-1 staged double kernel)");
+        h->opt_kernel = (int)value;
+    } else if (k == "inflight_div") {
+        if (value < 1 || value > (1 << 30)) return fail(BISBM_ERR_ARG, "inflight_div must be >= 1");
+        h->opt_inflight_div = (uint32_t)value;
+    } else if (k == "generic") {
+        h->opt_generic = value != 0;
+    } else {
+        return fail(BISBM_ERR_ARG, "unknown option '%s'", name);
+    }
+    return BISBM_OK;
+}
+
+int bisbm_parallel_transition(bisbm_handle* h, uint32_t chain, uint32_t v, uint32_t s, double* dS, double* log_accu) {
+    int rc = need_chains(h);
+    if (rc) return rc;
+    if (chain >= h->n_chains) return fail(BISBM_ERR_ARG, "chain %u out of range", chain);
+    const uint32_t ka = h->h_ka[chain], kb = h->h_kb[chain];
+    if (v >= h->n || s >= ka + kb) return fail(BISBM_ERR_ARG, "vertex or block out of range");
+    const bool va = v < h->na;
+    if ((s < ka) != va) {   // cross-type proposal: +inf before accu_r_ is touched (src/metropolis_hasting.cc:121-123)
+        if (dS) *dS = INFINITY;
+        if (log_accu) *log_accu = NAN;
+        return BISBM_OK;
+    }
+    uint32_t wpc = 32;
+    const int kernel = plan_kernel(h, &wpc);
+    if (kernel != KERN_S2_F32 && kernel != KERN_S2_F64)
+        return fail(BISBM_ERR_STATE, "bisbm_parallel_transition needs the staged sweep kernel (K or degrees too large for it)");
+    const uint32_t type = va ? 0 : 1;
+    rc = sync_labels8(h);
+    if (rc) return rc;
+    const uint32_t kmax = type ? h->KB : h->KA;
+    const uint32_t tot = h->n_chains * kmax;
+    logq_refresh_kernel<<<(tot + 127) / 128, 128, 0, h->stream>>>(sview(h), tview(h, false), h->d_lq, h->d_lq_soa, h->n_chains, type);
+    CU(cudaMemsetAsync(h->d_kat_out, 0xff, 2 * sizeof(double), h->stream));   // NaN: "not written"
+    LaunchPlan lp;
+    memset(&lp, 0, sizeof lp);
+    lp.kernel = kernel; lp.smem = true; lp.hist_bytes = 1; lp.wpc = wpc; lp.warps_used = 1; lp.ctas_per_group = 1; lp.slice = 1;
+    lp.smem_bytes = sweep2_layout(h->KA, h->KB, type, wpc, kernel == KERN_S2_F32 ? 4u : 8u).total;
+    SweepParams P = base_params(h, type);
+    P.n_groups = 1; P.group_offset = chain / 32;
+    P.ctas_per_group = 1; P.warps_used = 1; P.pos_begin = 0; P.pos_end = 1; P.exclusive = 1;
+    P.schedule = BISBM_CONSTANT; P.p0 = 1.0f; P.p1 = 0.0f;
+    P.kat_mode = 1; P.kat_chain = chain; P.kat_v = v; P.kat_s = va ? s : s - ka;
+    const bool stale = h->lab32_stale;
+    rc = (kernel == KERN_S2_F64) ? launch_sweep2<double>(h, P, lp, 1) : launch_sweep2<float>(h, P, lp, 1);
+    h->lab32_stale = stale;   // nothing was written
+    if (rc) return rc;
+    double out[2];
+    CU(cudaMemcpyAsync(out, h->d_kat_out, sizeof out, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    if (std::isnan(out[0]) && std::isnan(out[1])) { out[0] = 0.0; out[1] = 0.0; }   // s == r: dS = 0, accu_r = 1 (:109-112)
+    if (dS) *dS = out[0];
+    if (log_accu) *log_accu = out[1];
+    return BISBM_OK;
+}
+
 int bisbm_marginals_device(bisbm_handle* h, void** dev_ptr, uint64_t* n_elems, uint32_t* width) {
     int rc = need_chains(h);
     if (rc) return rc;
@@ -1026,6 +1135,12 @@ int bisbm_last_timing(bisbm_handle* h, double* sweep_ms, uint64_t* launches, uin
     if (sweep_ms) *sweep_ms = h->last_ms;
     if (launches) *launches = h->last_launches;
     if (moves) *moves = h->last_moves;
+    return BISBM_OK;
+}
+
+int bisbm_sweep_launches(bisbm_handle* h, uint64_t* sweep_kernel_launches) {
+    if (!h || !sweep_kernel_launches) return fail(BISBM_ERR_ARG, "null argument");
+    *sweep_kernel_launches = h->last_sweep_launches;
     return BISBM_OK;
 }
 

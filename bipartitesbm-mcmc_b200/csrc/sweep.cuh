@@ -72,6 +72,13 @@ struct SweepParams {
     uint64_t step_base;              // global step index of position 0 of this half sweep
     int schedule;
     float p0, p1;
+    // sweep2_kernel (sweep2.cuh)
+    int32_t* nr_next;                // sliced launches: where the n_r view is added
+    int32_t* nr_live;                // exact n_r counters for blocks small enough to empty within a launch
+    uint32_t group_offset;           // first chain group of this launch (0 except for single-group launches)
+    uint32_t kat_mode;               // 1: evaluate ONE forced proposal (kat_v -> own-type block kat_s of chain kat_chain) and write
+    uint32_t kat_chain, kat_v, kat_s;   //    {dS, log accu_r} to kat_out instead of accepting / committing (bisbm_parallel_transition)
+    double* kat_out;
 };
 
 // temperature of global step t (same five schedules as src/metropolis_hasting.cc:10-37,

@@ -1,0 +1,771 @@
+// sweep2.cuh -- the staged-count sweep kernel of parallel mode (round 2), one kernel text for both
+// arithmetic types: sweep2_kernel<double, ..> evaluates a move in DOUBLE like the reference's
+// transition_ratio (src/metropolis_hasting.cc:103-192) and is the default; sweep2_kernel<float, ..>
+// is the optional fp32 / MUFU form (bisbm_set_precision).
+//
+// Mapping as in sweep.cuh: LANE = CHAIN, one warp per vertex, half sweeps alternate types, the chain
+// group's counts live in shared memory laid out [entry][lane].  What is new here:
+//   * double arithmetic without conversions on the XU pipe: counts become doubles by splicing the
+//     integer under the exponent of 2^52 (one DADD each), products of up to 32 count ratios are folded
+//     into ONE logarithm per vertex, 1/(e_t + eps K) comes from a per-launch table (e_t of the frozen
+//     type cannot change during a half sweep), reciprocals are MUFU.RCP64H + two Newton steps;
+//   * neighbour labels arrive as whole 32-byte rows (lane -> 8 bytes of one row, 8 rows per load
+//     instruction), ONE VERTEX AHEAD, and are transposed through a per-warp tile in shared memory
+//     ([chain][edge], 36-byte pitch: conflict-free both ways) -- the five serial gather round trips of
+//     the round-1 kernel are gone and the proposal's random neighbour label comes from the tile too;
+//   * the warp's u8 neighbour-block histogram is updated with one shared atomic per edge (old value =
+//     c), four edges of a chunk are independent instruction streams;
+//   * the commit walks the edges again (2 shared reductions per edge) instead of all K bins;
+//   * n_r has a per-CTA view in shared memory like m_rs / e_r; only blocks small enough to empty
+//     within one slice (or every block, when one CTA owns the group: then the view is exact) use an
+//     exact atomic decrement-and-check for the "would empty block r" veto of apply_mcmc_moves
+//     (src/blockmodel.cc:467-471);
+//   * the CTA's share of the slice is prepared once (Feistel position -> vertex, CSR row, degree) and
+//     handed out to warps dynamically (no warp waits for the slowest one's static share);
+//   * staging is one thread issuing bulk-async copies (cp.async.bulk + mbarrier); publishing is one
+//     thread issuing bulk-async REDUCTIONS of the staged arrays themselves (cp.reduce.async.bulk
+//     .add.s32): the host pre-loads the next base with -(ctas_per_group - 1) * base, so the sum of all
+//     CTAs' staged copies is base + sum of their deltas -- no base re-read, no per-entry atomics.
+//
+// Per move this is still the arithmetic of the reference's step():
+//   proposal   single_vertex_change      reference src/blockmodel.cc:613-637
+//   dS, accu_r transition_ratio          reference src/metropolis_hasting.cc:103-192
+//   accept     step                      reference src/metropolis_hasting.cc:42-62
+//   commit     apply_mcmc_moves          reference src/blockmodel.cc:461-503
+#pragma once
+#include "sweep.cuh"
+
+namespace bisbm {
+
+#define BISBM_LN2F 0.69314718055994530942f
+#define BISBM_LOG2EF 1.44269504088896340736f
+
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ float f_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float f_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float f_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+#else
+inline float f_lg2(float x) { return log2f(x); }
+inline float f_ex2(float x) { return exp2f(x); }
+inline float f_rcp(float x) { return 1.0f / x; }
+#endif
+
+// ---- arithmetic of one move, by type ---------------------------------------------------------
+// lg() is the type's native logarithm (natural log for double, log2 on the MUFU unit for float);
+// unit() converts lg units to natural-log units, ex() inverts lg().
+template <typename R> struct Ar;
+
+template <> struct Ar<double> {
+    static constexpr int FOLD = 32;       // count ratios multiplied between logarithms (32 factors < 2^31 fit a double)
+    static constexpr bool SPLIT = true;   // accumulate sum (m+1-c1) inv, sum (m_s+c1) inv, sum c1 inv separately
+    BISBM_HD static double unit() { return 1.0; }
+    BISBM_HD static double inv_unit() { return 1.0; }
+    // exact conversion of a 32-bit unsigned integer: 2^52 + x has x as its low mantissa word
+    BISBM_HD static double cvt(uint32_t x) {
+#ifdef __CUDA_ARCH__
+        return __hiloint2double(0x43300000, (int)x) - 4503599627370496.0;
+#else
+        return (double)x;
+#endif
+    }
+    BISBM_HD static double cvt_small(uint32_t x) { return cvt(x); }
+    BISBM_HD static double cvt_s(int x) {
+#ifdef __CUDA_ARCH__
+        return __hiloint2double(0x43300000, (int)((uint32_t)x ^ 0x80000000u)) - 4503601774854144.0;   // 2^52 + 2^31
+#else
+        return (double)x;
+#endif
+    }
+    BISBM_HD static double rcp(double x) {   // x > 0, normal: MUFU.RCP64H (2^-23) + two Newton steps
+#ifdef __CUDA_ARCH__
+        double r;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+        r = fma(fma(-x, r, 1.0), r, r);
+        r = fma(fma(-x, r, 1.0), r, r);
+        return r;
+#else
+        return 1.0 / x;
+#endif
+    }
+    BISBM_HD static double lg(double x) { return log(x); }
+    BISBM_HD static double ex(double x) { return exp(x); }
+    BISBM_HD static double u01(uint32_t w) { return (cvt(w) + 0.5) * (1.0 / 4294967296.0); }
+    // U < x / 2^32 for the 32-bit draw w
+    BISBM_HD static bool draw_below(uint32_t w, double x32) { return cvt(w) < x32; }
+};
+
+template <> struct Ar<float> {
+    static constexpr int FOLD = 4;        // 4 factors < 2^31 stay inside fp32 range
+    static constexpr bool SPLIT = false;  // (m - 2c - 1) and m_s are formed exactly before the multiply
+    BISBM_HD static float unit() { return BISBM_LN2F; }
+    BISBM_HD static float inv_unit() { return BISBM_LOG2EF; }
+    BISBM_HD static float cvt(uint32_t x) { return (float)(int)x; }
+    BISBM_HD static float cvt_small(uint32_t x) {   // x <= 255: splice under the exponent of 2^23 (no XU-pipe conversion)
+#ifdef __CUDA_ARCH__
+        return __uint_as_float(0x4B000000u | x) - 8388608.0f;
+#else
+        return (float)x;
+#endif
+    }
+    BISBM_HD static float cvt_s(int x) { return (float)x; }
+    BISBM_HD static float rcp(float x) { return f_rcp(x); }
+    BISBM_HD static float lg(float x) { return f_lg2(x); }
+    BISBM_HD static float ex(float x) { return f_ex2(x); }
+    BISBM_HD static float u01(uint32_t w) { return ((float)(w >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+    BISBM_HD static bool draw_below(uint32_t w, float x32) {
+#ifdef __CUDA_ARCH__
+        return w < __float2uint_rz(x32);     // saturates at 2^32 - 1
+#else
+        return (double)w < (double)x32;
+#endif
+    }
+};
+
+// running sums of the one-pass evaluation of transition_ratio (header of sweep.cuh): with c1 = c + 1,
+//   A = m_rt + 1 - c1 = m_rt - c,  B = m_st + c1 = m_st + 1 + c,  inv = 1 / (e_t + eps K)
+//   sA = sum A inv, sB = sum B inv, sC = sum c1 inv   (SPLIT; accu0 = sB - sC + eps w, accu1 = sA - sC + eps w)
+//   sA = sum (A - c1) inv, sB = sum (B - c1) inv      (!SPLIT)
+//   w = sum inv, num / den = running products of A / B, lg = lg() of the products folded so far
+template <typename R> struct MAcc { R sA, sB, sC, w, num, den, lg; };
+template <typename R> BISBM_HD void macc_init(MAcc<R>& A) {
+    A.sA = (R)0; A.sB = (R)0; A.sC = (R)0; A.w = (R)0; A.num = (R)1; A.den = (R)1; A.lg = (R)0;
+}
+template <typename R> BISBM_HD void macc_edge(MAcc<R>& A, int m_r, int m_s, uint32_t c1, R inv) {
+    const R dC = Ar<R>::cvt_small(c1);
+    const R dA = Ar<R>::cvt((uint32_t)m_r + 1u - c1);
+    const R dB = Ar<R>::cvt((uint32_t)m_s + c1);
+    if (Ar<R>::SPLIT) {
+        A.sA = fma(dA, inv, A.sA);
+        A.sB = fma(dB, inv, A.sB);
+        A.sC = fma(dC, inv, A.sC);
+    } else {
+        A.sA = fma(dA - dC, inv, A.sA);
+        A.sB = fma(dB - dC, inv, A.sB);
+    }
+    A.w += inv;
+    A.num *= dA;
+    A.den *= dB;
+}
+template <typename R> BISBM_HD void macc_fold(MAcc<R>& A) {
+    A.lg += Ar<R>::lg(A.num * Ar<R>::rcp(A.den));
+    A.num = (R)1; A.den = (R)1;
+}
+
+// e_r terms: [lgamma(e_s+d+1) - lgamma(e_s+1)] - [lgamma(e_r+1) - lgamma(e_r-d+1)] by the midpoint
+// Euler-Maclaurin difference of sweep.cuh (block_degree_delta); *ok = false (midpoints < 32 d) -> the caller
+// takes the Stirling / lgamma form.
+template <typename R> BISBM_HD R bdd_fast(int e_r, int e_s, int d, bool* ok) {
+    const R D = Ar<R>::cvt_small((uint32_t)d);
+    const R cs = Ar<R>::cvt((uint32_t)e_s) + (R)0.5 * (D + (R)1), cr = Ar<R>::cvt((uint32_t)e_r) - (R)0.5 * (D - (R)1);
+    *ok = (cs >= (R)32 * D) && (cr >= (R)32 * D);
+    const R is = Ar<R>::rcp(cs), ir = Ar<R>::rcp(cr);
+    const R is2 = is * is, ir2 = ir * ir, D2 = D * D;
+    const R k3 = D * (D2 - (R)1) * (R)(1.0 / 24.0);
+    const R k5 = D * (((R)3 * D2 - (R)10) * D2 + (R)7) * (R)(1.0 / 960.0);
+    return D * Ar<R>::unit() * Ar<R>::lg(cs * ir) - k3 * (is2 - ir2) - k5 * (is2 * is2 - ir2 * ir2);
+}
+
+// log q(e+de, n+dn) - log q(e, n) from the block's second-order expansion (logq_refresh_kernel);
+// *ok = false when the block has none or has drifted out of its range
+template <typename R> BISBM_HD R logq_fast(const LogqExp& q, int e, int n, int de, int dn, bool* ok) {
+    const int x = e - q.e0, y = n - q.n0;
+    const int ax = x < 0 ? -x : x, ay = y < 0 ? -y : y, ad = de < 0 ? -de : de;
+    const int re = q.e0 >> 4, rn = q.n0 >> 4;
+    *ok = (q.valid != 0u) && ax <= re && ay <= rn && ad <= re;
+    const R dx = Ar<R>::cvt_s(x), dy = Ar<R>::cvt_s(y), De = Ar<R>::cvt_s(de), Dn = Ar<R>::cvt_s(dn);
+    return (R)q.fe * De + (R)q.fn * Dn + (R)0.5 * (R)q.fee * (De * De + (R)2 * dx * De) +
+           (R)q.fen * (dx * Dn + dy * De + De * Dn) + (R)0.5 * (R)q.fnn * (Dn * Dn + (R)2 * dy * Dn);
+}
+
+// dS (natural-log units) and the logarithm of the Hastings factor accu1 / accu0 (lg units) of one move
+template <typename R>
+BISBM_HD void move_finish(const MAcc<R>& A, int eta_r, int eta_s, R bdd, R lqr, R lqs, uint32_t d, R eps, R* dS, R* lh) {
+    const R er = Ar<R>::cvt((uint32_t)(eta_r > 0 ? eta_r : 1)), es = Ar<R>::cvt((uint32_t)eta_s + 1u);
+    // log( prod (m_rt-c)/(m_st+1+c) * eta_r/(eta_s+1) )
+    const R prod = (A.num * Ar<R>::rcp(A.den)) * (er * Ar<R>::rcp(es));
+    *dS = Ar<R>::unit() * (A.lg + Ar<R>::lg(prod)) + ((d == 0) ? (R)0 : bdd) + lqr + lqs;
+    const R ew = eps * A.w;
+    const R a0 = Ar<R>::SPLIT ? A.sB - A.sC : A.sB, a1 = Ar<R>::SPLIT ? A.sA - A.sC : A.sA;
+    *lh = (d == 0) ? (R)0 : Ar<R>::lg((a1 + ew) * Ar<R>::rcp(a0 + ew));
+}
+
+// ---- shared-memory layout (byte offsets; every array is a multiple of 16 bytes) ---------------------
+//   int32 sM  [KA*KB][32]       m_rs of the group
+//   int32 sEo [kown][32]        e_r of the moving type (read / write)
+//   int32 sNo [kown][32]        n_r of the moving type (read / write view)
+//   int32 sEp [kopp][32]        e_t of the frozen type (read only: constant during a half sweep)
+//   R     sInv[kopp][32]        1 / (e_t + eps K)
+//   u32   sSmall[ceil(kown/32)][32]   bit b: block b of this lane's chain needs the exact n_r veto
+//   uint4 sVtx[S2_VB]           the CTA's prepared vertices {vertex, CSR row offset, degree, degree index}
+//   u8x4  hist[warps][ceil(kopp/4)][32]
+//   u8    tile[warps][32 lanes][36]   neighbour labels of the warp's vertex, [chain][edge]
+//   ctl   mbarrier (8 bytes) + vertex counter
+struct Sweep2Layout { uint32_t oM, oEo, oNo, oEp, oInv, oSmall, oVtx, oHist, oTile, oCtl, total; };
+enum { S2_VB = 448, S2_TILE = 32 * 36 };
+
+inline
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+Sweep2Layout sweep2_layout(uint32_t KA, uint32_t KB, uint32_t type, uint32_t warps, uint32_t rsize) {
+    const uint32_t kown = type ? KB : KA, kopp = type ? KA : KB;
+    Sweep2Layout L;
+    uint32_t o = 0;
+    L.oM = o; o += KA * KB * 128u;
+    L.oEo = o; o += kown * 128u;
+    L.oNo = o; o += kown * 128u;
+    L.oEp = o; o += kopp * 128u;
+    L.oInv = o; o += kopp * 32u * rsize;
+    L.oSmall = o; o += ((kown + 31u) / 32u) * 128u;
+    L.oVtx = o; o += (uint32_t)S2_VB * 16u;
+    L.oHist = o; o += warps * ((kopp + 3u) / 4u) * 128u;
+    L.oTile = o; o += warps * (uint32_t)S2_TILE;
+    L.oCtl = o; o += 64u;
+    L.total = o;
+    return L;
+}
+
+#ifdef __CUDACC__
+
+// ---- PTX helpers -------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t sh_ld_u8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sh_st_u8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t sh_ld_u32v(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sh_st_u32v(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ uint4 sh_ld_v4(uint32_t a) {
+    uint4 v; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v;
+}
+__device__ __forceinline__ uint32_t sh_atom_add_u32(uint32_t a, uint32_t v) {
+    uint32_t o; asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(o) : "r"(a), "r"(v) : "memory"); return o;
+}
+__device__ __forceinline__ int sh_atom_add_s32(uint32_t a, int v) {
+    int o; asm volatile("atom.shared.add.s32 %0, [%1], %2;" : "=r"(o) : "r"(a), "r"(v) : "memory"); return o;
+}
+template <typename R> __device__ __forceinline__ R sh_ld_real(uint32_t a);
+template <> __device__ __forceinline__ double sh_ld_real<double>(uint32_t a) { double v; asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
+template <> __device__ __forceinline__ float sh_ld_real<float>(uint32_t a) { float v; asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t phase) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(mbar), "r"(phase) : "memory");
+    } while (!ok);
+}
+// bulk-async copy global -> shared (completion counted in bytes on the mbarrier); 16-byte aligned, size % 16 == 0
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(mbar) : "memory");
+}
+// bulk-async reduction shared -> global: dst[i] += src[i] (int32), performed by the L2
+__device__ __forceinline__ void bulk_red_add_s32(void* dst, uint32_t src, uint32_t bytes) {
+    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.s32 [%0], [%1], %2;"
+                 :: "l"(__cvta_generic_to_global(dst)), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_wait_all() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// the rare double-precision completions, out of line (arguments by value)
+__device__ __noinline__ static double slow2_block_degree_delta(int e_r, int e_s, int d) { return block_degree_delta(e_r, e_s, d); }
+__device__ __noinline__ static double slow2_logq_delta(const double* qtab, uint32_t qn, uint32_t qk, int e, int n, int de, int dn) {
+    Tables tb; tb.lg = nullptr; tb.lg_n = 0; tb.qtab = qtab; tb.qn = qn; tb.qk = qk;
+    return logq_delta_exact(tb, e, n, de, dn);
+}
+// 1/T of global step t; T == 0 is returned as a negative value
+__device__ __noinline__ static double slow2_beta(int schedule, float p0, float p1, uint64_t t) {
+    const double T = par_temperature(schedule, p0, p1, t);
+    return (T == 0.0) ? -1.0 : 1.0 / T;
+}
+
+// next base of a sliced launch: every CTA of a group adds its whole staged copy (base + its deltas) into
+// `next`, so next starts at -(ctas_per_group - 1) * base for the arrays the CTAs publish (m_rs, and e_r / n_r of
+// the moving type) and at base for the frozen type's e_r / n_r.  nr_live := n_r (exact veto counters).
+__global__ void sweep2_preinit_kernel(const int32_t* __restrict__ m, const int32_t* __restrict__ e, const int32_t* __restrict__ nr,
+                                      int32_t* __restrict__ m2, int32_t* __restrict__ e2, int32_t* __restrict__ nr2,
+                                      int32_t* __restrict__ nr_live, uint32_t n_m, uint32_t n_e, uint32_t KA, uint32_t KB,
+                                      uint32_t type, uint32_t mult) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_m) m2[i] = (int32_t)(0u - mult * (uint32_t)m[i]);
+    if (i < n_e) {
+        const uint32_t slot = (i >> 5) % (KA + KB);
+        const bool own = type ? (slot >= KA) : (slot < KA);
+        const uint32_t ev = (uint32_t)e[i], nv = (uint32_t)nr[i];
+        e2[i] = (int32_t)(own ? 0u - mult * ev : ev);
+        nr2[i] = (int32_t)(own ? 0u - mult * nv : nv);
+        nr_live[i] = (int32_t)nv;
+    }
+}
+
+// KF > 0: Ka == Kb == KF padded strides and the moving type TYPE fixed at compile time; KF == 0: from SweepParams.
+// 512 threads (16 warps x 128 registers), one CTA per SM.  Preconditions (plan_sweep): max degree <= 255 (u8
+// histogram bins), K per type <= 256 (u8 labels).
+template <typename R, int KF, int TYPE>
+__global__ void __launch_bounds__(512, 1) sweep2_kernel(const __grid_constant__ SweepParams P) {
+    typedef Ar<R> AR;
+    extern __shared__ __align__(128) unsigned char s2_smem[];
+    unsigned char* const smem_raw = s2_smem;
+    constexpr uint32_t FULL = 0xffffffffu;
+    uint32_t lane, warp;
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(warp));
+    warp >>= 5;
+    const uint32_t wpc = blockDim.x >> 5;
+    const GraphView& G = P.g;
+    const uint32_t type = KF ? (uint32_t)TYPE : P.type;
+    const uint32_t C = P.s.C, KB = KF ? (uint32_t)KF : P.s.KB, KA = KF ? (uint32_t)KF : P.s.KA, W = P.s.W, KK = KA + KB;
+    const uint32_t kown_max = type ? KB : KA, kopp_max = type ? KA : KB;
+    const uint32_t group = P.group_offset + blockIdx.x % P.n_groups;
+    const uint32_t cta_in_group = blockIdx.x / P.n_groups;
+    const uint32_t own_off = type ? KA : 0, opp_off = type ? 0 : KA;
+
+    int32_t* const gM = P.s.m + (size_t)group * KA * KB * GROUP;
+    int32_t* const gE = P.s.e + (size_t)group * KK * GROUP;
+    int32_t* const gNR = P.s.nr + (size_t)group * KK * GROUP;
+    int32_t* const gLIVE = P.nr_live + (size_t)group * KK * GROUP + (size_t)own_off * 32;
+    int32_t* const gETA = P.s.eta + (size_t)group * KK * W * GROUP + (size_t)own_off * W * 32;
+    const LogqExp* const gLQ = P.lq + ((size_t)group * KK + own_off) * GROUP;
+
+    const uint32_t c = group * 32 + lane;
+    const bool live = (c < P.n_chains) && P.active[c];
+    const uint32_t cc = (c < P.s.C) ? c : 0;
+    const uint32_t ka = P.s.ka[cc], kb = P.s.kb[cc], K = ka + kb;
+    const uint32_t kown = type ? kb : ka;
+    const R eps = (R)P.s.eps;
+    const R epsK32 = (R)(P.s.eps * (double)K * 4294967296.0);   // threshold scale of the uniform-vs-categorical test
+
+    const Sweep2Layout L = sweep2_layout(KA, KB, type, wpc, (uint32_t)sizeof(R));
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    int32_t* const sM = reinterpret_cast<int32_t*>(smem_raw + L.oM);
+    int32_t* const sEo = reinterpret_cast<int32_t*>(smem_raw + L.oEo);
+    int32_t* const sNo = reinterpret_cast<int32_t*>(smem_raw + L.oNo);
+    int32_t* const sEp = reinterpret_cast<int32_t*>(smem_raw + L.oEp);
+    R* const sInv = reinterpret_cast<R*>(smem_raw + L.oInv);
+    uint32_t* const sSmall = reinterpret_cast<uint32_t*>(smem_raw + L.oSmall);
+    uint4* const sVtx = reinterpret_cast<uint4*>(smem_raw + L.oVtx);
+    uint32_t* const sCtr = reinterpret_cast<uint32_t*>(smem_raw + L.oCtl + 16);
+    const uint32_t mbar = sbase + L.oCtl;
+    const uint32_t hist_words = (kopp_max + 3u) / 4u;
+
+    // ---- stage the group's counts: one thread, bulk-async copies ----
+    if (threadIdx.x == 0) {
+        mbar_init(mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t bM = KA * KB * 128u, bO = kown_max * 128u, bP = kopp_max * 128u;
+        mbar_expect_tx(mbar, bM + 2u * bO + bP);
+        for (uint32_t off = 0; off < bM; off += 32768u)
+            bulk_g2s(sbase + L.oM + off, reinterpret_cast<const char*>(gM) + off, min(32768u, bM - off), mbar);
+        bulk_g2s(sbase + L.oEo, gE + own_off * 32, bO, mbar);
+        bulk_g2s(sbase + L.oNo, gNR + own_off * 32, bO, mbar);
+        bulk_g2s(sbase + L.oEp, gE + opp_off * 32, bP, mbar);
+    }
+    {   // meanwhile: clear the histograms
+        uint32_t* const hw = reinterpret_cast<uint32_t*>(smem_raw + L.oHist);
+        for (uint32_t i = threadIdx.x; i < wpc * hist_words * 32u; i += blockDim.x) hw[i] = 0u;
+    }
+
+    // ---- the CTA's share of the slice: positions pos_begin + cta + j * ctas_per_group, j < cnt ----
+    const uint32_t nv = type ? G.nb : G.na, v0 = type ? G.na : 0;
+    const uint32_t cpg = P.ctas_per_group;
+    const uint32_t span = P.pos_end - P.pos_begin;
+    const uint32_t cnt = P.kat_mode ? 1u : ((span > cta_in_group) ? (span - cta_in_group + cpg - 1u) / cpg : 0u);
+    const uint64_t pkey = (P.sweep * 2 + type) * 0x9E3779B97F4A7C15ull + (uint64_t)group * 0xD1B54A32D192ED03ull;
+    auto prepare = [&](uint32_t j0) -> uint32_t {   // entries j0 .. j0 + nb - 1 into sVtx; all threads
+        const uint32_t nb = (cnt > j0) ? min((uint32_t)S2_VB, cnt - j0) : 0u;
+        for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) {
+            uint4 b;
+            if (P.kat_mode) b.x = P.kat_v;
+            else b.x = v0 + feistel_perm(P.pos_begin + cta_in_group + (j0 + i) * cpg, nv, P.half_bits, pkey);
+            b.y = G.row_ptr[b.x];
+            b.z = G.row_ptr[b.x + 1] - b.y;
+            b.w = G.degidx[b.x];
+            sVtx[i] = b;
+        }
+        if (threadIdx.x == 0) *sCtr = 0u;
+        return nb;
+    };
+    uint32_t nb = prepare(0);
+    mbar_wait(mbar, 0);
+    __syncthreads();
+    // tables derived from the staged counts
+    for (uint32_t i = threadIdx.x; i < kopp_max * 32u; i += blockDim.x) {
+        const uint32_t ci = min(group * 32u + (i & 31u), C - 1u);
+        const double Kc = (double)(P.s.ka[ci] + P.s.kb[ci]);
+        sInv[i] = (R)(1.0 / ((double)sEp[i] + P.s.eps * Kc));
+    }
+    {
+        // a block is "small" when it could empty within this launch without this CTA noticing: only then the veto
+        // needs an exact counter.  One CTA per group: the shared view is exact, every block takes the exact path.
+        const int thresh = P.exclusive ? 0x7fffffff : (int)min(span, 0x7ffffff0u) + 1;
+        const uint32_t words = (kown_max + 31u) / 32u;
+        for (uint32_t i = threadIdx.x; i < words * 32u; i += blockDim.x) {
+            const uint32_t w = i >> 5, l = i & 31u;
+            uint32_t bits = 0;
+            for (uint32_t b = 0; b < 32u && w * 32u + b < kown_max; ++b)
+                if (sNo[(w * 32u + b) * 32u + l] <= thresh) bits |= 1u << b;
+            sSmall[i] = bits;
+        }
+    }
+    __syncthreads();
+
+    // lane-private shared byte addresses (entry j of this chain at +j*128)
+    const uint32_t lane4 = lane * 4u;
+    const uint32_t M_base = sbase + L.oM + lane4;
+    const uint32_t Eo_base = sbase + L.oEo + lane4;
+    const uint32_t No_base = sbase + L.oNo + lane4;
+    const uint32_t Ep_base = sbase + L.oEp + lane4;
+    const uint32_t Inv_base = sbase + L.oInv + lane * (uint32_t)sizeof(R);
+    constexpr uint32_t IS = 32u * (uint32_t)sizeof(R);             // bytes between inv entries of one lane
+    const uint32_t Small_base = sbase + L.oSmall + lane4;
+    const uint32_t hist_base = sbase + L.oHist + warp * hist_words * 128u + lane4;
+    const uint32_t tile_w = sbase + L.oTile + warp * (uint32_t)S2_TILE;
+    const uint32_t tile_lane = tile_w + lane * 36u;                               // this chain's labels, edge e at +e
+    const uint32_t tile_st = tile_w + (lane & 3u) * 288u + (lane >> 2);            // store base: chains 8 (lane%4) + i, row lane/4 (+ 8 j)
+    // m(x_own, t_opp) at M_base + x*SX + t*ST  (bytes)
+    const uint32_t SX = (type ? 1u : KB) * 128u, ST = (type ? KB : 1u) * 128u;
+    // the group's label rows: chain-minor u8, 32 bytes per vertex and group
+    uint64_t LAB8 = (uint64_t)__cvta_generic_to_global(P.lab8 + (size_t)(group * 32u < C ? group * 32u : 0u));
+    asm volatile("" : "+l"(LAB8));
+    const uint32_t key0 = (uint32_t)P.seeds[cc], key1 = (uint32_t)(P.seeds[cc] >> 32);
+    const bool const_T = (P.schedule == 3);
+    const bool movable_chain = live && (kown != 1);
+    const uint32_t kat_lane = P.kat_mode ? (P.kat_chain & 31u) : 32u;
+
+    uint32_t n_acc = 0;
+    double ds_sum = 0.0;
+
+    // neighbour label rows of a vertex: lane l loads 8 bytes (chains 8 (l%4) ..) of row l/4 + 8 j, j = 0..3
+    uint32_t ids[4];
+    uint2 rows[4];
+    auto load_ids = [&](uint32_t row0, uint32_t dcnt) {       // dcnt <= 32 neighbours starting at CSR offset row0
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t rho = (lane >> 2) + 8u * j;
+            ids[j] = 0u;
+            if (rho < dcnt) asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(ids[j]) : "l"(__cvta_generic_to_global(G.col + row0 + rho)));
+        }
+    };
+    auto load_rows = [&](uint32_t dcnt) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t rho = (lane >> 2) + 8u * j;
+            rows[j].x = 0u; rows[j].y = 0u;
+            if (rho < dcnt)
+                asm volatile("{\n\t.reg .u64 a;\n\tmad.wide.u32 a, %2, %3, %4;\n\tld.global.cg.v2.u32 {%0, %1}, [a];\n\t}"
+                             : "=r"(rows[j].x), "=r"(rows[j].y) : "r"(ids[j]), "r"(C), "l"(LAB8 + (uint64_t)((lane & 3u) * 8u)));
+        }
+    };
+    auto store_tile = [&](uint32_t dcnt) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (8u * j < dcnt) {
+                const uint32_t a = tile_st + 8u * j;
+                sh_st_u8(a, rows[j].x);          sh_st_u8(a + 36u, rows[j].x >> 8);
+                sh_st_u8(a + 72u, rows[j].x >> 16);  sh_st_u8(a + 108u, rows[j].x >> 24);
+                sh_st_u8(a + 144u, rows[j].y);       sh_st_u8(a + 180u, rows[j].y >> 8);
+                sh_st_u8(a + 216u, rows[j].y >> 16); sh_st_u8(a + 252u, rows[j].y >> 24);
+            }
+        }
+    };
+    auto lab_ld = [&](uint32_t vtx) -> uint32_t {     // label of vertex vtx in this lane's chain
+        uint32_t x;
+        asm volatile("{\n\t.reg .u64 a;\n\tmad.wide.u32 a, %1, %2, %3;\n\tld.global.cg.u8 %0, [a];\n\t}" : "=r"(x) : "r"(vtx), "r"(C), "l"(LAB8 + (uint64_t)lane));
+        return x;
+    };
+    auto lab_st = [&](uint32_t vtx, uint32_t x) {
+        asm volatile("{\n\t.reg .u64 a;\n\tmad.wide.u32 a, %0, %1, %2;\n\tst.global.u8 [a], %3;\n\t}" :: "r"(vtx), "r"(C), "l"(LAB8 + (uint64_t)lane), "r"(x) : "memory");
+    };
+    auto pop = [&]() -> uint32_t {
+        uint32_t i = 0;
+        if (lane == 0) i = atomicAdd(sCtr, 1u);
+        return __shfl_sync(FULL, i, 0);
+    };
+
+    for (uint32_t j0 = 0;;) {
+        if (warp < P.warps_used) {
+            // pipeline: while vertex k is evaluated, the rows and the own label of vertex k+1 are in flight
+            uint32_t nxt = pop();
+            uint4 ninfo = make_uint4(0, 0, 0, 0);
+            uint32_t r_nxt = 0;
+            if (nxt < nb) {
+                ninfo = sVtx[nxt];
+                load_ids(ninfo.y, min(ninfo.z, 32u));
+                load_rows(min(ninfo.z, 32u));
+                r_nxt = lab_ld(ninfo.x);
+            }
+            while (nxt < nb) {
+                const uint4 cur = ninfo;
+                const uint32_t v = cur.x, d = cur.z, didx = cur.w, r = r_nxt;
+                const uint32_t pos_index = j0 + nxt;      // this vertex's index within the CTA's share
+                __syncwarp();
+                store_tile(min(d, 32u));
+                __syncwarp();
+                // next vertex: ids now, rows after the pass (when the ids have arrived)
+                nxt = pop();
+                if (nxt < nb) {
+                    ninfo = sVtx[nxt];
+                    load_ids(ninfo.y, min(ninfo.z, 32u));
+                }
+                const uint32_t d_n = (nxt < nb) ? min(ninfo.z, 32u) : 0u;
+                auto issue_next = [&]() {
+                    if (nxt < nb) { load_rows(d_n); r_nxt = lab_ld(ninfo.x); }
+                };
+
+                // ---- the draw of this move: Philox4x32-10, counter = (vertex, sweep, chain seed), pool-wide key ----
+                u32x4 ctr; ctr.x = v; ctr.y = (uint32_t)P.sweep; ctr.z = key0; ctr.w = key1;
+                const u32x4 ra = philox4x32(ctr, (uint32_t)(P.sweep >> 32) ^ 0xA4093822u, 0x299F31D0u);
+                const uint32_t ry = ra.y, rz = ra.z, rw = ra.w;
+                // the proposal's random neighbour (differs per lane): its label is in the tile
+                uint32_t tq = 0;
+                if (d != 0u) {
+                    const uint32_t e = mulhi32(ra.x, d);
+                    if (d <= 32u) tq = sh_ld_u8(tile_lane + e);
+                    else tq = (e < 32u) ? sh_ld_u8(tile_lane + e) : lab_ld(G.col[cur.y + e]);
+                }
+                tq = min(tq, kopp_max - 1u);
+                R beta = (R)1 / (R)P.p0;
+                if (!const_T) beta = (R)slow2_beta(P.schedule, P.p0, P.p1, P.step_base + P.pos_begin + cta_in_group + (uint64_t)pos_index * cpg);
+                const bool T_zero = beta < (R)0;
+
+                // ---- proposal (single_vertex_change), branch-free ----
+                const int e_t = sh_ld(Ep_base + tq * 128u);
+                const R inv_t = sh_ld_real<R>(Inv_base + tq * IS);
+                // U < eps K / (e_t + eps K), both sides scaled by 2^32
+                const bool uniform_pick = (d == 0u) || AR::draw_below(ry, epsK32 * inv_t);
+                const uint32_t sg = mulhi32(rz, K);      // uniform over ALL K blocks (either type)
+                const bool sg_a = sg < ka;
+                const uint32_t s_uni = sg_a ? sg : sg - ka;
+                // categorical over row m[t][.]: s = #{x : cum_x <= z}; wz tracks cum - z - 1 (negative while cum <= z)
+                int wz = -(int)mulhi32(rz, (uint32_t)e_t) - 1;
+                uint32_t cnt_le = 0;
+                {
+                    uint32_t a = M_base + tq * ST;
+#pragma unroll 8
+                    for (uint32_t x = 0; x < kown_max; ++x, a += SX) {   // uniform bound; blocks >= kown hold 0
+                        wz += sh_ld(a);
+                        cnt_le += ((uint32_t)wz) >> 31;
+                    }
+                }
+                const uint32_t s_cat = cnt_le < kown ? cnt_le : kown - 1;
+                // a uniform draw that falls on a block of the other type is rejected (dS = +inf): s stays r for it
+                bool cross = movable_chain && uniform_pick && (sg_a != (type == 0));
+                uint32_t s = (movable_chain && !cross) ? (uniform_pick ? s_uni : s_cat) : r;   // own-type local index
+                if (P.kat_mode) { cross = false; s = (lane == kat_lane) ? P.kat_s : r; }
+                const bool eval = live && (s != r);
+                const int n_r = sh_ld(No_base + r * 128u);
+                if (!__any_sync(FULL, eval)) {
+                    // s == r (dS = 0, accu_r = 1): accepted at T > 0 unless the block would empty, rejected at T == 0
+                    // (src/metropolis_hasting.cc:47-52)
+                    if (live && !cross && !T_zero && n_r != 1 && !P.kat_mode) ++n_acc;
+                    issue_next();
+                    continue;
+                }
+                // counts that stay in global memory (eta), requested before the pass
+                const int eta_r = ldc(&gETA[(r * W + didx) * 32 + lane]);
+                const int eta_s = ldc(&gETA[(s * W + didx) * 32 + lane]);
+
+                // ---- one pass over v's neighbours: dS and the Hastings factor (transition_ratio).  Every lane
+                //      runs it (masked lanes cost the same issue slots); only `eval` lanes may commit. ----
+                MAcc<R> A; macc_init(A);
+                const uint32_t Mr = M_base + r * SX, Ms = M_base + s * SX;
+                auto edge1 = [&](uint32_t t) {
+                    const uint32_t sh3 = (t & 3u) << 3;
+                    const uint32_t old = sh_atom_add_u32(hist_base + ((t >> 2) << 7), 1u << sh3);
+                    const uint32_t off = t * ST;
+                    const int m_r = sh_ld(Mr + off), m_s = sh_ld(Ms + off);
+                    const R inv = sh_ld_real<R>(Inv_base + t * IS);
+                    macc_edge(A, m_r, m_s, ((old >> sh3) & 0xffu) + 1u, inv);
+                };
+                auto edge4 = [&](uint32_t Lc) {
+                    const uint32_t t0 = Lc & 0xffu, t1 = (Lc >> 8) & 0xffu, t2 = (Lc >> 16) & 0xffu, t3 = Lc >> 24;
+                    const uint32_t h0 = (t0 & 3u) << 3, h1 = (t1 & 3u) << 3, h2 = (t2 & 3u) << 3, h3 = (t3 & 3u) << 3;
+                    // the four histogram updates in edge order (a repeated label must see the earlier increment)
+                    const uint32_t o0 = sh_atom_add_u32(hist_base + ((t0 >> 2) << 7), 1u << h0);
+                    const uint32_t o1 = sh_atom_add_u32(hist_base + ((t1 >> 2) << 7), 1u << h1);
+                    const uint32_t o2 = sh_atom_add_u32(hist_base + ((t2 >> 2) << 7), 1u << h2);
+                    const uint32_t o3 = sh_atom_add_u32(hist_base + ((t3 >> 2) << 7), 1u << h3);
+                    const uint32_t f0 = t0 * ST, f1 = t1 * ST, f2 = t2 * ST, f3 = t3 * ST;
+                    const int r0 = sh_ld(Mr + f0), s0 = sh_ld(Ms + f0), r1 = sh_ld(Mr + f1), s1 = sh_ld(Ms + f1);
+                    const int r2 = sh_ld(Mr + f2), s2 = sh_ld(Ms + f2), r3 = sh_ld(Mr + f3), s3 = sh_ld(Ms + f3);
+                    const R i0 = sh_ld_real<R>(Inv_base + t0 * IS), i1 = sh_ld_real<R>(Inv_base + t1 * IS);
+                    const R i2 = sh_ld_real<R>(Inv_base + t2 * IS), i3 = sh_ld_real<R>(Inv_base + t3 * IS);
+                    macc_edge(A, r0, s0, ((o0 >> h0) & 0xffu) + 1u, i0);
+                    macc_edge(A, r1, s1, ((o1 >> h1) & 0xffu) + 1u, i1);
+                    macc_edge(A, r2, s2, ((o2 >> h2) & 0xffu) + 1u, i2);
+                    macc_edge(A, r3, s3, ((o3 >> h3) & 0xffu) + 1u, i3);
+                };
+                for (uint32_t e0 = 0; e0 < d; e0 += 32u) {
+                    const uint32_t nrem = min(32u, d - e0);
+                    if (e0) {   // hubs: later blocks of 32 neighbours are fetched in place
+                        __syncwarp();
+                        uint32_t keep_ids[4];    // ids[] holds the NEXT vertex's neighbours; rows[] is free (already in the tile)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) keep_ids[j] = ids[j];
+                        load_ids(cur.y + e0, nrem);
+                        load_rows(nrem);
+                        store_tile(nrem);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) ids[j] = keep_ids[j];
+                        __syncwarp();
+                        if (AR::FOLD >= 32) macc_fold(A);
+                    }
+                    const uint32_t nch = (nrem + 3u) >> 2;
+                    uint32_t Lw = sh_ld_u32v(tile_lane);
+                    for (uint32_t q = 0; q < nch; ++q) {
+                        const uint32_t Lc = Lw;
+                        if (q + 1u < nch) Lw = sh_ld_u32v(tile_lane + 4u * (q + 1u));
+                        const uint32_t c4 = nrem - 4u * q;
+                        if (c4 >= 4u) edge4(Lc);
+                        else {
+                            edge1(Lc & 0xffu);
+                            if (c4 > 1u) edge1((Lc >> 8) & 0xffu);
+                            if (c4 > 2u) edge1((Lc >> 16) & 0xffu);
+                        }
+                        if (AR::FOLD < 32) macc_fold(A);
+                    }
+                }
+                issue_next();
+                __syncwarp();
+
+                // ---- dS, accept (step) ----
+                bool go;
+                R dS;
+                const int n_s = sh_ld(No_base + s * 128u);
+                {
+                    const int e_r = sh_ld(Eo_base + r * 128u), e_s = sh_ld(Eo_base + s * 128u);
+                    bool ok_b, ok_r, ok_s;
+                    R bdd = bdd_fast<R>(e_r, e_s, (int)d, &ok_b);
+                    auto load_q = [&](uint32_t slot) -> LogqExp {   // 32 bytes of this (block, chain); constant during the launch
+                        const uint4* p = reinterpret_cast<const uint4*>(gLQ + slot * 32u + lane);
+                        const uint4 a = __ldg(p), b = __ldg(p + 1);
+                        LogqExp q;
+                        q.e0 = (int)a.x; q.n0 = (int)a.y; q.fe = __uint_as_float(a.z); q.fn = __uint_as_float(a.w);
+                        q.fee = __uint_as_float(b.x); q.fen = __uint_as_float(b.y); q.fnn = __uint_as_float(b.z); q.valid = b.w;
+                        return q;
+                    };
+                    R lqr = logq_fast<R>(load_q(r), e_r, n_r, -(int)d, -1, &ok_r);
+                    R lqs = logq_fast<R>(load_q(s), e_s, n_s, (int)d, 1, &ok_s);
+                    if (__any_sync(FULL, eval && !(ok_b && ok_r && ok_s))) {
+                        if (eval && !ok_b) bdd = (R)slow2_block_degree_delta(e_r, e_s, (int)d);
+                        if (eval && !ok_r) lqr = (R)slow2_logq_delta(P.tb.qtab, P.tb.qn, P.tb.qk, e_r, n_r, -(int)d, -1);
+                        if (eval && !ok_s) lqs = (R)slow2_logq_delta(P.tb.qtab, P.tb.qn, P.tb.qk, e_s, n_s, (int)d, 1);
+                        __syncwarp();
+                    }
+                    R lh;
+                    move_finish<R>(A, eta_r, eta_s, bdd, lqr, lqs, d, eps, &dS, &lh);
+                    const R a2 = lh - dS * (beta * AR::inv_unit());          // lg of the acceptance ratio
+                    const bool go_hot = (a2 > (R)0) || (AR::u01(rw) < AR::ex(a2));
+                    go = eval && (T_zero ? (dS < (R)0) : go_hot);
+                    if (P.kat_mode) {
+                        if (lane == kat_lane && eval) { P.kat_out[0] = (double)dS; P.kat_out[1] = (double)(lh * AR::unit()); }
+                        go = false;
+                    }
+                    // s == r: see above
+                    if (live && !cross && s == r && !T_zero && n_r != 1 && !P.kat_mode) ++n_acc;
+                    if (go) {
+                        // the "would empty block r" veto of apply_mcmc_moves: exact where it can matter
+                        const uint32_t small_r = (sh_ld_u32v(Small_base + (r >> 5) * 128u) >> (r & 31u)) & 1u;
+                        if (small_r) {
+                            if (P.exclusive) {
+                                const int old = sh_atom_add_s32(No_base + r * 128u, -1);
+                                if (old <= 1) { sh_red_add(No_base + r * 128u, 1); go = false; }
+                            } else {
+                                const int old = atomicSub(&gLIVE[r * 32 + lane], 1);
+                                if (old <= 1) { atomicAdd(&gLIVE[r * 32 + lane], 1); go = false; }
+                                else sh_red_add(No_base + r * 128u, -1);
+                            }
+                        } else {
+                            sh_red_add(No_base + r * 128u, -1);
+                        }
+                    }
+                }
+                __syncwarp();
+
+                // ---- commit (apply_mcmc_moves) and clear the histogram ----
+                const bool any_go = __any_sync(FULL, go);
+                if (d <= 32u) {
+                    if (any_go) {     // walk the edges again: m(r,t) -= 1, m(s,t) += 1 for the lanes that move
+                        const int g1 = go ? 1 : 0;
+                        const uint32_t nch = (d + 3u) >> 2;
+                        for (uint32_t q = 0; q < nch; ++q) {
+                            const uint32_t Lc = sh_ld_u32v(tile_lane + 4u * q);
+                            const uint32_t c4 = d - 4u * q;
+                            const uint32_t f0 = (Lc & 0xffu) * ST;
+                            sh_red_add(Mr + f0, -g1); sh_red_add(Ms + f0, g1);
+                            if (c4 > 1u) { const uint32_t f1 = ((Lc >> 8) & 0xffu) * ST; sh_red_add(Mr + f1, -g1); sh_red_add(Ms + f1, g1); }
+                            if (c4 > 2u) { const uint32_t f2 = ((Lc >> 16) & 0xffu) * ST; sh_red_add(Mr + f2, -g1); sh_red_add(Ms + f2, g1); }
+                            if (c4 > 3u) { const uint32_t f3 = (Lc >> 24) * ST; sh_red_add(Mr + f3, -g1); sh_red_add(Ms + f3, g1); }
+                        }
+                    }
+                    for (uint32_t w = 0; w < hist_words; ++w) sh_st_u32v(hist_base + w * 128u, 0u);
+                } else {              // hubs: the histogram is k_t
+                    uint32_t ha = hist_base;
+                    for (uint32_t w = 0; w < hist_words; ++w, ha += 128u) {
+                        uint32_t word = sh_ld_u32v(ha);
+                        sh_st_u32v(ha, 0u);
+                        word = go ? word : 0u;
+#pragma unroll
+                        for (uint32_t b = 0; b < 4; ++b) {
+                            const uint32_t t = w * 4u + b;
+                            if (t < kopp_max) {
+                                const int kk = (int)((word >> (8u * b)) & 0xffu);
+                                sh_red_add(Mr + t * ST, -kk); sh_red_add(Ms + t * ST, kk);
+                            }
+                        }
+                    }
+                }
+                if (go) {
+                    sh_red_add(Eo_base + r * 128u, -(int)d);
+                    sh_red_add(Eo_base + s * 128u, (int)d);
+                    sh_red_add(No_base + s * 128u, 1);
+                    if (!P.exclusive && ((sh_ld_u32v(Small_base + (s >> 5) * 128u) >> (s & 31u)) & 1u)) atomicAdd(&gLIVE[s * 32 + lane], 1);
+                    atomicSub(&gETA[(r * W + didx) * 32 + lane], 1);
+                    atomicAdd(&gETA[(s * W + didx) * 32 + lane], 1);
+                    lab_st(v, s);
+                    ++n_acc;
+                    ds_sum += (double)dS;
+                }
+            }
+        }
+        j0 += (uint32_t)S2_VB;
+        if (j0 >= cnt) break;
+        __syncthreads();
+        nb = prepare(j0);
+        __syncthreads();
+    }
+    if (warp < P.warps_used && live) {
+        if (n_acc) atomicAdd(&P.accepted[c], (unsigned long long)n_acc);
+        if (ds_sum != 0.0) atomicAdd(&P.dS_accum[c], ds_sum);
+    }
+
+    // ---- publish the staged counts ----
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // shared-memory writes of this thread -> visible to the bulk engine
+    __syncthreads();
+    if (P.kat_mode) return;
+    if (P.exclusive) {
+        copy_i4(gM, sM, KA * KB * 32);
+        copy_i4(gE + own_off * 32, sEo, kown_max * 32);
+        copy_i4(gNR + own_off * 32, sNo, kown_max * 32);
+    } else if (threadIdx.x == 0) {
+        char* const nM = reinterpret_cast<char*>(P.m_next + (size_t)group * KA * KB * GROUP);
+        const uint32_t bM = KA * KB * 128u, bO = kown_max * 128u;
+        for (uint32_t off = 0; off < bM; off += 32768u) bulk_red_add_s32(nM + off, sbase + L.oM + off, min(32768u, bM - off));
+        bulk_red_add_s32(P.e_next + (size_t)group * KK * GROUP + own_off * 32, sbase + L.oEo, bO);
+        bulk_red_add_s32(P.nr_next + (size_t)group * KK * GROUP + own_off * 32, sbase + L.oNo, bO);
+        bulk_commit_wait_all();
+    }
+}
+
+#endif  // __CUDACC__
+
+}  // namespace bisbm

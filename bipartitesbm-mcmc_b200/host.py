@@ -65,12 +65,15 @@ SIGNATURES = {
     "bisbm_marginalize": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, _u64p, C.c_uint32]),
     "bisbm_marginals_clear": (C.c_int, [C.c_void_p]),
     "bisbm_set_precision": (C.c_int, [C.c_void_p, C.c_int]),
+    "bisbm_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
+    "bisbm_parallel_transition": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, _dp, _dp]),
     "bisbm_sweep_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
                                    C.POINTER(C.c_uint32)]),
     "bisbm_marginals_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), _u64p, _u32p]),
     "bisbm_get_marginals": (C.c_int, [C.c_void_p, _u32p]),
     "bisbm_marginal_argmax": (C.c_int, [C.c_void_p, _u32p]),
     "bisbm_last_timing": (C.c_int, [C.c_void_p, _dp, _u64p, _u64p]),
+    "bisbm_sweep_launches": (C.c_int, [C.c_void_p, _u64p]),
     "bisbm_stream": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "bisbm_info": (C.c_int, [C.c_void_p, _u32p, _u64p, _u32p, _u32p]),
     "bisbm_get_labels": (C.c_int, [C.c_void_p, C.c_uint32, _u32p]),
@@ -214,11 +217,22 @@ class ChainPool:
         _check(self.L.bisbm_marginalize(self.g.h, burn_in, sweeps, every, _p(seeds, C.c_uint64), max_inflight))
 
     def set_precision(self, mode):
-        """'fp32' (default: fp32 move arithmetic where the fast kernel applies) or 'fp64'."""
+        """'fp64' (default: the move is evaluated in double like the reference) or 'fp32'."""
         _check(self.L.bisbm_set_precision(self.g.h, {"fp32": 0, "fp64": 1}.get(mode, mode)))
 
+    def set_option(self, name, value):
+        """Tuning options of the parallel sweep: 'inflight_div', 'kernel', 'generic' (include/bisbm.h)."""
+        _check(self.L.bisbm_set_option(self.g.h, name.encode(), int(value)))
+
+    def parallel_transition(self, chain, v, s):
+        """(dS, log accu_r) of moving v to global block s, by the parallel sweep kernel's own device code."""
+        dS, la = C.c_double(), C.c_double()
+        _check(self.L.bisbm_parallel_transition(self.g.h, chain, v, s, C.byref(dS), C.byref(la)))
+        return dS.value, la.value
+
     def sweep_info(self):
-        """(kernel, warps per CTA, CTAs per chain group, slice) of the last parallel call; kernel 2 = fp32."""
+        """(kernel, warps per CTA, CTAs per chain group, slice) of the last parallel call; kernel 3 = sweep2<double>,
+        2 = sweep2<float>, 1 = round-1 staged double kernel, 0 = counts in L2."""
         k, w, c, sl = C.c_int(), C.c_uint32(), C.c_uint32(), C.c_uint32()
         _check(self.L.bisbm_sweep_info(self.g.h, C.byref(k), C.byref(w), C.byref(c), C.byref(sl)))
         return k.value, w.value, c.value, sl.value
@@ -247,6 +261,11 @@ class ChainPool:
         ms, la, mv = C.c_double(), C.c_uint64(), C.c_uint64()
         _check(self.L.bisbm_last_timing(self.g.h, C.byref(ms), C.byref(la), C.byref(mv)))
         return ms.value, la.value, mv.value
+
+    def sweep_launches(self):
+        x = C.c_uint64()
+        _check(self.L.bisbm_sweep_launches(self.g.h, C.byref(x)))
+        return x.value
 
     # -- replay mode
     def replay_init(self, chain, engine_seed, gen_seed=12345, randomize=False):

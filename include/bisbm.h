@@ -106,16 +106,25 @@ int bisbm_marginalize(bisbm_handle* h, uint64_t burn_in, uint64_t sweeps, uint64
                       uint32_t max_inflight);
 int bisbm_marginals_clear(bisbm_handle* h);
 /* Arithmetic of the parallel sweep's per-move evaluation (dS, Hastings factor, accept test).  The reference
- * computes transition_ratio in double (src/metropolis_hasting.cc:103-192); parallel mode is only statistically
- * equivalent to it anyway, and by default evaluates the move in fp32 (|error of the log acceptance ratio|
- * <~ 2e-5) with integer counts and commits exact.  BISBM_PRECISION_FP64 keeps the whole evaluation in double.
- * Replay mode is always strict double. */
+ * computes transition_ratio in double (src/metropolis_hasting.cc:103-192) and so does parallel mode by default
+ * (BISBM_PRECISION_FP64).  BISBM_PRECISION_FP32 evaluates the move in fp32 on the MUFU unit (|error of the log
+ * acceptance ratio| <~ 2e-5); counts and commits stay exact integers either way.  Replay mode is always strict double. */
 enum { BISBM_PRECISION_FP32 = 0, BISBM_PRECISION_FP64 = 1 };
 int bisbm_set_precision(bisbm_handle* h, int mode);
+/* Tuning options of the parallel sweep (no environment variables are read):
+ *   "inflight_div"  default in-flight bound of bisbm_anneal(max_inflight = 0) = half sweep / value (default 64)
+ *   "kernel"        -1 automatic; 0 force counts in L2; 1 force the round-1 staged double kernel (A/B runs)
+ *   "generic"       1: never take the Ka = Kb = 32 compile-time specialisation */
+int bisbm_set_option(bisbm_handle* h, const char* name, int64_t value);
 /* which sweep kernel the last parallel call launched and how the half sweep was cut:
- * kernel 0 = double arithmetic, counts in L2; 1 = double, counts staged in shared memory; 2 = fp32, staged counts;
+ * kernel 0 = double arithmetic, counts in L2 (sweep_kernel); 1 = round-1 staged double kernel; 2 = sweep2_kernel<float>;
+ * 3 = sweep2_kernel<double> (staged counts, the default);
  * slice = vertices of the visiting order per launch (the staleness bound between CTAs of one chain group) */
 int bisbm_sweep_info(bisbm_handle* h, int* kernel, uint32_t* warps_per_cta, uint32_t* ctas_per_group, uint32_t* slice);
+/* transition_ratio (src/metropolis_hasting.cc:103-192) for moving v to global block s in chain `chain`, evaluated by the
+ * PARALLEL sweep kernel's own device code (one forced proposal through sweep2_kernel, nothing committed): dS and
+ * log(accu_r) in the handle's current precision.  Cross-type targets give dS = +inf (log_accu NaN), s == r gives 0, 0. */
+int bisbm_parallel_transition(bisbm_handle* h, uint32_t chain, uint32_t v, uint32_t s, double* dS, double* log_accu);
 /* device pointer + element count of the histogram, for an in-place NCCL all-reduce */
 int bisbm_marginals_device(bisbm_handle* h, void** dev_ptr, uint64_t* n_elems, uint32_t* width);
 int bisbm_get_marginals(bisbm_handle* h, uint32_t* hist);          /* [n][width], global block ids */
@@ -123,6 +132,8 @@ int bisbm_marginal_argmax(bisbm_handle* h, uint32_t* labels);      /* [n] */
 /* device-side sweep timing of the last parallel call: total kernel ms (CUDA events on the
  * handle's stream), kernel launches, and single-vertex moves attempted */
 int bisbm_last_timing(bisbm_handle* h, double* sweep_ms, uint64_t* launches, uint64_t* moves);
+/* of those launches, how many were the sweep kernel itself (one per slice of a half sweep) */
+int bisbm_sweep_launches(bisbm_handle* h, uint64_t* sweep_kernel_launches);
 /* stream the handle launches on (cudaStream_t as void*) */
 int bisbm_stream(bisbm_handle* h, void** stream);
 

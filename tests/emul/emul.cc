@@ -14,7 +14,7 @@
 
 #include "../../bipartitesbm-mcmc_b200/csrc/replay.cuh"
 #include "../../bipartitesbm-mcmc_b200/csrc/sweep.cuh"
-#include "../../bipartitesbm-mcmc_b200/csrc/sweep_fast.cuh"
+#include "../../bipartitesbm-mcmc_b200/csrc/sweep2.cuh"
 
 using namespace bisbm;
 
@@ -200,10 +200,12 @@ void emul_par_dS(void* p, uint32_t v, uint32_t sg, int use_taylor, double* dS, d
     *accu = d == 0 ? 1.0 : a1 / a0;
 }
 
-// the fp32 kernel's arithmetic (sweep_fast.cuh: facc_edge / facc_fold / f_block_degree_delta / f_logq_delta)
-// for the same move; *fell_back counts the terms that took the double-precision completion
-void emul_par_dS_f32(void* p, uint32_t v, uint32_t sg, int use_taylor, double* dS, double* log_accu, int* fell_back) {
-    Emul* s = (Emul*)p;
+}  // extern "C"
+
+// the staged kernel's arithmetic (sweep2.cuh: macc_edge / macc_fold / bdd_fast / logq_fast / move_finish) for the same
+// move, in R = float or double; *fell_back counts the terms that took the out-of-line double completion
+template <typename R>
+static void par2_dS(Emul* s, uint32_t v, uint32_t sg, int use_taylor, double* dS, double* log_accu, int* fell_back) {
     ReplayCtx x = ctx(s);
     const bool va = v < s->na;
     const uint32_t r = s->labels[(size_t)v * s->C + s->chain];
@@ -212,17 +214,17 @@ void emul_par_dS_f32(void* p, uint32_t v, uint32_t sg, int use_taylor, double* d
     const uint32_t own_off = va ? 0 : KA, opp_off = va ? KA : 0;
     const uint32_t sx = va ? KB : 1, st = va ? 1 : KB;
     const int32_t* Mr = s->m.data() + (size_t)r * sx; const int32_t* Ms = s->m.data() + (size_t)sl * sx;
-    const float eps = (float)s->eps;
     const uint32_t d = s->row_ptr[v + 1] - s->row_ptr[v];
-    FAcc A; facc_init(A);
+    MAcc<R> A; macc_init(A);
     std::vector<int> cnt(kopp, 0);
     for (uint32_t e = 0; e < d; ++e) {
         uint32_t nb = s->col[s->row_ptr[v] + e];
         uint32_t t = s->labels[(size_t)nb * s->C + s->chain];
         int c = cnt[t]++;
-        float inv = (float)(1.0 / ((double)s->e[opp_off + t] + s->eps * (double)(KA + KB)));
-        facc_edge(A, Mr[(size_t)t * st], Ms[(size_t)t * st], c + 1, inv);
-        if ((e & 3u) == 3u || e + 1 == d) facc_fold(A);
+        R inv = (R)(1.0 / ((double)s->e[opp_off + t] + s->eps * (double)(KA + KB)));
+        macc_edge<R>(A, Mr[(size_t)t * st], Ms[(size_t)t * st], (uint32_t)c + 1u, inv);
+        // the kernel folds after every chunk of 4 edges (float) or after every block of 32 (double)
+        if (Ar<R>::FOLD < 32 ? ((e & 3u) == 3u || e + 1 == d) : ((e & 31u) == 31u && e + 1 < d)) macc_fold(A);
     }
     int e_r = s->e[own_off + r], e_s = s->e[own_off + sl], n_r = s->nr[own_off + r], n_s = s->nr[own_off + sl];
     uint32_t didx = s->degidx[v];
@@ -250,18 +252,24 @@ void emul_par_dS_f32(void* p, uint32_t v, uint32_t sg, int use_taylor, double* d
         qr = mk(e_r + e_r / 40, n_r - n_r / 50); qs = mk(e_s - e_s / 40, n_s + n_s / 50);
     }
     bool ok_b, ok_r, ok_s;
-    float bdd = f_block_degree_delta(e_r, e_s, (int)d, &ok_b);
-    float lqr = f_logq_delta(qr, e_r, n_r, -(int)d, -1, &ok_r);
-    float lqs = f_logq_delta(qs, e_s, n_s, (int)d, 1, &ok_s);
+    R bdd = bdd_fast<R>(e_r, e_s, (int)d, &ok_b);
+    R lqr = logq_fast<R>(qr, e_r, n_r, -(int)d, -1, &ok_r);
+    R lqs = logq_fast<R>(qs, e_s, n_s, (int)d, 1, &ok_s);
     *fell_back = (!ok_b) + (!ok_r) + (!ok_s);
-    if (!ok_b) bdd = (float)block_degree_delta(e_r, e_s, (int)d);
-    if (!ok_r) lqr = (float)logq_delta_exact(tb, e_r, n_r, -(int)d, -1);
-    if (!ok_s) lqs = (float)logq_delta_exact(tb, e_s, n_s, (int)d, 1);
-    float out = BISBM_LN2F * (A.lg + f_lg2((float)(eta_r > 0 ? eta_r : 1) * f_rcp((float)(eta_s + 1))));
-    out += ((d == 0) ? 0.f : bdd) + lqr + lqs;
-    const float ew = eps * A.w;
+    if (!ok_b) bdd = (R)block_degree_delta(e_r, e_s, (int)d);
+    if (!ok_r) lqr = (R)logq_delta_exact(tb, e_r, n_r, -(int)d, -1);
+    if (!ok_s) lqs = (R)logq_delta_exact(tb, e_s, n_s, (int)d, 1);
+    R out, lh;
+    move_finish<R>(A, eta_r, eta_s, bdd, lqr, lqs, d, (R)s->eps, &out, &lh);
     *dS = (double)out;
-    *log_accu = d == 0 ? 0.0 : (double)(BISBM_LN2F * f_lg2((A.a1 + ew) * f_rcp(A.a0 + ew)));
+    *log_accu = (double)(lh * Ar<R>::unit());
+}
+
+extern "C" {
+
+void emul_par2_dS(void* p, uint32_t v, uint32_t sg, int use_taylor, int fp32, double* dS, double* log_accu, int* fell_back) {
+    if (fp32) par2_dS<float>((Emul*)p, v, sg, use_taylor, dS, log_accu, fell_back);
+    else par2_dS<double>((Emul*)p, v, sg, use_taylor, dS, log_accu, fell_back);
 }
 
 double emul_entropy_accum(void* p) { return ((Emul*)p)->rs.entropy_accum; }

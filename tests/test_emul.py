@@ -22,7 +22,7 @@ pu = C.POINTER(C.c_uint32)
 def emul():
     src = os.path.join(EMUL_DIR, "emul.cc")
     deps = [src] + [os.path.join(ROOT, "bipartitesbm-mcmc_b200", "csrc", f) for f in
-                    ("devmath.cuh", "state.cuh", "replay.cuh", "sweep.cuh", "sweep_fast.cuh")]
+                    ("devmath.cuh", "state.cuh", "replay.cuh", "sweep.cuh", "sweep2.cuh")]
     if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-x", "c++",
                                "-o", LIB, src, "-lm"])
@@ -40,8 +40,8 @@ def emul():
     L.emul_words.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.emul_transition.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.emul_par_dS.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
-    L.emul_par_dS_f32.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double),
-                                  C.POINTER(C.c_int)]
+    L.emul_par2_dS.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.POINTER(C.c_double),
+                               C.POINTER(C.c_double), C.POINTER(C.c_int)]
     L.emul_lgamma_diff.restype = C.c_double
     L.emul_lgamma_diff.argtypes = [C.c_double, C.c_double]
     L.emul_block_degree_delta.restype = C.c_double
@@ -125,11 +125,13 @@ def test_parallel_move_arithmetic_matches_reference(emul, name, taylor, tol):
 
 @pytest.mark.parametrize("name,taylor", [("c1_seed1", 0), ("c2_abrupt", 0), ("c2_const_k46", 0), ("big_blocks", 0),
                                          ("big_blocks", 1), ("isolated", 0)])
-def test_fp32_move_arithmetic_matches_reference(emul, name, taylor):
-    """The fp32 kernel's per-move arithmetic (sweep_fast.cuh) vs the reference's transition_ratio known answers.
-    What the accept test consumes is a = log(accu_r) - dS / T: the tolerance is ABSOLUTE on dS and on log(accu_r),
-    2e-5 * max(1, |dS| / 8) -- i.e. an acceptance probability off by a factor exp(2e-5) at worst -- where the
-    host's log2f / exp2f / division stand in for the device's lg2/ex2/rcp.approx (2^-22 relative)."""
+@pytest.mark.parametrize("fp32", [0, 1])
+def test_staged_kernel_move_arithmetic_matches_reference(emul, name, taylor, fp32):
+    """The staged sweep kernel's per-move arithmetic (sweep2.cuh, R = double / float) vs the reference's transition_ratio
+    known answers.  double: 1e-9 relative on dS (north-star), 1e-12 relative on accu_r (2e-6 absolute on dS where the
+    second-order log q expansion is evaluated 2.5% away from its expansion point).  float: what the accept test consumes is
+    a = log(accu_r) - dS / T, so the tolerance is ABSOLUTE, 2e-5 * max(1, |dS| / 8) -- an acceptance probability off by a
+    factor exp(2e-5) at worst -- with the host's log2f / exp2f / division standing in for lg2/ex2/rcp.approx."""
     g = load_golden(name)
     h = _create(emul, g)
     checked = 0
@@ -139,13 +141,18 @@ def test_fp32_move_arithmetic_matches_reference(emul, name, taylor):
         if np.isinf(dS) or r == s:
             continue
         d, a, fb = C.c_double(), C.c_double(), C.c_int()
-        emul.emul_par_dS_f32(h, int(v), int(s), taylor, C.byref(d), C.byref(a), C.byref(fb))
-        tol = 2e-5 * max(1.0, abs(dS) / 8.0) + (2e-6 if taylor else 0.0)
-        assert abs(d.value - dS) <= tol, (v, s, d.value, dS)
-        assert abs(a.value - np.log(ar)) <= 2e-5 * max(1.0, abs(np.log(ar))), (v, s, a.value, np.log(ar))
+        emul.emul_par2_dS(h, int(v), int(s), taylor, fp32, C.byref(d), C.byref(a), C.byref(fb))
+        if fp32:
+            tol = 2e-5 * max(1.0, abs(dS) / 8.0) + (2e-6 if taylor else 0.0)
+            assert abs(d.value - dS) <= tol, (v, s, d.value, dS)
+            assert abs(a.value - np.log(ar)) <= 2e-5 * max(1.0, abs(np.log(ar))), (v, s, a.value, np.log(ar))
+        else:
+            tol = 2e-6 if taylor else 1e-9 * max(1.0, abs(dS))
+            assert abs(d.value - dS) <= tol, (v, s, d.value, dS)
+            assert abs(a.value - np.log(ar)) <= 1e-12 * max(1.0, abs(np.log(ar))), (v, s, a.value, np.log(ar))
         worst = max(worst, abs(d.value - dS))
         checked += 1
-    print(name, "fp32 dS worst abs error", worst, "over", checked)
+    print(name, "fp32" if fp32 else "fp64", "dS worst abs error", worst, "over", checked)
     assert checked > 0
     emul.emul_destroy(h)
 

@@ -80,21 +80,18 @@ def test_early_stop_and_abrupt_cool(host):
 
 
 def test_statistical_parity_with_oracle_nmi_and_entropy(host):
-    """R oracle chains vs R GPU chains on bisbm-1000 at (Ka,Kb)=(4,6), randomised
+    """128 oracle chains vs 128 GPU chains on bisbm-1000 at (Ka,Kb)=(4,6), randomised
     starts, abrupt_cool T0 = 1e5 steps then greedy, 200 sweeps; compare the samples of final
-    entropy() and of NMI against the planted file partition with a two-sample KS test."""
+    entropy() and of NMI against the planted file partition with a two-sample KS test (p > 0.01).  The oracle
+    samples are the q46_* arrays of tests/golden/parity_mid.npz (tests/golden/make_parity_fixture.py)."""
     from scipy.stats import ks_2samp
     g = load_golden("c2_const_k46")
+    fx = load_golden("parity_mid")
     na, nb, edges, mb = g["na"], g["nb"], g["edges"], g["labels0"]
     n = na + nb
-    R = 24
-    ent_o, nmi_o, acc_o = [], [], []
-    for s in range(R):
-        o = port.PortChain(n, na, nb, edges, mb, 4, 6, 1.0, 1000 + s, 2000 + s)
-        o.init(True)
-        acc_o.append(o.anneal("abrupt_cool", 1e5, 0, 200 * n, 10 ** 9))
-        ent_o.append(o.entropy())
-        nmi_o.append(nmi(o.labels(), mb))
+    R = 128
+    ent_o, nmi_o, acc_o = fx["q46_entropy"], fx["q46_nmi"], fx["q46_accept"]
+    assert len(ent_o) >= 128
     graph = host.Graph(edges, na, nb)
     pool = host.ChainPool(graph, np.tile(mb, (R, 1)), 4, 6, 1.0)
     seeds = np.arange(R, dtype=np.uint64) + 77
@@ -106,11 +103,11 @@ def test_statistical_parity_with_oracle_nmi_and_entropy(host):
     check_invariants(pool, edges, na, nb, [0, R - 1])
     p_ent = ks_2samp(ent_o, ent_g).pvalue
     p_nmi = ks_2samp(nmi_o, nmi_g).pvalue
-    print("entropy oracle %.1f+-%.1f gpu %.1f+-%.1f p=%.3f | nmi oracle %.3f gpu %.3f p=%.3f | acc %.4f %.4f" % (
+    p_acc = ks_2samp(acc_o, acc_g).pvalue
+    print("entropy oracle %.1f+-%.1f gpu %.1f+-%.1f p=%.3f | nmi oracle %.3f gpu %.3f p=%.3f | acc %.4f %.4f p=%.3f | plan %s" % (
         np.mean(ent_o), np.std(ent_o), np.mean(ent_g), np.std(ent_g), p_ent, np.mean(nmi_o), np.mean(nmi_g), p_nmi,
-        np.mean(acc_o), np.mean(acc_g)))
-    assert p_ent > 0.01 and p_nmi > 0.01
-    assert abs(np.mean(acc_o) - np.mean(acc_g)) < 3 * np.std(acc_o) / np.sqrt(R) + 3 * np.std(acc_g) / np.sqrt(R) + 0.01
+        np.mean(acc_o), np.mean(acc_g), p_acc, pool.sweep_info()))
+    assert p_ent > 0.01 and p_nmi > 0.01 and p_acc > 0.01
 
 
 def test_marginals_match_oracle(host):
@@ -121,7 +118,7 @@ def test_marginals_match_oracle(host):
     g = load_golden("c2_const_k46")
     na, nb, edges, mb = g["na"], g["nb"], g["edges"], g["labels0"]
     n = na + nb
-    R, burn, sweeps, every = 16, 30, 120, 4
+    R, burn, sweeps, every = 64, 30, 120, 4
     hist_o = np.zeros((n, 10), dtype=np.int64)
     for s in range(R):
         o = port.PortChain(n, na, nb, edges, mb, 4, 6, 1.0, 300 + s, 400 + s)
@@ -290,17 +287,18 @@ def test_k32_specialised_kernel(host):
 
 
 def test_fp32_kernel_is_selected_and_matches_double_statistically(host):
-    """The default parallel path is the fp32 kernel (sweep_fast.cuh) where it applies; BISBM_PRECISION_FP64 switches
-    the same pool to the double kernel.  The two use different draw streams, so the comparison is statistical:
-    final description length and acceptance of 96 + 96 strictly sequential chains on the oracle-parity workload."""
+    """The default parallel path evaluates a move in double (sweep2_kernel<double>); BISBM_PRECISION_FP32 switches
+    the same pool to the fp32 instantiation.  The two use different arithmetic on the same draws, so the comparison is
+    statistical: final description length and acceptance of 128 + 128 strictly sequential chains on the oracle-parity
+    workload."""
     from scipy.stats import ks_2samp
     g = load_golden("c2_const_k46")
     na, nb, edges, mb = g["na"], g["nb"], g["edges"], g["labels0"]
     n = na + nb
     graph = host.Graph(edges, na, nb)
-    R = 96
+    R = 128
     out = {}
-    for prec, want_kernel in (("fp32", 2), ("fp64", 1)):
+    for prec, want_kernel in (("fp32", 2), ("fp64", 3)):
         pool = host.ChainPool(graph, np.tile(mb, (R, 1)), 4, 6, 1.0)
         pool.set_precision(prec)
         seeds = np.arange(R, dtype=np.uint64) + 4242
@@ -314,12 +312,12 @@ def test_fp32_kernel_is_selected_and_matches_double_statistically(host):
     p_acc = ks_2samp(out["fp32"][1], out["fp64"][1]).pvalue
     print("fp32 vs fp64: entropy %.1f / %.1f (KS p=%.3f), acceptance %.4f / %.4f (KS p=%.3f)" % (
         out["fp32"][0].mean(), out["fp64"][0].mean(), p_ent, out["fp32"][1].mean(), out["fp64"][1].mean(), p_acc))
-    assert p_ent > 0.001 and p_acc > 0.001
+    assert p_ent > 0.01 and p_acc > 0.01
 
 
 def test_full_size_c3_properties(host):
     """BASELINE configs[2] at FULL size (1M nodes / 10M edges, Ka = Kb = 32, 256 chains on one GPU) through
-    size-independent properties: after sweeps of the default plan (fp32 kernel, 18 CTAs per chain group, slices of
+    size-independent properties: after sweeps of the default plan (sweep2_kernel<double>, 18 CTAs per chain group, slices of
     n/64) the device counts of any chain equal a from-scratch rebuild from its labels (m_rs, e_r, n_r, eta -- so no
     delta was lost or applied twice across the ~130 slice launches of a sweep), every block stays non-empty, the
     accumulated dS tracks the true change of the description length, and chains started from different
@@ -337,7 +335,7 @@ def test_full_size_c3_properties(host):
     acc, sw = pool.anneal("constant", 1.0, 0.0, 2 * (na + nb), 10 ** 18, seeds)
     kern, wpc, cpg, sl = pool.sweep_info()
     # slices: at most n/64 vertices (the default staleness bound) and a whole number of vertices per warp
-    assert kern == 2 and cpg * (C // 32) <= 148 and na // 64 - cpg * wpc < sl <= na // 64 and sl % (cpg * wpc) == 0
+    assert kern == 3 and cpg * (C // 32) <= 148 and na // 64 - cpg * wpc < sl <= na // 64 and sl % (cpg * wpc) == 0
     assert (sw == 2).all() and (acc > 0.5).all() and (acc < 1.0).all()
     check_invariants(pool, edges, na, nb, [0, 131, 255])
     e2 = pool.entropy()
@@ -356,7 +354,7 @@ def test_cooling_schedules_match_oracle_on_southern_women(host, schedule, p0, p1
     """BASELINE configs[0] (southernWomen, K = 5 + 5, eps = 1e-3) under the three time-dependent cooling schedules:
     128 oracle chains vs 128 GPU chains (n = 32, so every GPU chain is strictly sequential), randomised starts,
     150 sweeps.  Two-sample KS on the final description length and on the acceptance ratio: the temperature of
-    every step, the T -> 0 handling and the fp32 accept test have to agree with the reference's anneal()."""
+    every step, the T -> 0 handling and the accept test have to agree with the reference's anneal()."""
     from scipy.stats import ks_2samp
     g = load_golden("c1_seed1")
     na, nb, edges, lab0 = g["na"], g["nb"], g["edges"], g["labels0"]
@@ -381,4 +379,53 @@ def test_cooling_schedules_match_oracle_on_southern_women(host, schedule, p0, p1
     p_acc = ks_2samp(acc_o, acc_g).pvalue
     print("%s: entropy oracle %.2f+-%.2f gpu %.2f+-%.2f p=%.3f | acceptance %.4f %.4f p=%.3f" % (
         schedule, np.mean(ent_o), np.std(ent_o), np.mean(ent_g), np.std(ent_g), p_ent, np.mean(acc_o), np.mean(acc_g), p_acc))
-    assert p_ent > 0.001 and p_acc > 0.001
+    assert p_ent > 0.01 and p_acc > 0.01
+
+
+@pytest.mark.parametrize("ka,kb", [(10, 120), (6, 200), (5, 200), (36, 36), (38, 37)])
+def test_asymmetric_and_borderline_k(host, ka, kb):
+    """K shapes around the limits of shared-memory staging: the kernel (staged counts / counts in L2) is chosen once per
+    call for BOTH half sweeps -- the two keep different label arrays current, so a per-type choice would lose moves --
+    and the histogram commit never leaves a lane's bins.  Counts must equal a rebuild from the labels."""
+    na = nb = 3000
+    edges = planted(na, nb, 6, 6, 60000, 23)
+    graph = host.Graph(edges, na, nb)
+    C = 40
+    lab0 = np.concatenate([np.arange(na) % ka, ka + np.arange(nb) % kb]).astype(np.uint32)
+    pool = host.ChainPool(graph, np.tile(lab0, (C, 1)), ka, kb, 1.0)
+    seeds = np.arange(C, dtype=np.uint64) + 61
+    pool.randomize(seeds)
+    acc, sw = pool.anneal("constant", 1.0, 0.0, 3 * (na + nb), 10 ** 9, seeds)
+    assert (sw == 3).all() and (acc > 0).all()
+    check_invariants(pool, edges, na, nb, [0, 31, 39])
+    kern = pool.sweep_info()[0]
+    assert kern == (3 if max(ka, kb) <= 38 else 0)
+    f1 = pool.entropy()
+    d0 = np.array([pool.entropy_accum(c) for c in (0, 39)])
+    pool.anneal("constant", 1.0, 0.0, 1 * (na + nb), 10 ** 9, seeds + np.uint64(7), max_inflight=1)
+    check_invariants(pool, edges, na, nb, [0, 39])
+    f2 = pool.entropy()
+    for k, c in enumerate((0, 39)):
+        assert abs((f2[c] - f1[c]) - (pool.entropy_accum(c) - d0[k])) <= 1e-6 * abs(f1[c])
+
+
+def test_two_handles_on_two_devices_or_one(host):
+    """Function attributes (dynamic shared memory limit) are per device and tracked per handle: a second handle, on
+    another GPU when the box has one, runs its first big-shared-memory launch without help from the first."""
+    import ctypes as C_
+    L = host.load_library()
+    import torch
+    ndev = torch.cuda.device_count()
+    na = nb = 2000
+    edges = planted(na, nb, 32, 32, 40000, 3)
+    pools = []
+    for dev in range(min(ndev, 2) if ndev > 1 else 1):
+        for rep in range(2 if ndev == 1 else 1):
+            graph = host.Graph(edges, na, nb, device=dev)
+            pool = host.ChainPool(graph, np.tile(planted_labels(na, nb, 32, 32), (32, 1)), 32, 32, 1.0)
+            seeds = np.arange(32, dtype=np.uint64) + 1
+            pool.randomize(seeds)
+            pool.anneal("constant", 1.0, 0.0, 2 * (na + nb), 10 ** 9, seeds)
+            check_invariants(pool, edges, na, nb, [0, 31])
+            pools.append(pool)
+    assert len(pools) >= 1

@@ -1,0 +1,149 @@
+"""Parity of the parallel sweep AT THE BENCHMARKED OPERATING POINT, and of its device arithmetic.
+
+* bisbm_parallel_transition runs ONE forced proposal through the sweep kernel's own device code (sweep2_kernel in
+  KAT mode: same staging, same neighbour pass, same dS assembly) and is compared with the reference's
+  transition_ratio known answers (tests/golden/*.npz kat_* vectors, generated from the unmodified reference build):
+  double 1e-9 relative, float 2e-5 absolute -- including the out-of-range completions (small blocks: exact log q
+  table and Stirling form) and, on the mid-size graph, the per-block log q expansions.
+* On a mid-size planted graph (40k + 40k nodes, 600k edges, K = 8 + 8: the oracle is still feasible, the GPU already
+  takes the SLICED MULTI-CTA plan of the benchmark: 8 chain groups x 18 CTAs, default in-flight bound) 256 GPU chains
+  are compared with 128 oracle chains (tests/golden/parity_mid.npz) by two-sample KS tests on the final description
+  length, the acceptance ratio and the NMI against the planted partition; max_inflight = 1 (strictly sequential
+  chains) is the control.
+"""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden
+from helpers import nmi, planted, planted_labels
+
+pytestmark = pytest.mark.gpu
+
+KAT_GOLDENS = ["c1_seed1", "c1_seed42", "c2_abrupt", "c2_const_k46", "big_blocks", "isolated"]
+
+
+def _kat_check(pool, chain, kv, ks, kd, ka, lab, precision):
+    worst_ds, worst_la, checked = 0.0, 0.0, 0
+    for v, s, dS, ar in zip(kv, ks, kd, ka):
+        d, la = pool.parallel_transition(chain, int(v), int(s))
+        if np.isinf(dS):
+            assert np.isinf(d) and d > 0
+            continue
+        if s == lab[v]:
+            assert d == 0.0 and la == 0.0     # r == s: dS = 0, accu_r = 1
+            continue
+        if precision == "fp64":
+            assert abs(d - dS) <= 1e-9 * max(1.0, abs(dS)), (v, s, d, dS)
+            assert abs(la - np.log(ar)) <= 1e-9 * max(1.0, abs(np.log(ar))), (v, s, la, np.log(ar))
+        else:
+            assert abs(d - dS) <= 2e-5 * max(1.0, abs(dS) / 8.0), (v, s, d, dS)
+            assert abs(la - np.log(ar)) <= 2e-5 * max(1.0, abs(np.log(ar))), (v, s, la, np.log(ar))
+        worst_ds = max(worst_ds, abs(d - dS) / max(1.0, abs(dS)))
+        worst_la = max(worst_la, abs(la - np.log(ar)))
+        checked += 1
+    return worst_ds, worst_la, checked
+
+
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+@pytest.mark.parametrize("name", KAT_GOLDENS)
+def test_parallel_kernel_transition_kats(host, name, precision):
+    g = load_golden(name)
+    na, nb = g["na"], g["nb"]
+    graph = host.Graph(g["edges"], na, nb)
+    C = 35     # the chain under test sits in the second chain group, next to padding lanes
+    pool = host.ChainPool(graph, np.tile(g["init_labels"], (C, 1)), int(g["ka"]), int(g["kb"]), float(g["eps"]))
+    pool.set_precision(precision)
+    w1, w2, n = _kat_check(pool, 33, g["kat_v"], g["kat_s"], g["kat_dS"], g["kat_accu"], g["init_labels"], precision)
+    print("%s %s: %d known answers, worst rel dS error %.2e, worst |log accu error| %.2e" % (name, precision, n, w1, w2))
+    assert n > 0
+    # nothing was committed
+    assert (pool.labels(33) == g["init_labels"]).all()
+    assert (pool.m(33) == g["init_m"]).all() and (pool.n_r(33) == g["init_n_r"]).all()
+
+
+def _mid():
+    fx = load_golden("parity_mid")
+    na, nb, ka, kb = int(fx["na"]), int(fx["nb"]), int(fx["ka"]), int(fx["kb"])
+    edges = planted(na, nb, ka, kb, int(fx["n_edges"]), int(fx["graph_seed"]))
+    assert hashlib.sha1(np.ascontiguousarray(edges).tobytes()).hexdigest() == str(fx["edges_sha1"])
+    return fx, na, nb, ka, kb, edges
+
+
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+def test_parallel_kernel_transition_kats_large_blocks(host, precision):
+    """Blocks with e_r = 75 000, n_r = 5 000: log q takes the asymptotic branch in the reference
+    (src/support/int_part.cc:73-98) and the per-block second-order expansion in the kernel."""
+    fx, na, nb, ka, kb, edges = _mid()
+    lab = planted_labels(na, nb, ka, kb)
+    graph = host.Graph(edges, na, nb)
+    pool = host.ChainPool(graph, np.tile(lab, (33, 1)), ka, kb, 1.0)
+    pool.set_precision(precision)
+    assert abs(pool.entropy(32) - float(fx["init_entropy"])) <= 1e-9 * float(fx["init_entropy"])
+    w1, w2, n = _kat_check(pool, 32, fx["kat_v"], fx["kat_s"], fx["kat_dS"], fx["kat_accu"], lab, precision)
+    print("mid graph %s: %d known answers, worst rel dS error %.2e, worst |log accu error| %.2e" % (precision, n, w1, w2))
+    assert n > 100
+
+
+def _run_mid(host, proto, inflight, C, precision="fp64", inflight_div=None):
+    fx, na, nb, ka, kb, edges = _mid()
+    n = na + nb
+    lab = planted_labels(na, nb, ka, kb)
+    graph = host.Graph(edges, na, nb)
+    pool = host.ChainPool(graph, np.tile(lab, (C, 1)), ka, kb, 1.0)
+    pool.set_precision(precision)
+    if inflight_div:
+        pool.set_option("inflight_div", inflight_div)
+    seeds = np.arange(C, dtype=np.uint64) + 31337
+    if proto == "tr":
+        pool.randomize(seeds)
+    sweeps = int(fx["sweeps_%s" % proto])
+    acc, sw = pool.anneal("constant", 1.0, 0.0, sweeps * n, 10 ** 18, seeds, max_inflight=inflight)
+    assert (sw == sweeps).all()
+    ent = pool.entropy()
+    labs = pool.labels()
+    nm = np.array([nmi(labs[c], lab) for c in range(0, C, max(1, C // 64))])
+    return fx, pool, ent, acc, nm
+
+
+def _report(tag, fx, proto, ent, acc, nm, info):
+    from scipy.stats import ks_2samp
+    p_ent = ks_2samp(fx["%s_entropy" % proto], ent).pvalue
+    p_acc = ks_2samp(fx["%s_accept" % proto], acc).pvalue
+    p_nmi = ks_2samp(fx["%s_nmi" % proto], nm).pvalue
+    rec = {"test": tag, "protocol": proto, "plan": {"kernel": info[0], "warps_per_cta": info[1], "ctas_per_group": info[2], "slice": info[3]},
+           "oracle": {"entropy_mean": float(np.mean(fx["%s_entropy" % proto])), "entropy_sd": float(np.std(fx["%s_entropy" % proto])),
+                      "accept_mean": float(np.mean(fx["%s_accept" % proto])), "nmi_mean": float(np.mean(fx["%s_nmi" % proto])), "chains": int(len(fx["%s_entropy" % proto]))},
+           "gpu": {"entropy_mean": float(ent.mean()), "entropy_sd": float(ent.std()), "accept_mean": float(acc.mean()), "nmi_mean": float(nm.mean()), "chains": int(len(ent))},
+           "ks_p": {"entropy": float(p_ent), "accept": float(p_acc), "nmi": float(p_nmi)}}
+    print(json.dumps(rec))
+    try:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "parity_operating_point.jsonl"), "a") as f:
+            f.write(json.dumps(rec) + "\n")
+    except Exception:
+        pass
+    return p_ent, p_acc, p_nmi
+
+
+@pytest.mark.parametrize("proto", ["eq", "tr"])
+def test_parity_with_oracle_at_the_benchmarked_plan(host, proto):
+    """256 chains = 8 chain groups x 18 CTAs x 16 warps, default in-flight bound: the plan bench.py times."""
+    fx, pool, ent, acc, nm = _run_mid(host, proto, 0, 256)
+    info = pool.sweep_info()
+    assert info[0] == 3 and info[2] > 1 and info[3] < int(fx["na"])       # staged double kernel, several CTAs per group, sliced
+    p_ent, p_acc, p_nmi = _report("default_plan", fx, proto, ent, acc, nm, info)
+    assert p_ent > 0.01 and p_acc > 0.01 and p_nmi > 0.01
+
+
+@pytest.mark.parametrize("proto", ["eq", "tr"])
+def test_parity_with_oracle_sequential_control(host, proto):
+    """The same comparison with max_inflight = 1 (strictly sequential chains: no stale reads at all)."""
+    fx, pool, ent, acc, nm = _run_mid(host, proto, 1, 128)
+    info = pool.sweep_info()
+    assert info[2] == 1
+    p_ent, p_acc, p_nmi = _report("sequential_control", fx, proto, ent, acc, nm, info)
+    assert p_ent > 0.01 and p_acc > 0.01 and p_nmi > 0.01
