@@ -83,7 +83,6 @@ struct bisbm_handle {
     uint8_t* d_lab8 = nullptr;                 // u8 shadow of the labels for the shared-memory sweep
     double eps = 1.0;
     LogqExp* d_lq = nullptr;
-    uint32_t* d_lq_soa = nullptr;
     uint64_t* d_seeds = nullptr;
     uint8_t* d_active = nullptr;
     unsigned long long *d_accepted = nullptr, *d_u = nullptr, *d_sweeps = nullptr;
@@ -120,7 +119,7 @@ void dfree(T*& p) {
 
 void free_chains(bisbm_handle* h) {
     dfree(h->d_ka); dfree(h->d_kb); dfree(h->d_labels); dfree(h->d_labels_tmp);
-    dfree(h->d_m); dfree(h->d_e); dfree(h->d_nr); dfree(h->d_eta); dfree(h->d_lq); dfree(h->d_lq_soa); dfree(h->d_m2); dfree(h->d_e2); dfree(h->d_nr2); dfree(h->d_nr_live); dfree(h->d_kat_out); dfree(h->d_lab8);
+    dfree(h->d_m); dfree(h->d_e); dfree(h->d_nr); dfree(h->d_eta); dfree(h->d_lq); dfree(h->d_m2); dfree(h->d_e2); dfree(h->d_nr2); dfree(h->d_nr_live); dfree(h->d_kat_out); dfree(h->d_lab8);
     dfree(h->d_seeds); dfree(h->d_active); dfree(h->d_accepted); dfree(h->d_u); dfree(h->d_sweeps);
     dfree(h->d_dS); dfree(h->d_entmin); dfree(h->d_ent_out); dfree(h->d_nactive); dfree(h->d_hist);
     for (auto& kv : h->replay) { dfree(kv.second.d_rs); dfree(kv.second.d_vlist); dfree(kv.second.d_kh); }
@@ -504,7 +503,7 @@ SweepParams base_params(bisbm_handle* h, uint32_t type) {
     P.g = gview(h); P.s = sview(h); P.tb = tview(h, false);
     P.lab8 = h->d_lab8; P.m_next = h->d_m2; P.e_next = h->d_e2; P.nr_next = h->d_nr2; P.nr_live = h->d_nr_live;
     P.seeds = h->d_seeds; P.active = h->d_active; P.accepted = h->d_accepted; P.dS_accum = h->d_dS;
-    P.lq = h->d_lq; P.lq_soa = h->d_lq_soa;
+    P.lq = h->d_lq;
     P.n_chains = h->n_chains; P.type = type; P.n_groups = h->C / 32;
     P.kopp_max = type ? h->KA : h->KB;
     P.half_bits = feistel_half_bits(type ? h->nb : h->na);
@@ -525,7 +524,7 @@ int launch_full_sweep(bisbm_handle* h, int schedule, float p0, float p1, uint64_
         if (rc) return rc;
         const uint32_t kmax = type ? h->KB : h->KA;
         const uint32_t tot = h->n_chains * kmax;
-        logq_refresh_kernel<<<(tot + 127) / 128, 128, 0, h->stream>>>(sview(h), tview(h, false), h->d_lq, h->d_lq_soa, h->n_chains, type);
+        logq_refresh_kernel<<<(tot + 127) / 128, 128, 0, h->stream>>>(sview(h), tview(h, false), h->d_lq, h->n_chains, type);
         h->last_launches += 1;
         const uint32_t n_m = h->C * h->KA * h->KB, n_e = h->C * (h->KA + h->KB);
         const bool sliced = lp.smem && lp.ctas_per_group > 1;
@@ -703,7 +702,6 @@ int bisbm_set_chains(bisbm_handle* h, uint32_t n_chains, const uint32_t* ka, con
         CU(cudaMalloc(&h->d_kat_out, 2 * sizeof(double)));
         CU(cudaMalloc(&h->d_eta, (size_t)C * KK * h->W * sizeof(int32_t)));
         CU(cudaMalloc(&h->d_lq, (size_t)C * KK * sizeof(LogqExp)));
-        CU(cudaMalloc(&h->d_lq_soa, (size_t)C * KK * 8 * sizeof(uint32_t)));
         CU(cudaMalloc(&h->d_seeds, C * sizeof(uint64_t)));
         CU(cudaMalloc(&h->d_active, C));
         CU(cudaMalloc(&h->d_accepted, C * sizeof(unsigned long long)));
@@ -723,7 +721,6 @@ int bisbm_set_chains(bisbm_handle* h, uint32_t n_chains, const uint32_t* ka, con
     std::copy(ka, ka + n_chains, h->h_ka.begin());
     std::copy(kb, kb + n_chains, h->h_kb.begin());
     CU(cudaMemsetAsync(h->d_lq, 0, (size_t)C * KK * sizeof(LogqExp), h->stream));
-    CU(cudaMemsetAsync(h->d_lq_soa, 0, (size_t)C * KK * 8 * sizeof(uint32_t), h->stream));
     CU(cudaMemsetAsync(h->d_dS, 0, C * sizeof(double), h->stream));
     CU(cudaMemsetAsync(h->d_active, 0, C, h->stream));
     CU(cudaMemsetAsync(h->d_active, 1, n_chains, h->stream));
@@ -1073,7 +1070,7 @@ int bisbm_parallel_transition(bisbm_handle* h, uint32_t chain, uint32_t v, uint3
     if (rc) return rc;
     const uint32_t kmax = type ? h->KB : h->KA;
     const uint32_t tot = h->n_chains * kmax;
-    logq_refresh_kernel<<<(tot + 127) / 128, 128, 0, h->stream>>>(sview(h), tview(h, false), h->d_lq, h->d_lq_soa, h->n_chains, type);
+    logq_refresh_kernel<<<(tot + 127) / 128, 128, 0, h->stream>>>(sview(h), tview(h, false), h->d_lq, h->n_chains, type);
     CU(cudaMemsetAsync(h->d_kat_out, 0xff, 2 * sizeof(double), h->stream));   // NaN: "not written"
     LaunchPlan lp;
     memset(&lp, 0, sizeof lp);

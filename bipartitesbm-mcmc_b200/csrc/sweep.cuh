@@ -39,11 +39,14 @@
 
 namespace bisbm {
 
-// second-order expansion of f(e,n) = log q(e,n) about (e0,n0) for one (chain, block slot)
+// expansion of f(e,n) = log q(e,n) about (e0,n0) for one (chain, block slot): second order in (e, n) plus the third
+// order in e.  First derivatives in double (they multiply the degree / one node: fe * d ~ 0.1, fn ~ 10), the rest float.
+// 48 bytes.
 struct LogqExp {
     int32_t e0, n0;
-    float fe, fn, fee, fen, fnn;
-    uint32_t valid;
+    double fe, fn;
+    float fee, fen, fnn, feee;
+    uint32_t valid, pad;
 };
 
 struct SweepParams {
@@ -58,7 +61,6 @@ struct SweepParams {
     unsigned long long* accepted;    // [C]
     double* dS_accum;                // [C]
     const LogqExp* lq;               // [C/32][KA+KB][32]
-    const uint32_t* lq_soa;          // the same, field-major for coalesced lane = chain loads: [C/32][KA+KB][8][32]
     uint32_t n_chains;               // real chains (<= C)
     uint32_t type;                   // 0: move type-a vertices, 1: type-b
     uint32_t n_groups;               // C / 32
@@ -136,10 +138,11 @@ BISBM_NOINLINE_HD static double logq_delta_exact(const Tables& tb, int e, int n,
 BISBM_HD double logq_delta(const Tables& tb, const LogqExp& q, int e, int n, int de, int dn) {
     int x = e - q.e0, y = n - q.n0;
     int ax = x < 0 ? -x : x, ay = y < 0 ? -y : y, ad = de < 0 ? -de : de;
-    if (q.valid && ax <= (q.e0 >> 4) && ay <= (q.n0 >> 4) && ad <= (q.e0 >> 4)) {
+    if (q.valid && ax <= (q.e0 >> 4) && ay <= (q.n0 >> 4) && ad <= (q.e0 >> 10)) {
         double dx = (double)x, dy = (double)y, De = (double)de, Dn = (double)dn;
-        return (double)q.fe * De + (double)q.fn * Dn + 0.5 * (double)q.fee * (De * De + 2.0 * dx * De) +
-               (double)q.fen * (dx * Dn + dy * De + De * Dn) + 0.5 * (double)q.fnn * (Dn * Dn + 2.0 * dy * Dn);
+        return q.fe * De + q.fn * Dn + 0.5 * (double)q.fee * (De * De + 2.0 * dx * De) +
+               (double)q.fen * (dx * Dn + dy * De + De * Dn) + 0.5 * (double)q.fnn * (Dn * Dn + 2.0 * dy * Dn) +
+               (double)q.feee * De * ((1.0 / 6.0) * De * De + 0.5 * dx * (De + dx));
     }
     return logq_delta_exact(tb, e, n, de, dn);
 }
@@ -172,9 +175,40 @@ __device__ __forceinline__ int cnt_ld(const int32_t* p) {
     return __ldcg(p);
 }
 
+#endif  // __CUDACC__ (reopened below)
+
+// Coefficients of the expansion about (e0, n0) by central differences of the reference's asymptotic formula
+// (log_q_approx, src/support/int_part.cc:73-98): first derivatives with a small step (truncation: third derivative
+// times h^2 / 6 times the degree, below 1e-10), second / third derivatives with a larger one (round-off).  Blocks too
+// small for the asymptotic branch, or where the expansion would be poor, get valid = 0 and take the exact routine.
+BISBM_HD LogqExp logq_expand(const Tables& tb, int e0, int n0) {
+    LogqExp q;
+    q.e0 = e0; q.n0 = n0; q.fe = 0.0; q.fn = 0.0; q.fee = q.fen = q.fnn = q.feee = 0.f; q.valid = 0; q.pad = 0;
+    if (e0 >= 16384 && n0 >= 1024 && 2 * (int64_t)n0 <= (int64_t)e0) {
+        const int h1 = (e0 >> 13) > 1 ? (e0 >> 13) : 1, k1 = (n0 >> 11) > 1 ? (n0 >> 11) : 1;
+        const int he = e0 >> 10, hn = n0 >> 8;
+        const double f00 = log_q_approx(tb, e0, n0);
+        q.fe = (log_q_approx(tb, e0 + h1, n0) - log_q_approx(tb, e0 - h1, n0)) / (2.0 * (double)h1);
+        q.fn = (log_q_approx(tb, e0, n0 + k1) - log_q_approx(tb, e0, n0 - k1)) / (2.0 * (double)k1);
+        const double fp0 = log_q_approx(tb, e0 + he, n0), fm0 = log_q_approx(tb, e0 - he, n0);
+        const double fq0 = log_q_approx(tb, e0 + 2 * he, n0), fn0 = log_q_approx(tb, e0 - 2 * he, n0);
+        const double f0p = log_q_approx(tb, e0, n0 + hn), f0m = log_q_approx(tb, e0, n0 - hn);
+        const double fpp = log_q_approx(tb, e0 + he, n0 + hn), fpm = log_q_approx(tb, e0 + he, n0 - hn);
+        const double fmp = log_q_approx(tb, e0 - he, n0 + hn), fmm = log_q_approx(tb, e0 - he, n0 - hn);
+        const double He = (double)he, Hn = (double)hn;
+        q.fee = (float)((fp0 - 2.0 * f00 + fm0) / (He * He));
+        q.fnn = (float)((f0p - 2.0 * f00 + f0m) / (Hn * Hn));
+        q.fen = (float)((fpp - fpm - fmp + fmm) / (4.0 * He * Hn));
+        q.feee = (float)((fq0 - 2.0 * fp0 + 2.0 * fm0 - fn0) / (2.0 * He * He * He));
+        q.valid = 1;
+    }
+    return q;
+}
+
+#ifdef __CUDACC__
 // Refresh the log q expansions of the blocks of one type (they only change during that
 // type's half sweep).  One thread per (chain, block).
-__global__ void logq_refresh_kernel(StateView s, Tables tb, LogqExp* lq, uint32_t* lq_soa, uint32_t n_chains, uint32_t type) {
+__global__ void logq_refresh_kernel(StateView s, Tables tb, LogqExp* lq, uint32_t n_chains, uint32_t type) {
     uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t kmax = type ? s.KB : s.KA;
     if (idx >= n_chains * kmax) return;
@@ -184,37 +218,9 @@ __global__ void logq_refresh_kernel(StateView s, Tables tb, LogqExp* lq, uint32_
     uint32_t slot = (type ? s.KA : 0) + b;
     const size_t off = cnt_base(c, (size_t)s.KA + s.KB) + (size_t)slot * GROUP;
     LogqExp q;
-    q.e0 = 0; q.n0 = 0; q.fe = q.fn = q.fee = q.fen = q.fnn = 0.f; q.valid = 0;
-    if (b < kc) {
-        int e0 = s.e[off];
-        int n0 = s.nr[off];
-        q.e0 = e0; q.n0 = n0;
-        if (e0 >= 16384 && n0 >= 1024 && 2 * (int64_t)n0 <= (int64_t)e0) {
-            int he = e0 >> 10, hn = n0 >> 8;
-            double f00 = log_q_approx(tb, e0, n0);
-            double fp0 = log_q_approx(tb, e0 + he, n0), fm0 = log_q_approx(tb, e0 - he, n0);
-            double f0p = log_q_approx(tb, e0, n0 + hn), f0m = log_q_approx(tb, e0, n0 - hn);
-            double fpp = log_q_approx(tb, e0 + he, n0 + hn), fpm = log_q_approx(tb, e0 + he, n0 - hn);
-            double fmp = log_q_approx(tb, e0 - he, n0 + hn), fmm = log_q_approx(tb, e0 - he, n0 - hn);
-            double He = (double)he, Hn = (double)hn;
-            q.fe = (float)((fp0 - fm0) / (2.0 * He));
-            q.fn = (float)((f0p - f0m) / (2.0 * Hn));
-            q.fee = (float)((fp0 - 2.0 * f00 + fm0) / (He * He));
-            q.fnn = (float)((f0p - 2.0 * f00 + f0m) / (Hn * Hn));
-            q.fen = (float)((fpp - fpm - fmp + fmm) / (4.0 * He * Hn));
-            q.valid = 1;
-        }
-    }
+    q.e0 = 0; q.n0 = 0; q.fe = q.fn = 0.0; q.fee = q.fen = q.fnn = q.feee = 0.f; q.valid = 0; q.pad = 0;
+    if (b < kc) q = logq_expand(tb, s.e[off], s.nr[off]);
     lq[off] = q;
-    // field-major copy; a block without expansion is stored as e0 = n0 = 0 (never in range)
-    uint32_t* o = lq_soa + ((size_t)(c / GROUP) * ((size_t)s.KA + s.KB) + slot) * 8 * GROUP + (c % GROUP);
-    o[0 * GROUP] = q.valid ? (uint32_t)q.e0 : 0u;
-    o[1 * GROUP] = q.valid ? (uint32_t)q.n0 : 0u;
-    o[2 * GROUP] = __float_as_uint(q.fe);
-    o[3 * GROUP] = __float_as_uint(q.fn);
-    o[4 * GROUP] = __float_as_uint(q.fee);
-    o[5 * GROUP] = __float_as_uint(q.fen);
-    o[6 * GROUP] = __float_as_uint(q.fnn);
 }
 
 // shared memory of the SMEM variant, in this order:

@@ -33,6 +33,7 @@
 //   accept     step                      reference src/metropolis_hasting.cc:42-62
 //   commit     apply_mcmc_moves          reference src/blockmodel.cc:461-503
 #pragma once
+#include <string.h>
 #include "sweep.cuh"
 
 namespace bisbm {
@@ -55,6 +56,88 @@ inline float f_rcp(float x) { return 1.0f / x; }
 // unit() converts lg units to natural-log units, ex() inverts lg().
 template <typename R> struct Ar;
 
+// ---- branch-free double log / exp for the move arithmetic -------------------------------------------
+// The arguments here are positive, finite and normal (ratios of products of counts; acceptance exponents), so the
+// special-case branches of the library routines are not needed -- and without them the three logarithms of one
+// move are straight-line code the compiler interleaves.  fdlibm's algorithms (e_log.c / e_exp.c) and constants.
+BISBM_HD int32_t dbl_hi(double x) {
+#ifdef __CUDA_ARCH__
+    return __double2hiint(x);
+#else
+    uint64_t u; memcpy(&u, &x, 8); return (int32_t)(u >> 32);
+#endif
+}
+BISBM_HD int32_t dbl_lo(double x) {
+#ifdef __CUDA_ARCH__
+    return __double2loint(x);
+#else
+    uint64_t u; memcpy(&u, &x, 8); return (int32_t)(uint32_t)u;
+#endif
+}
+BISBM_HD double dbl_make(int32_t hi, int32_t lo) {
+#ifdef __CUDA_ARCH__
+    return __hiloint2double(hi, lo);
+#else
+    uint64_t u = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo; double x; memcpy(&x, &u, 8); return x;
+#endif
+}
+BISBM_HD double dbl_rcp(double x) {   // x > 0, normal: MUFU.RCP64H (2^-23) + two Newton steps
+#ifdef __CUDA_ARCH__
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(fma(-x, r, 1.0), r, r);
+    r = fma(fma(-x, r, 1.0), r, r);
+    return r;
+#else
+    return 1.0 / x;
+#endif
+}
+// natural logarithm of a positive normal double, < 1 ulp
+BISBM_HD double dlog(double x) {
+    const int32_t hx = dbl_hi(x);
+    const int32_t mant = hx & 0x000fffff;
+    const int32_t adj = (mant >= 0x6a09f) ? 1 : 0;                    // mantissa above sqrt(2): halve it
+    const int32_t k = (hx >> 20) - 1023 + adj;
+    const double m = dbl_make(mant | (0x3ff00000 - (adj << 20)), dbl_lo(x));   // in [sqrt(1/2), sqrt(2))
+    const double f = m - 1.0;
+    const double s = f * dbl_rcp(2.0 + f);
+    const double z = s * s, w = z * z;
+    const double t1 = w * fma(w, fma(w, 1.531383769920937332e-01, 2.222219843214978396e-01), 3.999999999940941908e-01);
+    const double t2 = z * fma(w, fma(w, fma(w, 1.479819860511658591e-01, 1.818357216161805012e-01), 2.857142874366239149e-01),
+                              6.666666666666735130e-01);
+    const double R = t1 + t2;
+    const double hfsq = 0.5 * f * f;
+    const double dk = (double)k;
+    // k ln2_hi - ((hfsq - (s (hfsq + R) + k ln2_lo)) - f)
+    return fma(dk, 6.93147180369123816490e-01, f - (hfsq - fma(s, hfsq + R, dk * 1.90821492927058770002e-10)));
+}
+// e^x for |x| <= 700 (clamped), < 1 ulp
+BISBM_HD double dexp(double x) {
+    x = x < -700.0 ? -700.0 : (x > 700.0 ? 700.0 : x);
+    const double magic = 6755399441055744.0;                          // 1.5 * 2^52: rounds to nearest integer
+    const double kd = fma(x, 1.44269504088896338700e+00, magic);
+    const int32_t k = dbl_lo(kd);
+    const double dk = kd - magic;
+    double r = fma(dk, -6.93147180369123816490e-01, x);
+    r = fma(dk, -1.90821492927058770002e-10, r);
+    // e^r on |r| <= ln2 / 2: Taylor to r^13 (next term 4e-18)
+    double p = 1.6059043836821613e-10;
+    p = fma(p, r, 2.08767569878681e-09);
+    p = fma(p, r, 2.505210838544172e-08);
+    p = fma(p, r, 2.755731922398589e-07);
+    p = fma(p, r, 2.7557319223985893e-06);
+    p = fma(p, r, 2.48015873015873e-05);
+    p = fma(p, r, 1.984126984126984e-04);
+    p = fma(p, r, 1.3888888888888889e-03);
+    p = fma(p, r, 8.333333333333333e-03);
+    p = fma(p, r, 4.1666666666666664e-02);
+    p = fma(p, r, 1.6666666666666666e-01);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    return dbl_make(dbl_hi(p) + (k << 20), dbl_lo(p));                 // p * 2^k (result normal: |x| <= 700)
+}
+
 template <> struct Ar<double> {
     static constexpr int FOLD = 32;       // count ratios multiplied between logarithms (32 factors < 2^31 fit a double)
     static constexpr bool SPLIT = true;   // accumulate sum (m+1-c1) inv, sum (m_s+c1) inv, sum c1 inv separately
@@ -62,7 +145,7 @@ template <> struct Ar<double> {
     BISBM_HD static double inv_unit() { return 1.0; }
     // exact conversion of a 32-bit unsigned integer: 2^52 + x has x as its low mantissa word
     BISBM_HD static double cvt(uint32_t x) {
-#ifdef __CUDA_ARCH__
+#if defined(__CUDA_ARCH__) && defined(BISBM_CVT_MAGIC)
         return __hiloint2double(0x43300000, (int)x) - 4503599627370496.0;
 #else
         return (double)x;
@@ -70,25 +153,15 @@ template <> struct Ar<double> {
     }
     BISBM_HD static double cvt_small(uint32_t x) { return cvt(x); }
     BISBM_HD static double cvt_s(int x) {
-#ifdef __CUDA_ARCH__
+#if defined(__CUDA_ARCH__) && defined(BISBM_CVT_MAGIC)
         return __hiloint2double(0x43300000, (int)((uint32_t)x ^ 0x80000000u)) - 4503601774854144.0;   // 2^52 + 2^31
 #else
         return (double)x;
 #endif
     }
-    BISBM_HD static double rcp(double x) {   // x > 0, normal: MUFU.RCP64H (2^-23) + two Newton steps
-#ifdef __CUDA_ARCH__
-        double r;
-        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-        r = fma(fma(-x, r, 1.0), r, r);
-        r = fma(fma(-x, r, 1.0), r, r);
-        return r;
-#else
-        return 1.0 / x;
-#endif
-    }
-    BISBM_HD static double lg(double x) { return log(x); }
-    BISBM_HD static double ex(double x) { return exp(x); }
+    BISBM_HD static double rcp(double x) { return dbl_rcp(x); }
+    BISBM_HD static double lg(double x) { return dlog(x); }
+    BISBM_HD static double ex(double x) { return dexp(x); }
     BISBM_HD static double u01(uint32_t w) { return (cvt(w) + 0.5) * (1.0 / 4294967296.0); }
     // U < x / 2^32 for the 32-bit draw w
     BISBM_HD static bool draw_below(uint32_t w, double x32) { return cvt(w) < x32; }
@@ -171,10 +244,11 @@ template <typename R> BISBM_HD R logq_fast(const LogqExp& q, int e, int n, int d
     const int x = e - q.e0, y = n - q.n0;
     const int ax = x < 0 ? -x : x, ay = y < 0 ? -y : y, ad = de < 0 ? -de : de;
     const int re = q.e0 >> 4, rn = q.n0 >> 4;
-    *ok = (q.valid != 0u) && ax <= re && ay <= rn && ad <= re;
+    *ok = (q.valid != 0u) && ax <= re && ay <= rn && ad <= (q.e0 >> 10);   // |de| <= e0/1024: the 4th-order remainder in de stays below 1e-10
     const R dx = Ar<R>::cvt_s(x), dy = Ar<R>::cvt_s(y), De = Ar<R>::cvt_s(de), Dn = Ar<R>::cvt_s(dn);
     return (R)q.fe * De + (R)q.fn * Dn + (R)0.5 * (R)q.fee * (De * De + (R)2 * dx * De) +
-           (R)q.fen * (dx * Dn + dy * De + De * Dn) + (R)0.5 * (R)q.fnn * (Dn * Dn + (R)2 * dy * Dn);
+           (R)q.fen * (dx * Dn + dy * De + De * Dn) + (R)0.5 * (R)q.fnn * (Dn * Dn + (R)2 * dy * Dn) +
+           (R)q.feee * De * ((R)(1.0 / 6.0) * De * De + (R)0.5 * dx * (De + dx));
 }
 
 // dS (natural-log units) and the logarithm of the Hastings factor accu1 / accu0 (lg units) of one move
@@ -386,9 +460,9 @@ __global__ void __launch_bounds__(512, 1) sweep2_kernel(const __grid_constant__ 
             uint4 b;
             if (P.kat_mode) b.x = P.kat_v;
             else b.x = v0 + feistel_perm(P.pos_begin + cta_in_group + (j0 + i) * cpg, nv, P.half_bits, pkey);
-            b.y = G.row_ptr[b.x];
-            b.z = G.row_ptr[b.x + 1] - b.y;
-            b.w = G.degidx[b.x];
+            b.y = __ldcg(G.row_ptr + b.x);          // (.cg: nothing of the graph is reused through L1, which holds the log q expansions)
+            b.z = __ldcg(G.row_ptr + b.x + 1) - b.y;
+            b.w = __ldcg(G.degidx + b.x);
             sVtx[i] = b;
         }
         if (threadIdx.x == 0) *sCtr = 0u;
@@ -452,7 +526,7 @@ __global__ void __launch_bounds__(512, 1) sweep2_kernel(const __grid_constant__ 
         for (int j = 0; j < 4; ++j) {
             const uint32_t rho = (lane >> 2) + 8u * j;
             ids[j] = 0u;
-            if (rho < dcnt) asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(ids[j]) : "l"(__cvta_generic_to_global(G.col + row0 + rho)));
+            if (rho < dcnt) asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(ids[j]) : "l"(__cvta_generic_to_global(G.col + row0 + rho)));
         }
     };
     auto load_rows = [&](uint32_t dcnt) {
@@ -530,7 +604,7 @@ __global__ void __launch_bounds__(512, 1) sweep2_kernel(const __grid_constant__ 
                 if (d != 0u) {
                     const uint32_t e = mulhi32(ra.x, d);
                     if (d <= 32u) tq = sh_ld_u8(tile_lane + e);
-                    else tq = (e < 32u) ? sh_ld_u8(tile_lane + e) : lab_ld(G.col[cur.y + e]);
+                    else tq = (e < 32u) ? sh_ld_u8(tile_lane + e) : lab_ld(__ldcg(G.col + cur.y + e));
                 }
                 tq = min(tq, kopp_max - 1u);
                 R beta = (R)1 / (R)P.p0;
@@ -570,9 +644,6 @@ __global__ void __launch_bounds__(512, 1) sweep2_kernel(const __grid_constant__ 
                     issue_next();
                     continue;
                 }
-                // counts that stay in global memory (eta), requested before the pass
-                const int eta_r = ldc(&gETA[(r * W + didx) * 32 + lane]);
-                const int eta_s = ldc(&gETA[(s * W + didx) * 32 + lane]);
 
                 // ---- one pass over v's neighbours: dS and the Hastings factor (transition_ratio).  Every lane
                 //      runs it (masked lanes cost the same issue slots); only `eval` lanes may commit. ----
@@ -619,18 +690,18 @@ __global__ void __launch_bounds__(512, 1) sweep2_kernel(const __grid_constant__ 
                         __syncwarp();
                         if (AR::FOLD >= 32) macc_fold(A);
                     }
-                    const uint32_t nch = (nrem + 3u) >> 2;
+                    const uint32_t nfull = nrem >> 2, tail = nrem & 3u;
                     uint32_t Lw = sh_ld_u32v(tile_lane);
-                    for (uint32_t q = 0; q < nch; ++q) {
+                    for (uint32_t q = 0; q < nfull; ++q) {
                         const uint32_t Lc = Lw;
-                        if (q + 1u < nch) Lw = sh_ld_u32v(tile_lane + 4u * (q + 1u));
-                        const uint32_t c4 = nrem - 4u * q;
-                        if (c4 >= 4u) edge4(Lc);
-                        else {
-                            edge1(Lc & 0xffu);
-                            if (c4 > 1u) edge1((Lc >> 8) & 0xffu);
-                            if (c4 > 2u) edge1((Lc >> 16) & 0xffu);
-                        }
+                        Lw = sh_ld_u32v(tile_lane + 4u * (q + 1u));     // (the row has a pad word: q + 1 <= 8 stays inside)
+                        edge4(Lc);
+                        if (AR::FOLD < 32) macc_fold(A);
+                    }
+                    if (tail) {
+                        edge1(Lw & 0xffu);
+                        if (tail > 1u) edge1((Lw >> 8) & 0xffu);
+                        if (tail > 2u) edge1((Lw >> 16) & 0xffu);
                         if (AR::FOLD < 32) macc_fold(A);
                     }
                 }
@@ -640,21 +711,28 @@ __global__ void __launch_bounds__(512, 1) sweep2_kernel(const __grid_constant__ 
                 // ---- dS, accept (step) ----
                 bool go;
                 R dS;
+                // what stays in global memory -- eta (L2, updated by atomics) and the two log q expansions (read only) -- is
+                // requested first; the e_r terms below only need shared memory and cover part of the latency
+                const int eta_r = ldc(&gETA[(r * W + didx) * 32 + lane]);
+                const int eta_s = ldc(&gETA[(s * W + didx) * 32 + lane]);
                 const int n_s = sh_ld(No_base + s * 128u);
                 {
                     const int e_r = sh_ld(Eo_base + r * 128u), e_s = sh_ld(Eo_base + s * 128u);
                     bool ok_b, ok_r, ok_s;
-                    R bdd = bdd_fast<R>(e_r, e_s, (int)d, &ok_b);
-                    auto load_q = [&](uint32_t slot) -> LogqExp {   // 32 bytes of this (block, chain); constant during the launch
+                    auto load_q = [&](uint32_t slot) -> LogqExp {   // 48 bytes of this (block, chain); constant during the launch
                         const uint4* p = reinterpret_cast<const uint4*>(gLQ + slot * 32u + lane);
-                        const uint4 a = __ldg(p), b = __ldg(p + 1);
+                        const uint4 a = __ldg(p), b = __ldg(p + 1), c4 = __ldg(p + 2);
                         LogqExp q;
-                        q.e0 = (int)a.x; q.n0 = (int)a.y; q.fe = __uint_as_float(a.z); q.fn = __uint_as_float(a.w);
-                        q.fee = __uint_as_float(b.x); q.fen = __uint_as_float(b.y); q.fnn = __uint_as_float(b.z); q.valid = b.w;
+                        q.e0 = (int)a.x; q.n0 = (int)a.y; q.fe = __hiloint2double((int)a.w, (int)a.z);
+                        q.fn = __hiloint2double((int)b.y, (int)b.x);
+                        q.fee = __uint_as_float(b.z); q.fen = __uint_as_float(b.w);
+                        q.fnn = __uint_as_float(c4.x); q.feee = __uint_as_float(c4.y); q.valid = c4.z; q.pad = 0;
                         return q;
                     };
-                    R lqr = logq_fast<R>(load_q(r), e_r, n_r, -(int)d, -1, &ok_r);
-                    R lqs = logq_fast<R>(load_q(s), e_s, n_s, (int)d, 1, &ok_s);
+                    const LogqExp q_r = load_q(r), q_s = load_q(s);
+                    R bdd = bdd_fast<R>(e_r, e_s, (int)d, &ok_b);
+                    R lqr = logq_fast<R>(q_r, e_r, n_r, -(int)d, -1, &ok_r);
+                    R lqs = logq_fast<R>(q_s, e_s, n_s, (int)d, 1, &ok_s);
                     if (__any_sync(FULL, eval && !(ok_b && ok_r && ok_s))) {
                         if (eval && !ok_b) bdd = (R)slow2_block_degree_delta(e_r, e_s, (int)d);
                         if (eval && !ok_r) lqr = (R)slow2_logq_delta(P.tb.qtab, P.tb.qn, P.tb.qk, e_r, n_r, -(int)d, -1);

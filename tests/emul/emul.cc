@@ -175,22 +175,7 @@ void emul_par_dS(void* p, uint32_t v, uint32_t sg, int use_taylor, double* dS, d
     LogqExp qr, qs;
     memset(&qr, 0, sizeof qr); memset(&qs, 0, sizeof qs);
     if (use_taylor) {
-        auto mk = [&](int e0, int n0) {
-            LogqExp q; memset(&q, 0, sizeof q); q.e0 = e0; q.n0 = n0;
-            if (e0 >= 16384 && n0 >= 1024 && 2 * (int64_t)n0 <= (int64_t)e0) {
-                int he = e0 >> 10, hn = n0 >> 8;
-                double f00 = log_q_approx(tb, e0, n0);
-                double fp0 = log_q_approx(tb, e0 + he, n0), fm0 = log_q_approx(tb, e0 - he, n0);
-                double f0p = log_q_approx(tb, e0, n0 + hn), f0m = log_q_approx(tb, e0, n0 - hn);
-                double fpp = log_q_approx(tb, e0 + he, n0 + hn), fpm = log_q_approx(tb, e0 + he, n0 - hn);
-                double fmp = log_q_approx(tb, e0 - he, n0 + hn), fmm = log_q_approx(tb, e0 - he, n0 - hn);
-                double He = he, Hn = hn;
-                q.fe = (float)((fp0 - fm0) / (2 * He)); q.fn = (float)((f0p - f0m) / (2 * Hn));
-                q.fee = (float)((fp0 - 2 * f00 + fm0) / (He * He)); q.fnn = (float)((f0p - 2 * f00 + f0m) / (Hn * Hn));
-                q.fen = (float)((fpp - fpm - fmp + fmm) / (4 * He * Hn)); q.valid = 1;
-            }
-            return q;
-        };
+        auto mk = [&](int e0, int n0) { return logq_expand(tb, e0, n0); };
         // expansion point deliberately off the current point, to exercise the drift terms
         qr = mk(e_r + e_r / 40, n_r - n_r / 50); qs = mk(e_s - e_s / 40, n_s + n_s / 50);
     }
@@ -233,22 +218,7 @@ static void par2_dS(Emul* s, uint32_t v, uint32_t sg, int use_taylor, double* dS
     LogqExp qr, qs;
     memset(&qr, 0, sizeof qr); memset(&qs, 0, sizeof qs);
     if (use_taylor) {
-        auto mk = [&](int e0, int n0) {
-            LogqExp q; memset(&q, 0, sizeof q); q.e0 = e0; q.n0 = n0;
-            if (e0 >= 16384 && n0 >= 1024 && 2 * (int64_t)n0 <= (int64_t)e0) {
-                int he = e0 >> 10, hn = n0 >> 8;
-                double f00 = log_q_approx(tb, e0, n0);
-                double fp0 = log_q_approx(tb, e0 + he, n0), fm0 = log_q_approx(tb, e0 - he, n0);
-                double f0p = log_q_approx(tb, e0, n0 + hn), f0m = log_q_approx(tb, e0, n0 - hn);
-                double fpp = log_q_approx(tb, e0 + he, n0 + hn), fpm = log_q_approx(tb, e0 + he, n0 - hn);
-                double fmp = log_q_approx(tb, e0 - he, n0 + hn), fmm = log_q_approx(tb, e0 - he, n0 - hn);
-                double He = he, Hn = hn;
-                q.fe = (float)((fp0 - fm0) / (2 * He)); q.fn = (float)((f0p - f0m) / (2 * Hn));
-                q.fee = (float)((fp0 - 2 * f00 + fm0) / (He * He)); q.fnn = (float)((f0p - 2 * f00 + f0m) / (Hn * Hn));
-                q.fen = (float)((fpp - fpm - fmp + fmm) / (4 * He * Hn)); q.valid = 1;
-            }
-            return q;
-        };
+        auto mk = [&](int e0, int n0) { return logq_expand(tb, e0, n0); };
         qr = mk(e_r + e_r / 40, n_r - n_r / 50); qs = mk(e_s - e_s / 40, n_s + n_s / 50);
     }
     bool ok_b, ok_r, ok_s;
@@ -287,6 +257,17 @@ void emul_words(void* p, uint64_t* ew, uint64_t* gw) {
     *gw = ((uint64_t)s->rs.gen[626] << 32) | s->rs.gen[625];
 }
 double emul_lgamma_diff(double x, double d) { return lgamma_diff(x, d); }
+// log q expansion about (e0, n0) evaluated at (e0 + x, n0 + y) for the move (de, dn), and the exact difference
+void emul_logq_expansion(int e0, int n0, int x, int y, int de, int dn, double* approx, double* exact, int* ok) {
+    Tables tb; memset(&tb, 0, sizeof tb);
+    LogqExp q = logq_expand(tb, e0, n0);
+    bool o;
+    *approx = logq_fast<double>(q, e0 + x, n0 + y, de, dn, &o);
+    *ok = o ? 1 : 0;
+    *exact = log_q_approx(tb, e0 + x + de, n0 + y + dn) - log_q_approx(tb, e0 + x, n0 + y);
+}
+double emul_dlog(double x) { return dlog(x); }
+double emul_dexp(double x) { return dexp(x); }
 double emul_block_degree_delta(int e_r, int e_s, int d) { return block_degree_delta(e_r, e_s, d); }
 double emul_log_q_approx(uint64_t n, uint64_t k) { Tables tb; memset(&tb, 0, sizeof tb); return log_q_approx(tb, n, k); }
 uint32_t emul_feistel(uint32_t i, uint32_t n, uint64_t key) { return feistel_perm(i, n, feistel_half_bits(n), key); }

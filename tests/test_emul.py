@@ -42,6 +42,10 @@ def emul():
     L.emul_par_dS.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.emul_par2_dS.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.POINTER(C.c_double),
                                C.POINTER(C.c_double), C.POINTER(C.c_int)]
+    L.emul_logq_expansion.argtypes = [C.c_int] * 6 + [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]
+    for fn in (L.emul_dlog, L.emul_dexp):
+        fn.restype = C.c_double
+        fn.argtypes = [C.c_double]
     L.emul_lgamma_diff.restype = C.c_double
     L.emul_lgamma_diff.argtypes = [C.c_double, C.c_double]
     L.emul_block_degree_delta.restype = C.c_double
@@ -155,6 +159,43 @@ def test_staged_kernel_move_arithmetic_matches_reference(emul, name, taylor, fp3
     print(name, "fp32" if fp32 else "fp64", "dS worst abs error", worst, "over", checked)
     assert checked > 0
     emul.emul_destroy(h)
+
+
+def test_branch_free_log_and_exp(emul):
+    """dlog / dexp of sweep2.cuh (the double kernel's logarithm and exponential) against libm: < 1.5 ulp."""
+    rng = np.random.default_rng(0)
+    xs = np.concatenate([np.exp(rng.uniform(-700, 700, 20000)), rng.uniform(0.5, 2.0, 20000), 1.0 + rng.uniform(-1e-6, 1e-6, 2000),
+                         np.array([1.0, 2.0, 0.5, np.sqrt(2.0), np.nextafter(np.sqrt(2.0), 2), 1e-300, 1e300, 3.0, 7.6e4])])
+    for x in xs:
+        got, want = emul.emul_dlog(float(x)), np.log(x)
+        assert abs(got - want) <= 3.4e-16 * max(abs(want), 1e-300) + 1e-323, (x, got, want)
+    ys = np.concatenate([rng.uniform(-700, 700, 20000), rng.uniform(-1, 1, 20000), np.array([0.0, -1e-17, 1e-17, -700.0, 700.0, -745.0])])
+    for y in ys:
+        got, want = emul.emul_dexp(float(y)), np.exp(max(min(y, 700.0), -700.0))
+        assert abs(got - want) <= 3.4e-16 * want, (y, got, want)
+
+
+def test_logq_expansion_accuracy(emul):
+    """The per-block expansion of log q (sweep.cuh logq_expand / sweep2.cuh logq_fast) against differences of the
+    reference's asymptotic formula: at the expansion point (what bisbm_parallel_transition sees right after a refresh)
+    1e-9 on the term; drifted by 1% of the block (typical within one half sweep) 1e-6; at the edge of the validity range
+    (6% drift) 1e-4 (small blocks; large ones are 10-100x better, see the printed worst cases)."""
+    worst = {}
+    for e0, n0 in [(75000, 5000), (312500, 15625), (20000, 1100), (5 * 10 ** 6, 2 * 10 ** 5), (40000, 20000)]:
+        for frac, tol in [(0.0, 1e-9), (0.01, 1e-6), (1.0 / 16.0, 1e-4)]:
+            for sx in (-1, 1):
+                for sy in (-1, 0, 1):
+                    x, y = int(sx * frac * e0), int(sy * frac * n0 * 0.999)
+                    for de, dn in [(-1, -1), (20, 1), (-20, -1), (60, 1), (-200, -1), (255, 1)]:
+                        a, ex, ok = C.c_double(), C.c_double(), C.c_int()
+                        emul.emul_logq_expansion(e0, n0, x, y, de, dn, C.byref(a), C.byref(ex), C.byref(ok))
+                        if not ok.value:
+                            continue
+                        err = abs(a.value - ex.value)
+                        scale = max(1.0, abs(de) / 20.0)
+                        worst[frac] = max(worst.get(frac, 0.0), err / scale)
+                        assert err <= tol * scale, (e0, n0, x, y, de, dn, a.value, ex.value)
+    print("log q expansion: worst |error| (scaled to degree 20) by drift:", worst)
 
 
 def test_lgamma_diff(emul):

@@ -399,7 +399,7 @@ def test_asymmetric_and_borderline_k(host, ka, kb):
     assert (sw == 3).all() and (acc > 0).all()
     check_invariants(pool, edges, na, nb, [0, 31, 39])
     kern = pool.sweep_info()[0]
-    assert kern == (3 if max(ka, kb) <= 38 else 0)
+    assert kern == (0 if ka * kb * 128 > 200 * 1024 else 3)
     f1 = pool.entropy()
     d0 = np.array([pool.entropy_accum(c) for c in (0, 39)])
     pool.anneal("constant", 1.0, 0.0, 1 * (na + nb), 10 ** 9, seeds + np.uint64(7), max_inflight=1)
