@@ -321,25 +321,35 @@ def main():
                             "inflight_bound": "half sweep / %d" % (args.inflight_div or 64)}
     dtype = "f32+int32 (dS summed in f64)" if kern == 2 else "f64+int32"
 
-    # -------- e2e: host buffers in, host buffers out, every step
-    out_host = torch.empty((C, n), dtype=torch.int32).pin_memory()
-    pool.labels(out=out_host.numpy().view(np.uint32))
-    labels_host.copy_(out_host)
+    # -------- e2e: host buffers in, host buffers out, every step (8-bit labels: K = ka + kb <= 256 here)
+    lab_dtype = torch.uint8 if ka + kb <= 256 else torch.int32
+    np_view = (lambda t: t.numpy()) if lab_dtype == torch.uint8 else (lambda t: t.numpy().view(np.uint32))
+    in_host = torch.empty((C, n), dtype=lab_dtype).pin_memory()
+    out_host = torch.empty((C, n), dtype=lab_dtype).pin_memory()
+    pool.labels(out=np_view(out_host))
+    in_host.copy_(out_host)
+    # a changed byte per step so the library cannot take its "labels unchanged -> keep the counts" shortcut
+    def perturb(t, step):
+        a = np_view(t)
+        v = step % n
+        a[0, v] = (a[0, v] + 1) % ka if v < na else ka + (a[0, v] - ka + 1) % kb
     for _ in range(1):
-        pool.set_labels(labels_host.numpy().view(np.uint32))
+        pool.set_labels(np_view(in_host))
         pool.anneal("constant", 1.0, 0.0, duration, 10 ** 18, seeds)
-        pool.labels(out=out_host.numpy().view(np.uint32))
+        pool.labels(out=np_view(out_host))
     barrier()
     t1 = time.perf_counter()
     e2e_moves = 0
-    for _ in range(args.steps):
-        pool.set_labels(labels_host.numpy().view(np.uint32))          # H2D: C*n*4 bytes
+    for step in range(args.steps):
+        perturb(in_host, step)
+        pool.set_labels(np_view(in_host))                             # H2D: C*n label bytes (+ count rebuild on the device)
         pool.anneal("constant", 1.0, 0.0, duration, 10 ** 18, seeds)
-        pool.labels(out=out_host.numpy().view(np.uint32))             # D2H: C*n*4 bytes
-        labels_host, out_host = out_host, labels_host
+        pool.labels(out=np_view(out_host))                            # D2H: C*n label bytes
+        in_host, out_host = out_host, in_host
         e2e_moves += pool.last_timing()[2]
     barrier()
     e2e_wall = time.perf_counter() - t1
+    label_bytes = C * n * (1 if lab_dtype == torch.uint8 else 4)
     te = torch.tensor([e2e_wall], dtype=torch.float64, device="cuda")
     me = torch.tensor([float(e2e_moves)], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -390,7 +400,8 @@ def main():
                              "avg_launch_ms": ev_ms / sweep_launches, "peak_source": peak_src,
                              "sweep_kernel_launches": int(sweep_launches),
                              "note": "CUDA events on libbisbm's stream around each step; they also span the small kernels between the sweep launches (log q refresh, bookkeeping, next-base initialisation: profiles/r02_launch_shares.txt)"},
-                "e2e": {"value": e2e_value, "unit": "moves/s", "h2d_bytes_per_step": C * n * 4, "d2h_bytes_per_step": C * n * 4},
+                "e2e": {"value": e2e_value, "unit": "moves/s", "h2d_bytes_per_step": label_bytes, "d2h_bytes_per_step": label_bytes,
+                        "api": "bisbm_set_chains_u8 (pinned host labels in) -> bisbm_anneal -> bisbm_get_all_labels_u8 (host labels out), every step"},
                 "gpu_launches": int(launches), "clocks": clocks, "extra": extra}
         traffic_file = os.path.join(ROOT, "profiles", "sweep_kernel_traffic.json")
         if os.path.exists(traffic_file):

@@ -103,7 +103,7 @@ struct bisbm_handle {
     uint32_t opt_inflight_div = 64;    // default in-flight bound = half sweep / this
     int opt_generic = 0;               // 1: never take the Ka = Kb = 32 specialisation
     std::set<const void*> attr_done;   // kernels whose shared-memory limit is raised on this handle's device
-    uint64_t last_sweep_launches = 0;
+    uint64_t last_sweep_launches = 0, last_marginal_launches = 0;
     uint32_t last_wpc = 0, last_cpg = 0, last_slice = 0;   // launch plan of the last half sweep
     int last_kernel = -1;                                   // KERN_* of the last parallel call
     bool lab32_stale = false;   // the staged kernels only write the u8 label shadow; i32 labels refreshed on demand
@@ -375,7 +375,10 @@ int validate_schedule(int schedule, float p0, float p1, uint64_t duration) {
 }
 
 // kernels of the parallel sweep (bisbm_sweep_info reports which one ran)
-enum { KERN_L2 = 0, KERN_STAGED_OLD = 1, KERN_S2_F32 = 2, KERN_S2_F64 = 3 };
+enum { KERN_L2 = 0, KERN_STAGED_OLD = 1, KERN_S2_F32 = 2, KERN_S2_F64 = 3, KERN_S2L_F32 = 4, KERN_S2L_F64 = 5 };
+static inline bool kern_is_s2(int k) { return k >= KERN_S2_F32; }
+static inline bool kern_is_s2_staged(int k) { return k == KERN_S2_F32 || k == KERN_S2_F64; }
+static inline bool kern_is_f32(int k) { return k == KERN_S2_F32 || k == KERN_S2L_F32; }
 
 struct LaunchPlan {
     int kernel;               // KERN_*
@@ -405,10 +408,17 @@ int plan_kernel(const bisbm_handle* h, uint32_t* wpc_out) {
     }
     if (hb == 1 && k8) {
         const uint32_t rs = h->precision == BISBM_PRECISION_FP32 ? 4u : 8u;
+        if (h->opt_kernel != KERN_S2L_F64)
+            for (uint32_t w : {16u, 8u, 4u})
+                if (sweep2_layout(h->KA, h->KB, 0, w, rs).total <= kSmemMax && sweep2_layout(h->KA, h->KB, 1, w, rs).total <= kSmemMax) {
+                    *wpc_out = w;
+                    return rs == 4 ? KERN_S2_F32 : KERN_S2_F64;
+                }
+        // K too large for staged counts: the same kernel with m_rs / e_r / n_r in L2
         for (uint32_t w : {16u, 8u, 4u})
-            if (sweep2_layout(h->KA, h->KB, 0, w, rs).total <= kSmemMax && sweep2_layout(h->KA, h->KB, 1, w, rs).total <= kSmemMax) {
+            if (sweep2_layout(h->KA, h->KB, 0, w, rs, false).total <= kSmemMax && sweep2_layout(h->KA, h->KB, 1, w, rs, false).total <= kSmemMax) {
                 *wpc_out = w;
-                return rs == 4 ? KERN_S2_F32 : KERN_S2_F64;
+                return rs == 4 ? KERN_S2L_F32 : KERN_S2L_F64;
             }
     }
     return KERN_L2;
@@ -425,7 +435,7 @@ int plan_sweep(bisbm_handle* h, uint32_t type, uint32_t max_inflight, int kernel
     const uint32_t hb = h->max_degree <= 255u ? 1 : (h->max_degree <= 65535u ? 2 : 4);
     lp->hist_bytes = (int)hb;
     lp->kernel = kernel;
-    lp->smem = kernel != KERN_L2;
+    lp->smem = kernel != KERN_L2 && kernel != KERN_S2L_F32 && kernel != KERN_S2L_F64;
     if (kernel == KERN_L2) {
         wpc = 32;
         if (sweep_smem_bytes(false, h->KA, h->KB, type, wpc, hb) > 220 * 1024) wpc = 16;
@@ -449,8 +459,8 @@ int plan_sweep(bisbm_handle* h, uint32_t type, uint32_t max_inflight, int kernel
         lp->slice = std::max<uint32_t>(cpg * wpc, lp->slice / (cpg * wpc) * (cpg * wpc));
     }
     else lp->slice = std::max<uint32_t>(nv, 1);
-    if (kernel == KERN_S2_F32 || kernel == KERN_S2_F64)
-        lp->smem_bytes = sweep2_layout(h->KA, h->KB, type, wpc, kernel == KERN_S2_F32 ? 4u : 8u).total;
+    if (kern_is_s2(kernel))
+        lp->smem_bytes = sweep2_layout(h->KA, h->KB, type, wpc, kern_is_f32(kernel) ? 4u : 8u, kern_is_s2_staged(kernel)).total;
     else
         lp->smem_bytes = sweep_smem_bytes(lp->smem, h->KA, h->KB, type, wpc, hb);
     return BISBM_OK;
@@ -479,11 +489,11 @@ int launch_sweep_h(bisbm_handle* h, const SweepParams& P, const LaunchPlan& lp) 
     return launch_sweep_nt<SMEM, uint32_t>(h, P, lp);
 }
 
-template <typename R, int KF, int TYPE>
+template <typename R, int KF, int TYPE, bool STAGED = true>
 int launch_sweep2_t(bisbm_handle* h, const SweepParams& P, const LaunchPlan& lp, unsigned grid) {
-    int rc = ensure_smem_attr(h, (const void*)sweep2_kernel<R, KF, TYPE>, (int)kSmemMax);
+    int rc = ensure_smem_attr(h, (const void*)sweep2_kernel<R, KF, TYPE, STAGED>, (int)kSmemMax);
     if (rc) return rc;
-    sweep2_kernel<R, KF, TYPE><<<grid, lp.wpc * 32, lp.smem_bytes, h->stream>>>(P);
+    sweep2_kernel<R, KF, TYPE, STAGED><<<grid, lp.wpc * 32, lp.smem_bytes, h->stream>>>(P);
     CU(cudaGetLastError());
     h->lab32_stale = true;    // the staged kernels only write the u8 label shadow
     return BISBM_OK;
@@ -491,6 +501,7 @@ int launch_sweep2_t(bisbm_handle* h, const SweepParams& P, const LaunchPlan& lp,
 
 template <typename R>
 int launch_sweep2(bisbm_handle* h, const SweepParams& P, const LaunchPlan& lp, unsigned grid) {
+    if (!lp.smem) return launch_sweep2_t<R, 0, 0, false>(h, P, lp, grid);
     // compile-time strides for the common Ka = Kb = 32 pool (BASELINE configs[2])
     if (h->KA == 32 && h->KB == 32 && !h->opt_generic)
         return P.type ? launch_sweep2_t<R, 32, 1>(h, P, lp, grid) : launch_sweep2_t<R, 32, 0>(h, P, lp, grid);
@@ -528,7 +539,7 @@ int launch_full_sweep(bisbm_handle* h, int schedule, float p0, float p1, uint64_
         h->last_launches += 1;
         const uint32_t n_m = h->C * h->KA * h->KB, n_e = h->C * (h->KA + h->KB);
         const bool sliced = lp.smem && lp.ctas_per_group > 1;
-        const bool s2 = kernel == KERN_S2_F32 || kernel == KERN_S2_F64;
+        const bool s2 = kern_is_s2(kernel);
         h->last_wpc = lp.wpc; h->last_cpg = lp.ctas_per_group; h->last_slice = lp.slice;
         h->last_kernel = kernel;
         for (uint32_t pos = 0; pos < nv; pos += lp.slice) {
@@ -550,8 +561,8 @@ int launch_full_sweep(bisbm_handle* h, int schedule, float p0, float p1, uint64_
             P.step_base = sweep_in_call * (uint64_t)h->n + (type ? h->na : 0);
             P.schedule = schedule; P.p0 = p0; P.p1 = p1;
             const unsigned grid = P.n_groups * lp.ctas_per_group;
-            if (kernel == KERN_S2_F64) rc = launch_sweep2<double>(h, P, lp, grid);
-            else if (kernel == KERN_S2_F32) rc = launch_sweep2<float>(h, P, lp, grid);
+            if (s2 && !kern_is_f32(kernel)) rc = launch_sweep2<double>(h, P, lp, grid);
+            else if (s2) rc = launch_sweep2<float>(h, P, lp, grid);
             else rc = lp.smem ? launch_sweep_h<true>(h, P, lp) : launch_sweep_h<false>(h, P, lp);
             if (rc) return rc;
             h->last_launches += 1;
@@ -669,8 +680,11 @@ int bisbm_destroy(bisbm_handle* h) {
     return BISBM_OK;
 }
 
-int bisbm_set_chains(bisbm_handle* h, uint32_t n_chains, const uint32_t* ka, const uint32_t* kb,
-                     const uint32_t* labels, double eps) {
+}  // extern "C"
+
+template <typename InT>
+static int set_chains_impl(bisbm_handle* h, uint32_t n_chains, const uint32_t* ka, const uint32_t* kb,
+                           const InT* labels, double eps) {
     if (!h || !ka || !kb || !labels) return fail(BISBM_ERR_ARG, "null argument");
     if (n_chains == 0) return fail(BISBM_ERR_ARG, "n_chains must be > 0");
     if (!(eps > 0.0)) return fail(BISBM_ERR_ARG, "epsilon must be > 0");
@@ -683,7 +697,10 @@ int bisbm_set_chains(bisbm_handle* h, uint32_t n_chains, const uint32_t* ka, con
     const uint32_t C = (n_chains + 31) / 32 * 32;
     const uint32_t n = h->n;
     const size_t KK = (size_t)KA + KB;
-    const bool reuse = h->n_chains == n_chains && h->C == C && h->KA == KA && h->KB == KB && h->d_labels;
+    bool reuse = h->n_chains == n_chains && h->C == C && h->KA == KA && h->KB == KB && h->d_labels;
+    // same K per chain and same epsilon as well: the counts stay valid if the labels turn out to be the ones held already
+    bool same_model = reuse && h->eps == eps;
+    for (uint32_t c = 0; same_model && c < n_chains; ++c) same_model = h->h_ka[c] == ka[c] && h->h_kb[c] == kb[c];
     if (!reuse) {
         free_chains(h);
         h->n_chains = n_chains; h->C = C; h->KA = KA; h->KB = KB;
@@ -728,20 +745,32 @@ int bisbm_set_chains(bisbm_handle* h, uint32_t n_chains, const uint32_t* ka, con
     CU(cudaMemcpyAsync(h->d_kb, h->h_kb.data(), C * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
     // host labels [chain][node], global ids  ->  chain-minor, type-local (device transpose)
     {
-        uint32_t* stage = reinterpret_cast<uint32_t*>(h->d_labels_tmp);
-        CU(cudaMemcpyAsync(stage, labels, (size_t)n_chains * n * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+        InT* stage = reinterpret_cast<InT*>(h->d_labels_tmp);
+        CU(cudaMemcpyAsync(stage, labels, (size_t)n_chains * n * sizeof(InT), cudaMemcpyHostToDevice, h->stream));
         unsigned long long* d_bad = reinterpret_cast<unsigned long long*>(h->d_accepted);
+        uint32_t* d_changed = reinterpret_cast<uint32_t*>(h->d_accepted + 1);
         CU(cudaMemsetAsync(d_bad, 0xff, sizeof(unsigned long long), h->stream));
+        CU(cudaMemsetAsync(d_changed, 0, sizeof(unsigned long long), h->stream));
         dim3 grid((n + 31) / 32, C / 32), block(32, 8);
-        import_labels_kernel<<<grid, block, 0, h->stream>>>(stage, h->d_labels, n, h->na, n_chains, C, h->d_ka, h->d_kb, d_bad);
+        // (in place: every element is read, compared and rewritten by one thread)
+        import_labels_kernel<InT><<<grid, block, 0, h->stream>>>(stage, h->d_labels, n, h->na, n_chains, C, h->d_ka, h->d_kb, d_bad,
+                                                              same_model ? h->d_labels : nullptr, d_changed);
         CU(cudaGetLastError());
-        unsigned long long bad = 0;
-        CU(cudaMemcpyAsync(&bad, d_bad, sizeof bad, cudaMemcpyDeviceToHost, h->stream));
+        unsigned long long res[2] = {0, 0};
+        CU(cudaMemcpyAsync(res, d_bad, sizeof res, cudaMemcpyDeviceToHost, h->stream));
         CU(cudaStreamSynchronize(h->stream));
+        const unsigned long long bad = res[0];
+        if (same_model && bad == ~0ull && res[1] == 0) {
+            // the caller handed back exactly the labels the handle holds (e.g. a checkpoint round trip): the counts
+            // built from them are still right
+            CU(cudaMemsetAsync(h->d_accepted, 0, 2 * sizeof(unsigned long long), h->stream));
+            CU(cudaStreamSynchronize(h->stream));
+            return BISBM_OK;
+        }
         if (bad != ~0ull) {
             const unsigned long long idx = bad - 1;
             const uint32_t c = (uint32_t)(idx / n), v = (uint32_t)(idx % n);
-            const uint32_t g = labels[idx];
+            const uint32_t g = (uint32_t)labels[idx];
             free_chains(h);
             return fail(BISBM_ERR_ARG, "chain %u node %u: block %u is not a type-%c block (ka=%u kb=%u)", c, v, g,
                         v < h->na ? 'a' : 'b', ka[c], kb[c]);
@@ -751,6 +780,21 @@ int bisbm_set_chains(bisbm_handle* h, uint32_t n_chains, const uint32_t* ka, con
     if (rc) return rc;
     CU(cudaStreamSynchronize(h->stream));
     return BISBM_OK;
+}
+
+extern "C" {
+
+int bisbm_set_chains(bisbm_handle* h, uint32_t n_chains, const uint32_t* ka, const uint32_t* kb,
+                     const uint32_t* labels, double eps) {
+    return set_chains_impl<uint32_t>(h, n_chains, ka, kb, labels, eps);
+}
+
+int bisbm_set_chains_u8(bisbm_handle* h, uint32_t n_chains, const uint32_t* ka, const uint32_t* kb,
+                        const uint8_t* labels, double eps) {
+    if (ka && kb)
+        for (uint32_t c = 0; c < n_chains; ++c)
+            if ((uint64_t)ka[c] + kb[c] > 256) return fail(BISBM_ERR_ARG, "chain %u: ka + kb > 256 does not fit 8-bit labels", c);
+    return set_chains_impl<uint8_t>(h, n_chains, ka, kb, labels, eps);
 }
 
 int bisbm_randomize(bisbm_handle* h, const uint64_t* seeds) {
@@ -992,15 +1036,19 @@ int bisbm_marginalize(bisbm_handle* h, uint64_t burn_in, uint64_t sweeps, uint64
     }
     h->last_launches = 0; h->last_sweep_launches = 0; h->last_moves = 0; h->last_ms = 0.0;
     CU(cudaEventRecord(h->ev0, h->stream));
-    const uint64_t tot = (uint64_t)h->n * h->C;
+    h->last_marginal_launches = 0;
     for (uint64_t sw = 0; sw < burn_in + sweeps; ++sw) {
         rc = launch_full_sweep(h, BISBM_CONSTANT, 1.0f, 0.0f, sw, max_inflight);
         if (rc) return rc;
         if (sw >= burn_in && ((sw - burn_in + 1) % every) == 0) {
-            rc = sync_labels32(h);
-            if (rc) return rc;
-            marginal_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(gview(h), sview(h), h->n_chains,
-                                                                                 h->d_hist, h->hist_width);
+            // straight from the array the sweep kernel keeps current: the u8 shadow (staged kernels) or the i32 labels
+            const uint64_t mw = (uint64_t)h->n * (h->C / 32);
+            const unsigned mgrid = (unsigned)((mw * 32 + 255) / 256);
+            if (h->lab32_stale)
+                marginal_kernel<uint8_t><<<mgrid, 256, 0, h->stream>>>(gview(h), h->d_lab8, h->C, h->d_ka, h->n_chains, h->d_hist, h->hist_width);
+            else
+                marginal_kernel<int32_t><<<mgrid, 256, 0, h->stream>>>(gview(h), h->d_labels, h->C, h->d_ka, h->n_chains, h->d_hist, h->hist_width);
+            h->last_marginal_launches += 1;
             h->last_launches += 1;
         }
     }
@@ -1036,7 +1084,8 @@ int bisbm_set_option(bisbm_handle* h, const char* name, int64_t value) {
     if (!h || !name) return fail(BISBM_ERR_ARG, "null argument");
     const std::string k(name);
     if (k == "kernel") {
-        if (value < -1 || value > KERN_STAGED_OLD) return fail(BISBM_ERR_ARG, "kernel: -1 (automatic), 0 (counts in L2) or 1 (round-1 staged double kernel)");
+        if (value != -1 && value != KERN_L2 && value != KERN_STAGED_OLD && value != KERN_S2L_F64)
+            return fail(BISBM_ERR_ARG, "kernel: -1 (automatic), 0 (round-1 kernel, counts in L2), 1 (round-1 staged double kernel) or 5 (sweep2, counts in L2)");
         h->opt_kernel = (int)value;
     } else if (k == "inflight_div") {
         if (value < 1 || value > (1 << 30)) return fail(BISBM_ERR_ARG, "inflight_div must be >= 1");
@@ -1063,8 +1112,8 @@ int bisbm_parallel_transition(bisbm_handle* h, uint32_t chain, uint32_t v, uint3
     }
     uint32_t wpc = 32;
     const int kernel = plan_kernel(h, &wpc);
-    if (kernel != KERN_S2_F32 && kernel != KERN_S2_F64)
-        return fail(BISBM_ERR_STATE, "bisbm_parallel_transition needs the staged sweep kernel (K or degrees too large for it)");
+    if (!kern_is_s2(kernel))
+        return fail(BISBM_ERR_STATE, "bisbm_parallel_transition needs the sweep2 kernel (degrees > 255 or K > 256 per type take the round-1 kernel)");
     const uint32_t type = va ? 0 : 1;
     rc = sync_labels8(h);
     if (rc) return rc;
@@ -1074,15 +1123,15 @@ int bisbm_parallel_transition(bisbm_handle* h, uint32_t chain, uint32_t v, uint3
     CU(cudaMemsetAsync(h->d_kat_out, 0xff, 2 * sizeof(double), h->stream));   // NaN: "not written"
     LaunchPlan lp;
     memset(&lp, 0, sizeof lp);
-    lp.kernel = kernel; lp.smem = true; lp.hist_bytes = 1; lp.wpc = wpc; lp.warps_used = 1; lp.ctas_per_group = 1; lp.slice = 1;
-    lp.smem_bytes = sweep2_layout(h->KA, h->KB, type, wpc, kernel == KERN_S2_F32 ? 4u : 8u).total;
+    lp.kernel = kernel; lp.smem = kern_is_s2_staged(kernel); lp.hist_bytes = 1; lp.wpc = wpc; lp.warps_used = 1; lp.ctas_per_group = 1; lp.slice = 1;
+    lp.smem_bytes = sweep2_layout(h->KA, h->KB, type, wpc, kern_is_f32(kernel) ? 4u : 8u, lp.smem).total;
     SweepParams P = base_params(h, type);
     P.n_groups = 1; P.group_offset = chain / 32;
     P.ctas_per_group = 1; P.warps_used = 1; P.pos_begin = 0; P.pos_end = 1; P.exclusive = 1;
     P.schedule = BISBM_CONSTANT; P.p0 = 1.0f; P.p1 = 0.0f;
     P.kat_mode = 1; P.kat_chain = chain; P.kat_v = v; P.kat_s = va ? s : s - ka;
     const bool stale = h->lab32_stale;
-    rc = (kernel == KERN_S2_F64) ? launch_sweep2<double>(h, P, lp, 1) : launch_sweep2<float>(h, P, lp, 1);
+    rc = kern_is_f32(kernel) ? launch_sweep2<float>(h, P, lp, 1) : launch_sweep2<double>(h, P, lp, 1);
     h->lab32_stale = stale;   // nothing was written
     if (rc) return rc;
     double out[2];
@@ -1157,18 +1206,32 @@ int bisbm_info(bisbm_handle* h, uint32_t* n, uint64_t* n_edges, uint32_t* max_de
     return BISBM_OK;
 }
 
-int bisbm_get_all_labels(bisbm_handle* h, uint32_t* labels) {
+}  // extern "C"
+
+template <typename OutT>
+static int get_all_labels_impl(bisbm_handle* h, OutT* labels) {
     int rc = need_chains(h);
     if (rc) return rc;
     const uint32_t n = h->n, C = h->C;
     if (!h->d_labels_tmp) CU(cudaMalloc(&h->d_labels_tmp, (size_t)n * C * sizeof(int32_t)));
-    uint32_t* stage = reinterpret_cast<uint32_t*>(h->d_labels_tmp);
+    OutT* stage = reinterpret_cast<OutT*>(h->d_labels_tmp);
     dim3 grid((n + 31) / 32, C / 32), block(32, 8);
-    export_labels_kernel<<<grid, block, 0, h->stream>>>(h->d_labels, stage, n, h->na, h->n_chains, C, h->d_ka);
+    export_labels_kernel<OutT><<<grid, block, 0, h->stream>>>(h->d_labels, stage, n, h->na, h->n_chains, C, h->d_ka);
     CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(labels, stage, (size_t)h->n_chains * n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(labels, stage, (size_t)h->n_chains * n * sizeof(OutT), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return BISBM_OK;
+}
+
+extern "C" {
+
+int bisbm_get_all_labels(bisbm_handle* h, uint32_t* labels) { return get_all_labels_impl<uint32_t>(h, labels); }
+
+int bisbm_get_all_labels_u8(bisbm_handle* h, uint8_t* labels) {
+    if (!h) return fail(BISBM_ERR_ARG, "null handle");
+    for (uint32_t c = 0; c < h->n_chains; ++c)
+        if (h->h_ka[c] + h->h_kb[c] > 256) return fail(BISBM_ERR_ARG, "chain %u: ka + kb > 256 does not fit 8-bit labels", c);
+    return get_all_labels_impl<uint8_t>(h, labels);
 }
 
 int bisbm_get_labels(bisbm_handle* h, uint32_t chain, uint32_t* labels) {

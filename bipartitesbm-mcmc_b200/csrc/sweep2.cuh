@@ -251,16 +251,24 @@ template <typename R> BISBM_HD R logq_fast(const LogqExp& q, int e, int n, int d
            (R)q.feee * De * ((R)(1.0 / 6.0) * De * De + (R)0.5 * dx * (De + dx));
 }
 
-// dS (natural-log units) and the logarithm of the Hastings factor accu1 / accu0 (lg units) of one move
-template <typename R>
-BISBM_HD void move_finish(const MAcc<R>& A, int eta_r, int eta_s, R bdd, R lqr, R lqs, uint32_t d, R eps, R* dS, R* lh) {
-    const R er = Ar<R>::cvt((uint32_t)(eta_r > 0 ? eta_r : 1)), es = Ar<R>::cvt((uint32_t)eta_s + 1u);
-    // log( prod (m_rt-c)/(m_st+1+c) * eta_r/(eta_s+1) )
-    const R prod = (A.num * Ar<R>::rcp(A.den)) * (er * Ar<R>::rcp(es));
-    *dS = Ar<R>::unit() * (A.lg + Ar<R>::lg(prod)) + ((d == 0) ? (R)0 : bdd) + lqr + lqs;
+// dS (natural-log units) and the logarithm of the Hastings factor accu1 / accu0 (lg units) of one move, in two steps so
+// the kernel can order them around its global loads: move_local needs only the running sums, move_finish adds eta and
+// the block terms.
+template <typename R> BISBM_HD void move_local(const MAcc<R>& A, uint32_t d, R eps, R* ratio, R* lh) {
+    *ratio = A.num * Ar<R>::rcp(A.den);          // prod (m_rt-c)/(m_st+1+c) not yet folded into A.lg
     const R ew = eps * A.w;
     const R a0 = Ar<R>::SPLIT ? A.sB - A.sC : A.sB, a1 = Ar<R>::SPLIT ? A.sA - A.sC : A.sA;
     *lh = (d == 0) ? (R)0 : Ar<R>::lg((a1 + ew) * Ar<R>::rcp(a0 + ew));
+}
+template <typename R> BISBM_HD R move_lgm(const MAcc<R>& A, R ratio, int eta_r, int eta_s) {
+    const R er = Ar<R>::cvt((uint32_t)(eta_r > 0 ? eta_r : 1)), es = Ar<R>::cvt((uint32_t)eta_s + 1u);
+    return A.lg + Ar<R>::lg(ratio * (er * Ar<R>::rcp(es)));      // lg( prod * eta_r / (eta_s + 1) )
+}
+template <typename R>
+BISBM_HD void move_finish(const MAcc<R>& A, int eta_r, int eta_s, R bdd, R lqr, R lqs, uint32_t d, R eps, R* dS, R* lh) {
+    R ratio;
+    move_local<R>(A, d, eps, &ratio, lh);
+    *dS = Ar<R>::unit() * move_lgm<R>(A, ratio, eta_r, eta_s) + ((d == 0) ? (R)0 : bdd) + lqr + lqs;
 }
 
 // ---- shared-memory layout (byte offsets; every array is a multiple of 16 bytes) ---------------------
@@ -281,16 +289,16 @@ inline
 #ifdef __CUDACC__
 __host__ __device__
 #endif
-Sweep2Layout sweep2_layout(uint32_t KA, uint32_t KB, uint32_t type, uint32_t warps, uint32_t rsize) {
+Sweep2Layout sweep2_layout(uint32_t KA, uint32_t KB, uint32_t type, uint32_t warps, uint32_t rsize, bool staged = true) {
     const uint32_t kown = type ? KB : KA, kopp = type ? KA : KB;
     Sweep2Layout L;
     uint32_t o = 0;
-    L.oM = o; o += KA * KB * 128u;
-    L.oEo = o; o += kown * 128u;
-    L.oNo = o; o += kown * 128u;
+    L.oM = o; o += staged ? KA * KB * 128u : 0u;        // counts in L2 (staged = false): only the read-only tables,
+    L.oEo = o; o += staged ? kown * 128u : 0u;          // the vertex batch, the histograms and the label tiles
+    L.oNo = o; o += staged ? kown * 128u : 0u;
     L.oEp = o; o += kopp * 128u;
     L.oInv = o; o += kopp * 32u * rsize;
-    L.oSmall = o; o += ((kown + 31u) / 32u) * 128u;
+    L.oSmall = o; o += staged ? ((kown + 31u) / 32u) * 128u : 0u;
     L.oVtx = o; o += (uint32_t)S2_VB * 16u;
     L.oHist = o; o += warps * ((kopp + 3u) / 4u) * 128u;
     L.oTile = o; o += warps * (uint32_t)S2_TILE;
@@ -319,6 +327,12 @@ template <typename R> __device__ __forceinline__ R sh_ld_real(uint32_t a);
 template <> __device__ __forceinline__ double sh_ld_real<double>(uint32_t a) { double v; asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
 template <> __device__ __forceinline__ float sh_ld_real<float>(uint32_t a) { float v; asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
 
+// 0, but only the hardware knows: `x + opaque_zero(y)` makes x's consumers wait for y without changing any value.
+// Used to order the arithmetic after the pass: everything that needs only shared memory first, the values loaded
+// from global memory (eta, log q expansions) last, so their latency is covered by work instead of a stall.
+__device__ __forceinline__ int opaque_zero(double y) { int z; asm("and.b32 %0, %1, 0;" : "=r"(z) : "r"(__double2loint(y))); return z; }
+__device__ __forceinline__ int opaque_zero(float y) { int z; asm("and.b32 %0, %1, 0;" : "=r"(z) : "r"(__float_as_int(y))); return z; }
+
 __device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(mbar), "r"(count) : "memory");
 }
@@ -345,6 +359,17 @@ __device__ __forceinline__ void bulk_red_add_s32(void* dst, uint32_t src, uint32
 __device__ __forceinline__ void bulk_commit_wait_all() {
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// counts kept in L2 (STAGED = false): every read goes to L2 (ld.global.cg: other SMs update them with reductions)
+__device__ __forceinline__ int gl_ld(uint64_t base, uint32_t off) {
+    int v; asm("{\n\t.reg .u64 a;\n\tcvt.u64.u32 a, %2;\n\tadd.u64 a, a, %1;\n\tld.global.cg.s32 %0, [a];\n\t}" : "=r"(v) : "l"(base), "r"(off)); return v;
+}
+__device__ __forceinline__ void gl_red(uint64_t base, uint32_t off, int v) {
+    asm volatile("{\n\t.reg .u64 a;\n\tcvt.u64.u32 a, %1;\n\tadd.u64 a, a, %0;\n\tred.global.add.s32 [a], %2;\n\t}" :: "l"(base), "r"(off), "r"(v) : "memory");
+}
+__device__ __forceinline__ int gl_atom(uint64_t base, uint32_t off, int v) {
+    int o; asm volatile("{\n\t.reg .u64 a;\n\tcvt.u64.u32 a, %2;\n\tadd.u64 a, a, %1;\n\tatom.global.add.s32 %0, [a], %3;\n\t}" : "=r"(o) : "l"(base), "r"(off), "r"(v) : "memory"); return o;
 }
 
 // the rare double-precision completions, out of line (arguments by value)
@@ -381,7 +406,9 @@ __global__ void sweep2_preinit_kernel(const int32_t* __restrict__ m, const int32
 // KF > 0: Ka == Kb == KF padded strides and the moving type TYPE fixed at compile time; KF == 0: from SweepParams.
 // 512 threads (16 warps x 128 registers), one CTA per SM.  Preconditions (plan_sweep): max degree <= 255 (u8
 // histogram bins), K per type <= 256 (u8 labels).
-template <typename R, int KF, int TYPE>
+// STAGED = false: K too large for shared memory -- m_rs / e_r / n_r stay in L2 (loads .cg, commits by global reductions,
+// every CTA sees every committed move at once: no slices, no staging, no publish); the rest of the kernel is the same.
+template <typename R, int KF, int TYPE, bool STAGED = true>
 __global__ void __launch_bounds__(512, 1) sweep2_kernel(const __grid_constant__ SweepParams P) {
     typedef Ar<R> AR;
     extern __shared__ __align__(128) unsigned char s2_smem[];
@@ -415,7 +442,7 @@ __global__ void __launch_bounds__(512, 1) sweep2_kernel(const __grid_constant__ 
     const R eps = (R)P.s.eps;
     const R epsK32 = (R)(P.s.eps * (double)K * 4294967296.0);   // threshold scale of the uniform-vs-categorical test
 
-    const Sweep2Layout L = sweep2_layout(KA, KB, type, wpc, (uint32_t)sizeof(R));
+    const Sweep2Layout L = sweep2_layout(KA, KB, type, wpc, (uint32_t)sizeof(R), STAGED);
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem_raw);
     int32_t* const sM = reinterpret_cast<int32_t*>(smem_raw + L.oM);
     int32_t* const sEo = reinterpret_cast<int32_t*>(smem_raw + L.oEo);
@@ -429,19 +456,23 @@ __global__ void __launch_bounds__(512, 1) sweep2_kernel(const __grid_constant__ 
     const uint32_t hist_words = (kopp_max + 3u) / 4u;
 
     // ---- stage the group's counts: one thread, bulk-async copies ----
-    if (threadIdx.x == 0) {
-        mbar_init(mbar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const uint32_t bM = KA * KB * 128u, bO = kown_max * 128u, bP = kopp_max * 128u;
-        mbar_expect_tx(mbar, bM + 2u * bO + bP);
-        for (uint32_t off = 0; off < bM; off += 32768u)
-            bulk_g2s(sbase + L.oM + off, reinterpret_cast<const char*>(gM) + off, min(32768u, bM - off), mbar);
-        bulk_g2s(sbase + L.oEo, gE + own_off * 32, bO, mbar);
-        bulk_g2s(sbase + L.oNo, gNR + own_off * 32, bO, mbar);
-        bulk_g2s(sbase + L.oEp, gE + opp_off * 32, bP, mbar);
+    if (STAGED) {
+        if (threadIdx.x == 0) {
+            mbar_init(mbar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint32_t bM = KA * KB * 128u, bO = kown_max * 128u, bP = kopp_max * 128u;
+            mbar_expect_tx(mbar, bM + 2u * bO + bP);
+            for (uint32_t off = 0; off < bM; off += 32768u)
+                bulk_g2s(sbase + L.oM + off, reinterpret_cast<const char*>(gM) + off, min(32768u, bM - off), mbar);
+            bulk_g2s(sbase + L.oEo, gE + own_off * 32, bO, mbar);
+            bulk_g2s(sbase + L.oNo, gNR + own_off * 32, bO, mbar);
+            bulk_g2s(sbase + L.oEp, gE + opp_off * 32, bP, mbar);
+        }
+    } else {
+        for (uint32_t i = threadIdx.x; i < kopp_max * 32u; i += blockDim.x) sEp[i] = __ldcg(gE + opp_off * 32 + i);
     }
     {   // meanwhile: clear the histograms
         uint32_t* const hw = reinterpret_cast<uint32_t*>(smem_raw + L.oHist);
@@ -469,7 +500,7 @@ __global__ void __launch_bounds__(512, 1) sweep2_kernel(const __grid_constant__ 
         return nb;
     };
     uint32_t nb = prepare(0);
-    mbar_wait(mbar, 0);
+    if (STAGED) mbar_wait(mbar, 0);
     __syncthreads();
     // tables derived from the staged counts
     for (uint32_t i = threadIdx.x; i < kopp_max * 32u; i += blockDim.x) {
@@ -477,7 +508,7 @@ __global__ void __launch_bounds__(512, 1) sweep2_kernel(const __grid_constant__ 
         const double Kc = (double)(P.s.ka[ci] + P.s.kb[ci]);
         sInv[i] = (R)(1.0 / ((double)sEp[i] + P.s.eps * Kc));
     }
-    {
+    if (STAGED) {
         // a block is "small" when it could empty within this launch without this CTA noticing: only then the veto
         // needs an exact counter.  One CTA per group: the shared view is exact, every block takes the exact path.
         const int thresh = P.exclusive ? 0x7fffffff : (int)min(span, 0x7ffffff0u) + 1;
@@ -505,8 +536,19 @@ __global__ void __launch_bounds__(512, 1) sweep2_kernel(const __grid_constant__ 
     const uint32_t tile_w = sbase + L.oTile + warp * (uint32_t)S2_TILE;
     const uint32_t tile_lane = tile_w + lane * 36u;                               // this chain's labels, edge e at +e
     const uint32_t tile_st = tile_w + (lane & 3u) * 288u + (lane >> 2);            // store base: chains 8 (lane%4) + i, row lane/4 (+ 8 j)
-    // m(x_own, t_opp) at M_base + x*SX + t*ST  (bytes)
+    // m(x_own, t_opp) at byte offset x*SX + t*ST of this lane's view of m_rs
     const uint32_t SX = (type ? 1u : KB) * 128u, ST = (type ? KB : 1u) * 128u;
+    // count accessors: shared-memory views (STAGED) or the arrays in L2
+    const uint64_t gMl = (uint64_t)__cvta_generic_to_global(gM + lane);
+    const uint64_t gEol = (uint64_t)__cvta_generic_to_global(gE + own_off * 32 + lane);
+    const uint64_t gNol = (uint64_t)__cvta_generic_to_global(gNR + own_off * 32 + lane);
+    auto m_ld = [&](uint32_t off) -> int { if constexpr (STAGED) return sh_ld(M_base + off); else return gl_ld(gMl, off); };
+    auto m_red = [&](uint32_t off, int v) { if constexpr (STAGED) sh_red_add(M_base + off, v); else gl_red(gMl, off, v); };
+    auto eo_ld = [&](uint32_t blk) -> int { if constexpr (STAGED) return sh_ld(Eo_base + blk * 128u); else return gl_ld(gEol, blk * 128u); };
+    auto eo_red = [&](uint32_t blk, int v) { if constexpr (STAGED) sh_red_add(Eo_base + blk * 128u, v); else gl_red(gEol, blk * 128u, v); };
+    auto no_ld = [&](uint32_t blk) -> int { if constexpr (STAGED) return sh_ld(No_base + blk * 128u); else return gl_ld(gNol, blk * 128u); };
+    auto no_red = [&](uint32_t blk, int v) { if constexpr (STAGED) sh_red_add(No_base + blk * 128u, v); else gl_red(gNol, blk * 128u, v); };
+    constexpr int SAFE_NR = 8192;   // counts in L2: more than any number of concurrently evaluated moves of one chain
     // the group's label rows: chain-minor u8, 32 bytes per vertex and group
     uint64_t LAB8 = (uint64_t)__cvta_generic_to_global(P.lab8 + (size_t)(group * 32u < C ? group * 32u : 0u));
     asm volatile("" : "+l"(LAB8));
@@ -579,10 +621,12 @@ __global__ void __launch_bounds__(512, 1) sweep2_kernel(const __grid_constant__ 
             }
             while (nxt < nb) {
                 const uint4 cur = ninfo;
-                const uint32_t v = cur.x, d = cur.z, didx = cur.w, r = r_nxt;
+                uint32_t v = cur.x;
+                const uint32_t d = cur.z, didx = cur.w, r = r_nxt;
                 const uint32_t pos_index = j0 + nxt;      // this vertex's index within the CTA's share
                 __syncwarp();
                 store_tile(min(d, 32u));
+                asm volatile("" : "+r"(v));               // the draw (pure ALU on v) goes AFTER the tile stores: it covers their drain
                 __syncwarp();
                 // next vertex: ids now, rows after the pass (when the ids have arrived)
                 nxt = pop();
@@ -623,10 +667,10 @@ __global__ void __launch_bounds__(512, 1) sweep2_kernel(const __grid_constant__ 
                 int wz = -(int)mulhi32(rz, (uint32_t)e_t) - 1;
                 uint32_t cnt_le = 0;
                 {
-                    uint32_t a = M_base + tq * ST;
+                    uint32_t a = tq * ST;
 #pragma unroll 8
                     for (uint32_t x = 0; x < kown_max; ++x, a += SX) {   // uniform bound; blocks >= kown hold 0
-                        wz += sh_ld(a);
+                        wz += m_ld(a);
                         cnt_le += ((uint32_t)wz) >> 31;
                     }
                 }
@@ -636,7 +680,7 @@ __global__ void __launch_bounds__(512, 1) sweep2_kernel(const __grid_constant__ 
                 uint32_t s = (movable_chain && !cross) ? (uniform_pick ? s_uni : s_cat) : r;   // own-type local index
                 if (P.kat_mode) { cross = false; s = (lane == kat_lane) ? P.kat_s : r; }
                 const bool eval = live && (s != r);
-                const int n_r = sh_ld(No_base + r * 128u);
+                const int n_r = no_ld(r);
                 if (!__any_sync(FULL, eval)) {
                     // s == r (dS = 0, accu_r = 1): accepted at T > 0 unless the block would empty, rejected at T == 0
                     // (src/metropolis_hasting.cc:47-52)
@@ -648,12 +692,12 @@ __global__ void __launch_bounds__(512, 1) sweep2_kernel(const __grid_constant__ 
                 // ---- one pass over v's neighbours: dS and the Hastings factor (transition_ratio).  Every lane
                 //      runs it (masked lanes cost the same issue slots); only `eval` lanes may commit. ----
                 MAcc<R> A; macc_init(A);
-                const uint32_t Mr = M_base + r * SX, Ms = M_base + s * SX;
+                const uint32_t Mr = r * SX, Ms = s * SX;
                 auto edge1 = [&](uint32_t t) {
                     const uint32_t sh3 = (t & 3u) << 3;
                     const uint32_t old = sh_atom_add_u32(hist_base + ((t >> 2) << 7), 1u << sh3);
                     const uint32_t off = t * ST;
-                    const int m_r = sh_ld(Mr + off), m_s = sh_ld(Ms + off);
+                    const int m_r = m_ld(Mr + off), m_s = m_ld(Ms + off);
                     const R inv = sh_ld_real<R>(Inv_base + t * IS);
                     macc_edge(A, m_r, m_s, ((old >> sh3) & 0xffu) + 1u, inv);
                 };
@@ -666,8 +710,8 @@ __global__ void __launch_bounds__(512, 1) sweep2_kernel(const __grid_constant__ 
                     const uint32_t o2 = sh_atom_add_u32(hist_base + ((t2 >> 2) << 7), 1u << h2);
                     const uint32_t o3 = sh_atom_add_u32(hist_base + ((t3 >> 2) << 7), 1u << h3);
                     const uint32_t f0 = t0 * ST, f1 = t1 * ST, f2 = t2 * ST, f3 = t3 * ST;
-                    const int r0 = sh_ld(Mr + f0), s0 = sh_ld(Ms + f0), r1 = sh_ld(Mr + f1), s1 = sh_ld(Ms + f1);
-                    const int r2 = sh_ld(Mr + f2), s2 = sh_ld(Ms + f2), r3 = sh_ld(Mr + f3), s3 = sh_ld(Ms + f3);
+                    const int r0 = m_ld(Mr + f0), s0 = m_ld(Ms + f0), r1 = m_ld(Mr + f1), s1 = m_ld(Ms + f1);
+                    const int r2 = m_ld(Mr + f2), s2 = m_ld(Ms + f2), r3 = m_ld(Mr + f3), s3 = m_ld(Ms + f3);
                     const R i0 = sh_ld_real<R>(Inv_base + t0 * IS), i1 = sh_ld_real<R>(Inv_base + t1 * IS);
                     const R i2 = sh_ld_real<R>(Inv_base + t2 * IS), i3 = sh_ld_real<R>(Inv_base + t3 * IS);
                     macc_edge(A, r0, s0, ((o0 >> h0) & 0xffu) + 1u, i0);
@@ -715,9 +759,9 @@ __global__ void __launch_bounds__(512, 1) sweep2_kernel(const __grid_constant__ 
                 // requested first; the e_r terms below only need shared memory and cover part of the latency
                 const int eta_r = ldc(&gETA[(r * W + didx) * 32 + lane]);
                 const int eta_s = ldc(&gETA[(s * W + didx) * 32 + lane]);
-                const int n_s = sh_ld(No_base + s * 128u);
+                const int n_s = no_ld(s);
                 {
-                    const int e_r = sh_ld(Eo_base + r * 128u), e_s = sh_ld(Eo_base + s * 128u);
+                    const int e_r = eo_ld(r), e_s = eo_ld(s);
                     bool ok_b, ok_r, ok_s;
                     auto load_q = [&](uint32_t slot) -> LogqExp {   // 48 bytes of this (block, chain); constant during the launch
                         const uint4* p = reinterpret_cast<const uint4*>(gLQ + slot * 32u + lane);
@@ -729,8 +773,17 @@ __global__ void __launch_bounds__(512, 1) sweep2_kernel(const __grid_constant__ 
                         q.fnn = __uint_as_float(c4.x); q.feee = __uint_as_float(c4.y); q.valid = c4.z; q.pad = 0;
                         return q;
                     };
-                    const LogqExp q_r = load_q(r), q_s = load_q(s);
+                    LogqExp q_r = load_q(r), q_s = load_q(s);
+                    // (1) shared memory only: the e_r terms, the Hastings factor, the count-ratio product
                     R bdd = bdd_fast<R>(e_r, e_s, (int)d, &ok_b);
+                    R ratio, lh;
+                    move_local<R>(A, d, eps, &ratio, &lh);
+                    // (2) eta (L2): log( prod * eta_r / (eta_s + 1) )
+                    const int z1 = opaque_zero(bdd) | opaque_zero(lh) | opaque_zero(ratio);
+                    const R lgm = move_lgm<R>(A, ratio, eta_r + z1, eta_s + z1);
+                    // (3) the log q expansions (L1 / L2)
+                    const int z2 = opaque_zero(lgm);
+                    q_r.e0 += z2; q_s.e0 += z2;
                     R lqr = logq_fast<R>(q_r, e_r, n_r, -(int)d, -1, &ok_r);
                     R lqs = logq_fast<R>(q_s, e_s, n_s, (int)d, 1, &ok_s);
                     if (__any_sync(FULL, eval && !(ok_b && ok_r && ok_s))) {
@@ -739,8 +792,7 @@ __global__ void __launch_bounds__(512, 1) sweep2_kernel(const __grid_constant__ 
                         if (eval && !ok_s) lqs = (R)slow2_logq_delta(P.tb.qtab, P.tb.qn, P.tb.qk, e_s, n_s, (int)d, 1);
                         __syncwarp();
                     }
-                    R lh;
-                    move_finish<R>(A, eta_r, eta_s, bdd, lqr, lqs, d, eps, &dS, &lh);
+                    dS = AR::unit() * lgm + ((d == 0u) ? (R)0 : bdd) + lqr + lqs;
                     const R a2 = lh - dS * (beta * AR::inv_unit());          // lg of the acceptance ratio
                     const bool go_hot = (a2 > (R)0) || (AR::u01(rw) < AR::ex(a2));
                     go = eval && (T_zero ? (dS < (R)0) : go_hot);
@@ -752,18 +804,28 @@ __global__ void __launch_bounds__(512, 1) sweep2_kernel(const __grid_constant__ 
                     if (live && !cross && s == r && !T_zero && n_r != 1 && !P.kat_mode) ++n_acc;
                     if (go) {
                         // the "would empty block r" veto of apply_mcmc_moves: exact where it can matter
-                        const uint32_t small_r = (sh_ld_u32v(Small_base + (r >> 5) * 128u) >> (r & 31u)) & 1u;
-                        if (small_r) {
-                            if (P.exclusive) {
-                                const int old = sh_atom_add_s32(No_base + r * 128u, -1);
-                                if (old <= 1) { sh_red_add(No_base + r * 128u, 1); go = false; }
+                        if constexpr (STAGED) {
+                            const uint32_t small_r = (sh_ld_u32v(Small_base + (r >> 5) * 128u) >> (r & 31u)) & 1u;
+                            if (small_r) {
+                                if (P.exclusive) {
+                                    const int old = sh_atom_add_s32(No_base + r * 128u, -1);
+                                    if (old <= 1) { sh_red_add(No_base + r * 128u, 1); go = false; }
+                                } else {
+                                    const int old = atomicSub(&gLIVE[r * 32 + lane], 1);
+                                    if (old <= 1) { atomicAdd(&gLIVE[r * 32 + lane], 1); go = false; }
+                                    else sh_red_add(No_base + r * 128u, -1);
+                                }
                             } else {
-                                const int old = atomicSub(&gLIVE[r * 32 + lane], 1);
-                                if (old <= 1) { atomicAdd(&gLIVE[r * 32 + lane], 1); go = false; }
-                                else sh_red_add(No_base + r * 128u, -1);
+                                sh_red_add(No_base + r * 128u, -1);
                             }
                         } else {
-                            sh_red_add(No_base + r * 128u, -1);
+                            // n_r was read from L2 a moment ago; fewer than SAFE_NR moves of this chain can be in flight, so a
+                            // block that large cannot empty and a fire-and-forget reduction is enough
+                            if (n_r > SAFE_NR) no_red(r, -1);
+                            else {
+                                const int old = gl_atom(gNol, r * 128u, -1);
+                                if (old <= 1) { no_red(r, 1); go = false; }
+                            }
                         }
                     }
                 }
@@ -779,10 +841,10 @@ __global__ void __launch_bounds__(512, 1) sweep2_kernel(const __grid_constant__ 
                             const uint32_t Lc = sh_ld_u32v(tile_lane + 4u * q);
                             const uint32_t c4 = d - 4u * q;
                             const uint32_t f0 = (Lc & 0xffu) * ST;
-                            sh_red_add(Mr + f0, -g1); sh_red_add(Ms + f0, g1);
-                            if (c4 > 1u) { const uint32_t f1 = ((Lc >> 8) & 0xffu) * ST; sh_red_add(Mr + f1, -g1); sh_red_add(Ms + f1, g1); }
-                            if (c4 > 2u) { const uint32_t f2 = ((Lc >> 16) & 0xffu) * ST; sh_red_add(Mr + f2, -g1); sh_red_add(Ms + f2, g1); }
-                            if (c4 > 3u) { const uint32_t f3 = (Lc >> 24) * ST; sh_red_add(Mr + f3, -g1); sh_red_add(Ms + f3, g1); }
+                            m_red(Mr + f0, -g1); m_red(Ms + f0, g1);
+                            if (c4 > 1u) { const uint32_t f1 = ((Lc >> 8) & 0xffu) * ST; m_red(Mr + f1, -g1); m_red(Ms + f1, g1); }
+                            if (c4 > 2u) { const uint32_t f2 = ((Lc >> 16) & 0xffu) * ST; m_red(Mr + f2, -g1); m_red(Ms + f2, g1); }
+                            if (c4 > 3u) { const uint32_t f3 = (Lc >> 24) * ST; m_red(Mr + f3, -g1); m_red(Ms + f3, g1); }
                         }
                     }
                     for (uint32_t w = 0; w < hist_words; ++w) sh_st_u32v(hist_base + w * 128u, 0u);
@@ -797,16 +859,17 @@ __global__ void __launch_bounds__(512, 1) sweep2_kernel(const __grid_constant__ 
                             const uint32_t t = w * 4u + b;
                             if (t < kopp_max) {
                                 const int kk = (int)((word >> (8u * b)) & 0xffu);
-                                sh_red_add(Mr + t * ST, -kk); sh_red_add(Ms + t * ST, kk);
+                                if (STAGED || kk != 0) { m_red(Mr + t * ST, -kk); m_red(Ms + t * ST, kk); }
                             }
                         }
                     }
                 }
                 if (go) {
-                    sh_red_add(Eo_base + r * 128u, -(int)d);
-                    sh_red_add(Eo_base + s * 128u, (int)d);
-                    sh_red_add(No_base + s * 128u, 1);
-                    if (!P.exclusive && ((sh_ld_u32v(Small_base + (s >> 5) * 128u) >> (s & 31u)) & 1u)) atomicAdd(&gLIVE[s * 32 + lane], 1);
+                    eo_red(r, -(int)d);
+                    eo_red(s, (int)d);
+                    no_red(s, 1);
+                    if constexpr (STAGED)
+                        if (!P.exclusive && ((sh_ld_u32v(Small_base + (s >> 5) * 128u) >> (s & 31u)) & 1u)) atomicAdd(&gLIVE[s * 32 + lane], 1);
                     atomicSub(&gETA[(r * W + didx) * 32 + lane], 1);
                     atomicAdd(&gETA[(s * W + didx) * 32 + lane], 1);
                     lab_st(v, s);
@@ -829,7 +892,7 @@ __global__ void __launch_bounds__(512, 1) sweep2_kernel(const __grid_constant__ 
     // ---- publish the staged counts ----
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // shared-memory writes of this thread -> visible to the bulk engine
     __syncthreads();
-    if (P.kat_mode) return;
+    if (P.kat_mode || !STAGED) return;
     if (P.exclusive) {
         copy_i4(gM, sM, KA * KB * 32);
         copy_i4(gE + own_off * 32, sEo, kown_max * 32);

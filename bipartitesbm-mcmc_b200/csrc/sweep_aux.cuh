@@ -107,16 +107,21 @@ __global__ void randomize_kernel(GraphView G, const int32_t* in, int32_t* out, u
 // ---- label import / export: host layout [chain][node] with GLOBAL block ids  <->  device
 //      layout [node][C] chain-minor, type-local.  32x32 tiles through shared memory so both
 //      sides are coalesced.  `bad` receives 1 + (chain * n + node) of the first invalid label. ----
-__global__ void import_labels_kernel(const uint32_t* __restrict__ in, int32_t* __restrict__ out, uint32_t n,
+// InT = uint32_t or uint8_t (host label element type).  `prev` (may be null): the labels the handle holds now; *changed is
+// set when any imported label differs from them (the caller then skips the count rebuild).
+template <typename InT>
+__global__ void import_labels_kernel(const InT* __restrict__ in, int32_t* __restrict__ out, uint32_t n,
                                      uint32_t na, uint32_t n_chains, uint32_t C, const uint32_t* __restrict__ ka,
-                                     const uint32_t* __restrict__ kb, unsigned long long* bad) {
+                                     const uint32_t* __restrict__ kb, unsigned long long* bad,
+                                     const int32_t* __restrict__ prev, uint32_t* changed) {
     __shared__ uint32_t tile[32][33];
     const uint32_t v0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
     for (uint32_t j = threadIdx.y; j < 32; j += blockDim.y) {
         const uint32_t c = c0 + j, v = v0 + threadIdx.x;
-        tile[j][threadIdx.x] = (c < n_chains && v < n) ? in[(size_t)c * n + v] : 0u;
+        tile[j][threadIdx.x] = (c < n_chains && v < n) ? (uint32_t)in[(size_t)c * n + v] : 0u;
     }
     __syncthreads();
+    bool diff = false;
     for (uint32_t j = threadIdx.y; j < 32; j += blockDim.y) {
         const uint32_t v = v0 + j, c = c0 + threadIdx.x;
         if (v >= n) continue;
@@ -129,11 +134,14 @@ __global__ void import_labels_kernel(const uint32_t* __restrict__ in, int32_t* _
             else { ok = (g >= kac) && (g < kac + kbc); l = (int32_t)(g - kac); }
             if (!ok) { atomicMin(bad, 1ull + (unsigned long long)c * n + v); l = 0; }
         }
+        if (prev && prev[(size_t)v * C + c] != l) diff = true;
         out[(size_t)v * C + c] = l;
     }
+    if (changed && __any_sync(0xffffffffu, diff) && (threadIdx.x == 0)) atomicOr(changed, 1u);
 }
 
-__global__ void export_labels_kernel(const int32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t n,
+template <typename OutT>
+__global__ void export_labels_kernel(const int32_t* __restrict__ in, OutT* __restrict__ out, uint32_t n,
                                      uint32_t na, uint32_t n_chains, uint32_t C, const uint32_t* __restrict__ ka) {
     __shared__ uint32_t tile[32][33];
     const uint32_t v0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -149,7 +157,7 @@ __global__ void export_labels_kernel(const int32_t* __restrict__ in, uint32_t* _
     __syncthreads();
     for (uint32_t j = threadIdx.y; j < 32; j += blockDim.y) {
         const uint32_t c = c0 + j, v = v0 + threadIdx.x;
-        if (c < n_chains && v < n) out[(size_t)c * n + v] = tile[threadIdx.x][j];
+        if (c < n_chains && v < n) out[(size_t)c * n + v] = (OutT)tile[threadIdx.x][j];
     }
 }
 
@@ -190,15 +198,25 @@ __global__ void bookkeep_kernel(uint32_t n_chains, uint8_t* active, const double
     if (u[c] >= steps_await) { active[c] = 0; atomicSub(n_active, 1u); }
 }
 
-// marginal accumulation: hist[v][g] += #chains with global label g at v
-__global__ void marginal_kernel(GraphView G, StateView S, uint32_t n_chains, uint32_t* hist, uint32_t width) {
-    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (uint64_t)G.n * S.C) return;
-    const uint32_t v = (uint32_t)(idx / S.C), c = (uint32_t)(idx % S.C);
-    if (c >= n_chains) return;
-    const uint32_t l = (uint32_t)S.labels[idx];
-    const uint32_t g = v < G.na ? l : S.ka[c] + l;
-    atomicAdd(&hist[(size_t)v * width + g], 1u);
+// marginal accumulation: hist[v][g] += #chains with global label g at v.  One warp per (vertex, chain group): the 32
+// chains' labels are ONE 128-byte line of the chain-minor i32 labels (or one 32-byte sector of the u8 shadow, LabT =
+// uint8_t); lanes holding the same label elect one of them, which adds their count -- a handful of atomics per warp
+// instead of 32.
+template <typename LabT>
+__global__ void marginal_kernel(GraphView G, const LabT* __restrict__ labels, uint32_t C, const uint32_t* __restrict__ ka,
+                                uint32_t n_chains, uint32_t* hist, uint32_t width) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t n_groups = C / 32;
+    const uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= (uint64_t)G.n * n_groups) return;
+    const uint32_t v = (uint32_t)(w / n_groups), c = (uint32_t)(w % n_groups) * 32 + lane;
+    uint32_t g = 0xffffffffu;     // padding lanes: a key of their own, never added
+    if (c < n_chains) {
+        const uint32_t l = (uint32_t)labels[(size_t)v * C + c];
+        g = v < G.na ? l : ka[c] + l;
+    }
+    const uint32_t peers = __match_any_sync(0xffffffffu, g);
+    if (g != 0xffffffffu && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&hist[(size_t)v * width + g], (uint32_t)__popc(peers));
 }
 
 __global__ void marginal_argmax_kernel(uint32_t n, const uint32_t* hist, uint32_t width, uint32_t* out) {

@@ -52,6 +52,7 @@ SIGNATURES = {
     "bisbm_create_csr": (C.c_int, [C.c_uint32, C.c_uint32, _u32p, _u32p, C.c_int, C.POINTER(C.c_void_p)]),
     "bisbm_destroy": (C.c_int, [C.c_void_p]),
     "bisbm_set_chains": (C.c_int, [C.c_void_p, C.c_uint32, _u32p, _u32p, C.c_void_p, C.c_double]),
+    "bisbm_set_chains_u8": (C.c_int, [C.c_void_p, C.c_uint32, _u32p, _u32p, C.c_void_p, C.c_double]),
     "bisbm_randomize": (C.c_int, [C.c_void_p, _u64p]),
     "bisbm_replay_init": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]),
     "bisbm_replay_anneal": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int, C.c_float, C.c_float, C.c_uint64, C.c_uint64,
@@ -78,6 +79,7 @@ SIGNATURES = {
     "bisbm_info": (C.c_int, [C.c_void_p, _u32p, _u64p, _u32p, _u32p]),
     "bisbm_get_labels": (C.c_int, [C.c_void_p, C.c_uint32, _u32p]),
     "bisbm_get_all_labels": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "bisbm_get_all_labels_u8": (C.c_int, [C.c_void_p, C.c_void_p]),
     "bisbm_get_m": (C.c_int, [C.c_void_p, C.c_uint32, _i32p]),
     "bisbm_get_m_r": (C.c_int, [C.c_void_p, C.c_uint32, _i32p]),
     "bisbm_get_n_r": (C.c_int, [C.c_void_p, C.c_uint32, _i32p]),
@@ -179,9 +181,11 @@ class ChainPool:
     def __init__(self, graph, labels, ka, kb, epsilon):
         self.g = graph
         self.L = graph.L
-        labels = np.ascontiguousarray(labels, dtype=np.uint32)
+        if not (isinstance(labels, np.ndarray) and labels.dtype == np.uint8):
+            labels = np.ascontiguousarray(labels, dtype=np.uint32)
         if labels.ndim == 1:
             labels = labels[None, :]
+        labels = np.ascontiguousarray(labels)
         self.n_chains = labels.shape[0]
         assert labels.shape[1] == graph.n
         self.ka = np.ascontiguousarray(np.broadcast_to(np.asarray(ka, dtype=np.uint32), (self.n_chains,)))
@@ -191,10 +195,11 @@ class ChainPool:
 
     # -- state in
     def set_labels(self, labels):
-        """labels: uint32 [n_chains][n] (numpy array, or any object with .ctypes / data_ptr())."""
+        """labels: uint32 or uint8 [n_chains][n], global block ids (numpy array, or a torch tensor of that element size)."""
         ptr = labels.data_ptr() if hasattr(labels, "data_ptr") else labels.ctypes.data
-        _check(self.L.bisbm_set_chains(self.g.h, self.n_chains, _p(self.ka, C.c_uint32), _p(self.kb, C.c_uint32),
-                                       C.c_void_p(ptr), self.epsilon))
+        item = labels.element_size() if hasattr(labels, "element_size") else labels.dtype.itemsize
+        fn = self.L.bisbm_set_chains_u8 if item == 1 else self.L.bisbm_set_chains
+        _check(fn(self.g.h, self.n_chains, _p(self.ka, C.c_uint32), _p(self.kb, C.c_uint32), C.c_void_p(ptr), self.epsilon))
 
     def randomize(self, seeds):
         seeds = np.ascontiguousarray(seeds, dtype=np.uint64)
@@ -305,7 +310,9 @@ class ChainPool:
             if out is None:
                 out = np.zeros((self.n_chains, self.g.n), dtype=np.uint32)
             ptr = out.data_ptr() if hasattr(out, "data_ptr") else out.ctypes.data
-            _check(self.L.bisbm_get_all_labels(self.g.h, C.c_void_p(ptr)))
+            item = out.element_size() if hasattr(out, "element_size") else out.dtype.itemsize
+            fn = self.L.bisbm_get_all_labels_u8 if item == 1 else self.L.bisbm_get_all_labels
+            _check(fn(self.g.h, C.c_void_p(ptr)))
             return out
         o = np.zeros(self.g.n, dtype=np.uint32)
         _check(self.L.bisbm_get_labels(self.g.h, chain, _p(o, C.c_uint32)))

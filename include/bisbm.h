@@ -70,6 +70,11 @@ int bisbm_destroy(bisbm_handle* h);
  * eta_rk on the device.  eps is the reference's epsilon (-E). */
 int bisbm_set_chains(bisbm_handle* h, uint32_t n_chains, const uint32_t* ka, const uint32_t* kb,
                      const uint32_t* labels, double eps);
+/* The same with 8-bit labels (global block ids, needs ka[c] + kb[c] <= 256): a quarter of the host <-> device bytes. */
+int bisbm_set_chains_u8(bisbm_handle* h, uint32_t n_chains, const uint32_t* ka, const uint32_t* kb,
+                        const uint8_t* labels, double eps);
+/* Both forms compare the incoming labels with the ones the handle already holds (same chain count, K and epsilon): when
+ * nothing changed -- a caller handing back what it read, e.g. after a checkpoint -- the counts are kept, not rebuilt. */
 /* Parallel-mode --randomize: permutes each chain's labels within type a and within
  * type b with a counter-based RNG keyed by seeds[c] (same block sizes as shuffle_bisbm,
  * src/blockmodel.cc:672-679, different stream), then rebuilds the counts. */
@@ -113,12 +118,14 @@ enum { BISBM_PRECISION_FP32 = 0, BISBM_PRECISION_FP64 = 1 };
 int bisbm_set_precision(bisbm_handle* h, int mode);
 /* Tuning options of the parallel sweep (no environment variables are read):
  *   "inflight_div"  default in-flight bound of bisbm_anneal(max_inflight = 0) = half sweep / value (default 64)
- *   "kernel"        -1 automatic; 0 force counts in L2; 1 force the round-1 staged double kernel (A/B runs)
+ *   "kernel"        -1 automatic; 0 / 1 force the round-1 kernels (counts in L2 / staged, double); 5 force sweep2 with
+ *                   counts in L2 (A/B runs and tests)
  *   "generic"       1: never take the Ka = Kb = 32 compile-time specialisation */
 int bisbm_set_option(bisbm_handle* h, const char* name, int64_t value);
 /* which sweep kernel the last parallel call launched and how the half sweep was cut:
- * kernel 0 = double arithmetic, counts in L2 (sweep_kernel); 1 = round-1 staged double kernel; 2 = sweep2_kernel<float>;
- * 3 = sweep2_kernel<double> (staged counts, the default);
+ * kernel 0 = round-1 sweep_kernel (double, counts in L2: hubs of degree > 255, K > 256 per type); 1 = round-1 staged
+ * double kernel; 2 / 3 = sweep2_kernel<float / double>, counts staged in shared memory (3 is the default);
+ * 4 / 5 = sweep2_kernel<float / double>, counts in L2 (K too large for shared memory);
  * slice = vertices of the visiting order per launch (the staleness bound between CTAs of one chain group) */
 int bisbm_sweep_info(bisbm_handle* h, int* kernel, uint32_t* warps_per_cta, uint32_t* ctas_per_group, uint32_t* slice);
 /* transition_ratio (src/metropolis_hasting.cc:103-192) for moving v to global block s in chain `chain`, evaluated by the
@@ -141,6 +148,7 @@ int bisbm_stream(bisbm_handle* h, void** stream);
 int bisbm_info(bisbm_handle* h, uint32_t* n, uint64_t* n_edges, uint32_t* max_degree, uint32_t* n_chains);
 int bisbm_get_labels(bisbm_handle* h, uint32_t chain, uint32_t* labels);          /* [n] global ids */
 int bisbm_get_all_labels(bisbm_handle* h, uint32_t* labels);                     /* [n_chains][n] */
+int bisbm_get_all_labels_u8(bisbm_handle* h, uint8_t* labels);                   /* [n_chains][n], ka + kb <= 256 */
 int bisbm_get_m(bisbm_handle* h, uint32_t chain, int32_t* m);                    /* [K][K] symmetric */
 int bisbm_get_m_r(bisbm_handle* h, uint32_t chain, int32_t* e_r);                /* [K] */
 int bisbm_get_n_r(bisbm_handle* h, uint32_t chain, int32_t* n_r);                /* [K] */

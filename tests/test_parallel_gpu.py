@@ -175,9 +175,11 @@ def test_large_graph_invariants_and_logq_expansion(host):
         assert abs((f2[c] - f1[c]) - pool2.entropy_accum(c)) <= 1e-6 * abs(f1[c])
 
 
-def test_large_k_uses_global_counts_path(host):
+@pytest.mark.parametrize("kernel", [-1, 0])
+def test_large_k_uses_global_counts_path(host, kernel):
     """K too large for shared-memory staging (KA*KB*128 B > 220 KB): counts stay in L2, commits are
-    global atomics.  Same invariants; sequential chains are exact."""
+    global atomics -- sweep2_kernel<.., STAGED = false> (kernel 5) by default, the round-1 kernel (0) on request.
+    Same invariants; sequential chains are exact."""
     na = nb = 3000
     ka = kb = 48
     edges = planted(na, nb, 8, 8, 60000, 11)
@@ -185,16 +187,19 @@ def test_large_k_uses_global_counts_path(host):
     C = 33
     lab0 = np.concatenate([np.arange(na) % ka, ka + np.arange(nb) % kb]).astype(np.uint32)
     pool = host.ChainPool(graph, np.tile(lab0, (C, 1)), ka, kb, 1.0)
+    pool.set_option("kernel", kernel)
     seeds = np.arange(C, dtype=np.uint64) + 31
     pool.randomize(seeds)
     e1 = pool.entropy()
     pool.anneal("constant", 1.0, 0.0, 4 * (na + nb), 10 ** 9, seeds)
+    assert pool.sweep_info()[0] == (5 if kernel == -1 else 0)
     check_invariants(pool, edges, na, nb, [0, 31, 32])
     pool.anneal("abrupt_cool", 2.0 * (na + nb), 0.0, 6 * (na + nb), 10 ** 9, seeds, max_inflight=1)
     check_invariants(pool, edges, na, nb, [0, 32])
     e2 = pool.entropy()
     assert (e2 < e1).all()
     pool2 = host.ChainPool(graph, np.tile(lab0, (C, 1)), ka, kb, 1.0)
+    pool2.set_option("kernel", kernel)
     pool2.randomize(seeds)
     f1 = pool2.entropy()
     pool2.anneal("constant", 1.0, 0.0, 2 * (na + nb), 10 ** 9, seeds, max_inflight=1)
@@ -399,7 +404,7 @@ def test_asymmetric_and_borderline_k(host, ka, kb):
     assert (sw == 3).all() and (acc > 0).all()
     check_invariants(pool, edges, na, nb, [0, 31, 39])
     kern = pool.sweep_info()[0]
-    assert kern == (0 if ka * kb * 128 > 200 * 1024 else 3)
+    assert kern in (3, 5)      # sweep2_kernel<double>: staged counts (fewer warps when shared memory is short) or counts in L2
     f1 = pool.entropy()
     d0 = np.array([pool.entropy_accum(c) for c in (0, 39)])
     pool.anneal("constant", 1.0, 0.0, 1 * (na + nb), 10 ** 9, seeds + np.uint64(7), max_inflight=1)
@@ -429,3 +434,32 @@ def test_two_handles_on_two_devices_or_one(host):
             check_invariants(pool, edges, na, nb, [0, 31])
             pools.append(pool)
     assert len(pools) >= 1
+
+
+def test_u8_labels_round_trip_and_rebuild_skip(host):
+    """The 8-bit label entry points carry the same labels as the 32-bit ones; handing back exactly the labels the handle
+    holds keeps its counts (no rebuild), a single changed label rebuilds them."""
+    g = load_golden("c2_const_k46")
+    na, nb, edges = g["na"], g["nb"], g["edges"]
+    graph = host.Graph(edges, na, nb)
+    C = 37
+    pool = host.ChainPool(graph, np.tile(g["labels0"], (C, 1)), 4, 6, 1.0)
+    seeds = np.arange(C, dtype=np.uint64) + 5
+    pool.randomize(seeds)
+    pool.anneal("constant", 1.0, 0.0, 5 * (na + nb), 10 ** 9, seeds)
+    l32 = pool.labels()
+    l8 = pool.labels(out=np.zeros((C, na + nb), dtype=np.uint8))
+    assert l8.dtype == np.uint8 and (l8 == l32).all()
+    acc0 = pool.entropy_accum(3)
+    pool.set_labels(l8)                      # unchanged: counts kept
+    check_invariants(pool, edges, na, nb, [0, 36])
+    l8b = l8.copy()
+    l8b[36, 999] = 4 + (l8b[36, 999] - 4 + 1) % 6
+    pool.set_labels(l8b)                     # one label changed: counts rebuilt
+    check_invariants(pool, edges, na, nb, [0, 36])
+    assert (pool.labels(36) == l8b[36]).all()
+    pool.anneal("constant", 1.0, 0.0, 2 * (na + nb), 10 ** 9, seeds)
+    check_invariants(pool, edges, na, nb, [0, 36])
+    bad = l8b.copy(); bad[1, 0] = 7          # a type-b block id on a type-a node
+    with pytest.raises(host.BisbmError):
+        pool.set_labels(bad)

@@ -48,15 +48,18 @@ def _kat_check(pool, chain, kv, ks, kd, ka, lab, precision):
     return worst_ds, worst_la, checked
 
 
+@pytest.mark.parametrize("counts", ["staged", "l2"])
 @pytest.mark.parametrize("precision", ["fp64", "fp32"])
 @pytest.mark.parametrize("name", KAT_GOLDENS)
-def test_parallel_kernel_transition_kats(host, name, precision):
+def test_parallel_kernel_transition_kats(host, name, precision, counts):
     g = load_golden(name)
     na, nb = g["na"], g["nb"]
     graph = host.Graph(g["edges"], na, nb)
     C = 35     # the chain under test sits in the second chain group, next to padding lanes
     pool = host.ChainPool(graph, np.tile(g["init_labels"], (C, 1)), int(g["ka"]), int(g["kb"]), float(g["eps"]))
     pool.set_precision(precision)
+    if counts == "l2":
+        pool.set_option("kernel", 5)      # sweep2_kernel<.., STAGED = false>: the large-K form of the same kernel
     w1, w2, n = _kat_check(pool, 33, g["kat_v"], g["kat_s"], g["kat_dS"], g["kat_accu"], g["init_labels"], precision)
     print("%s %s: %d known answers, worst rel dS error %.2e, worst |log accu error| %.2e" % (name, precision, n, w1, w2))
     assert n > 0
