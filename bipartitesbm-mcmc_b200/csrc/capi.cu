@@ -55,8 +55,24 @@ struct ReplaySlot {
 
 }  // namespace
 
+// device-resident graph + exact log q table: read-only after creation, shared (ref-counted) by every handle made
+// from the same graph with bisbm_share_graph
+struct GraphDev {
+    int device = 0;
+    uint32_t *row_ptr = nullptr, *col = nullptr, *degidx = nullptr;
+    double* qtab = nullptr;
+    ~GraphDev() {
+        cudaSetDevice(device);
+        if (row_ptr) cudaFree(row_ptr);
+        if (col) cudaFree(col);
+        if (degidx) cudaFree(degidx);
+        if (qtab) cudaFree(qtab);
+    }
+};
+
 struct bisbm_handle {
     int device = 0;
+    std::shared_ptr<GraphDev> gdev;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int sm_count = 148;
@@ -245,6 +261,9 @@ int finish_graph(bisbm_handle* h, std::vector<uint32_t>& col) {
         CU(cudaMalloc(&h->d_qtab, q.size() * sizeof(double)));
         CU(cudaMemcpy(h->d_qtab, q.data(), q.size() * sizeof(double), cudaMemcpyHostToDevice));
     }
+    h->gdev = std::make_shared<GraphDev>();
+    h->gdev->device = h->device;
+    h->gdev->row_ptr = h->d_row_ptr; h->gdev->col = h->d_col; h->gdev->degidx = h->d_degidx; h->gdev->qtab = h->d_qtab;
     return BISBM_OK;
 }
 
@@ -672,7 +691,9 @@ int bisbm_destroy(bisbm_handle* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     free_chains(h);
-    dfree(h->d_row_ptr); dfree(h->d_col); dfree(h->d_degidx); dfree(h->d_qtab); dfree(h->d_lg);
+    if (h->gdev) h->gdev.reset();          // the last handle sharing the graph frees it
+    else { dfree(h->d_row_ptr); dfree(h->d_col); dfree(h->d_degidx); dfree(h->d_qtab); }   // creation failed half way
+    dfree(h->d_lg);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -682,10 +703,10 @@ int bisbm_destroy(bisbm_handle* h) {
 
 }  // extern "C"
 
-template <typename InT>
-static int set_chains_impl(bisbm_handle* h, uint32_t n_chains, const uint32_t* ka, const uint32_t* kb,
-                           const InT* labels, double eps) {
-    if (!h || !ka || !kb || !labels) return fail(BISBM_ERR_ARG, "null argument");
+// buffers and per-chain constants of a pool of n_chains chains (everything of bisbm_set_chains except the labels);
+// *same_model: same shapes, K per chain and epsilon as the pool the handle already holds
+static int alloc_chains(bisbm_handle* h, uint32_t n_chains, const uint32_t* ka, const uint32_t* kb, double eps, bool* same_model_out) {
+    if (!h || !ka || !kb) return fail(BISBM_ERR_ARG, "null argument");
     if (n_chains == 0) return fail(BISBM_ERR_ARG, "n_chains must be > 0");
     if (!(eps > 0.0)) return fail(BISBM_ERR_ARG, "epsilon must be > 0");
     CU(cudaSetDevice(h->device));
@@ -743,6 +764,18 @@ static int set_chains_impl(bisbm_handle* h, uint32_t n_chains, const uint32_t* k
     CU(cudaMemsetAsync(h->d_active, 1, n_chains, h->stream));
     CU(cudaMemcpyAsync(h->d_ka, h->h_ka.data(), C * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(h->d_kb, h->h_kb.data(), C * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+    *same_model_out = same_model;
+    return BISBM_OK;
+}
+
+template <typename InT>
+static int set_chains_impl(bisbm_handle* h, uint32_t n_chains, const uint32_t* ka, const uint32_t* kb,
+                           const InT* labels, double eps) {
+    if (!labels) return fail(BISBM_ERR_ARG, "null argument");
+    bool same_model = false;
+    int rc0 = alloc_chains(h, n_chains, ka, kb, eps, &same_model);
+    if (rc0) return rc0;
+    const uint32_t n = h->n, C = h->C;
     // host labels [chain][node], global ids  ->  chain-minor, type-local (device transpose)
     {
         InT* stage = reinterpret_cast<InT*>(h->d_labels_tmp);
@@ -1077,6 +1110,110 @@ int bisbm_set_precision(bisbm_handle* h, int mode) {
     if (!h) return fail(BISBM_ERR_ARG, "null handle");
     if (mode != BISBM_PRECISION_FP32 && mode != BISBM_PRECISION_FP64) return fail(BISBM_ERR_ARG, "unknown precision mode %d", mode);
     h->precision = mode;
+    return BISBM_OK;
+}
+
+int bisbm_share_graph(bisbm_handle* src, bisbm_handle** out) {
+    if (!src || !out) return fail(BISBM_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (!src->gdev) return fail(BISBM_ERR_STATE, "source handle has no graph");
+    CU(cudaSetDevice(src->device));
+    std::unique_ptr<bisbm_handle> h(new bisbm_handle());
+    h->device = src->device; h->gdev = src->gdev; h->sm_count = src->sm_count;
+    h->n = src->n; h->na = src->na; h->nb = src->nb; h->W = src->W; h->max_degree = src->max_degree; h->n_edges = src->n_edges;
+    h->h_row_ptr = src->h_row_ptr; h->h_degvals = src->h_degvals; h->ent_base = src->ent_base;
+    h->d_row_ptr = src->d_row_ptr; h->d_col = src->d_col; h->d_degidx = src->d_degidx; h->d_qtab = src->d_qtab;
+    h->qn = src->qn; h->qk = src->qk;
+    h->precision = src->precision; h->opt_inflight_div = src->opt_inflight_div;
+    CU(cudaStreamCreate(&h->stream));
+    CU(cudaEventCreate(&h->ev0));
+    CU(cudaEventCreate(&h->ev1));
+    *out = h.release();
+    return BISBM_OK;
+}
+
+// chains started from equal-size blocks in node order (the reference's `-n` with equal sizes), labels written on the device
+static int set_chains_equal_blocks(bisbm_handle* h, uint32_t n_chains, const uint32_t* ka, const uint32_t* kb, double eps) {
+    bool same_model = false;
+    int rc = alloc_chains(h, n_chains, ka, kb, eps, &same_model);
+    if (rc) return rc;
+    const uint64_t tot = (uint64_t)h->n * h->C;
+    equal_blocks_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(h->d_labels, h->n, h->na, h->nb, h->C, h->n_chains, h->d_ka, h->d_kb);
+    CU(cudaGetLastError());
+    rc = rebuild_counts(h);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(h->stream));
+    return BISBM_OK;
+}
+
+// K class of a chain: both types padded to the same power of two (>= 8), so that chains of similar K share strides,
+// small-K chains keep the staged kernel and only large-K chains take the counts-in-L2 form
+static uint32_t k_class(uint32_t ka, uint32_t kb) {
+    uint32_t k = std::max(ka, kb), c = 8;
+    while (c < k) c <<= 1;
+    return c;
+}
+
+int bisbm_grid_search(bisbm_handle* g, uint32_t n_points, const uint32_t* ka, const uint32_t* kb, uint32_t restarts, double eps,
+                      int schedule, float p0, float p1, uint64_t duration, uint64_t steps_await, uint64_t seed,
+                      uint32_t max_inflight, double* entropy, double* accept, uint32_t* best_chain, uint32_t* best_labels,
+                      double* stats) {
+    if (!g || !ka || !kb || !entropy) return fail(BISBM_ERR_ARG, "null argument");
+    if (n_points == 0 || restarts == 0) return fail(BISBM_ERR_ARG, "need at least one (Ka, Kb) point and one restart");
+    const uint32_t n = g->n, na = g->na, nb = g->nb;
+    for (uint32_t p = 0; p < n_points; ++p)
+        if (ka[p] == 0 || kb[p] == 0 || ka[p] > na || kb[p] > nb)
+            return fail(BISBM_ERR_ARG, "point %u: (Ka, Kb) = (%u, %u) needs 1 <= Ka <= na, 1 <= Kb <= nb", p, ka[p], kb[p]);
+    std::map<uint32_t, std::vector<uint32_t>> buckets;      // K class -> points
+    for (uint32_t p = 0; p < n_points; ++p) buckets[k_class(ka[p], kb[p])].push_back(p);
+    double best = INFINITY;
+    uint64_t total_moves = 0;
+    double total_ms = 0.0;
+    if (best_chain) *best_chain = 0;
+    std::vector<uint32_t> cka, ckb;
+    std::vector<uint64_t> seeds;
+    std::vector<double> ent, acc;
+    std::vector<uint64_t> sw;
+    for (auto& kv : buckets) {
+        const std::vector<uint32_t>& pts = kv.second;
+        const uint32_t nc = (uint32_t)pts.size() * restarts;
+        bisbm_handle* sub = nullptr;
+        int rc = bisbm_share_graph(g, &sub);
+        if (rc) return rc;
+        // initial labels: equal-size blocks in node order (the reference's `-n` with equal sizes,
+        // src/mcmc_main.cc:302-326), then --randomize
+        cka.resize(nc); ckb.resize(nc); seeds.resize(nc);
+        for (uint32_t i = 0; i < nc; ++i) {
+            const uint32_t p = pts[i / restarts], q = i % restarts;
+            cka[i] = ka[p]; ckb[i] = kb[p];
+            seeds[i] = seed * 0x9E3779B97F4A7C15ull + ((uint64_t)p << 20) + q + 1;
+        }
+        rc = set_chains_equal_blocks(sub, nc, cka.data(), ckb.data(), eps);
+        if (!rc) rc = bisbm_randomize(sub, seeds.data());
+        ent.resize(nc); acc.resize(nc); sw.resize(nc);
+        if (!rc) rc = bisbm_anneal(sub, schedule, p0, p1, duration, steps_await, seeds.data(), max_inflight, acc.data(), sw.data());
+        if (!rc) rc = bisbm_entropy_all(sub, ent.data());
+        if (!rc) {
+            total_ms += sub->last_ms;
+            for (uint32_t i = 0; i < nc; ++i) total_moves += sw[i] * (uint64_t)n;
+            uint32_t arg = 0;
+            for (uint32_t i = 0; i < nc; ++i) {
+                const uint32_t chain = pts[i / restarts] * restarts + i % restarts;
+                entropy[chain] = ent[i];
+                if (accept) accept[chain] = acc[i];
+                if (ent[i] < ent[arg]) arg = i;
+            }
+            if (ent[arg] < best) {
+                best = ent[arg];
+                if (best_chain) *best_chain = pts[arg / restarts] * restarts + arg % restarts;
+                if (best_labels) rc = bisbm_get_labels(sub, arg, best_labels);
+            }
+        }
+        const std::string err = g_err;
+        bisbm_destroy(sub);
+        if (rc) { g_err = err; return rc; }
+    }
+    if (stats) { stats[0] = (double)total_moves; stats[1] = total_ms; stats[2] = (double)buckets.size(); stats[3] = best; }
     return BISBM_OK;
 }
 

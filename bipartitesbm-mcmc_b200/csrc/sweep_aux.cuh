@@ -88,6 +88,17 @@ __global__ void build_e_kernel(StateView S, uint32_t n_chains) {  // compute_m_r
     S.e[cnt_base(c, (size_t)KA + KB) + (size_t)slot * GROUP] = (int32_t)sum;
 }
 
+// equal-size blocks in node order: block of type-a node v = v * ka / na (likewise type b), chain-minor type-local labels
+__global__ void equal_blocks_kernel(int32_t* __restrict__ out, uint32_t n, uint32_t na, uint32_t nb, uint32_t C, uint32_t n_chains,
+                                    const uint32_t* __restrict__ ka, const uint32_t* __restrict__ kb) {
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (uint64_t)n * C) return;
+    const uint32_t v = (uint32_t)(idx / C), c = (uint32_t)(idx % C);
+    int32_t l = 0;
+    if (c < n_chains) l = v < na ? (int32_t)((uint64_t)v * ka[c] / na) : (int32_t)((uint64_t)(v - na) * kb[c] / nb);
+    out[idx] = l;
+}
+
 // parallel-mode --randomize: per chain, permute the labels of each type with a keyed
 // Feistel permutation (keeps block sizes, like shuffle_bisbm)
 __global__ void randomize_kernel(GraphView G, const int32_t* in, int32_t* out, uint32_t C, uint32_t n_chains,

@@ -51,6 +51,9 @@ SIGNATURES = {
     "bisbm_create": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint64, _u32p, _u32p, C.c_int, C.POINTER(C.c_void_p)]),
     "bisbm_create_csr": (C.c_int, [C.c_uint32, C.c_uint32, _u32p, _u32p, C.c_int, C.POINTER(C.c_void_p)]),
     "bisbm_destroy": (C.c_int, [C.c_void_p]),
+    "bisbm_share_graph": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "bisbm_grid_search": (C.c_int, [C.c_void_p, C.c_uint32, _u32p, _u32p, C.c_uint32, C.c_double, C.c_int, C.c_float, C.c_float,
+                                    C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, _dp, _dp, _u32p, _u32p, _dp]),
     "bisbm_set_chains": (C.c_int, [C.c_void_p, C.c_uint32, _u32p, _u32p, C.c_void_p, C.c_double]),
     "bisbm_set_chains_u8": (C.c_int, [C.c_void_p, C.c_uint32, _u32p, _u32p, C.c_void_p, C.c_double]),
     "bisbm_randomize": (C.c_int, [C.c_void_p, _u64p]),
@@ -164,6 +167,25 @@ class Graph:
             self.close()
         except Exception:
             pass
+
+
+def grid_search(graph, points, restarts, epsilon, schedule, p0, p1, duration, steps_await, seed=1, max_inflight=0):
+    """det_k_bisbm-style (Ka, Kb) search over the C ABI (bisbm_grid_search): returns (entropy [points][restarts],
+    acceptance [points][restarts], (best point index, best restart), best labels [n], stats dict)."""
+    if isinstance(schedule, str):
+        schedule = SCHEDULES[schedule]
+    pts = np.asarray(points, dtype=np.uint32).reshape(-1, 2)
+    ka = np.ascontiguousarray(pts[:, 0]); kb = np.ascontiguousarray(pts[:, 1])
+    ent = np.zeros(len(pts) * restarts, dtype=np.float64)
+    acc = np.zeros(len(pts) * restarts, dtype=np.float64)
+    best = C.c_uint32()
+    lab = np.zeros(graph.n, dtype=np.uint32)
+    stats = np.zeros(8, dtype=np.float64)
+    _check(graph.L.bisbm_grid_search(graph.h, len(pts), _p(ka, C.c_uint32), _p(kb, C.c_uint32), restarts, float(epsilon),
+                                     schedule, p0, p1, duration, steps_await, seed, max_inflight, _p(ent, C.c_double),
+                                     _p(acc, C.c_double), C.byref(best), _p(lab, C.c_uint32), _p(stats, C.c_double)))
+    return (ent.reshape(len(pts), restarts), acc.reshape(len(pts), restarts), (best.value // restarts, best.value % restarts), lab,
+            {"moves": stats[0], "device_ms": stats[1], "buckets": int(stats[2]), "best_entropy": stats[3]})
 
 
 def edge_to_adj(edge_list, N, na=None, nb=None, device=0):

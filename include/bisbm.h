@@ -62,6 +62,9 @@ int bisbm_create(uint32_t na, uint32_t nb, uint64_t n_edges, const uint32_t* ea,
 int bisbm_create_csr(uint32_t na, uint32_t nb, const uint32_t* row_ptr, const uint32_t* col_idx,
                      int device, bisbm_handle** out);
 int bisbm_destroy(bisbm_handle* h);
+/* A second handle over the SAME device-resident graph (ref-counted, read only): its own chains, stream and options.
+ * This is how several pools of chains -- e.g. one per K class of a (Ka, Kb) grid -- run over one copy of the graph. */
+int bisbm_share_graph(bisbm_handle* src, bisbm_handle** out);
 
 /* ---- chains ------------------------------------------------------------------------
  * Replaces the blockmodel_t state + init_bisbm (src/blockmodel.hh:92-143,
@@ -132,6 +135,16 @@ int bisbm_sweep_info(bisbm_handle* h, int* kernel, uint32_t* warps_per_cta, uint
  * PARALLEL sweep kernel's own device code (one forced proposal through sweep2_kernel, nothing committed): dS and
  * log(accu_r) in the handle's current precision.  Cross-type targets give dS = +inf (log_accu NaN), s == r gives 0, 0. */
 int bisbm_parallel_transition(bisbm_handle* h, uint32_t chain, uint32_t v, uint32_t s, double* dS, double* log_accu);
+/* det_k_bisbm-style model selection in process (the caller of bin/mcmc named by reference README.md:7, one subprocess and
+ * one 800 MB q-cache build per grid point there): n_points (Ka, Kb) pairs x `restarts` randomised restarts are annealed
+ * as parallel chains -- bucketed by K class so that small-K chains keep the staged kernel -- and scored by entropy()
+ * (src/blockmodel.cc:753-787).  Initial partitions: equal-size blocks in node order (reference `-n`), then randomised.
+ * entropy / accept: [n_points * restarts], chain p * restarts + q; best_chain: index of the minimum; best_labels: [n]
+ * global block ids of that chain (may be NULL); stats (may be NULL): {moves attempted, device ms, K buckets, best entropy}. */
+int bisbm_grid_search(bisbm_handle* graph, uint32_t n_points, const uint32_t* ka, const uint32_t* kb, uint32_t restarts,
+                      double eps, int schedule, float p0, float p1, uint64_t duration, uint64_t steps_await, uint64_t seed,
+                      uint32_t max_inflight, double* entropy, double* accept, uint32_t* best_chain, uint32_t* best_labels,
+                      double* stats);
 /* device pointer + element count of the histogram, for an in-place NCCL all-reduce */
 int bisbm_marginals_device(bisbm_handle* h, void** dev_ptr, uint64_t* n_elems, uint32_t* width);
 int bisbm_get_marginals(bisbm_handle* h, uint32_t* hist);          /* [n][width], global block ids */

@@ -463,3 +463,23 @@ def test_u8_labels_round_trip_and_rebuild_skip(host):
     bad = l8b.copy(); bad[1, 0] = 7          # a type-b block id on a type-a node
     with pytest.raises(host.BisbmError):
         pool.set_labels(bad)
+
+
+def test_grid_search_driver_finds_the_planted_k(host):
+    """BASELINE configs[3] through the in-process (Ka, Kb) search driver (bisbm_grid_search): a grid around the planted
+    (4, 6) of bisbm-1000 plus two large-K points (a different K class: separate pool over the shared graph), 4 restarts
+    each, abrupt_cool annealing; the description-length minimum must land on or next to the planted point, and the
+    returned best partition must score the reported minimum."""
+    g = load_golden("c2_const_k46")
+    na, nb, edges = g["na"], g["nb"], g["edges"]
+    n = na + nb
+    graph = host.Graph(edges, na, nb)
+    points = [(a, b) for a in (2, 3, 4, 5, 6, 8) for b in (3, 4, 6, 8, 12)] + [(20, 24), (40, 44)]
+    ent, acc, best, lab, stats = host.grid_search(graph, points, 4, 1.0, "abrupt_cool", 60.0 * n, 0.0, 120 * n, 10 ** 9, seed=3)
+    assert ent.shape == (len(points), 4) and np.isfinite(ent).all() and stats["buckets"] == 4
+    bp = points[best[0]]
+    print("grid minimum at", bp, "entropy", ent.min(), "stats", stats)
+    assert ent[best] == ent.min() and abs(bp[0] - 4) <= 2 and abs(bp[1] - 6) <= 2
+    pool = host.ChainPool(graph, lab, bp[0], bp[1], 1.0)
+    assert abs(pool.entropy(0) - ent.min()) <= 1e-9 * abs(ent.min())
+    assert stats["moves"] == len(points) * 4 * 120 * n
