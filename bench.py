@@ -181,6 +181,174 @@ def cpu_procs(per_proc_gb):
     return max(1, min(cores, int(avail_gb * 0.5 / per_proc_gb), 64))
 
 
+# ------------------------------------------------------------------------------ BASELINE configs[3]
+C4_VALUES = (2, 3, 4, 6, 8, 12, 16, 24, 32, 48, 64)
+
+
+def bench_c4(args, rank, world, local_rank):
+    """(Ka, Kb) in C4_VALUES^2 x 8 restarts = 968 chains on the C3 graph (throughput subset),
+    abrupt_cool annealing, through bisbm_grid_search; grid points are dealt round-robin to the GPUs."""
+    import torch
+    import torch.distributed as dist
+    pkg = importlib.import_module("bipartitesbm-mcmc_b200")
+    host = pkg.host
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    na = nb = args.nodes // 2
+    n = na + nb
+    edges = planted(na, nb, args.k, args.k, args.edges, 0)
+    graph = host.Graph(edges, na, nb, device=local_rank)
+    points = [(a, b) for a in C4_VALUES for b in C4_VALUES]
+    mine = points[rank::world]
+    restarts = 8
+    sweeps = args.sweeps_per_step
+    hot = max(1, sweeps // 2)
+
+    def step(seed):
+        return host.grid_search(graph, mine, restarts, 1.0, "abrupt_cool", float(hot * n), 0.0, sweeps * n, 10 ** 18, seed=seed)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(100 + i)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    t0 = time.perf_counter()
+    moves, dev_ms, best = 0.0, 0.0, (float("inf"), None)
+    for i in range(args.steps):
+        ent, acc, bi, lab, st = step(i + 1)
+        moves += st["moves"]; dev_ms += st["device_ms"]
+        if ent.min() < best[0]:
+            best = (float(ent.min()), mine[bi[0]])
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    t = torch.tensor([wall, dev_ms], dtype=torch.float64, device="cuda")
+    tmin = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([moves], dtype=torch.float64, device="cuda")
+    be = torch.tensor([best[0], float(best[1][0]), float(best[1][1])], dtype=torch.float64, device="cuda")
+    gathered = [be]
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        gathered = [torch.zeros_like(be) for _ in range(world)]
+        dist.all_gather(gathered, be)           # the best partition's score and (Ka, Kb) of every rank
+    if rank == 0:
+        g = min((x.tolist() for x in gathered), key=lambda x: x[0])
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        bytes_per_move = 16.0 + 8.0 * (2.0 * args.edges / n) + 4.0 * 0.5
+        achieved = bytes_per_move * float(tot[0]) / world / (float(t[1]) * 1e-3) / 1e9
+        line = {"metric": "vertex-moves/sec", "value": float(tot[0]) / float(t[0]), "unit": "moves/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(t[0]) / args.steps * 1e3, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64+int32", "data": "synthetic",
+                "config": {"workload": "C4: (Ka,Kb) in %s^2 x %d restarts = %d chains on the planted SBM %d nodes / %d edges, abrupt_cool (%d hot + %d greedy sweeps per step), bisbm_grid_search, grid points round-robin over %d GPU(s)" % (
+                    list(C4_VALUES), restarts, len(points) * restarts, n, args.edges, hot, sweeps - hot, world),
+                    "l2": "inputs larger than L2", "k_buckets": "max(Ka,Kb) padded to 8/16/32 (staged counts) and 64 (counts in L2)"},
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                             "bytes_per_move": bytes_per_move, "note": "per-GPU algorithmic bytes over the slowest rank's device time"},
+                "imbalance": {"device_ms_max": float(t[1]), "device_ms_min": float(tmin[0]), "max_over_min": float(t[1]) / max(float(tmin[0]), 1e-9)},
+                "best": {"entropy": g[0], "ka": int(g[1]), "kb": int(g[2]), "planted": [args.k, args.k]},
+                "e2e": {"value": float(tot[0]) / float(t[0]), "unit": "moves/s", "h2d_bytes_per_step": 8 * len(mine), "d2h_bytes_per_step": 8 * len(mine) * restarts * 2 + 4 * n,
+                        "api": "bisbm_grid_search: (Ka,Kb) list in, per-chain entropy + best labels out, every step (value is already end to end)"},
+                "gpu_launches": None, "clocks": clocks}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def bench_marginalize(args, rank, world, local_rank):
+    """BASELINE configs[1] wording (burn-in, then sample every 10 sweeps) on the C3 graph: sweeps + histogram accumulation,
+    and the marginal kernel alone against its N x chains x 12 B per sample roofline."""
+    import torch
+    import torch.distributed as dist
+    pkg = importlib.import_module("bipartitesbm-mcmc_b200")
+    host = pkg.host
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    na = nb = args.nodes // 2
+    n = na + nb
+    ka = kb = args.k
+    C = args.chains
+    edges = planted(na, nb, ka, kb, args.edges, 0)
+    graph = host.Graph(edges, na, nb, device=local_rank)
+    pool = host.ChainPool(graph, np.broadcast_to(planted_labels(na, nb, ka, kb), (C, n)), ka, kb, 1.0)
+    seeds = pkg.dist.chain_seeds(0, pkg.dist.shard_chains(C * world, rank, world))
+    every, samples = 10, max(1, args.sweeps_per_step // 2)
+    pool.marginals_clear()
+    for _ in range(args.warmup):
+        pool.marginalize(0, every, every, seeds)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    dev_ms, moves = 0.0, 0
+    for _ in range(args.steps):
+        pool.marginalize(0, every * samples, every, seeds)
+        ms_, _la, mv_ = pool.last_timing()
+        dev_ms += ms_; moves += mv_
+    if world > 1:
+        pkg.dist.allreduce_marginals(host.marginals_tensor(pool))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    wall = time.perf_counter() - t0
+    # the marginal kernel alone: samples of the resident labels back to back
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stream = torch.cuda.ExternalStream(pool.stream())
+    reps = 20
+    with torch.cuda.stream(stream):
+        pool.marginal_sample()
+        ev0.record(stream)
+        for _ in range(reps):
+            pool.marginal_sample()
+        ev1.record(stream)
+    torch.cuda.synchronize()
+    k_ms = ev0.elapsed_time(ev1) / reps
+    t = torch.tensor([wall], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(moves)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        alg = 12.0 * n * C            # SURVEY.md 8(d): per sample N x (4 B label read + 8 B histogram read-modify-write) per chain
+        line = {"metric": "vertex-moves/sec", "value": float(tot[0]) / float(t[0]), "unit": "moves/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": float(t[0]) / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64+int32", "data": "synthetic",
+                "config": {"workload": "marginalization on the planted SBM %d nodes / %d edges, Ka=Kb=%d, %d chains/GPU from the planted partition, T=1, one sample into the per-node label histogram every %d sweeps, %d samples per step" % (n, args.edges, ka, C, every, samples),
+                           "l2": "inputs larger than L2"},
+                "roofline": {"bound": "hbm", "kernel": "marginal_kernel<u8>", "achieved": alg / (k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": alg / (k_ms * 1e-3) / 1e9 / peak, "traffic": None, "alg_bytes_per_launch": alg, "avg_launch_ms": k_ms,
+                             "note": "algorithmic bytes per sample = N x chains x 12 B (SURVEY.md 8(d)); the kernel reads 1 B per label from the u8 shadow and adds once per distinct label of a 32-chain group, so its real traffic is below that"},
+                "marginal_share_of_step": k_ms * samples * args.steps / max(dev_ms, 1e-9),
+                "e2e": {"value": float(tot[0]) / float(t[0]), "unit": "moves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                        "api": "bisbm_marginalize (histogram stays on the device; all-reduced once at the end when N > 1)"},
+                "gpu_launches": None}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 # ------------------------------------------------------------------------------ main
 def main():
     ap = argparse.ArgumentParser()
@@ -195,9 +363,14 @@ def main():
     ap.add_argument("--sweeps-per-step", type=int, default=SWEEPS_PER_STEP)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-moves", type=int, default=2000000, help="CPU sample: moves per process per step")
+    ap.add_argument("--workload", default="c3", choices=["c3", "c4", "marginalize"],
+                    help="c3: BASELINE configs[2] (headline); c4: configs[3], the (Ka,Kb) grid x 8 restarts through the in-process "
+                         "search driver, points sharded over the GPUs; marginalize: configs[1] wording on the C3 graph "
+                         "(sample every 10 sweeps into the device histogram)")
     ap.add_argument("--precision", default="fp64", choices=["fp64", "fp32"],
                     help="arithmetic of a move: fp64 like the reference's transition_ratio (headline) or fp32")
     ap.add_argument("--inflight-div", type=int, default=0, help="in-flight bound = half sweep / this (0: library default)")
+    ap.add_argument("--warps", type=int, default=0, help="experiment builds only: warps per CTA (20, 24)")
     ap.add_argument("--no-fp32-extra", action="store_true", help="skip the short fp32 run reported under 'extra'")
     args = ap.parse_args()
 
@@ -243,6 +416,11 @@ def main():
         print(json.dumps(line))
         return 0
 
+    if args.workload == "c4":
+        return bench_c4(args, rank, world, local_rank)
+    if args.workload == "marginalize":
+        return bench_marginalize(args, rank, world, local_rank)
+
     # ---------------- our arm
     import torch
     import torch.distributed as dist
@@ -264,6 +442,8 @@ def main():
     pool.set_precision(args.precision)
     if args.inflight_div:
         pool.set_option("inflight_div", args.inflight_div)
+    if args.warps:
+        pool.set_option("warps", args.warps)
     seeds = pkg.dist.chain_seeds(0, chain_ids)
     pool.randomize(seeds)
     duration = args.sweeps_per_step * n

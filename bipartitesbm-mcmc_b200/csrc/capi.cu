@@ -118,6 +118,7 @@ struct bisbm_handle {
     int opt_kernel = -1;               // -1: automatic; KERN_L2 / KERN_STAGED_OLD force the round-1 double kernels
     uint32_t opt_inflight_div = 64;    // default in-flight bound = half sweep / this
     int opt_generic = 0;               // 1: never take the Ka = Kb = 32 specialisation
+    uint32_t opt_warps = 16;           // warps per CTA of the staged sweep2 kernel (experiment builds: 20, 24)
     std::set<const void*> attr_done;   // kernels whose shared-memory limit is raised on this handle's device
     uint64_t last_sweep_launches = 0, last_marginal_launches = 0;
     uint32_t last_wpc = 0, last_cpg = 0, last_slice = 0;   // launch plan of the last half sweep
@@ -428,7 +429,7 @@ int plan_kernel(const bisbm_handle* h, uint32_t* wpc_out) {
     if (hb == 1 && k8) {
         const uint32_t rs = h->precision == BISBM_PRECISION_FP32 ? 4u : 8u;
         if (h->opt_kernel != KERN_S2L_F64)
-            for (uint32_t w : {16u, 8u, 4u})
+            for (uint32_t w : {h->opt_warps, 16u, 8u, 4u})
                 if (sweep2_layout(h->KA, h->KB, 0, w, rs).total <= kSmemMax && sweep2_layout(h->KA, h->KB, 1, w, rs).total <= kSmemMax) {
                     *wpc_out = w;
                     return rs == 4 ? KERN_S2_F32 : KERN_S2_F64;
@@ -508,11 +509,11 @@ int launch_sweep_h(bisbm_handle* h, const SweepParams& P, const LaunchPlan& lp) 
     return launch_sweep_nt<SMEM, uint32_t>(h, P, lp);
 }
 
-template <typename R, int KF, int TYPE, bool STAGED = true>
+template <typename R, int KF, int TYPE, bool STAGED = true, int NT = 512>
 int launch_sweep2_t(bisbm_handle* h, const SweepParams& P, const LaunchPlan& lp, unsigned grid) {
-    int rc = ensure_smem_attr(h, (const void*)sweep2_kernel<R, KF, TYPE, STAGED>, (int)kSmemMax);
+    int rc = ensure_smem_attr(h, (const void*)sweep2_kernel<R, KF, TYPE, STAGED, NT>, (int)kSmemMax);
     if (rc) return rc;
-    sweep2_kernel<R, KF, TYPE, STAGED><<<grid, lp.wpc * 32, lp.smem_bytes, h->stream>>>(P);
+    sweep2_kernel<R, KF, TYPE, STAGED, NT><<<grid, lp.wpc * 32, lp.smem_bytes, h->stream>>>(P);
     CU(cudaGetLastError());
     h->lab32_stale = true;    // the staged kernels only write the u8 label shadow
     return BISBM_OK;
@@ -522,8 +523,13 @@ template <typename R>
 int launch_sweep2(bisbm_handle* h, const SweepParams& P, const LaunchPlan& lp, unsigned grid) {
     if (!lp.smem) return launch_sweep2_t<R, 0, 0, false>(h, P, lp, grid);
     // compile-time strides for the common Ka = Kb = 32 pool (BASELINE configs[2])
-    if (h->KA == 32 && h->KB == 32 && !h->opt_generic)
+    if (h->KA == 32 && h->KB == 32 && !h->opt_generic) {
+#ifdef BISBM_WARP_VARIANTS
+        if (lp.wpc == 24) return P.type ? launch_sweep2_t<R, 32, 1, true, 768>(h, P, lp, grid) : launch_sweep2_t<R, 32, 0, true, 768>(h, P, lp, grid);
+        if (lp.wpc == 20) return P.type ? launch_sweep2_t<R, 32, 1, true, 640>(h, P, lp, grid) : launch_sweep2_t<R, 32, 0, true, 640>(h, P, lp, grid);
+#endif
         return P.type ? launch_sweep2_t<R, 32, 1>(h, P, lp, grid) : launch_sweep2_t<R, 32, 0>(h, P, lp, grid);
+    }
     return launch_sweep2_t<R, 0, 0>(h, P, lp, grid);
 }
 
@@ -1035,6 +1041,26 @@ int bisbm_anneal(bisbm_handle* h, int schedule, float p0, float p1, uint64_t dur
     return BISBM_OK;
 }
 
+// one sample of every chain's current labels into the histogram, straight from the array the sweep kernel keeps
+// current: the u8 shadow (sweep2 kernels) or the i32 labels
+static int launch_marginal(bisbm_handle* h) {
+    const uint64_t mw = (uint64_t)h->n * (h->C / 32);
+    const unsigned mgrid = (unsigned)((mw * 32 + 255) / 256);
+    if (h->lab32_stale)
+        marginal_kernel<uint8_t><<<mgrid, 256, 0, h->stream>>>(gview(h), h->d_lab8, h->C, h->d_ka, h->n_chains, h->d_hist, h->hist_width);
+    else
+        marginal_kernel<int32_t><<<mgrid, 256, 0, h->stream>>>(gview(h), h->d_labels, h->C, h->d_ka, h->n_chains, h->d_hist, h->hist_width);
+    CU(cudaGetLastError());
+    return BISBM_OK;
+}
+
+int bisbm_marginal_sample(bisbm_handle* h) {
+    int rc = need_chains(h);
+    if (rc) return rc;
+    if (!h->d_hist) { rc = bisbm_marginals_clear(h); if (rc) return rc; }
+    return launch_marginal(h);
+}
+
 int bisbm_marginals_clear(bisbm_handle* h) {
     int rc = need_chains(h);
     if (rc) return rc;
@@ -1074,13 +1100,8 @@ int bisbm_marginalize(bisbm_handle* h, uint64_t burn_in, uint64_t sweeps, uint64
         rc = launch_full_sweep(h, BISBM_CONSTANT, 1.0f, 0.0f, sw, max_inflight);
         if (rc) return rc;
         if (sw >= burn_in && ((sw - burn_in + 1) % every) == 0) {
-            // straight from the array the sweep kernel keeps current: the u8 shadow (staged kernels) or the i32 labels
-            const uint64_t mw = (uint64_t)h->n * (h->C / 32);
-            const unsigned mgrid = (unsigned)((mw * 32 + 255) / 256);
-            if (h->lab32_stale)
-                marginal_kernel<uint8_t><<<mgrid, 256, 0, h->stream>>>(gview(h), h->d_lab8, h->C, h->d_ka, h->n_chains, h->d_hist, h->hist_width);
-            else
-                marginal_kernel<int32_t><<<mgrid, 256, 0, h->stream>>>(gview(h), h->d_labels, h->C, h->d_ka, h->n_chains, h->d_hist, h->hist_width);
+            rc = launch_marginal(h);
+            if (rc) return rc;
             h->last_marginal_launches += 1;
             h->last_launches += 1;
         }
@@ -1227,6 +1248,9 @@ int bisbm_set_option(bisbm_handle* h, const char* name, int64_t value) {
     } else if (k == "inflight_div") {
         if (value < 1 || value > (1 << 30)) return fail(BISBM_ERR_ARG, "inflight_div must be >= 1");
         h->opt_inflight_div = (uint32_t)value;
+    } else if (k == "warps") {
+        if (value != 16 && value != 20 && value != 24) return fail(BISBM_ERR_ARG, "warps: 16, 20 or 24");
+        h->opt_warps = (uint32_t)value;
     } else if (k == "generic") {
         h->opt_generic = value != 0;
     } else {

@@ -408,8 +408,8 @@ __global__ void sweep2_preinit_kernel(const int32_t* __restrict__ m, const int32
 // histogram bins), K per type <= 256 (u8 labels).
 // STAGED = false: K too large for shared memory -- m_rs / e_r / n_r stay in L2 (loads .cg, commits by global reductions,
 // every CTA sees every committed move at once: no slices, no staging, no publish); the rest of the kernel is the same.
-template <typename R, int KF, int TYPE, bool STAGED = true>
-__global__ void __launch_bounds__(512, 1) sweep2_kernel(const __grid_constant__ SweepParams P) {
+template <typename R, int KF, int TYPE, bool STAGED = true, int NT = 512>
+__global__ void __launch_bounds__(NT, 1) sweep2_kernel(const __grid_constant__ SweepParams P) {
     typedef Ar<R> AR;
     extern __shared__ __align__(128) unsigned char s2_smem[];
     unsigned char* const smem_raw = s2_smem;
@@ -778,14 +778,14 @@ __global__ void __launch_bounds__(512, 1) sweep2_kernel(const __grid_constant__ 
                     R bdd = bdd_fast<R>(e_r, e_s, (int)d, &ok_b);
                     R ratio, lh;
                     move_local<R>(A, d, eps, &ratio, &lh);
-                    // (2) eta (L2): log( prod * eta_r / (eta_s + 1) )
-                    const int z1 = opaque_zero(bdd) | opaque_zero(lh) | opaque_zero(ratio);
-                    const R lgm = move_lgm<R>(A, ratio, eta_r + z1, eta_s + z1);
-                    // (3) the log q expansions (L1 / L2)
-                    const int z2 = opaque_zero(lgm);
-                    q_r.e0 += z2; q_s.e0 += z2;
+                    // (2) the log q expansions (L1 / L2), gated behind the two logarithms above
+                    const int z1 = opaque_zero(bdd) | opaque_zero(lh);
+                    q_r.e0 += z1; q_s.e0 += z1;
                     R lqr = logq_fast<R>(q_r, e_r, n_r, -(int)d, -1, &ok_r);
                     R lqs = logq_fast<R>(q_s, e_s, n_s, (int)d, 1, &ok_s);
+                    // (3) eta (L2, the longest wait) last: log( prod * eta_r / (eta_s + 1) )
+                    const int z2 = opaque_zero(lqr) | opaque_zero(lqs) | opaque_zero(ratio);
+                    const R lgm = move_lgm<R>(A, ratio, eta_r + z2, eta_s + z2);
                     if (__any_sync(FULL, eval && !(ok_b && ok_r && ok_s))) {
                         if (eval && !ok_b) bdd = (R)slow2_block_degree_delta(e_r, e_s, (int)d);
                         if (eval && !ok_r) lqr = (R)slow2_logq_delta(P.tb.qtab, P.tb.qn, P.tb.qk, e_r, n_r, -(int)d, -1);
@@ -836,15 +836,19 @@ __global__ void __launch_bounds__(512, 1) sweep2_kernel(const __grid_constant__ 
                 if (d <= 32u) {
                     if (any_go) {     // walk the edges again: m(r,t) -= 1, m(s,t) += 1 for the lanes that move
                         const int g1 = go ? 1 : 0;
-                        const uint32_t nch = (d + 3u) >> 2;
-                        for (uint32_t q = 0; q < nch; ++q) {
-                            const uint32_t Lc = sh_ld_u32v(tile_lane + 4u * q);
-                            const uint32_t c4 = d - 4u * q;
-                            const uint32_t f0 = (Lc & 0xffu) * ST;
-                            m_red(Mr + f0, -g1); m_red(Ms + f0, g1);
-                            if (c4 > 1u) { const uint32_t f1 = ((Lc >> 8) & 0xffu) * ST; m_red(Mr + f1, -g1); m_red(Ms + f1, g1); }
-                            if (c4 > 2u) { const uint32_t f2 = ((Lc >> 16) & 0xffu) * ST; m_red(Mr + f2, -g1); m_red(Ms + f2, g1); }
-                            if (c4 > 3u) { const uint32_t f3 = (Lc >> 24) * ST; m_red(Mr + f3, -g1); m_red(Ms + f3, g1); }
+                        const uint32_t dMs = Ms - Mr;          // m(s,t) sits at a fixed distance from m(r,t)
+                        auto move1 = [&](uint32_t t) { const uint32_t f = Mr + t * ST; m_red(f, -g1); m_red(f + dMs, g1); };
+                        const uint32_t nfull = d >> 2, tail = d & 3u;
+                        uint32_t q4 = tile_lane;
+                        for (uint32_t q = 0; q < nfull; ++q, q4 += 4u) {
+                            const uint32_t Lc = sh_ld_u32v(q4);
+                            move1(Lc & 0xffu); move1((Lc >> 8) & 0xffu); move1((Lc >> 16) & 0xffu); move1(Lc >> 24);
+                        }
+                        if (tail) {
+                            const uint32_t Lc = sh_ld_u32v(q4);
+                            move1(Lc & 0xffu);
+                            if (tail > 1u) move1((Lc >> 8) & 0xffu);
+                            if (tail > 2u) move1((Lc >> 16) & 0xffu);
                         }
                     }
                     for (uint32_t w = 0; w < hist_words; ++w) sh_st_u32v(hist_base + w * 128u, 0u);

@@ -68,6 +68,7 @@ SIGNATURES = {
                                _dp, _u64p]),
     "bisbm_marginalize": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, _u64p, C.c_uint32]),
     "bisbm_marginals_clear": (C.c_int, [C.c_void_p]),
+    "bisbm_marginal_sample": (C.c_int, [C.c_void_p]),
     "bisbm_set_precision": (C.c_int, [C.c_void_p, C.c_int]),
     "bisbm_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
     "bisbm_parallel_transition": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, _dp, _dp]),
@@ -266,6 +267,15 @@ class ChainPool:
 
     def marginals_clear(self):
         _check(self.L.bisbm_marginals_clear(self.g.h))
+
+    def marginal_sample(self):
+        _check(self.L.bisbm_marginal_sample(self.g.h))
+
+    def stream(self):
+        """cudaStream_t (as int) the handle launches on."""
+        st = C.c_void_p()
+        _check(self.L.bisbm_stream(self.g.h, C.byref(st)))
+        return st.value or 0
 
     def marginals(self):
         ptr, ne, w = C.c_void_p(), C.c_uint64(), C.c_uint32()

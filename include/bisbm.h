@@ -113,6 +113,8 @@ int bisbm_anneal(bisbm_handle* h, int schedule, float p0, float p1, uint64_t dur
 int bisbm_marginalize(bisbm_handle* h, uint64_t burn_in, uint64_t sweeps, uint64_t every, const uint64_t* seeds,
                       uint32_t max_inflight);
 int bisbm_marginals_clear(bisbm_handle* h);
+/* adds ONE sample of every chain's current labels to the histogram (asynchronous on the handle's stream) */
+int bisbm_marginal_sample(bisbm_handle* h);
 /* Arithmetic of the parallel sweep's per-move evaluation (dS, Hastings factor, accept test).  The reference
  * computes transition_ratio in double (src/metropolis_hasting.cc:103-192) and so does parallel mode by default
  * (BISBM_PRECISION_FP64).  BISBM_PRECISION_FP32 evaluates the move in fp32 on the MUFU unit (|error of the log
