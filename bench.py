@@ -288,6 +288,8 @@ def bench_marginalize(args, rank, world, local_rank):
     pool = host.ChainPool(graph, np.broadcast_to(planted_labels(na, nb, ka, kb), (C, n)), ka, kb, 1.0)
     seeds = pkg.dist.chain_seeds(0, pkg.dist.shard_chains(C * world, rank, world))
     every, samples = 10, max(1, args.sweeps_per_step // 2)
+    if world > 1:
+        pkg.dist.init_pool_comm(pool)
     pool.marginals_clear()
     for _ in range(args.warmup):
         pool.marginalize(0, every, every, seeds)
@@ -301,7 +303,7 @@ def bench_marginalize(args, rank, world, local_rank):
         ms_, _la, mv_ = pool.last_timing()
         dev_ms += ms_; moves += mv_
     if world > 1:
-        pkg.dist.allreduce_marginals(host.marginals_tensor(pool))
+        pkg.dist.allreduce_marginals(pool)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -458,9 +460,10 @@ def main():
     for _ in range(args.warmup):
         pool.anneal("constant", 1.0, 0.0, duration, 10 ** 18, seeds)
     if world > 1:  # warm the one collective of the path too (NCCL communicator set-up is not a sweep cost)
+        pkg.dist.init_pool_comm(pool)            # the library's own communicator (bisbm_nccl_init)
         pool.marginals_clear()
         pool.marginalize(0, 1, 1, seeds)
-        pkg.dist.allreduce_marginals(host.marginals_tensor(pool))
+        pkg.dist.allreduce_marginals(pool)
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
@@ -478,8 +481,7 @@ def main():
         ms_, la_, mv_ = pool.last_timing()
         ev_ms += ms_; launches += la_; moves += mv_
         sweep_launches += pool.sweep_launches()
-        hist = host.marginals_tensor(pool)
-        pkg.dist.allreduce_marginals(hist)
+        pkg.dist.allreduce_marginals(pool)       # bisbm_marginals_allreduce: ncclAllReduce(sum, uint32) behind the C ABI
     barrier()
     wall = time.perf_counter() - t0
     clocks = sampler.stop()

@@ -7,6 +7,8 @@
 #include "../../include/bisbm.h"
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>     // types and prototypes only: libnccl.so.2 is loaded on first use (dlopen), not linked
 
 #include <algorithm>
 #include <cmath>
@@ -96,6 +98,7 @@ struct bisbm_handle {
     int32_t *d_m2 = nullptr, *d_e2 = nullptr, *d_nr2 = nullptr;  // "next" count buffers of the sliced shared-memory sweep
     int32_t* d_nr_live = nullptr;              // exact n_r counters of the blocks that could empty within one sliced launch
     double* d_kat_out = nullptr;               // {dS, log accu_r} of bisbm_parallel_transition
+    ncclComm_t comm = nullptr;                 // bisbm_nccl_init: communicator of the marginal-histogram all-reduce
     uint8_t* d_lab8 = nullptr;                 // u8 shadow of the labels for the shared-memory sweep
     double eps = 1.0;
     LogqExp* d_lq = nullptr;
@@ -632,6 +635,48 @@ int upload_seeds(bisbm_handle* h, const uint64_t* seeds) {
     return BISBM_OK;
 }
 
+
+// ---- NCCL, loaded on first use: the only collective of the path is one all-reduce of the marginal histogram ----
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi* nccl_api() {
+    static NcclApi api;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        // a process that already loaded an NCCL (e.g. through torch) keeps using that one
+        api.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (api.lib) {
+            api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.lib, "ncclGetUniqueId");
+            api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.lib, "ncclCommInitRank");
+            api.CommInitAll = (decltype(api.CommInitAll))dlsym(api.lib, "ncclCommInitAll");
+            api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.lib, "ncclCommDestroy");
+            api.AllReduce = (decltype(api.AllReduce))dlsym(api.lib, "ncclAllReduce");
+            api.GroupStart = (decltype(api.GroupStart))dlsym(api.lib, "ncclGroupStart");
+            api.GroupEnd = (decltype(api.GroupEnd))dlsym(api.lib, "ncclGroupEnd");
+            api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.lib, "ncclGetErrorString");
+            if (!api.GetUniqueId || !api.CommInitRank || !api.CommInitAll || !api.CommDestroy || !api.AllReduce || !api.GroupStart ||
+                !api.GroupEnd || !api.GetErrorString) { dlclose(api.lib); api.lib = nullptr; }
+        }
+    }
+    return api.lib ? &api : nullptr;
+}
+#define NC(call)                                                                                   \
+    do {                                                                                           \
+        ncclResult_t r_ = (call);                                                                  \
+        if (r_ != ncclSuccess)                                                                     \
+            return fail(BISBM_ERR_CUDA, "%s failed: %s (%s:%d)", #call, nccl_api()->GetErrorString(r_), __FILE__, __LINE__); \
+    } while (0)
+
 }  // namespace
 
 extern "C" {
@@ -696,6 +741,7 @@ int bisbm_destroy(bisbm_handle* h) {
     if (!h) return BISBM_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->comm && nccl_api()) { nccl_api()->CommDestroy(h->comm); h->comm = nullptr; }
     free_chains(h);
     if (h->gdev) h->gdev.reset();          // the last handle sharing the graph frees it
     else { dfree(h->d_row_ptr); dfree(h->d_col); dfree(h->d_degidx); dfree(h->d_qtab); }   // creation failed half way
@@ -1302,6 +1348,71 @@ int bisbm_parallel_transition(bisbm_handle* h, uint32_t chain, uint32_t v, uint3
     if (std::isnan(out[0]) && std::isnan(out[1])) { out[0] = 0.0; out[1] = 0.0; }   // s == r: dS = 0, accu_r = 1 (:109-112)
     if (dS) *dS = out[0];
     if (log_accu) *log_accu = out[1];
+    return BISBM_OK;
+}
+
+// ---------------------------------------------------------------- the one collective of the path
+int bisbm_nccl_get_unique_id(uint8_t* id128) {
+    if (!id128) return fail(BISBM_ERR_ARG, "null argument");
+    NcclApi* A = nccl_api();
+    if (!A) return fail(BISBM_ERR_STATE, "libnccl.so.2 not found");
+    ncclUniqueId id;
+    NC(A->GetUniqueId(&id));
+    memcpy(id128, id.internal, NCCL_UNIQUE_ID_BYTES);
+    return BISBM_OK;
+}
+
+int bisbm_nccl_init(bisbm_handle* h, int nranks, int rank, const uint8_t* id128) {
+    if (!h || !id128) return fail(BISBM_ERR_ARG, "null argument");
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(BISBM_ERR_ARG, "bad rank %d of %d", rank, nranks);
+    NcclApi* A = nccl_api();
+    if (!A) return fail(BISBM_ERR_STATE, "libnccl.so.2 not found");
+    CU(cudaSetDevice(h->device));
+    if (h->comm) { A->CommDestroy(h->comm); h->comm = nullptr; }
+    ncclUniqueId id;
+    memcpy(id.internal, id128, NCCL_UNIQUE_ID_BYTES);
+    NC(A->CommInitRank(&h->comm, nranks, id, rank));
+    return BISBM_OK;
+}
+
+int bisbm_marginals_allreduce(bisbm_handle* h) {
+    int rc = need_chains(h);
+    if (rc) return rc;
+    if (!h->d_hist) return fail(BISBM_ERR_STATE, "no marginal histogram yet");
+    if (!h->comm) return fail(BISBM_ERR_STATE, "call bisbm_nccl_init first");
+    NcclApi* A = nccl_api();
+    NC(A->AllReduce(h->d_hist, h->d_hist, (size_t)h->n * h->hist_width, ncclUint32, ncclSum, h->comm, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return BISBM_OK;
+}
+
+int bisbm_marginals_allreduce_local(bisbm_handle** hs, int n) {
+    if (!hs || n < 1) return fail(BISBM_ERR_ARG, "bad argument");
+    NcclApi* A = nccl_api();
+    if (!A) return fail(BISBM_ERR_STATE, "libnccl.so.2 not found");
+    std::vector<int> devs(n);
+    for (int i = 0; i < n; ++i) {
+        if (!hs[i] || !hs[i]->d_hist) return fail(BISBM_ERR_STATE, "handle %d has no marginal histogram", i);
+        if (hs[i]->n != hs[0]->n || hs[i]->hist_width != hs[0]->hist_width) return fail(BISBM_ERR_ARG, "handle %d: histogram shape differs", i);
+        devs[i] = hs[i]->device;
+    }
+    if (n == 1) return BISBM_OK;
+    std::vector<ncclComm_t> comms(n);
+    NC(A->CommInitAll(comms.data(), n, devs.data()));
+    const size_t count = (size_t)hs[0]->n * hs[0]->hist_width;
+    ncclResult_t r = A->GroupStart();
+    for (int i = 0; i < n && r == ncclSuccess; ++i)
+        r = A->AllReduce(hs[i]->d_hist, hs[i]->d_hist, count, ncclUint32, ncclSum, comms[i], hs[i]->stream);
+    if (r == ncclSuccess) r = A->GroupEnd(); else A->GroupEnd();
+    cudaError_t ce = cudaSuccess;
+    for (int i = 0; i < n; ++i) {
+        cudaSetDevice(hs[i]->device);
+        cudaError_t e = cudaStreamSynchronize(hs[i]->stream);
+        if (e != cudaSuccess) ce = e;
+    }
+    for (int i = 0; i < n; ++i) A->CommDestroy(comms[i]);
+    if (r != ncclSuccess) return fail(BISBM_ERR_CUDA, "NCCL all-reduce failed: %s", A->GetErrorString(r));
+    if (ce != cudaSuccess) return fail(BISBM_ERR_CUDA, "all-reduce: %s", cudaGetErrorString(ce));
     return BISBM_OK;
 }
 

@@ -27,6 +27,8 @@
 #include <string>
 #include <vector>
 
+#include <thread>
+
 #include "bisbm.h"
 
 namespace {
@@ -50,7 +52,7 @@ const Spec kSpecs[] = {
     {"help", 'h', 0},
     // README-only modes and the extensions of this build
     {"maximize", 0, 0}, {"estimate", 0, 0}, {"marginalize", 0, 0}, {"chains", 0, 1}, {"gen_seed", 0, 1},
-    {"device", 0, 1}, {"max_inflight", 0, 1},
+    {"device", 0, 1}, {"max_inflight", 0, 1}, {"gpus", 0, 1},
 };
 
 const Spec* find_spec(const std::string& tok) {
@@ -124,7 +126,10 @@ void usage(const char* argv0) {
                  "  --maximize | --marginalize | --estimate   mode (default: the reference's annealing path)\n"
                  "  --chains arg (=1)                     parallel chains on the GPU\n"
                  "  --gen_seed arg                        seed of the reference's second engine (std::random_device there)\n"
-                 "  --device arg (=0), --max_inflight arg (=0)\n";
+                 "  --device arg (=0), --max_inflight arg (=0)\n"
+                 "  --gpus arg (=1)                       GPUs of this node: the chains are dealt round-robin to devices\n"
+                 "                                        device .. device+gpus-1 (graph replicated); --marginalize sums the\n"
+                 "                                        per-node histograms with one NCCL all-reduce\n";
 }
 
 bool check(int rc) {
@@ -211,6 +216,9 @@ int main(int argc, char const* argv[]) {
     if (o.has("chains") && (!to_num(o.vals["chains"][0], chains) || chains == 0)) { std::cerr << "bad value for --chains\n"; return 1; }
     if (o.has("device") && !to_num(o.vals["device"][0], device)) { std::cerr << "bad value for --device\n"; return 1; }
     if (o.has("max_inflight") && !to_num(o.vals["max_inflight"][0], max_inflight)) { std::cerr << "bad value for --max_inflight\n"; return 1; }
+    size_t gpus = 1;
+    if (o.has("gpus") && (!to_num(o.vals["gpus"][0], gpus) || gpus == 0)) { std::cerr << "bad value for --gpus\n"; return 1; }
+    if (gpus > chains) gpus = chains;
 
     // ---- initial memberships, reference src/mcmc_main.cc:243-326
     std::vector<unsigned> n, z, memberships_init;
@@ -303,8 +311,6 @@ int main(int argc, char const* argv[]) {
         }
     }
 
-    bisbm_handle* h = nullptr;
-    if (!check(bisbm_create((uint32_t)NA, (uint32_t)NB, ea.size(), ea.data(), eb.data(), (int)device, &h))) return 1;
     int sched = -1;
     if (cooling_schedule == "exponential") sched = BISBM_EXPONENTIAL;
     if (cooling_schedule == "linear") sched = BISBM_LINEAR;
@@ -312,6 +318,63 @@ int main(int argc, char const* argv[]) {
     if (cooling_schedule == "constant") sched = BISBM_CONSTANT;
     if (cooling_schedule == "abrupt_cool") sched = BISBM_ABRUPT_COOL;
 
+    if (gpus > 1 && !o.has("estimate")) {
+        // ---- several GPUs of one node, one host thread per device: chain c runs on device (c mod gpus) with a seed that
+        //      depends only on c; the graph is replicated.  --marginalize: one NCCL all-reduce of the histograms.
+        const bool marg = o.has("marginalize");
+        std::vector<bisbm_handle*> hs(gpus, nullptr);
+        std::vector<std::string> errs(gpus);
+        std::vector<std::vector<double>> ent(gpus), acc(gpus);
+        std::vector<std::thread> th;
+        for (size_t g = 0; g < gpus; ++g)
+            th.emplace_back([&, g]() {
+                auto ok = [&](int rc) { if (rc != BISBM_OK) { errs[g] = bisbm_last_error(); return false; } return true; };
+                if (!ok(bisbm_create((uint32_t)NA, (uint32_t)NB, ea.size(), ea.data(), eb.data(), (int)(device + g), &hs[g]))) return;
+                std::vector<size_t> ids;
+                for (size_t c = g; c < chains; c += gpus) ids.push_back(c);
+                const size_t nc = ids.size();
+                std::vector<uint32_t> ka_v(nc, (uint32_t)KA), kb_v(nc, (uint32_t)KB), labels(nc * N);
+                for (size_t i = 0; i < nc; ++i)
+                    for (size_t v = 0; v < N; ++v) labels[i * N + v] = memberships_init[v];
+                std::vector<uint64_t> seeds(nc);
+                for (size_t i = 0; i < nc; ++i) seeds[i] = (uint64_t)seed * 0x9E3779B97F4A7C15ull + ids[i];
+                if (!ok(bisbm_set_chains(hs[g], (uint32_t)nc, ka_v.data(), kb_v.data(), labels.data(), epsilon))) return;
+                if (randomize && !ok(bisbm_randomize(hs[g], seeds.data()))) return;
+                acc[g].assign(nc, 0.0); ent[g].assign(nc, 0.0);
+                std::vector<uint64_t> sw(nc);
+                if (marg) {
+                    if (!ok(bisbm_marginals_clear(hs[g]))) return;
+                    if (!ok(bisbm_marginalize(hs[g], burn_in, sampling_steps, std::max<size_t>(sampling_frequency, 1), seeds.data(), (uint32_t)max_inflight))) return;
+                } else {
+                    if (sched >= 0 && !ok(bisbm_anneal(hs[g], sched, kw[0], kw[1], sampling_steps, steps_await, seeds.data(), (uint32_t)max_inflight, acc[g].data(), sw.data()))) return;
+                    if (!ok(bisbm_entropy_all(hs[g], ent[g].data()))) return;
+                }
+            });
+        for (auto& t : th) t.join();
+        for (size_t g = 0; g < gpus; ++g)
+            if (!errs[g].empty()) { std::cerr << "libbisbm (device " << device + g << "): " << errs[g] << "\n"; return 1; }
+        std::vector<uint32_t> out(N);
+        if (marg) {
+            if (!check(bisbm_marginals_allreduce_local(hs.data(), (int)gpus))) return 1;
+            if (!check(bisbm_marginal_argmax(hs[0], out.data()))) return 1;
+            output_vec(out, std::cout);
+        } else {
+            size_t bg = 0, bi = 0;
+            for (size_t g = 0; g < gpus; ++g)
+                for (size_t i = 0; i < ent[g].size(); ++i)
+                    if (ent[g][i] < ent[bg][bi]) { bg = g; bi = i; }
+            if (!check(bisbm_get_labels(hs[bg], (uint32_t)bi, out.data()))) return 1;
+            std::clog << "acceptance ratio " << acc[bg][bi] << "\n";
+            std::clog << "(Ka, Kb) = (" << KA << ", " << KB << ") \n";
+            std::clog << "entropy: " << ent[bg][bi] << "\n";
+            output_vec(out, std::cout);
+        }
+        for (auto* h : hs) bisbm_destroy(h);
+        return 0;
+    }
+
+    bisbm_handle* h = nullptr;
+    if (!check(bisbm_create((uint32_t)NA, (uint32_t)NB, ea.size(), ea.data(), eb.data(), (int)device, &h))) return 1;
     std::vector<uint32_t> ka_v(chains, (uint32_t)KA), kb_v(chains, (uint32_t)KB), labels(chains * N);
     for (size_t c = 0; c < chains; ++c)
         for (size_t v = 0; v < N; ++v) labels[c * N + v] = memberships_init[v];

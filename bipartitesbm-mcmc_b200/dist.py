@@ -18,11 +18,28 @@ def chain_seeds(base_seed, chain_ids):
     return (np.uint64(base_seed) * np.uint64(0x9E3779B97F4A7C15) + ids).astype(np.uint64)
 
 
-def allreduce_marginals(hist):
-    """In-place sum of the marginal histogram over ranks.  `hist` is a torch tensor: the device
-    histogram wrapped by host.marginals_tensor (NCCL over NVLink) or a CPU tensor (gloo)."""
+def init_pool_comm(pool):
+    """Give `pool`'s handle its own NCCL communicator over the torch.distributed world: rank 0 draws the unique id
+    (bisbm_nccl_get_unique_id), torch.distributed only carries those 128 bytes to the other ranks, every rank joins
+    with bisbm_nccl_init.  After this the marginal all-reduce runs entirely behind the C ABI."""
     import torch.distributed as dist
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+    from . import host
+    world, rank = dist.get_world_size(), dist.get_rank()
+    box = [host.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    pool.nccl_init(world, rank, box[0])
+
+
+def allreduce_marginals(hist):
+    """In-place sum of the marginal histogram over ranks.  `hist` is a ChainPool whose handle joined a communicator
+    (init_pool_comm): the library's own ncclAllReduce on the device-resident histogram over NVLink; or a torch tensor
+    (CPU tensor over gloo in the host-logic tests, or a wrapped device histogram)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return hist
+    if hasattr(hist, "marginals_allreduce"):
+        hist.marginals_allreduce()
+    else:
         dist.all_reduce(hist, op=dist.ReduceOp.SUM)
     return hist
 

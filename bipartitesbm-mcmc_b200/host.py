@@ -74,6 +74,10 @@ SIGNATURES = {
     "bisbm_parallel_transition": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, _dp, _dp]),
     "bisbm_sweep_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
                                    C.POINTER(C.c_uint32)]),
+    "bisbm_nccl_get_unique_id": (C.c_int, [C.c_void_p]),
+    "bisbm_nccl_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "bisbm_marginals_allreduce": (C.c_int, [C.c_void_p]),
+    "bisbm_marginals_allreduce_local": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
     "bisbm_marginals_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), _u64p, _u32p]),
     "bisbm_get_marginals": (C.c_int, [C.c_void_p, _u32p]),
     "bisbm_marginal_argmax": (C.c_int, [C.c_void_p, _u32p]),
@@ -168,6 +172,13 @@ class Graph:
             self.close()
         except Exception:
             pass
+
+
+def nccl_unique_id():
+    """128 bytes identifying a new NCCL communicator (rank 0 calls this, every rank passes it to ChainPool.nccl_init)."""
+    buf = (C.c_uint8 * 128)()
+    _check(load_library().bisbm_nccl_get_unique_id(buf))
+    return bytes(buf)
 
 
 def grid_search(graph, points, restarts, epsilon, schedule, p0, p1, duration, steps_await, seed=1, max_inflight=0):
@@ -267,6 +278,16 @@ class ChainPool:
 
     def marginals_clear(self):
         _check(self.L.bisbm_marginals_clear(self.g.h))
+
+    def nccl_init(self, nranks, rank, unique_id):
+        """Collective: join the NCCL communicator of the marginal all-reduce (unique_id: the 128 bytes rank 0 got from
+        nccl_unique_id(), passed to the other ranks by the caller)."""
+        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(unique_id))
+        _check(self.L.bisbm_nccl_init(self.g.h, nranks, rank, buf))
+
+    def marginals_allreduce(self):
+        """Collective: in-place NCCL all-reduce (sum) of the device-resident marginal histogram."""
+        _check(self.L.bisbm_marginals_allreduce(self.g.h))
 
     def marginal_sample(self):
         _check(self.L.bisbm_marginal_sample(self.g.h))

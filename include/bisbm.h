@@ -147,7 +147,17 @@ int bisbm_grid_search(bisbm_handle* graph, uint32_t n_points, const uint32_t* ka
                       double eps, int schedule, float p0, float p1, uint64_t duration, uint64_t steps_await, uint64_t seed,
                       uint32_t max_inflight, double* entropy, double* accept, uint32_t* best_chain, uint32_t* best_labels,
                       double* stats);
-/* device pointer + element count of the histogram, for an in-place NCCL all-reduce */
+/* ---- multi-GPU: chains are partitioned over GPUs (graph replicated); the only collective is ONE all-reduce (sum, uint32)
+ * of the per-node marginal histogram over NVLink.  libnccl.so.2 is loaded on first use (BISBM_ERR_STATE if absent).
+ * One process per GPU: rank 0 calls bisbm_nccl_get_unique_id and hands the 128 bytes to the other ranks by any means;
+ * every rank calls bisbm_nccl_init (collective), then bisbm_marginals_allreduce (collective, in place, on the handle's
+ * stream; returns when the sum is complete).  One process driving several GPUs: bisbm_marginals_allreduce_local over its
+ * handles (one per device). */
+int bisbm_nccl_get_unique_id(uint8_t* id128);
+int bisbm_nccl_init(bisbm_handle* h, int nranks, int rank, const uint8_t* id128);
+int bisbm_marginals_allreduce(bisbm_handle* h);
+int bisbm_marginals_allreduce_local(bisbm_handle** handles, int n);
+/* device pointer + element count of the histogram (for callers that bring their own collective) */
 int bisbm_marginals_device(bisbm_handle* h, void** dev_ptr, uint64_t* n_elems, uint32_t* width);
 int bisbm_get_marginals(bisbm_handle* h, uint32_t* hist);          /* [n][width], global block ids */
 int bisbm_marginal_argmax(bisbm_handle* h, uint32_t* labels);      /* [n] */

@@ -123,3 +123,34 @@ def test_membership_file_marginalize_and_estimate_modes(cli, tmp_path):
                        "--randomize", "-t", 100000, "-x", 2000, "-c", "abrupt_cool", "-a", 50000, "-d", 1)
     assert rc == 0, err
     assert np.array(out.split()).size == 1000 and "entropy:" in err
+
+
+@pytest.mark.gpu
+def test_gpus_mode_shards_chains_and_all_reduces(cli, tmp_path):
+    """--gpus N: chains dealt round-robin to N devices of the node by one process (graph replicated), the marginal
+    histograms summed by ONE NCCL all-reduce behind the C ABI (bisbm_marginals_allreduce_local).  On a single-GPU box the
+    second device does not exist and the command must fail cleanly; with two or more GPUs the label line must be a
+    valid partition that agrees with the single-GPU marginals on most nodes."""
+    import torch
+    g = load_golden("c2_const_k46")
+    path = write_edges(tmp_path, g)
+    mb = os.path.join(str(tmp_path), "mb.txt")
+    np.savetxt(mb, g["labels0"], fmt="%d")
+    args = ["-e", path, "-y", 500, 500, "--membership_path", mb, "--marginalize", "-b", 30, "-t", 120, "-f", 4, "--chains", 64,
+            "--seed", 5]
+    rc1, out1, err1 = run(cli, *args)
+    assert rc1 == 0, err1
+    lab1 = np.array(out1.split(), dtype=np.int64)
+    assert lab1.size == 1000
+    rc2, out2, err2 = run(cli, *args, "--gpus", 2)
+    if torch.cuda.device_count() < 2:
+        assert rc2 == 1 and "device 1 out of range" in err2
+        return
+    assert rc2 == 0, err2
+    lab2 = np.array(out2.split(), dtype=np.int64)
+    assert lab2.size == 1000 and (lab2[:500] < 4).all() and (lab2[500:] >= 4).all() and (lab2[500:] < 10).all()
+    assert (lab1 == lab2).mean() > 0.9
+    # maximisation over restarts on two devices
+    rc3, out3, err3 = run(cli, "-e", path, "-y", 500, 500, "--membership_path", mb, "-c", "abrupt_cool", "-a", 50000, "-t", 100000,
+                          "-x", 10 ** 9, "--chains", 16, "--gpus", 2, "--seed", 3)
+    assert rc3 == 0 and "entropy:" in err3 and len(out3.split()) == 1000
