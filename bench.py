@@ -269,6 +269,117 @@ def bench_c4(args, rank, world, local_rank):
     return 0
 
 
+def bench_c5(args, rank, world, local_rank):
+    """BASELINE configs[4] scaled to what one GPU's share looks like: planted SBM with Ka = Kb = 128 (counts in L2: the
+    staged kernel cannot hold 128 x 128 x 32 counters), --c5-nodes / --c5-edges (default 5M / 100M = 1/10 of the named
+    50M / 1B), 32 chains per GPU, T = 1; every GPU runs its own chains over the replicated graph and the per-node marginal
+    histograms (N x 256 x 4 B) are summed by the library's NCCL all-reduce, timed separately.  The reference cannot run
+    this shape (k_ alone is N x 256 x 4 B per chain plus adj_map_): its number comes from a 1/50-scale graph."""
+    import torch
+    import torch.distributed as dist
+    pkg = importlib.import_module("bipartitesbm-mcmc_b200")
+    host = pkg.host
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    na = nb = args.c5_nodes // 2
+    n = na + nb
+    K = 128
+    C = args.c5_chains
+    t_gen = time.perf_counter()
+    edges = planted(na, nb, K, K, args.c5_edges, 0)
+    t_gen = time.perf_counter() - t_gen
+    t_build = time.perf_counter()
+    graph = host.Graph(edges, na, nb, device=local_rank)
+    t_build = time.perf_counter() - t_build
+    lab = planted_labels(na, nb, K, K).astype(np.uint8 if 2 * K <= 256 else np.uint32)
+    pool = host.ChainPool(graph, np.broadcast_to(lab, (C, n)), K, K, 1.0)
+    seeds = pkg.dist.chain_seeds(0, pkg.dist.shard_chains(C * world, rank, world))
+    pool.randomize(seeds)
+    if world > 1:
+        pkg.dist.init_pool_comm(pool)
+    sweeps = args.sweeps_per_step
+    for _ in range(args.warmup):
+        pool.anneal("constant", 1.0, 0.0, 1 * n, 10 ** 18, seeds)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    dev_ms, moves, accs = 0.0, 0, []
+    for _ in range(args.steps):
+        acc, _sw = pool.anneal("constant", 1.0, 0.0, sweeps * n, 10 ** 18, seeds)
+        ms_, _la, mv_ = pool.last_timing()
+        dev_ms += ms_; moves += mv_; accs.append(float(acc.mean()))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    wall = time.perf_counter() - t0
+    # size-independent properties on one chain: the device counts equal a rebuild from its labels
+    l0 = pool.labels(C - 1).astype(np.int64)
+    ea, eb = edges[:, 0].astype(np.int64), edges[:, 1].astype(np.int64)
+    m_ab = np.bincount(l0[ea] * K + (l0[eb] - K), minlength=K * K).reshape(K, K)
+    m_dev = pool.m(C - 1)[:K, K:]
+    ok = bool((m_dev == m_ab).all() and (pool.n_r(C - 1) == np.bincount(l0, minlength=2 * K)).all())
+    # the one collective: histogram all-reduce
+    pool.marginals_clear()
+    pool.marginal_sample()
+    torch.cuda.synchronize()
+    ar_ms = None
+    if world > 1:
+        dist.barrier()
+        t1 = time.perf_counter()
+        pool.marginals_allreduce()
+        ar_ms = (time.perf_counter() - t1) * 1e3
+    kern, wpc_, cpg_, slice_ = pool.sweep_info()
+    t = torch.tensor([wall, dev_ms, ar_ms or 0.0], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(moves)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        bytes_per_move = 16.0 + 8.0 * (2.0 * args.c5_edges / n) + 4.0 * float(np.mean(accs))
+        achieved = bytes_per_move * float(tot[0]) / world / (float(t[1]) * 1e-3) / 1e9
+        hist_bytes = n * 2 * K * 4
+        line = {"metric": "vertex-moves/sec", "value": float(tot[0]) / float(t[0]), "unit": "moves/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": float(t[0]) / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64+int32", "data": "synthetic",
+                "config": {"workload": "C5 scaled: planted SBM %d nodes / %d edges, Ka=Kb=128, %d chains/GPU, T=1 (BASELINE configs[4] names 50M / 1B on 8 GPUs)" % (n, args.c5_edges, C),
+                           "l2": "inputs larger than L2", "sweep_plan": {"kernel": kern, "warps_per_cta": wpc_, "ctas_per_chain_group": cpg_, "slice": slice_},
+                           "graph_generate_s": t_gen, "graph_build_s": t_build},
+                "acceptance": float(np.mean(accs)), "invariants_ok": ok,
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                             "bytes_per_move": bytes_per_move, "kernel": "sweep2_kernel<double, counts in L2>"},
+                "allreduce": {"bytes": hist_bytes, "ms": float(t[2]) if world > 1 else None,
+                              "GBps_bus": (2.0 * (world - 1) / world * hist_bytes / (float(t[2]) * 1e-3) / 1e9) if world > 1 and float(t[2]) > 0 else None},
+                "e2e": {"value": float(tot[0]) / float(t[0]), "unit": "moves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": None}
+        if not args.no_cpu_baseline and world == 1:
+            try:
+                sna = snb = max(1000, args.c5_nodes // 10) // 2       # 1/50 of the NAMED 50M-node graph when c5_nodes is 5M
+                sedges = planted(sna, snb, K, K, max(1000, args.c5_edges // 10), 0)
+                path = os.path.join(tempfile.gettempdir(), "bisbm_bench_edges_c5_%d.npy" % os.getpid())
+                np.save(path, sedges)
+                kind = cpu_kind()
+                procs = max(1, min(cpu_procs(6.0), 8))
+                v, mv, worst = run_cpu_sample(path, sna, snb, K, K, max(100000, args.cpu_moves // 4), procs, kind)
+                os.unlink(path)
+                line["cpu_baseline"] = {"value": v, "unit": "moves/s", "cores": procs, "kind": kind,
+                                        "sample": "reference infeasible at the named size (k_ = N x 256 x 4 B per chain); measured on a 1/50-scale graph (%d nodes / %d edges, same mean degree and K): %d processes x %d moves of anneal() (T=1), %.1f s" % (
+                                            sna + snb, len(sedges), procs, mv // procs, worst)}
+            except Exception as ex:
+                line["cpu_baseline"] = {"value": None, "unit": "moves/s", "cores": 0, "kind": "unavailable", "sample": str(ex)[:200]}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def bench_marginalize(args, rank, world, local_rank):
     """BASELINE configs[1] wording (burn-in, then sample every 10 sweeps) on the C3 graph: sweeps + histogram accumulation,
     and the marginal kernel alone against its N x chains x 12 B per sample roofline."""
@@ -365,10 +476,13 @@ def main():
     ap.add_argument("--sweeps-per-step", type=int, default=SWEEPS_PER_STEP)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-moves", type=int, default=2000000, help="CPU sample: moves per process per step")
-    ap.add_argument("--workload", default="c3", choices=["c3", "c4", "marginalize"],
+    ap.add_argument("--workload", default="c3", choices=["c3", "c4", "c5", "marginalize"],
                     help="c3: BASELINE configs[2] (headline); c4: configs[3], the (Ka,Kb) grid x 8 restarts through the in-process "
                          "search driver, points sharded over the GPUs; marginalize: configs[1] wording on the C3 graph "
                          "(sample every 10 sweeps into the device histogram)")
+    ap.add_argument("--c5-nodes", type=int, default=5000000)
+    ap.add_argument("--c5-edges", type=int, default=100000000)
+    ap.add_argument("--c5-chains", type=int, default=32)
     ap.add_argument("--precision", default="fp64", choices=["fp64", "fp32"],
                     help="arithmetic of a move: fp64 like the reference's transition_ratio (headline) or fp32")
     ap.add_argument("--inflight-div", type=int, default=0, help="in-flight bound = half sweep / this (0: library default)")
@@ -422,6 +536,8 @@ def main():
         return bench_c4(args, rank, world, local_rank)
     if args.workload == "marginalize":
         return bench_marginalize(args, rank, world, local_rank)
+    if args.workload == "c5":
+        return bench_c5(args, rank, world, local_rank)
 
     # ---------------- our arm
     import torch

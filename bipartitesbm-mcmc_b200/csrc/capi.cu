@@ -22,6 +22,7 @@
 #include <string>
 #include <vector>
 
+#include "ingest.cuh"
 #include "replay.cuh"
 #include "sweep_aux.cuh"
 #include "sweep2.cuh"
@@ -121,6 +122,7 @@ struct bisbm_handle {
     int opt_kernel = -1;               // -1: automatic; KERN_L2 / KERN_STAGED_OLD force the round-1 double kernels
     uint32_t opt_inflight_div = 64;    // default in-flight bound = half sweep / this
     int opt_generic = 0;               // 1: never take the Ka = Kb = 32 specialisation
+    int opt_vary_k = 0;                // estimate mode: blocks may empty, K-dependent prior terms in dS
     uint32_t opt_warps = 16;           // warps per CTA of the staged sweep2 kernel (experiment builds: 20, 24)
     std::set<const void*> attr_done;   // kernels whose shared-memory limit is raised on this handle's device
     uint64_t last_sweep_launches = 0, last_marginal_launches = 0;
@@ -208,25 +210,59 @@ int ensure_lgamma_table(bisbm_handle* h) {
     return BISBM_OK;
 }
 
+// degree statistics shared by both creation paths: distinct degrees (compressed eta columns), the degree -> column
+// table, and -sum_v lgamma(d_v + 1) from the degree histogram (fixed summation order)
+void degree_stats(bisbm_handle* h, const std::vector<uint32_t>& deg, std::vector<uint32_t>& table, double* base) {
+    h->max_degree = 0;
+    for (uint32_t d : deg) h->max_degree = std::max(h->max_degree, d);
+    std::vector<uint64_t> cnt((size_t)h->max_degree + 1, 0);
+    for (uint32_t d : deg) cnt[d]++;
+    h->h_degvals.clear();
+    table.assign((size_t)h->max_degree + 1, 0);
+    *base = 0.0;
+    for (uint32_t d = 0; d <= h->max_degree; ++d)
+        if (cnt[d]) {
+            table[d] = (uint32_t)h->h_degvals.size();
+            h->h_degvals.push_back(d);
+            *base -= (double)cnt[d] * std::lgamma((double)d + 1.0);
+        }
+    h->W = (uint32_t)h->h_degvals.size();
+}
+
+// stream, events, exact log q table, shared graph object (after row_ptr / col / degidx are on the device)
+int finish_tables(bisbm_handle* h) {
+    CU(cudaSetDevice(h->device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, h->device));
+    h->sm_count = prop.multiProcessorCount;
+    CU(cudaStreamCreate(&h->stream));
+    CU(cudaEventCreate(&h->ev0));
+    CU(cudaEventCreate(&h->ev1));
+    // exact log q table for every (n, k) this graph can look up below the 10001 threshold
+    h->qn = (uint32_t)std::min<uint64_t>(h->n_edges, 10000);
+    h->qk = std::max<uint32_t>(1, std::min<uint32_t>(std::max(h->na, h->nb), h->qn));
+    {
+        std::vector<double> q;
+        build_qtab(q, h->qn, h->qk);
+        CU(cudaMalloc(&h->d_qtab, q.size() * sizeof(double)));
+        CU(cudaMemcpy(h->d_qtab, q.data(), q.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    h->gdev = std::make_shared<GraphDev>();
+    h->gdev->device = h->device;
+    h->gdev->row_ptr = h->d_row_ptr; h->gdev->col = h->d_col; h->gdev->degidx = h->d_degidx; h->gdev->qtab = h->d_qtab;
+    return BISBM_OK;
+}
+
+// ready CSR from the host (bisbm_create_csr): statistics on the host, arrays uploaded as they are
 int finish_graph(bisbm_handle* h, std::vector<uint32_t>& col) {
     const uint32_t n = h->n;
-    // distinct degrees -> compressed eta columns
-    std::vector<uint32_t> deg(n);
-    h->max_degree = 0;
-    for (uint32_t v = 0; v < n; ++v) {
-        deg[v] = h->h_row_ptr[v + 1] - h->h_row_ptr[v];
-        h->max_degree = std::max(h->max_degree, deg[v]);
-    }
-    h->h_degvals = deg;
-    std::sort(h->h_degvals.begin(), h->h_degvals.end());
-    h->h_degvals.erase(std::unique(h->h_degvals.begin(), h->h_degvals.end()), h->h_degvals.end());
-    h->W = (uint32_t)h->h_degvals.size();
-    std::vector<uint32_t> degidx(n);
-    for (uint32_t v = 0; v < n; ++v)
-        degidx[v] = (uint32_t)(std::lower_bound(h->h_degvals.begin(), h->h_degvals.end(), deg[v]) - h->h_degvals.begin());
-    // label-independent entropy terms (reference src/blockmodel.cc:755-757, 772-779)
+    std::vector<uint32_t> deg(n), table;
+    for (uint32_t v = 0; v < n; ++v) deg[v] = h->h_row_ptr[v + 1] - h->h_row_ptr[v];
     double base = 0.0;
-    for (uint32_t v = 0; v < n; ++v) base -= std::lgamma((double)deg[v] + 1.0);
+    degree_stats(h, deg, table, &base);
+    std::vector<uint32_t> degidx(n);
+    for (uint32_t v = 0; v < n; ++v) degidx[v] = table[deg[v]];
+    // multi-edge term of entropy() (reference src/blockmodel.cc:772-779)
     {
         std::vector<uint32_t> row;
         for (uint32_t v = 0; v < n; ++v) {
@@ -244,31 +280,110 @@ int finish_graph(bisbm_handle* h, std::vector<uint32_t>& col) {
     }
     h->ent_base = base;
     CU(cudaSetDevice(h->device));
-    cudaDeviceProp prop;
-    CU(cudaGetDeviceProperties(&prop, h->device));
-    h->sm_count = prop.multiProcessorCount;
-    CU(cudaStreamCreate(&h->stream));
-    CU(cudaEventCreate(&h->ev0));
-    CU(cudaEventCreate(&h->ev1));
     CU(cudaMalloc(&h->d_row_ptr, ((size_t)n + 1) * sizeof(uint32_t)));
     CU(cudaMalloc(&h->d_col, std::max<size_t>(col.size(), 1) * sizeof(uint32_t)));
     CU(cudaMalloc(&h->d_degidx, std::max<size_t>(n, 1) * sizeof(uint32_t)));
     CU(cudaMemcpy(h->d_row_ptr, h->h_row_ptr.data(), ((size_t)n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice));
     if (!col.empty()) CU(cudaMemcpy(h->d_col, col.data(), col.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     if (n) CU(cudaMemcpy(h->d_degidx, degidx.data(), (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    // exact log q table for every (n, k) this graph can look up below the 10001 threshold
-    h->qn = (uint32_t)std::min<uint64_t>(h->n_edges, 10000);
-    h->qk = std::max<uint32_t>(1, std::min<uint32_t>(std::max(h->na, h->nb), h->qn));
-    {
-        std::vector<double> q;
-        build_qtab(q, h->qn, h->qk);
-        CU(cudaMalloc(&h->d_qtab, q.size() * sizeof(double)));
-        CU(cudaMemcpy(h->d_qtab, q.data(), q.size() * sizeof(double), cudaMemcpyHostToDevice));
+    return finish_tables(h);
+}
+
+// edge list -> CSR ON THE DEVICE (ingest.cuh): edge_to_adj of the reference, src/graph_utilities.cc:36-49
+int ingest_edges_device(bisbm_handle* h, const uint32_t* ea, const uint32_t* eb) {
+    const uint32_t n = h->n;
+    const uint64_t E = h->n_edges, E2 = 2 * E;
+    CU(cudaSetDevice(h->device));
+    uint32_t *d_ea = nullptr, *d_eb = nullptr, *d_keys = nullptr, *d_vals = nullptr, *d_keys2 = nullptr, *d_deg = nullptr, *d_table = nullptr;
+    unsigned long long *d_bad = nullptr, *d_pk = nullptr, *d_pk2 = nullptr, *d_mult = nullptr;
+    void* d_tmp = nullptr;
+    auto cleanup = [&]() {
+        for (void* p : {(void*)d_ea, (void*)d_eb, (void*)d_keys, (void*)d_vals, (void*)d_keys2, (void*)d_deg, (void*)d_table, (void*)d_bad,
+                        (void*)d_pk, (void*)d_pk2, (void*)d_mult, d_tmp})
+            if (p) cudaFree(p);
+    };
+#define CUI(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return fail(BISBM_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } } while (0)
+    CUI(cudaMalloc(&h->d_row_ptr, ((size_t)n + 1) * sizeof(uint32_t)));
+    CUI(cudaMalloc(&h->d_col, std::max<uint64_t>(E2, 1) * sizeof(uint32_t)));
+    CUI(cudaMalloc(&h->d_degidx, std::max<size_t>(n, 1) * sizeof(uint32_t)));
+    CUI(cudaMalloc(&d_deg, ((size_t)n + 1) * sizeof(uint32_t)));
+    CUI(cudaMemset(d_deg, 0, ((size_t)n + 1) * sizeof(uint32_t)));
+    CUI(cudaMalloc(&d_bad, sizeof(unsigned long long)));
+    CUI(cudaMemset(d_bad, 0xff, sizeof(unsigned long long)));
+    std::vector<unsigned long long> mult(INGEST_MULT_BINS, 0);
+    if (E) {
+        CUI(cudaMalloc(&d_ea, E * sizeof(uint32_t)));
+        CUI(cudaMalloc(&d_eb, E * sizeof(uint32_t)));
+        CUI(cudaMemcpy(d_ea, ea, E * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        CUI(cudaMemcpy(d_eb, eb, E * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        CUI(cudaMalloc(&d_keys, E2 * sizeof(uint32_t)));
+        CUI(cudaMalloc(&d_vals, E2 * sizeof(uint32_t)));
+        CUI(cudaMalloc(&d_keys2, E2 * sizeof(uint32_t)));
+        const unsigned gb = (unsigned)((E + 255) / 256);
+        ingest_expand_kernel<<<gb, 256>>>(d_ea, d_eb, E, n, h->na, d_keys, d_vals, d_bad);
+        CUI(cudaGetLastError());
+        unsigned long long bad = 0;
+        CUI(cudaMemcpy(&bad, d_bad, sizeof bad, cudaMemcpyDeviceToHost));
+        if (bad != ~0ull) {
+            const unsigned long long i = bad / 4;
+            cleanup();
+            if ((bad & 3) == INGEST_BAD_RANGE) return fail(BISBM_ERR_ARG, "edge %llu: node id out of range", i);
+            return fail(BISBM_ERR_ARG, "edge %u-%u joins two nodes of the same type", ea[i], eb[i]);
+        }
+        // stable sort of the directed entries by source node: rows in file order
+        int bits = 1;
+        while (bits < 32 && (1ull << bits) < (uint64_t)n) ++bits;
+        size_t tmp_bytes = 0;
+        CUI(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys, d_keys2, d_vals, h->d_col, E2, 0, bits));
+        CUI(cudaMalloc(&d_tmp, std::max<size_t>(tmp_bytes, 16)));
+        CUI(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_keys, d_keys2, d_vals, h->d_col, E2, 0, bits));
+        ingest_degree_kernel<<<(unsigned)((E2 + 255) / 256), 256>>>(d_keys2, E2, d_deg);
+        CUI(cudaGetLastError());
+        cudaFree(d_tmp); d_tmp = nullptr;
+        cudaFree(d_keys); d_keys = nullptr; cudaFree(d_vals); d_vals = nullptr; cudaFree(d_keys2); d_keys2 = nullptr;
+        // multi-edge multiplicities: sort one 64-bit key per undirected edge, count runs
+        CUI(cudaMalloc(&d_pk, E * sizeof(unsigned long long)));
+        CUI(cudaMalloc(&d_pk2, E * sizeof(unsigned long long)));
+        CUI(cudaMalloc(&d_mult, INGEST_MULT_BINS * sizeof(unsigned long long)));
+        CUI(cudaMemset(d_mult, 0, INGEST_MULT_BINS * sizeof(unsigned long long)));
+        ingest_pair_keys_kernel<<<gb, 256>>>(d_ea, d_eb, E, d_pk);
+        CUI(cudaGetLastError());
+        tmp_bytes = 0;
+        CUI(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, d_pk, d_pk2, E, 0, 32 + bits));
+        CUI(cudaMalloc(&d_tmp, std::max<size_t>(tmp_bytes, 16)));
+        CUI(cub::DeviceRadixSort::SortKeys(d_tmp, tmp_bytes, d_pk, d_pk2, E, 0, 32 + bits));
+        ingest_multiplicity_kernel<<<gb, 256>>>(d_pk2, E, d_mult);
+        CUI(cudaGetLastError());
+        CUI(cudaMemcpy(mult.data(), d_mult, INGEST_MULT_BINS * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        if (mult[INGEST_MULT_BINS - 1]) { cleanup(); return fail(BISBM_ERR_ARG, "an edge is repeated %d times or more", INGEST_MULT_BINS - 1); }
     }
-    h->gdev = std::make_shared<GraphDev>();
-    h->gdev->device = h->device;
-    h->gdev->row_ptr = h->d_row_ptr; h->gdev->col = h->d_col; h->gdev->degidx = h->d_degidx; h->gdev->qtab = h->d_qtab;
-    return BISBM_OK;
+    // row offsets = exclusive scan of the degrees
+    {
+        size_t tmp_bytes = 0;
+        if (d_tmp) { cudaFree(d_tmp); d_tmp = nullptr; }
+        CUI(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_deg, h->d_row_ptr, (int)(n + 1)));
+        CUI(cudaMalloc(&d_tmp, std::max<size_t>(tmp_bytes, 16)));
+        CUI(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_deg, h->d_row_ptr, (int)(n + 1)));
+    }
+    h->h_row_ptr.resize((size_t)n + 1);
+    CUI(cudaMemcpy(h->h_row_ptr.data(), h->d_row_ptr, ((size_t)n + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    std::vector<uint32_t> deg(n), table;
+    for (uint32_t v = 0; v < n; ++v) deg[v] = h->h_row_ptr[v + 1] - h->h_row_ptr[v];
+    double base = 0.0;
+    degree_stats(h, deg, table, &base);
+    for (int L = 2; L < INGEST_MULT_BINS; ++L)
+        if (mult[L]) base += (double)mult[L] * std::lgamma((double)L + 1.0);
+    h->ent_base = base;
+    CUI(cudaMalloc(&d_table, table.size() * sizeof(uint32_t)));
+    CUI(cudaMemcpy(d_table, table.data(), table.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    if (n) {
+        ingest_degidx_kernel<<<(n + 255) / 256, 256>>>(d_deg, n, d_table, h->d_degidx);
+        CUI(cudaGetLastError());
+    }
+    CUI(cudaDeviceSynchronize());
+#undef CUI
+    cleanup();
+    return finish_tables(h);
 }
 
 int need_chains(bisbm_handle* h) {
@@ -421,7 +536,7 @@ const size_t kSmemMax = 227 * 1024;
 int plan_kernel(const bisbm_handle* h, uint32_t* wpc_out) {
     const uint32_t hb = h->max_degree <= 255u ? 1 : (h->max_degree <= 65535u ? 2 : 4);
     *wpc_out = 32;
-    if (h->opt_kernel == KERN_L2) return KERN_L2;
+    if (h->opt_kernel == KERN_L2 && !h->opt_vary_k) return KERN_L2;
     const bool k8 = h->KA <= 256 && h->KB <= 256;
     if (h->opt_kernel == KERN_STAGED_OLD) {
         for (uint32_t w : {32u, 16u})
@@ -547,6 +662,7 @@ SweepParams base_params(bisbm_handle* h, uint32_t type) {
     P.kopp_max = type ? h->KA : h->KB;
     P.half_bits = feistel_half_bits(type ? h->nb : h->na);
     P.kat_out = h->d_kat_out;
+    P.vary_k = (uint32_t)h->opt_vary_k;
     return P;
 }
 
@@ -722,19 +838,22 @@ int bisbm_create(uint32_t na, uint32_t nb, uint64_t n_edges, const uint32_t* ea,
     if (!out) return fail(BISBM_ERR_ARG, "null argument");
     *out = nullptr;
     if (n_edges && (!ea || !eb)) return fail(BISBM_ERR_ARG, "null edge arrays");
-    const uint64_t n = (uint64_t)na + nb;
+    const uint64_t n64 = (uint64_t)na + nb;
+    if (n64 == 0 || n64 > 0xfffffff0ull) return fail(BISBM_ERR_ARG, "bad node count");
     if (2 * n_edges >= 0xffffffffull) return fail(BISBM_ERR_ARG, "too many edges for 32-bit row offsets");
-    // edge_to_adj: push both directions, file order, multi-edges kept (reference
-    // src/graph_utilities.cc:36-49)
-    std::vector<uint32_t> row_ptr(n + 1, 0);
-    for (uint64_t i = 0; i < n_edges; ++i) {
-        if (ea[i] >= n || eb[i] >= n) return fail(BISBM_ERR_ARG, "edge %llu: node id out of range", (unsigned long long)i);
-        row_ptr[ea[i] + 1]++; row_ptr[eb[i] + 1]++;
-    }
-    for (uint64_t v = 0; v < n; ++v) row_ptr[v + 1] += row_ptr[v];
-    std::vector<uint32_t> fill(row_ptr.begin(), row_ptr.end() - 1), col(2 * n_edges);
-    for (uint64_t i = 0; i < n_edges; ++i) { col[fill[ea[i]]++] = eb[i]; col[fill[eb[i]]++] = ea[i]; }
-    return bisbm_create_csr(na, nb, row_ptr.data(), col.data(), device, out);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(BISBM_ERR_CUDA, "no CUDA device (libbisbm has no CPU path)");
+    if (device < 0 || device >= ndev) return fail(BISBM_ERR_ARG, "device %d out of range (%d devices)", device, ndev);
+    std::unique_ptr<bisbm_handle> h(new bisbm_handle());
+    h->device = device;
+    h->n = (uint32_t)n64; h->na = na; h->nb = nb; h->n_edges = n_edges;
+    // edge_to_adj on the device: both directions, file order within a row, multi-edges kept (reference
+    // src/graph_utilities.cc:36-49); validation (id range, bipartition) included
+    int rc = ingest_edges_device(h.get(), ea, eb);
+    if (rc) { const std::string err = g_err; bisbm_destroy(h.release()); g_err = err; return rc; }
+    *out = h.release();
+    return BISBM_OK;
 }
 
 int bisbm_destroy(bisbm_handle* h) {
@@ -1294,6 +1413,8 @@ int bisbm_set_option(bisbm_handle* h, const char* name, int64_t value) {
     } else if (k == "inflight_div") {
         if (value < 1 || value > (1 << 30)) return fail(BISBM_ERR_ARG, "inflight_div must be >= 1");
         h->opt_inflight_div = (uint32_t)value;
+    } else if (k == "vary_k") {
+        h->opt_vary_k = value != 0;
     } else if (k == "warps") {
         if (value != 16 && value != 20 && value != 24) return fail(BISBM_ERR_ARG, "warps: 16, 20 or 24");
         h->opt_warps = (uint32_t)value;
@@ -1584,10 +1705,24 @@ int bisbm_entropy_all(bisbm_handle* h, double* entropy) {
     int rc = need_chains(h);
     if (rc) return rc;
     entropy_kernel<<<h->n_chains, 256, 0, h->stream>>>(gview(h), sview(h), tview(h, false), h->ent_base, h->n_chains,
-                                                       h->d_ent_out);
+                                                       h->d_ent_out, h->opt_vary_k, nullptr);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(h->stream));
     CU(cudaMemcpy(entropy, h->d_ent_out, h->n_chains * sizeof(double), cudaMemcpyDeviceToHost));
+    return BISBM_OK;
+}
+
+int bisbm_occupied_blocks(bisbm_handle* h, uint32_t* ka_kb) {
+    int rc = need_chains(h);
+    if (rc) return rc;
+    if (!ka_kb) return fail(BISBM_ERR_ARG, "null argument");
+    uint32_t* d_k = nullptr;
+    CU(cudaMalloc(&d_k, (size_t)h->n_chains * 2 * sizeof(uint32_t)));
+    entropy_kernel<<<h->n_chains, 256, 0, h->stream>>>(gview(h), sview(h), tview(h, false), h->ent_base, h->n_chains, h->d_ent_out, 1, d_k);
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    if (e == cudaSuccess) e = cudaMemcpy(ka_kb, d_k, (size_t)h->n_chains * 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+    cudaFree(d_k);
+    if (e != cudaSuccess) return fail(BISBM_ERR_CUDA, "occupied_blocks: %s", cudaGetErrorString(e));
     return BISBM_OK;
 }
 

@@ -113,7 +113,7 @@ void usage(const char* argv0) {
                  "                                        sampling sweeps in --marginalize / --estimate.\n"
                  "  -f [ --sampling_frequency ] arg (=10) Sweeps between samples (--marginalize / --estimate).\n"
                  "  -z [ --bisbm_partition ] arg          bipartite number of blocks to be inferred.\n"
-                 "  --uni                                 (accepted, unused)\n"
+                 "  --uni                                 --estimate: print the 1D format (K = Ka + Kb)\n"
                  "  -c [ --cooling_schedule ] arg (=abrupt_cool)\n"
                  "                                        exponential, linear, logarithmic, constant, abrupt_cool.\n"
                  "  -a [ --cooling_schedule_kwargs ] arg  Schedule parameters.\n"
@@ -392,8 +392,14 @@ int main(int argc, char const* argv[]) {
             if (!check(bisbm_marginal_argmax(h, out.data()))) return 1;
             output_vec(out, std::cout);
         } else {
+            // README "estimation": the number of groups is sampled too.  -z (or the membership file) gives the upper
+            // bounds; blocks may empty and be re-populated ("vary_k"), and every printed sample carries the number of
+            // OCCUPIED blocks and the log-likelihood (minus the description length).  --uni prints the 1D format
+            // (K = Ka + Kb); the sampler itself keeps the bipartite constraint.
+            if (!check(bisbm_set_option(h, "vary_k", 1))) return 1;
             std::vector<double> acc(chains);
             std::vector<uint64_t> sw(chains);
+            std::vector<uint32_t> kk(2 * chains);
             if (burn_in && !check(bisbm_anneal(h, BISBM_CONSTANT, 1.f, 0.f, burn_in * N, std::numeric_limits<uint64_t>::max(), seeds.data(), (uint32_t)max_inflight, acc.data(), sw.data()))) return 1;
             const size_t f = std::max<size_t>(sampling_frequency, 1);
             const size_t n_samples = sampling_steps / f;
@@ -402,8 +408,11 @@ int main(int argc, char const* argv[]) {
                 if (!check(bisbm_anneal(h, BISBM_CONSTANT, 1.f, 0.f, f * N, std::numeric_limits<uint64_t>::max(), seeds.data(), (uint32_t)max_inflight, acc.data(), sw.data()))) return 1;
                 if (k < first_printed) continue;
                 double S = 0;
-                if (!check(bisbm_entropy(h, 0, &S)) || !check(bisbm_get_labels(h, 0, out.data()))) return 1;
-                std::cout << (k + 1) * f << "," << KA << "," << KB << "," << -S;
+                if (!check(bisbm_entropy(h, 0, &S)) || !check(bisbm_get_labels(h, 0, out.data())) || !check(bisbm_occupied_blocks(h, kk.data()))) return 1;
+                std::cout << (k + 1) * f << ",";
+                if (o.has("uni")) std::cout << kk[0] + kk[1];
+                else std::cout << kk[0] << "," << kk[1];
+                std::cout << "," << -S;
                 for (uint32_t x : out) std::cout << "," << x;
                 std::cout << "\n";
             }

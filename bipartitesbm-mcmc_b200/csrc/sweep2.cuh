@@ -378,6 +378,17 @@ __device__ __noinline__ static double slow2_logq_delta(const double* qtab, uint3
     Tables tb; tb.lg = nullptr; tb.lg_n = 0; tb.qtab = qtab; tb.qn = qn; tb.qk = qk;
     return logq_delta_exact(tb, e, n, de, dn);
 }
+// estimate mode: change of the K-dependent terms of entropy() (src/blockmodel.cc:780-782: lbinom(Ka Kb + E - 1, E) +
+// lbinom(na - 1, Ka - 1) + lbinom(nb - 1, Kb - 1)) when the number of occupied blocks of the moving type goes k -> k + dk
+__device__ __noinline__ static double slow2_prior_delta(double E, double n_own, double k_own, double k_opp, int dk) {
+    auto lbin = [](double N, double k) -> double {
+        if (N == 0.0 || k == 0.0 || k > N) return 0.0;
+        return lgamma(N + 1.0) - lgamma(k + 1.0) - lgamma(N - k + 1.0);
+    };
+    const double k2 = k_own + (double)dk;
+    return (lbin(k2 * k_opp + E - 1.0, E) + lbin(n_own - 1.0, k2 - 1.0)) - (lbin(k_own * k_opp + E - 1.0, E) + lbin(n_own - 1.0, k_own - 1.0));
+}
+
 // 1/T of global step t; T == 0 is returned as a negative value
 __device__ __noinline__ static double slow2_beta(int schedule, float p0, float p1, uint64_t t) {
     const double T = par_temperature(schedule, p0, p1, t);
@@ -522,6 +533,13 @@ __global__ void __launch_bounds__(NT, 1) sweep2_kernel(const __grid_constant__ S
         }
     }
     __syncthreads();
+
+    // estimate mode: occupied blocks of this lane's chain, per type (own type tracked through this warp's own moves)
+    int occ_own = 0, occ_opp = 0;
+    if (P.vary_k) {
+        for (uint32_t b = 0; b < kown_max; ++b) occ_own += (__ldcg(gNR + (own_off + b) * 32 + lane) > 0) ? 1 : 0;
+        for (uint32_t b = 0; b < kopp_max; ++b) occ_opp += (__ldcg(gNR + (opp_off + b) * 32 + lane) > 0) ? 1 : 0;
+    }
 
     // lane-private shared byte addresses (entry j of this chain at +j*128)
     const uint32_t lane4 = lane * 4u;
@@ -793,6 +811,15 @@ __global__ void __launch_bounds__(NT, 1) sweep2_kernel(const __grid_constant__ S
                         __syncwarp();
                     }
                     dS = AR::unit() * lgm + ((d == 0u) ? (R)0 : bdd) + lqr + lqs;
+                    if (P.vary_k) {
+                        // the move empties r and / or opens s: the K-dependent prior terms change with the occupied count
+                        const int dk = ((n_s == 0) ? 1 : 0) - ((n_r == 1) ? 1 : 0);
+                        if (__any_sync(FULL, eval && dk != 0)) {
+                            if (eval && dk != 0)
+                                dS += (R)slow2_prior_delta((double)G.n_edges, (double)nv, (double)occ_own, (double)occ_opp, dk);
+                            __syncwarp();
+                        }
+                    }
                     const R a2 = lh - dS * (beta * AR::inv_unit());          // lg of the acceptance ratio
                     const bool go_hot = (a2 > (R)0) || (AR::u01(rw) < AR::ex(a2));
                     go = eval && (T_zero ? (dS < (R)0) : go_hot);
@@ -802,7 +829,10 @@ __global__ void __launch_bounds__(NT, 1) sweep2_kernel(const __grid_constant__ S
                     }
                     // s == r: see above
                     if (live && !cross && s == r && !T_zero && n_r != 1 && !P.kat_mode) ++n_acc;
-                    if (go) {
+                    if (go && P.vary_k) {
+                        no_red(r, -1);                       // estimate mode: a block may empty
+                        occ_own += ((n_s == 0) ? 1 : 0) - ((n_r == 1) ? 1 : 0);
+                    } else if (go) {
                         // the "would empty block r" veto of apply_mcmc_moves: exact where it can matter
                         if constexpr (STAGED) {
                             const uint32_t small_r = (sh_ld_u32v(Small_base + (r >> 5) * 128u) >> (r & 31u)) & 1u;

@@ -244,11 +244,14 @@ __global__ void marginal_argmax_kernel(uint32_t n, const uint32_t* hist, uint32_
 // blockmodel_t::entropy (src/blockmodel.cc:753-787) for every chain: one CTA per chain,
 // fixed-order block reduction.  `base` holds the label-independent terms
 // -sum_v lgamma(d_v+1) + sum_{i>j, A_ij>1} lgamma(A_ij+1), computed once per graph.
-__global__ void entropy_kernel(GraphView G, StateView S, Tables tb, double base, uint32_t n_chains, double* out) {
+// occupied != 0 (estimate mode): the K-dependent terms use the number of NON-EMPTY blocks per type, also written to
+// k_out[2c], k_out[2c+1] when k_out is not null
+__global__ void entropy_kernel(GraphView G, StateView S, Tables tb, double base, uint32_t n_chains, double* out, int occupied,
+                               uint32_t* k_out) {
     const uint32_t c = blockIdx.x;
     if (c >= n_chains) return;
     const uint32_t KA = S.KA, KB = S.KB, W = S.W;
-    const uint32_t ka = S.ka[c], kb = S.kb[c];
+    uint32_t ka = S.ka[c], kb = S.kb[c];
     const int32_t* M = S.m + cnt_base(c, (size_t)KA * KB);           // entry j at [j * GROUP]
     const int32_t* E = S.e + cnt_base(c, (size_t)KA + KB);
     const int32_t* NR = S.nr + cnt_base(c, (size_t)KA + KB);
@@ -276,6 +279,13 @@ __global__ void entropy_kernel(GraphView G, StateView S, Tables tb, double base,
         __syncthreads();
     }
     if (threadIdx.x == 0) {
+        if (occupied) {
+            uint32_t oa = 0, ob = 0;
+            for (uint32_t q = 0; q < ka; ++q) oa += NR[(size_t)q * GROUP] > 0;
+            for (uint32_t q = 0; q < kb; ++q) ob += NR[(size_t)(KA + q) * GROUP] > 0;
+            ka = oa; kb = ob;
+            if (k_out) { k_out[2 * c] = oa; k_out[2 * c + 1] = ob; }
+        }
         double ent = base + red[0];
         const double Ed = (double)G.n_edges, na = (double)G.na, nb = (double)G.nb;
         const double kab = (double)ka * (double)kb;

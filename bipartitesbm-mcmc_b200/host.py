@@ -94,6 +94,7 @@ SIGNATURES = {
     "bisbm_get_eta": (C.c_int, [C.c_void_p, C.c_uint32, _u32p]),
     "bisbm_entropy": (C.c_int, [C.c_void_p, C.c_uint32, _dp]),
     "bisbm_entropy_all": (C.c_int, [C.c_void_p, _dp]),
+    "bisbm_occupied_blocks": (C.c_int, [C.c_void_p, _u32p]),
     "bisbm_entropy_accum": (C.c_int, [C.c_void_p, C.c_uint32, _dp]),
 }
 
@@ -403,6 +404,12 @@ class ChainPool:
         e = C.c_double()
         _check(self.L.bisbm_entropy(self.g.h, chain, C.byref(e)))
         return e.value
+
+    def occupied_blocks(self):
+        """[n_chains][2]: non-empty blocks per type (estimate mode's Ka, Kb)."""
+        out = np.zeros((self.n_chains, 2), dtype=np.uint32)
+        _check(self.L.bisbm_occupied_blocks(self.g.h, _p(out, C.c_uint32)))
+        return out
 
     def entropy_accum(self, chain):
         e = C.c_double()

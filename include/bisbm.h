@@ -125,7 +125,11 @@ int bisbm_set_precision(bisbm_handle* h, int mode);
  *   "inflight_div"  default in-flight bound of bisbm_anneal(max_inflight = 0) = half sweep / value (default 64)
  *   "kernel"        -1 automatic; 0 / 1 force the round-1 kernels (counts in L2 / staged, double); 5 force sweep2 with
  *                   counts in L2 (A/B runs and tests)
- *   "generic"       1: never take the Ka = Kb = 32 compile-time specialisation */
+ *   "generic"       1: never take the Ka = Kb = 32 compile-time specialisation
+ *   "vary_k"        1: estimate mode (README "estimation", no code in the reference snapshot): blocks may empty and be
+ *                   re-populated by the uniform part of the proposal (no "would empty block r" veto), the K-dependent
+ *                   terms of the description length enter dS with the number of OCCUPIED blocks, and bisbm_entropy*
+ *                   use the occupied counts too.  ka / kb of bisbm_set_chains are then upper bounds. */
 int bisbm_set_option(bisbm_handle* h, const char* name, int64_t value);
 /* which sweep kernel the last parallel call launched and how the half sweep was cut:
  * kernel 0 = round-1 sweep_kernel (double, counts in L2: hubs of degree > 255, K > 256 per type); 1 = round-1 staged
@@ -181,6 +185,8 @@ int bisbm_get_eta(bisbm_handle* h, uint32_t chain, uint32_t* eta);              
 /* blockmodel_t::entropy (src/blockmodel.cc:753-787), evaluated on the device */
 int bisbm_entropy(bisbm_handle* h, uint32_t chain, double* entropy);
 int bisbm_entropy_all(bisbm_handle* h, double* entropy);                         /* [n_chains] */
+/* number of non-empty blocks per type of every chain: ka_kb[2c], ka_kb[2c+1] (estimate mode's Ka, Kb columns) */
+int bisbm_occupied_blocks(bisbm_handle* h, uint32_t* ka_kb);
 /* blockmodel_t::get_entropy: running sum of accepted dS (src/blockmodel.hh:100) */
 int bisbm_entropy_accum(bisbm_handle* h, uint32_t chain, double* entropy_accum);
 

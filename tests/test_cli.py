@@ -118,6 +118,11 @@ def test_membership_file_marginalize_and_estimate_modes(cli, tmp_path):
     assert len(rows) == 3
     f0 = rows[0].split(",")
     assert f0[0] == "10" and f0[1] == "4" and f0[2] == "6" and float(f0[3]) < 0 and len(f0) == 4 + 1000
+    # --uni: the 1D output format (sweep, K, loglik, labels)
+    rc, out, err = run(cli, "-e", path, "-y", 500, 500, "--membership_path", mpath, "--estimate", "--uni", "-b", 5, "-t", 20, "-f", 10)
+    assert rc == 0, err
+    f0 = out.strip().split("\n")[0].split(",")
+    assert f0[0] == "10" and f0[1] == "10" and float(f0[2]) < 0 and len(f0) == 3 + 1000
     # parallel restarts
     rc, out, err = run(cli, "-e", path, "-y", 500, 500, "-n", 125, 125, 125, 125, 83, 83, 83, 83, 84, 84, "-z", 4, 6, "--chains", 16,
                        "--randomize", "-t", 100000, "-x", 2000, "-c", "abrupt_cool", "-a", 50000, "-d", 1)

@@ -483,3 +483,43 @@ def test_grid_search_driver_finds_the_planted_k(host):
     pool = host.ChainPool(graph, lab, bp[0], bp[1], 1.0)
     assert abs(pool.entropy(0) - ent.min()) <= 1e-9 * abs(ent.min())
     assert stats["moves"] == len(points) * 4 * 120 * n
+
+
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+def test_estimate_mode_variable_k(host, precision):
+    """README "estimation" mode (vary_k): blocks may empty and re-fill, the K-dependent terms of the description length
+    follow the number of occupied blocks.  Strictly sequential chains: the accumulated dS must equal the change of
+    entropy() (which counts occupied blocks in this mode) although blocks come and go; counts always equal a rebuild
+    from the labels."""
+    g = load_golden("c1_seed1")
+    na, nb, edges = g["na"], g["nb"], g["edges"]
+    graph = host.Graph(edges, na, nb)
+    C = 64
+    pool = host.ChainPool(graph, np.tile(g["labels0"], (C, 1)), 5, 5, 1.0)
+    pool.set_precision(precision)
+    pool.set_option("vary_k", 1)
+    seeds = np.arange(C, dtype=np.uint64) + 17
+    pool.randomize(seeds)
+    e0 = pool.entropy()
+    k0 = pool.occupied_blocks()
+    assert (k0 == 5).all()
+    emptied = 0
+    for rnd in range(6):
+        acc, sw = pool.anneal("constant", 2.0, 0.0, 30 * (na + nb), 10 ** 9, seeds + np.uint64(1000 * rnd), max_inflight=1)
+        kk = pool.occupied_blocks()
+        emptied += int((kk < 5).any())
+        for c in (0, 31, 63):
+            lab = pool.labels(c)
+            m, e, nr, eta = counts_from_labels(edges, na, nb, lab, 5, 5)
+            assert (pool.m(c) == m).all() and (pool.m_r(c) == e).all() and (pool.n_r(c) == nr).all() and (pool.eta(c) == eta).all()
+            assert kk[c, 0] == (nr[:5] > 0).sum() and kk[c, 1] == (nr[5:] > 0).sum()
+    assert emptied > 0       # at T = 2 on 32 nodes blocks do empty
+    e1 = pool.entropy()
+    tol = 1e-7 if precision == "fp64" else 2e-4
+    for c in (0, 31, 63):
+        assert abs((e1[c] - e0[c]) - pool.entropy_accum(c)) <= tol * abs(e0[c]), (c, e1[c] - e0[c], pool.entropy_accum(c))
+    # concurrent moves keep the counts consistent as well
+    pool.anneal("constant", 2.0, 0.0, 50 * (na + nb), 10 ** 9, seeds)
+    lab = pool.labels(5)
+    m, e, nr, eta = counts_from_labels(edges, na, nb, lab, 5, 5)
+    assert (pool.m(5) == m).all() and (pool.n_r(5) == nr).all() and (nr >= 0).all()
