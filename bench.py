@@ -576,7 +576,11 @@ def main():
     for _ in range(args.warmup):
         pool.anneal("constant", 1.0, 0.0, duration, 10 ** 18, seeds)
     if world > 1:  # warm the one collective of the path too (NCCL communicator set-up is not a sweep cost)
-        pkg.dist.init_pool_comm(pool)            # the library's own communicator (bisbm_nccl_init)
+        try:
+            pkg.dist.init_pool_comm(pool)        # the library's own communicator (bisbm_nccl_init)
+            config["collective"] = "bisbm_marginals_allreduce (ncclAllReduce behind the C ABI)"
+        except Exception as ex:                  # no loadable libnccl.so.2: torch.distributed's all-reduce on the same buffer
+            config["collective"] = "torch.distributed all_reduce (libbisbm could not set up NCCL: %s)" % str(ex)[:120]
         pool.marginals_clear()
         pool.marginalize(0, 1, 1, seeds)
         pkg.dist.allreduce_marginals(pool)

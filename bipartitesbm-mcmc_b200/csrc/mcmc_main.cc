@@ -219,6 +219,9 @@ int main(int argc, char const* argv[]) {
     size_t gpus = 1;
     if (o.has("gpus") && (!to_num(o.vals["gpus"][0], gpus) || gpus == 0)) { std::cerr << "bad value for --gpus\n"; return 1; }
     if (gpus > chains) gpus = chains;
+    // stdout carries the label line and nothing else: whatever NCCL has to say (its version banner under NCCL_DEBUG)
+    // goes to stderr unless the user chose a file
+    if (gpus > 1) setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0);
 
     // ---- initial memberships, reference src/mcmc_main.cc:243-326
     std::vector<unsigned> n, z, memberships_init;

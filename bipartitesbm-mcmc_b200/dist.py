@@ -28,6 +28,7 @@ def init_pool_comm(pool):
     box = [host.nccl_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(box, src=0)
     pool.nccl_init(world, rank, box[0])
+    pool._has_comm = True
 
 
 def allreduce_marginals(hist):
@@ -38,7 +39,11 @@ def allreduce_marginals(hist):
     if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
         return hist
     if hasattr(hist, "marginals_allreduce"):
-        hist.marginals_allreduce()
+        if getattr(hist, "_has_comm", False):
+            hist.marginals_allreduce()
+        else:   # a pool without its own communicator: torch's collective on the wrapped device histogram
+            from . import host
+            dist.all_reduce(host.marginals_tensor(hist), op=dist.ReduceOp.SUM)
     else:
         dist.all_reduce(hist, op=dist.ReduceOp.SUM)
     return hist

@@ -498,6 +498,37 @@ double ora_anneal(ora_chain* c, int schedule, float p0, float p1, uint64_t durat
     return (double)accepted / (double)duration;
 }
 
+/* NOT a reference function: anneal() with the visiting order of the GPU's parallel mode -- after the reference's
+ * shuffle of vlist, the type-a vertices are visited first (in their shuffled order, steps base .. base + na - 1),
+ * then the type-b vertices.  Everything else is ora_anneal.  The statistical-parity tests use it to tell the effect
+ * of that documented deviation (type-alternating half sweeps) from everything else. */
+double ora_anneal_alternating(ora_chain* c, int schedule, float p0, float p1, uint64_t duration, uint64_t steps_await) {
+    uint64_t N = c->n, accepted = 0, u = 0;
+    c->entropy_min = INFINITY;
+    uint64_t all_sweeps = duration / N;
+    c->sweeps_done = 0;
+    uint32_t* order = (uint32_t*)malloc(sizeof(uint32_t) * (N ? N : 1));
+    for (uint64_t sweep = 0; sweep < all_sweeps; ++sweep) {
+        ora_shuffle(c->vlist, N, &c->engine);
+        uint64_t k = 0;
+        for (uint64_t vi = 0; vi < N; ++vi) if (c->vlist[vi] < c->na) order[k++] = c->vlist[vi];
+        for (uint64_t vi = 0; vi < N; ++vi) if (c->vlist[vi] >= c->na) order[k++] = c->vlist[vi];
+        uint64_t base = N * sweep;
+        for (uint64_t vi = 0; vi < N; ++vi) {
+            double T = ora_schedule(schedule, p0, p1, base + vi);
+            if (ora_step(c, order[vi], T)) {
+                ++accepted;
+                if (c->entropy_accum < c->entropy_min) { c->entropy_min = c->entropy_accum; u = 0; }
+            }
+            if (T < 1.) ++u;
+        }
+        c->sweeps_done = sweep + 1;
+        if (u >= steps_await) { free(order); return (double)accepted / (double)((sweep + 1) * N); }
+    }
+    free(order);
+    return (double)accepted / (double)duration;
+}
+
 /* entropy (src/blockmodel.cc:753-787).  adj_map_ (std::map per node, ascending neighbour
  * id) is restated by sorting a copy of each adjacency row. */
 static int cmp_u32(const void* a, const void* b) {

@@ -49,6 +49,8 @@ ora_chain* ora_create(uint32_t n, uint32_t na, uint32_t nb, uint64_t n_edges, co
 void ora_destroy(ora_chain* c);
 void ora_init(ora_chain* c, int randomize);
 double ora_anneal(ora_chain* c, int schedule, float p0, float p1, uint64_t duration, uint64_t steps_await);
+/* anneal() with the type-alternating visiting order of the GPU's parallel mode (test aid, not a reference function) */
+double ora_anneal_alternating(ora_chain* c, int schedule, float p0, float p1, uint64_t duration, uint64_t steps_await);
 int ora_step(ora_chain* c, uint32_t v, double T);
 void ora_transition(ora_chain* c, uint32_t v, uint32_t s, double* dS, double* accu_r);
 double ora_log_q(const ora_chain* c, int n, int k);

@@ -39,6 +39,8 @@ def _load():
     L.ora_init.argtypes = [vp, C.c_int]
     L.ora_anneal.restype = dbl
     L.ora_anneal.argtypes = [vp, C.c_int, C.c_float, C.c_float, u64, u64]
+    L.ora_anneal_alternating.restype = dbl
+    L.ora_anneal_alternating.argtypes = [vp, C.c_int, C.c_float, C.c_float, u64, u64]
     L.ora_step.restype = C.c_int
     L.ora_step.argtypes = [vp, u32, dbl]
     L.ora_transition.argtypes = [vp, u32, u32, C.POINTER(dbl), C.POINTER(dbl)]
@@ -150,10 +152,13 @@ class PortChain:
     def init(self, randomize):
         self.L.ora_init(self.h, 1 if randomize else 0)
 
-    def anneal(self, schedule, p0, p1, duration, steps_await):
+    def anneal(self, schedule, p0, p1, duration, steps_await, alternate=False):
+        """alternate=True: the type-alternating visiting order of the GPU's parallel mode instead of the reference's
+        (ora_anneal_alternating; a test aid to isolate that documented deviation)."""
         if isinstance(schedule, str):
             schedule = SCHEDULES[schedule]
-        return self.L.ora_anneal(self.h, schedule, p0, p1, duration, steps_await)
+        fn = self.L.ora_anneal_alternating if alternate else self.L.ora_anneal
+        return fn(self.h, schedule, p0, p1, duration, steps_await)
 
     def step(self, v, T):
         return bool(self.L.ora_step(self.h, v, T))

@@ -50,9 +50,10 @@ def run_chain(args):
     edges, lab = _graph()
     n = NA + NB
     o = port.PortChain(n, NA, NB, edges, lab, KA, KB, 1.0, 7000 + s, 9000 + s)
-    o.init(proto == "tr")
-    sweeps = SWEEPS_TR if proto == "tr" else SWEEPS_EQ
-    acc = o.anneal("constant", 1.0, 0.0, sweeps * n, 10 ** 18)
+    o.init(proto.startswith("tr"))
+    sweeps = SWEEPS_TR if proto.startswith("tr") else SWEEPS_EQ
+    # "tr_alt": the same burn-in with the type-alternating visiting order of the GPU's parallel mode (oracle test aid)
+    acc = o.anneal("constant", 1.0, 0.0, sweeps * n, 10 ** 18, alternate=proto.endswith("_alt"))
     out = (o.entropy(), acc, nmi(o.labels(), lab))
     o.close()
     return out
@@ -73,6 +74,14 @@ def run_small(s):
 
 
 def main():
+    if "--only-alt" in sys.argv:      # add the tr_alt_* arrays to an existing fixture
+        z = dict(np.load(os.path.join(OUT, "parity_mid.npz")))
+        with Pool(min(8, os.cpu_count() or 1)) as pool:
+            res = np.array(pool.map(run_chain, [("tr_alt", s) for s in range(R)], chunksize=1))
+        z["tr_alt_entropy"], z["tr_alt_accept"], z["tr_alt_nmi"] = res[:, 0], res[:, 1], res[:, 2]
+        print("tr_alt entropy %.1f +- %.1f  accept %.4f +- %.4f  nmi %.4f" % (res[:, 0].mean(), res[:, 0].std(), res[:, 1].mean(), res[:, 1].std(), res[:, 2].mean()))
+        np.savez_compressed(os.path.join(OUT, "parity_mid.npz"), **z)
+        return
     edges, lab = _graph()
     n = NA + NB
     out = dict(na=NA, nb=NB, ka=KA, kb=KB, n_edges=NE, graph_seed=GSEED, R=R, sweeps_eq=SWEEPS_EQ, sweeps_tr=SWEEPS_TR,
@@ -90,7 +99,7 @@ def main():
                kat_dS=np.array(kd), kat_accu=np.array(ka_), init_entropy=o.entropy())
     o.close()
     with Pool(min(8, os.cpu_count() or 1)) as pool:
-        for proto in ("eq", "tr"):
+        for proto in ("eq", "tr", "tr_alt"):
             res = np.array(pool.map(run_chain, [(proto, s) for s in range(R)], chunksize=1))
             out["%s_entropy" % proto], out["%s_accept" % proto], out["%s_nmi" % proto] = res[:, 0], res[:, 1], res[:, 2]
             print(proto, "entropy %.1f +- %.1f  accept %.4f +- %.4f  nmi %.4f" % (
