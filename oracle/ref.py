@@ -73,6 +73,12 @@ def _load(log_rng):
     L.ref_spence.restype = dbl
     L.ref_spence.argtypes = [dbl]
     L.ref_init_tables.argtypes = [u64]
+    L.ref_merge_path.restype = dbl
+    L.ref_merge_path.argtypes = [vp, u64, u64, C.c_float, u64, u64]
+    L.ref_get_ka.restype = u64
+    L.ref_get_ka.argtypes = [vp]
+    L.ref_get_kb.restype = u64
+    L.ref_get_kb.argtypes = [vp]
     _libs[log_rng] = L
     return L
 
@@ -114,6 +120,14 @@ class RefChain:
         if isinstance(schedule, str):
             schedule = SCHEDULES[schedule]
         return self.L.ref_anneal(self.h, schedule, p0, p1, duration, steps_await)
+
+    def merge_path(self, KA, KB, p0, sampling_steps, steps_await):
+        """reference src/mcmc_main.cc:406-451 (labels with more blocks than -z): ladder of agg_merge + greedy sweeps, final
+        abrupt_cool anneal; returns entropy().  Afterwards labels() has (KA, KB) blocks."""
+        s = self.L.ref_merge_path(self.h, KA, KB, p0, sampling_steps, steps_await)
+        self.ka, self.kb = int(self.L.ref_get_ka(self.h)), int(self.L.ref_get_kb(self.h))
+        self.K = self.ka + self.kb
+        return s
 
     def anneal_seconds(self):
         return self.L.ref_last_anneal_seconds(self.h)

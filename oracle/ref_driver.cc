@@ -104,6 +104,37 @@ double ref_anneal(void* p, int schedule, float p0, float p1, uint64_t duration, 
 
 double ref_last_anneal_seconds(void* p) { return static_cast<ref_handle*>(p)->last_seconds; }
 
+// The reference's merge path for initial labels with MORE blocks than -z asks for (src/mcmc_main.cc:406-451, the
+// diff_a >= 0 && diff_b >= 0 branch): geospace ladder, agg_merge(engine, diff_a, diff_b, 10) per rung, one greedy sweep
+// (abrupt_cool with kwargs {0}) between rungs, then the final anneal(abrupt_cool, {p0}, sampling_steps).  The handle
+// must have been created with the labels' own (ka, kb) and initialised (ref_init(h, 0)).  Returns the final entropy().
+double ref_merge_path(void* p, uint64_t KA, uint64_t KB, float p0, uint64_t sampling_steps, uint64_t steps_await) {
+    auto* h = static_cast<ref_handle*>(p);
+    blockmodel_t& bm = *h->bm;
+    const double sigma = 1.01;
+    int diff_a = (int)bm.get_KA() - (int)KA, diff_b = (int)bm.get_KB() - (int)KB;
+    float_vec_t agg_kw(1, 0.);
+    const size_t N = h->n;
+    if (diff_a != 0 || diff_b != 0) {
+        int_vec_t ka_s, kb_s;
+        std::tie(ka_s, kb_s) = geospace(KA + diff_a, KA, KB + diff_b, KB, sigma);
+        if (ka_s.size() == 1) bm.agg_merge(h->engine, diff_a, diff_b, 10);
+        for (size_t i = 0; i + 1 < ka_s.size(); ++i) {
+            diff_a = -(ka_s[i + 1] - ka_s[i]);
+            diff_b = -(kb_s[i + 1] - kb_s[i]);
+            bm.agg_merge(h->engine, diff_a, diff_b, 10);
+            if (i != ka_s.size() - 2) h->mh.anneal(bm, &abrupt_cool_schedule, agg_kw, N * 1, steps_await, h->engine);
+        }
+    }
+    float_vec_t kw(2, 0);
+    kw[0] = p0;
+    h->mh.anneal(bm, &abrupt_cool_schedule, kw, sampling_steps, steps_await, h->engine);
+    h->ka = bm.get_KA(); h->kb = bm.get_KB();
+    return bm.entropy();
+}
+uint64_t ref_get_ka(void* p) { return static_cast<ref_handle*>(p)->bm->get_KA(); }
+uint64_t ref_get_kb(void* p) { return static_cast<ref_handle*>(p)->bm->get_KB(); }
+
 double ref_schedule(int schedule, float p0, float p1, uint64_t t) {
     float_vec_t kw(2, 0);
     kw[0] = p0; kw[1] = p1;
