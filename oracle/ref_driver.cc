@@ -14,6 +14,7 @@
 // linking it.
 #include "metropolis_hasting.cc"  // reference src/metropolis_hasting.cc, in place
 #include "graph_utilities.hh"
+#include "support/util.hh"       // geospace (reference src/support/util.hh:99-146), used by ref_merge_path
 
 #include <chrono>
 #include <cstdint>
