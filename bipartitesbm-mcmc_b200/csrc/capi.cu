@@ -128,7 +128,10 @@ struct bisbm_handle {
     uint64_t last_sweep_launches = 0, last_marginal_launches = 0;
     uint32_t last_wpc = 0, last_cpg = 0, last_slice = 0;   // launch plan of the last half sweep
     int last_kernel = -1;                                   // KERN_* of the last parallel call
-    bool lab32_stale = false;   // the staged kernels only write the u8 label shadow; i32 labels refreshed on demand
+    // two label arrays, refreshed from each other on demand: the canonical i32 labels (replay, round-1 kernels, 32-bit
+    // import / export) and the u8 shadow (sweep2 kernels, 8-bit import / export, marginals).  At most one is stale.
+    bool lab32_stale = false;
+    bool lab8_stale = true;
 };
 
 namespace {
@@ -402,8 +405,14 @@ int ensure_smem_attr(bisbm_handle* h, const void* fn, int bytes) {
     return BISBM_OK;
 }
 
+int sync_labels8(bisbm_handle* h);
+int sync_labels32(bisbm_handle* h);
+void wrote_labels32(bisbm_handle* h);
+void wrote_labels8(bisbm_handle* h);
+
 int rebuild_counts(bisbm_handle* h) {
     const size_t KK = (size_t)h->KA + h->KB;
+    const bool from8 = h->lab32_stale;      // the u8 shadow holds the current labels (8-bit import, sweep2 kernels)
     CU(cudaMemsetAsync(h->d_m, 0, (size_t)h->C * h->KA * h->KB * sizeof(int32_t), h->stream));
     CU(cudaMemsetAsync(h->d_e, 0, (size_t)h->C * KK * sizeof(int32_t), h->stream));
     CU(cudaMemsetAsync(h->d_nr, 0, (size_t)h->C * KK * sizeof(int32_t), h->stream));
@@ -411,11 +420,13 @@ int rebuild_counts(bisbm_handle* h) {
     const size_t staged_bytes = ((size_t)h->KA * h->KB + KK) * 128;
     if (staged_bytes <= 200 * 1024 && h->n >= 4096) {
         // m_rs / n_r accumulated per CTA in shared memory (the 2E * C atomics of compute_m stay on chip)
-        int rc = ensure_smem_attr(h, (const void*)build_counts_staged_kernel, 200 * 1024);
+        int rc = from8 ? ensure_smem_attr(h, (const void*)build_counts_staged_kernel<uint8_t>, 200 * 1024)
+                       : ensure_smem_attr(h, (const void*)build_counts_staged_kernel<int32_t>, 200 * 1024);
         if (rc) return rc;
         const uint32_t n_groups = h->C / 32;
         const uint32_t cpg = std::max<uint32_t>(1, (uint32_t)h->sm_count / n_groups);
-        build_counts_staged_kernel<<<n_groups * cpg, 1024, staged_bytes, h->stream>>>(gview(h), sview(h), h->n_chains, cpg);
+        if (from8) build_counts_staged_kernel<uint8_t><<<n_groups * cpg, 1024, staged_bytes, h->stream>>>(gview(h), sview(h), h->d_lab8, h->n_chains, cpg);
+        else build_counts_staged_kernel<int32_t><<<n_groups * cpg, 1024, staged_bytes, h->stream>>>(gview(h), sview(h), h->d_labels, h->n_chains, cpg);
         const uint32_t tot = h->n_chains * (uint32_t)KK;
         build_e_kernel<<<(tot + 255) / 256, 256, 0, h->stream>>>(sview(h), h->n_chains);
         CU(cudaGetLastError());
@@ -426,7 +437,8 @@ int rebuild_counts(bisbm_handle* h) {
     if (warps) {
         const uint64_t blocks = (warps + wpc - 1) / wpc;
         if (blocks > 0x7fffffffull) return fail(BISBM_ERR_ARG, "n * chains too large for one launch");
-        build_counts_kernel<<<(unsigned)blocks, wpc * 32, 0, h->stream>>>(gview(h), sview(h), h->n_chains);
+        if (from8) build_counts_kernel<uint8_t><<<(unsigned)blocks, wpc * 32, 0, h->stream>>>(gview(h), sview(h), h->d_lab8, h->n_chains);
+        else build_counts_kernel<int32_t><<<(unsigned)blocks, wpc * 32, 0, h->stream>>>(gview(h), sview(h), h->d_labels, h->n_chains);
     }
     const uint32_t tot = h->n_chains * (uint32_t)KK;
     build_e_kernel<<<(tot + 255) / 256, 256, 0, h->stream>>>(sview(h), h->n_chains);
@@ -453,6 +465,9 @@ int need_replay(bisbm_handle* h, uint32_t chain, ReplaySlot** out) {
     auto it = h->replay.find(chain);
     if (it == h->replay.end()) return fail(BISBM_ERR_STATE, "chain %u: call bisbm_replay_init first", chain);
     *out = &it->second;
+    rc = sync_labels32(h);      // replay reads and writes the canonical labels
+    if (rc) return rc;
+    wrote_labels32(h);
     return BISBM_OK;
 }
 
@@ -633,7 +648,7 @@ int launch_sweep2_t(bisbm_handle* h, const SweepParams& P, const LaunchPlan& lp,
     if (rc) return rc;
     sweep2_kernel<R, KF, TYPE, STAGED, NT><<<grid, lp.wpc * 32, lp.smem_bytes, h->stream>>>(P);
     CU(cudaGetLastError());
-    h->lab32_stale = true;    // the staged kernels only write the u8 label shadow
+    wrote_labels8(h);         // the sweep2 kernels only write the u8 label shadow
     return BISBM_OK;
 }
 
@@ -671,6 +686,14 @@ SweepParams base_params(bisbm_handle* h, uint32_t type) {
 int launch_full_sweep(bisbm_handle* h, int schedule, float p0, float p1, uint64_t sweep_in_call, uint32_t max_inflight) {
     uint32_t wpc = 32;
     const int kernel = plan_kernel(h, &wpc);
+    if (!kern_is_s2(kernel)) {   // the round-1 kernels read the canonical labels (counts in L2) or the shadow (staged) and write the canonical ones
+        int rc = sync_labels32(h);
+        if (rc) return rc;
+    }
+    {
+        int rc = sync_labels8(h);
+        if (rc) return rc;
+    }
     for (uint32_t type = 0; type < 2; ++type) {
         const uint32_t nv = type ? h->nb : h->na;
         if (nv == 0) continue;
@@ -703,11 +726,14 @@ int launch_full_sweep(bisbm_handle* h, int schedule, float p0, float p1, uint64_
             P.exclusive = sliced ? 0 : 1;
             P.sweep = h->sweep_epoch;
             P.step_base = sweep_in_call * (uint64_t)h->n + (type ? h->na : 0);
-            P.schedule = schedule; P.p0 = p0; P.p1 = p1;
+            P.schedule = schedule; P.p0 = p0; P.p1 = p1; P.beta0 = 1.0 / (double)p0;
             const unsigned grid = P.n_groups * lp.ctas_per_group;
             if (s2 && !kern_is_f32(kernel)) rc = launch_sweep2<double>(h, P, lp, grid);
             else if (s2) rc = launch_sweep2<float>(h, P, lp, grid);
-            else rc = lp.smem ? launch_sweep_h<true>(h, P, lp) : launch_sweep_h<false>(h, P, lp);
+            else {
+                rc = lp.smem ? launch_sweep_h<true>(h, P, lp) : launch_sweep_h<false>(h, P, lp);
+                if (!lp.smem) wrote_labels32(h);   // (the staged round-1 kernel writes both arrays)
+            }
             if (rc) return rc;
             h->last_launches += 1;
             h->last_sweep_launches += 1;
@@ -722,17 +748,20 @@ int launch_full_sweep(bisbm_handle* h, int schedule, float p0, float p1, uint64_
     return BISBM_OK;
 }
 
-// refresh the u8 label shadow from the canonical i32 labels (start of every parallel call: replay
-// moves, set_chains and randomize only write the canonical array)
+// refresh the u8 label shadow from the canonical i32 labels (replay moves, 32-bit set_chains, randomize and the round-1
+// kernels only write the canonical array); no-op while the shadow is current
 int sync_labels8(bisbm_handle* h) {
+    if (!h->lab8_stale) return BISBM_OK;
     const uint64_t total = (uint64_t)h->n * h->C;
     const uint64_t threads = (total + 3) / 4;
     labels8_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, h->stream>>>(h->d_labels, h->d_lab8, total);
     CU(cudaGetLastError());
+    h->lab8_stale = false;
     return BISBM_OK;
 }
 
-// refresh the canonical i32 labels from the u8 shadow (the fp32 kernel only writes the shadow)
+// refresh the canonical i32 labels from the u8 shadow (the sweep2 kernels and the 8-bit import only write the shadow);
+// called by whatever reads the canonical array, not eagerly
 int sync_labels32(bisbm_handle* h) {
     if (!h->lab32_stale) return BISBM_OK;
     const uint64_t total = (uint64_t)h->n * h->C;
@@ -742,6 +771,9 @@ int sync_labels32(bisbm_handle* h) {
     h->lab32_stale = false;
     return BISBM_OK;
 }
+// after a kernel wrote the canonical labels only / the shadow only
+void wrote_labels32(bisbm_handle* h) { h->lab32_stale = false; h->lab8_stale = true; }
+void wrote_labels8(bisbm_handle* h) { h->lab8_stale = false; h->lab32_stale = true; }
 
 int upload_seeds(bisbm_handle* h, const uint64_t* seeds) {
     std::vector<uint64_t> s(h->C, 0);
@@ -944,10 +976,14 @@ static int set_chains_impl(bisbm_handle* h, uint32_t n_chains, const uint32_t* k
                            const InT* labels, double eps) {
     if (!labels) return fail(BISBM_ERR_ARG, "null argument");
     bool same_model = false;
+    const bool had_chains = h->d_labels != nullptr;
     int rc0 = alloc_chains(h, n_chains, ka, kb, eps, &same_model);
     if (rc0) return rc0;
+    if (!same_model || !had_chains) { h->lab32_stale = false; h->lab8_stale = true; }   // nothing to compare with
     const uint32_t n = h->n, C = h->C;
-    // host labels [chain][node], global ids  ->  chain-minor, type-local (device transpose)
+    constexpr bool kU8 = sizeof(InT) == 1;
+    // host labels [chain][node], global ids  ->  chain-minor, type-local (device transpose).  8-bit labels go straight
+    // into the u8 shadow (what the sweep2 kernels read); 32-bit labels into the canonical array.
     {
         InT* stage = reinterpret_cast<InT*>(h->d_labels_tmp);
         CU(cudaMemcpyAsync(stage, labels, (size_t)n_chains * n * sizeof(InT), cudaMemcpyHostToDevice, h->stream));
@@ -955,10 +991,20 @@ static int set_chains_impl(bisbm_handle* h, uint32_t n_chains, const uint32_t* k
         uint32_t* d_changed = reinterpret_cast<uint32_t*>(h->d_accepted + 1);
         CU(cudaMemsetAsync(d_bad, 0xff, sizeof(unsigned long long), h->stream));
         CU(cudaMemsetAsync(d_changed, 0, sizeof(unsigned long long), h->stream));
-        dim3 grid((n + 31) / 32, C / 32), block(32, 8);
-        // (in place: every element is read, compared and rewritten by one thread)
-        import_labels_kernel<InT><<<grid, block, 0, h->stream>>>(stage, h->d_labels, n, h->na, n_chains, C, h->d_ka, h->d_kb, d_bad,
-                                                              same_model ? h->d_labels : nullptr, d_changed);
+        if constexpr (kU8) {
+            if (same_model) { int rc = sync_labels8(h); if (rc) return rc; }
+            dim3 grid((n + L8_NODES - 1) / L8_NODES, C / 32);
+            // (in place: every 16-byte piece is read, compared and rewritten by one thread)
+            import_labels8_kernel<<<grid, 256, 0, h->stream>>>(reinterpret_cast<const uint8_t*>(stage), h->d_lab8, n, h->na, n_chains, C,
+                                                               h->d_ka, h->d_kb, d_bad, same_model ? h->d_lab8 : nullptr, d_changed);
+            wrote_labels8(h);
+        } else {
+            if (same_model) { int rc = sync_labels32(h); if (rc) return rc; }
+            dim3 grid((n + 31) / 32, C / 32), block(32, 8);
+            import_labels_kernel<InT><<<grid, block, 0, h->stream>>>(stage, h->d_labels, n, h->na, n_chains, C, h->d_ka, h->d_kb, d_bad,
+                                                                  same_model ? h->d_labels : nullptr, d_changed);
+            wrote_labels32(h);
+        }
         CU(cudaGetLastError());
         unsigned long long res[2] = {0, 0};
         CU(cudaMemcpyAsync(res, d_bad, sizeof res, cudaMemcpyDeviceToHost, h->stream));
@@ -1007,12 +1053,15 @@ int bisbm_randomize(bisbm_handle* h, const uint64_t* seeds) {
     rc = upload_seeds(h, seeds);
     if (rc) return rc;
     if (!h->d_labels_tmp) CU(cudaMalloc(&h->d_labels_tmp, (size_t)h->n * h->C * sizeof(int32_t)));
+    rc = sync_labels32(h);
+    if (rc) return rc;
     const uint64_t tot = (uint64_t)h->n * h->C;
     randomize_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(
         gview(h), h->d_labels, h->d_labels_tmp, h->C, h->n_chains, h->d_seeds, feistel_half_bits(h->na),
         feistel_half_bits(h->nb));
     CU(cudaGetLastError());
     std::swap(h->d_labels, h->d_labels_tmp);
+    wrote_labels32(h);
     rc = rebuild_counts(h);
     if (rc) return rc;
     CU(cudaMemsetAsync(h->d_dS, 0, h->C * sizeof(double), h->stream));
@@ -1033,8 +1082,11 @@ int bisbm_replay_init(bisbm_handle* h, uint32_t chain, uint32_t engine_seed, uin
         CU(cudaMalloc(&sl.d_vlist, (size_t)h->n * sizeof(uint32_t)));
         CU(cudaMalloc(&sl.d_kh, (size_t)std::max(h->KA, h->KB) * sizeof(int32_t)));
     }
+    rc = sync_labels32(h);
+    if (rc) return rc;
     replay_init_kernel<<<1, 32, 0, h->stream>>>(rctx(h, chain, sl), engine_seed, gen_seed, randomize);
     CU(cudaGetLastError());
+    wrote_labels32(h);
     if (randomize) {  // compute_n_r / k / m / m_r / eta_rk after the shuffle
         rc = rebuild_counts(h);
         if (rc) return rc;
@@ -1182,8 +1234,6 @@ int bisbm_anneal(bisbm_handle* h, int schedule, float p0, float p1, uint64_t dur
             CU(cudaStreamSynchronize(h->stream));
         }
     }
-    rc = sync_labels32(h);
-    if (rc) return rc;
     CU(cudaEventRecord(h->ev1, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     CU(cudaGetLastError());
@@ -1271,8 +1321,6 @@ int bisbm_marginalize(bisbm_handle* h, uint64_t burn_in, uint64_t sweeps, uint64
             h->last_launches += 1;
         }
     }
-    rc = sync_labels32(h);
-    if (rc) return rc;
     CU(cudaEventRecord(h->ev1, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     CU(cudaGetLastError());
@@ -1326,6 +1374,7 @@ static int set_chains_equal_blocks(bisbm_handle* h, uint32_t n_chains, const uin
     const uint64_t tot = (uint64_t)h->n * h->C;
     equal_blocks_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(h->d_labels, h->n, h->na, h->nb, h->C, h->n_chains, h->d_ka, h->d_kb);
     CU(cudaGetLastError());
+    wrote_labels32(h);
     rc = rebuild_counts(h);
     if (rc) return rc;
     CU(cudaStreamSynchronize(h->stream));
@@ -1456,7 +1505,7 @@ int bisbm_parallel_transition(bisbm_handle* h, uint32_t chain, uint32_t v, uint3
     SweepParams P = base_params(h, type);
     P.n_groups = 1; P.group_offset = chain / 32;
     P.ctas_per_group = 1; P.warps_used = 1; P.pos_begin = 0; P.pos_end = 1; P.exclusive = 1;
-    P.schedule = BISBM_CONSTANT; P.p0 = 1.0f; P.p1 = 0.0f;
+    P.schedule = BISBM_CONSTANT; P.p0 = 1.0f; P.p1 = 0.0f; P.beta0 = 1.0;
     P.kat_mode = 1; P.kat_chain = chain; P.kat_v = v; P.kat_s = va ? s : s - ka;
     const bool stale = h->lab32_stale;
     rc = kern_is_f32(kernel) ? launch_sweep2<float>(h, P, lp, 1) : launch_sweep2<double>(h, P, lp, 1);
@@ -1608,8 +1657,17 @@ static int get_all_labels_impl(bisbm_handle* h, OutT* labels) {
     const uint32_t n = h->n, C = h->C;
     if (!h->d_labels_tmp) CU(cudaMalloc(&h->d_labels_tmp, (size_t)n * C * sizeof(int32_t)));
     OutT* stage = reinterpret_cast<OutT*>(h->d_labels_tmp);
-    dim3 grid((n + 31) / 32, C / 32), block(32, 8);
-    export_labels_kernel<OutT><<<grid, block, 0, h->stream>>>(h->d_labels, stage, n, h->na, h->n_chains, C, h->d_ka);
+    if constexpr (sizeof(OutT) == 1) {      // 8-bit labels: straight from the u8 shadow
+        rc = sync_labels8(h);
+        if (rc) return rc;
+        dim3 grid((n + L8_NODES - 1) / L8_NODES, C / 32);
+        export_labels8_kernel<<<grid, 256, 0, h->stream>>>(h->d_lab8, reinterpret_cast<uint8_t*>(stage), n, h->na, h->n_chains, C, h->d_ka);
+    } else {
+        rc = sync_labels32(h);
+        if (rc) return rc;
+        dim3 grid((n + 31) / 32, C / 32), block(32, 8);
+        export_labels_kernel<OutT><<<grid, block, 0, h->stream>>>(h->d_labels, stage, n, h->na, h->n_chains, C, h->d_ka);
+    }
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(labels, stage, (size_t)h->n_chains * n * sizeof(OutT), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
@@ -1632,6 +1690,8 @@ int bisbm_get_labels(bisbm_handle* h, uint32_t chain, uint32_t* labels) {
     if (rc) return rc;
     if (chain >= h->n_chains) return fail(BISBM_ERR_ARG, "chain %u out of range", chain);
     const uint32_t n = h->n;
+    rc = sync_labels32(h);
+    if (rc) return rc;
     std::vector<int32_t> lab(n);
     CU(cudaStreamSynchronize(h->stream));
     CU(cudaMemcpy2D(lab.data(), sizeof(int32_t), h->d_labels + chain, (size_t)h->C * sizeof(int32_t), sizeof(int32_t),

@@ -81,6 +81,7 @@ struct SweepParams {
     uint32_t kat_mode;               // 1: evaluate ONE forced proposal (kat_v -> own-type block kat_s of chain kat_chain) and write
     uint32_t kat_chain, kat_v, kat_s;   //    {dS, log accu_r} to kat_out instead of accepting / committing (bisbm_parallel_transition)
     double* kat_out;
+    double beta0;                    // 1 / p0, computed once on the host (constant schedule: 1/T of every step)
     uint32_t vary_k;                 // estimate mode (README "estimation"): blocks may empty and be re-populated; the K-dependent
                                      // prior terms of the description length enter dS with the OCCUPIED block counts
 };

@@ -11,7 +11,9 @@ namespace bisbm {
 
 // ---- state construction (init_bisbm: compute_n_r / compute_m / compute_m_r / compute_eta_rk,
 //      reference src/blockmodel.cc:681-746).  lane = chain, one warp per vertex. ----
-__global__ void build_counts_kernel(GraphView G, StateView S, uint32_t n_chains) {
+// LabT = int32_t (canonical labels) or uint8_t (the u8 shadow, when that is the array holding the current labels)
+template <typename LabT>
+__global__ void build_counts_kernel(GraphView G, StateView S, const LabT* __restrict__ labels, uint32_t n_chains) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t wpc = blockDim.x >> 5;
     const uint32_t n_groups = S.C / 32;
@@ -24,14 +26,14 @@ __global__ void build_counts_kernel(GraphView G, StateView S, uint32_t n_chains)
     if (c >= n_chains) return;
     const uint32_t KA = S.KA, KB = S.KB, W = S.W, KK = KA + KB;
     const bool tb = v >= G.na;
-    const uint32_t b = (uint32_t)S.labels[(size_t)v * S.C + c];
+    const uint32_t b = (uint32_t)labels[(size_t)v * S.C + c];
     const uint32_t slot = (tb ? KA : 0) + b;
     atomicAdd(&S.nr[((size_t)group * KK + slot) * GROUP + lane], 1);
     atomicAdd(&S.eta[(((size_t)group * KK + slot) * W + G.degidx[v]) * GROUP + lane], 1);
     if (!tb) {
         int32_t* M = S.m + (((size_t)group * KA + b) * KB) * GROUP + lane;
         for (uint32_t e = G.row_ptr[v]; e < G.row_ptr[v + 1]; ++e) {
-            const uint32_t t = (uint32_t)S.labels[(size_t)G.col[e] * S.C + c];
+            const uint32_t t = (uint32_t)labels[(size_t)G.col[e] * S.C + c];
             atomicAdd(&M[(size_t)t * GROUP], 1);
         }
     }
@@ -41,8 +43,9 @@ __global__ void build_counts_kernel(GraphView G, StateView S, uint32_t n_chains)
 // sweep kernels) and added to the global counts once at the end: 2E * C global atomics become shared-memory ones.
 // Used when the group's m_rs fits; eta (K x W x 32 per group) still goes straight to global memory.
 // grid = n_groups * ctas_per_group, dynamic shared memory = (KA*KB + KA+KB) * 128 bytes.
-__global__ void __launch_bounds__(1024, 1) build_counts_staged_kernel(GraphView G, StateView S, uint32_t n_chains,
-                                                                      uint32_t ctas_per_group) {
+template <typename LabT>
+__global__ void __launch_bounds__(1024, 1) build_counts_staged_kernel(GraphView G, StateView S, const LabT* __restrict__ labels,
+                                                                      uint32_t n_chains, uint32_t ctas_per_group) {
     extern __shared__ __align__(16) int32_t sm_counts[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
     const uint32_t n_groups = S.C / 32;
@@ -58,7 +61,7 @@ __global__ void __launch_bounds__(1024, 1) build_counts_staged_kernel(GraphView 
     for (uint32_t v = cta * wpc + warp; v < G.n; v += ctas_per_group * wpc) {
         if (!live) continue;
         const bool tb = v >= G.na;
-        const uint32_t b = (uint32_t)S.labels[(size_t)v * S.C + c];
+        const uint32_t b = (uint32_t)labels[(size_t)v * S.C + c];
         const uint32_t slot = (tb ? KA : 0) + b;
         atomicAdd(&sN[slot * 32 + lane], 1);
         atomicAdd(&gETA[((size_t)slot * W + G.degidx[v]) * GROUP], 1);
@@ -66,7 +69,7 @@ __global__ void __launch_bounds__(1024, 1) build_counts_staged_kernel(GraphView 
             int32_t* const row = sM + (b * KB) * 32 + lane;
             const uint32_t e1 = G.row_ptr[v + 1];
             for (uint32_t e = G.row_ptr[v]; e < e1; ++e)
-                atomicAdd(&row[(uint32_t)S.labels[(size_t)G.col[e] * S.C + c] * 32], 1);
+                atomicAdd(&row[(uint32_t)labels[(size_t)G.col[e] * S.C + c] * 32], 1);
         }
     }
     __syncthreads();
@@ -169,6 +172,91 @@ __global__ void export_labels_kernel(const int32_t* __restrict__ in, OutT* __res
     for (uint32_t j = threadIdx.y; j < 32; j += blockDim.y) {
         const uint32_t c = c0 + j, v = v0 + threadIdx.x;
         if (c < n_chains && v < n) out[(size_t)c * n + v] = (OutT)tile[threadIdx.x][j];
+    }
+}
+
+// ---- 8-bit label import / export straight to / from the u8 shadow (K per type <= 256): host layout u8 [chain][node] with
+//      GLOBAL block ids  <->  u8 [node][C] chain-minor, type-local.  Tiles of 32 chains x 128 nodes through shared memory;
+//      with n a multiple of 16 both sides move 16 bytes per thread.  grid = (ceil(n/128), C/32), 256 threads.
+//      `prev` (may be null, may alias `out`): the labels held now; *changed is set when an imported label differs. ----
+enum { L8_NODES = 128, L8_PITCH = 132 };
+__global__ void __launch_bounds__(256) import_labels8_kernel(const uint8_t* __restrict__ in, uint8_t* out, uint32_t n, uint32_t na,
+                                                             uint32_t n_chains, uint32_t C, const uint32_t* __restrict__ ka,
+                                                             const uint32_t* __restrict__ kb, unsigned long long* bad,
+                                                             const uint8_t* prev, uint32_t* changed) {
+    __shared__ __align__(16) uint8_t tile[32][L8_PITCH];
+    __shared__ uint32_t s_ka[32], s_kb[32];
+    const uint32_t v0 = blockIdx.x * L8_NODES, c0 = blockIdx.y * 32, tid = threadIdx.x;
+    if (tid < 32) { const uint32_t c = c0 + tid; s_ka[tid] = c < n_chains ? ka[c] : 1u; s_kb[tid] = c < n_chains ? kb[c] : 1u; }
+    {   // rows of the host array: thread -> chain tid/8, 16 nodes at (tid%8)*16
+        const uint32_t j = tid >> 3, q = (tid & 7u) * 16u, c = c0 + j;
+        uint4 w = make_uint4(0, 0, 0, 0);
+        if (c < n_chains) {
+            const uint8_t* src = in + (size_t)c * n + v0 + q;
+            if ((n & 15u) == 0u && v0 + q + 16u <= n) w = *reinterpret_cast<const uint4*>(src);
+            else {
+                uint8_t b[16];
+                for (uint32_t k = 0; k < 16; ++k) b[k] = (v0 + q + k < n) ? src[k] : (uint8_t)0;
+                memcpy(&w, b, 16);
+            }
+        }
+        uint32_t* t = reinterpret_cast<uint32_t*>(&tile[j][q]);
+        t[0] = w.x; t[1] = w.y; t[2] = w.z; t[3] = w.w;
+    }
+    __syncthreads();
+    // device rows: thread -> node tid/2, 16 chains at (tid%2)*16
+    const uint32_t i = tid >> 1, h = (tid & 1u) * 16u, v = v0 + i;
+    bool diff = false;
+    if (v < n) {
+        uint8_t o[16];
+#pragma unroll
+        for (uint32_t k = 0; k < 16; ++k) {
+            const uint32_t cl = h + k, c = c0 + cl, g = tile[cl][i];
+            uint32_t l = 0;
+            if (c < n_chains) {
+                const uint32_t kac = s_ka[cl], kbc = s_kb[cl];
+                bool ok;
+                if (v < na) { ok = g < kac; l = g; }
+                else { ok = (g >= kac) && (g < kac + kbc); l = g - kac; }
+                if (!ok) { atomicMin(bad, 1ull + (unsigned long long)c * n + v); l = 0; }
+            }
+            o[k] = (uint8_t)l;
+        }
+        uint4 w; memcpy(&w, o, 16);
+        uint4* dst = reinterpret_cast<uint4*>(out + (size_t)v * C + c0 + h);
+        if (prev) {
+            const uint4 p = *reinterpret_cast<const uint4*>(prev + (size_t)v * C + c0 + h);
+            diff = (p.x != w.x) || (p.y != w.y) || (p.z != w.z) || (p.w != w.w);
+        }
+        *dst = w;
+    }
+    if (changed && __any_sync(0xffffffffu, diff) && ((tid & 31u) == 0)) atomicOr(changed, 1u);
+}
+
+__global__ void __launch_bounds__(256) export_labels8_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, uint32_t n,
+                                                             uint32_t na, uint32_t n_chains, uint32_t C, const uint32_t* __restrict__ ka) {
+    __shared__ __align__(16) uint8_t tile[32][L8_PITCH];
+    __shared__ uint32_t s_ka[32];
+    const uint32_t v0 = blockIdx.x * L8_NODES, c0 = blockIdx.y * 32, tid = threadIdx.x;
+    if (tid < 32) { const uint32_t c = c0 + tid; s_ka[tid] = c < n_chains ? ka[c] : 0u; }
+    __syncthreads();
+    {
+        const uint32_t i = tid >> 1, h = (tid & 1u) * 16u, v = v0 + i;
+        uint8_t b[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        if (v < n) {
+            const uint4 w = *reinterpret_cast<const uint4*>(in + (size_t)v * C + c0 + h);
+            memcpy(b, &w, 16);
+        }
+#pragma unroll
+        for (uint32_t k = 0; k < 16; ++k) tile[h + k][i] = (uint8_t)(b[k] + ((v >= na) ? s_ka[h + k] : 0u));
+    }
+    __syncthreads();
+    const uint32_t j = tid >> 3, q = (tid & 7u) * 16u, c = c0 + j;
+    if (c < n_chains && v0 + q < n) {
+        const uint32_t* t = reinterpret_cast<const uint32_t*>(&tile[j][q]);
+        uint8_t* dst = out + (size_t)c * n + v0 + q;
+        if ((n & 15u) == 0u && v0 + q + 16u <= n) *reinterpret_cast<uint4*>(dst) = make_uint4(t[0], t[1], t[2], t[3]);
+        else for (uint32_t k = 0; k < 16 && v0 + q + k < n; ++k) dst[k] = tile[j][q + k];
     }
 }
 

@@ -478,6 +478,55 @@ def test_u8_labels_round_trip_and_rebuild_skip(host):
         pool.set_labels(bad)
 
 
+def test_label_arrays_stay_coherent(host):
+    """The handle keeps two label arrays (canonical i32, u8 shadow) and refreshes one from the other on demand.  Whatever
+    the order of 8-bit / 32-bit imports, parallel sweeps, replay moves and exports, every view shows the same labels and
+    the counts equal a rebuild from them.  n is a multiple of 16 (the 16-byte paths of the 8-bit import / export) and
+    large enough for the staged count builder."""
+    na = nb = 2560
+    ka, kb = 6, 9
+    edges = planted(na, nb, ka, kb, 40000, 3)
+    graph = host.Graph(edges, na, nb)
+    C = 45
+    lab0 = planted_labels(na, nb, ka, kb)
+    rng = np.random.default_rng(1)
+    labs = np.tile(lab0, (C, 1)).astype(np.uint8)
+    for c in range(C):      # every chain different
+        idx = rng.integers(0, na, 200)
+        labs[c, idx] = rng.integers(0, ka, 200)
+        idx = na + rng.integers(0, nb, 200)
+        labs[c, idx] = ka + rng.integers(0, kb, 200)
+    pool = host.ChainPool(graph, labs.astype(np.uint32), ka, kb, 1.0)
+    pool.set_labels(labs)                                    # 8-bit import over a 32-bit state: same labels, counts kept
+    assert (pool.labels() == labs).all()
+    check_invariants(pool, edges, na, nb, [0, 31, 32, 44])
+    labs2 = labs.copy(); labs2[44, na + 5] = ka + (labs2[44, na + 5] - ka + 1) % kb
+    pool.set_labels(labs2)                                   # 8-bit import, one label changed: counts rebuilt from the shadow
+    check_invariants(pool, edges, na, nb, [0, 44])
+    out8 = pool.labels(out=np.zeros((C, na + nb), dtype=np.uint8))
+    assert (out8 == labs2).all() and (pool.labels() == labs2).all() and (pool.labels(44) == labs2[44]).all()
+    seeds = np.arange(C, dtype=np.uint64) + 9
+    pool.anneal("constant", 1.0, 0.0, 3 * (na + nb), 10 ** 9, seeds)     # sweep2: writes the shadow only
+    a8 = pool.labels(out=np.zeros((C, na + nb), dtype=np.uint8))
+    a32 = pool.labels()
+    assert (a8 == a32).all() and not (a32 == labs2).all()
+    check_invariants(pool, edges, na, nb, [0, 17, 44])
+    pool.replay_init(3, 77)                                  # replay: reads and writes the canonical labels of chain 3
+    pool.replay_anneal(3, "constant", 1.0, 0.0, 2 * (na + nb), 10 ** 9)
+    b32 = pool.labels()
+    assert not (b32[3] == a32[3]).all() and (np.delete(b32, 3, 0) == np.delete(a32, 3, 0)).all()
+    pool.anneal("constant", 1.0, 0.0, 2 * (na + nb), 10 ** 9, seeds)     # the shadow must have picked up the replay moves
+    check_invariants(pool, edges, na, nb, [3, 4, 44])
+    c8 = pool.labels(out=np.zeros((C, na + nb), dtype=np.uint8))
+    pool.set_labels(c8)                                      # unchanged 8-bit labels: shortcut
+    pool.randomize(seeds)                                    # reads the canonical labels
+    check_invariants(pool, edges, na, nb, [0, 3, 44])
+    assert (np.sort(pool.labels(7)[:na]) == np.sort(c8[7, :na])).all()   # a permutation within the type
+    bad = c8.copy(); bad[2, na] = 0                          # a type-a block id on a type-b node
+    with pytest.raises(host.BisbmError):
+        pool.set_labels(bad)
+
+
 def test_grid_search_driver_finds_the_planted_k(host):
     """BASELINE configs[3] through the in-process (Ka, Kb) search driver (bisbm_grid_search): a grid around the planted
     (4, 6) of bisbm-1000 plus two large-K points (a different K class: separate pool over the shared graph), 4 restarts
