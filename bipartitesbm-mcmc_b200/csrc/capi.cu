@@ -19,11 +19,13 @@
 #include <map>
 #include <set>
 #include <memory>
+#include <numeric>
 #include <string>
 #include <vector>
 
 #include "ingest.cuh"
 #include "replay.cuh"
+#include "merge.cuh"
 #include "sweep_aux.cuh"
 #include "sweep2.cuh"
 
@@ -1187,6 +1189,310 @@ int bisbm_replay_rng_words(bisbm_handle* h, uint32_t chain, uint64_t* engine_wor
     if (gen_words) *gen_words = ((uint64_t)hs.gen[626] << 32) | hs.gen[625];
     return BISBM_OK;
 }
+
+}  // extern "C"
+
+// ---------------------------------------------------------------- agglomerative merge / split (replay chains)
+namespace {
+
+struct MergeScratch {
+    uint32_t *badj = nullptr, *badj_cnt = nullptr, *cand = nullptr, *n_cand = nullptr, *seen = nullptr, *first = nullptr, *map = nullptr;
+    double* cand_dS = nullptr;
+    ~MergeScratch() {
+        cudaFree(badj); cudaFree(badj_cnt); cudaFree(cand); cudaFree(n_cand); cudaFree(seen); cudaFree(first); cudaFree(map); cudaFree(cand_dS);
+    }
+};
+
+MergeCtx mctx(bisbm_handle* h, uint32_t chain, const ReplaySlot& sl, const MergeScratch& sc) {
+    MergeCtx x;
+    x.c = chain_ref(sview(h), chain, h->h_ka[chain], h->h_kb[chain]);
+    x.tb = tview(h, true);
+    x.rs = sl.d_rs;
+    x.eps = h->eps;
+    x.na = h->na; x.n = h->n;
+    x.badj = sc.badj; x.badj_cnt = sc.badj_cnt; x.stride = std::max(h->h_ka[chain], h->h_kb[chain]);
+    x.cand = sc.cand; x.cand_dS = sc.cand_dS; x.n_cand = sc.n_cand; x.seen = sc.seen; x.first = sc.first; x.map = sc.map;
+    return x;
+}
+
+// new block counts of one chain: host copy, device copy, counts rebuilt from the labels (init_bisbm)
+int set_chain_k(bisbm_handle* h, uint32_t chain, uint32_t ka, uint32_t kb) {
+    if (ka > h->KA || kb > h->KB) return fail(BISBM_ERR_STATE, "chain %u: (%u, %u) blocks exceed the pool's strides (%u, %u)", chain, ka, kb, h->KA, h->KB);
+    h->h_ka[chain] = ka; h->h_kb[chain] = kb;
+    CU(cudaMemcpyAsync(h->d_ka + chain, &h->h_ka[chain], sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_kb + chain, &h->h_kb[chain], sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return rebuild_counts(h);
+}
+
+// apply_block_moves (src/blockmodel.cc:505-553): every impacted block becomes the smallest member of its accepted set,
+// then the blocks are renumbered in order of first appearance over the nodes and the counts rebuilt (init_bisbm)
+int apply_block_moves(bisbm_handle* h, uint32_t chain, const ReplaySlot& sl, MergeScratch& sc, const std::vector<uint32_t>& rep) {
+    const uint32_t K = h->h_ka[chain] + h->h_kb[chain];
+    CU(cudaMemcpyAsync(sc.map, rep.data(), K * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemsetAsync(sc.first, 0xff, K * sizeof(uint32_t), h->stream));
+    MergeCtx x = mctx(h, chain, sl, sc);
+    merge_first_kernel<<<(h->n + 255) / 256, 256, 0, h->stream>>>(x);
+    CU(cudaGetLastError());
+    std::vector<uint32_t> first(K);
+    CU(cudaMemcpyAsync(first.data(), sc.first, K * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    std::vector<uint32_t> present;
+    for (uint32_t b = 0; b < K; ++b) if (first[b] != 0xffffffffu) present.push_back(b);
+    std::sort(present.begin(), present.end(), [&](uint32_t a, uint32_t b) { return first[a] < first[b]; });
+    std::vector<uint32_t> newid(K, 0);
+    uint32_t new_ka = 0;
+    for (uint32_t i = 0; i < present.size(); ++i) { newid[present[i]] = i; if (first[present[i]] < h->na) new_ka = i + 1; }
+    const uint32_t new_kb = (uint32_t)present.size() - new_ka;
+    // the reference's sanity check (n != K_ -> "[sanity check] inconsistency!"): type-a blocks must come first
+    for (uint32_t i = 0; i < new_ka; ++i) if (first[present[i]] >= h->na) return fail(BISBM_ERR_STATE, "agg_merge: blocks mix node types");
+    if (new_ka == 0 || new_kb == 0) return fail(BISBM_ERR_STATE, "agg_merge: a node type lost all its blocks");
+    std::vector<uint32_t> full(K);
+    for (uint32_t b = 0; b < K; ++b) full[b] = newid[rep[b]];
+    CU(cudaMemcpyAsync(sc.map, full.data(), K * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+    merge_relabel_kernel<<<(h->n + 255) / 256, 256, 0, h->stream>>>(x, new_ka);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(h->stream));
+    wrote_labels32(h);
+    return set_chain_k(h, chain, new_ka, new_kb);
+}
+
+// one pass of proposals + description-length changes: candidates in proposal order
+int merge_candidates(bisbm_handle* h, uint32_t chain, const ReplaySlot& sl, MergeScratch& sc, uint32_t first_block, uint32_t n_blocks,
+                     uint32_t nm, std::vector<uint32_t>& cand, std::vector<double>& dS) {
+    const uint32_t K = h->h_ka[chain] + h->h_kb[chain];
+    const uint64_t bits = (uint64_t)K * K;
+    CU(cudaMemsetAsync(sc.seen, 0, (bits + 31) / 32 * sizeof(uint32_t), h->stream));
+    MergeCtx x = mctx(h, chain, sl, sc);
+    merge_badj_kernel<<<(K + 127) / 128, 128, 0, h->stream>>>(x);
+    const size_t smem = 2 * MT_STATE_WORDS * sizeof(uint32_t) + (size_t)K * sizeof(double);
+    if (smem > 200 * 1024) return fail(BISBM_ERR_ARG, "agg_merge: K = %u blocks do not fit the proposal kernel's shared memory", K);
+    int rc = ensure_smem_attr(h, (const void*)merge_propose_kernel, 200 * 1024);
+    if (rc) return rc;
+    merge_propose_kernel<<<1, 32, smem, h->stream>>>(x, first_block, n_blocks, nm);
+    CU(cudaGetLastError());
+    uint32_t n_cand = 0;
+    CU(cudaMemcpyAsync(&n_cand, sc.n_cand, sizeof n_cand, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    cand.assign(2 * (size_t)n_cand, 0); dS.assign(n_cand, 0.0);
+    if (n_cand) {
+        merge_dS_kernel<<<(n_cand + 127) / 128, 128, 0, h->stream>>>(x, n_cand);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(cand.data(), sc.cand, 2 * (size_t)n_cand * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaMemcpyAsync(dS.data(), sc.cand_dS, (size_t)n_cand * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+    }
+    return BISBM_OK;
+}
+
+int alloc_merge_scratch(bisbm_handle* h, uint32_t chain, uint32_t nm, MergeScratch& sc) {
+    const uint32_t K = h->h_ka[chain] + h->h_kb[chain];
+    const uint32_t stride = std::max(h->h_ka[chain], h->h_kb[chain]);
+    const size_t max_cand = (size_t)nm * K;
+    CU(cudaMalloc(&sc.badj, (size_t)K * stride * sizeof(uint32_t)));
+    CU(cudaMalloc(&sc.badj_cnt, K * sizeof(uint32_t)));
+    CU(cudaMalloc(&sc.cand, 2 * max_cand * sizeof(uint32_t)));
+    CU(cudaMalloc(&sc.cand_dS, max_cand * sizeof(double)));
+    CU(cudaMalloc(&sc.n_cand, sizeof(uint32_t)));
+    CU(cudaMalloc(&sc.seen, ((uint64_t)K * K + 31) / 32 * sizeof(uint32_t)));
+    CU(cudaMalloc(&sc.first, K * sizeof(uint32_t)));
+    CU(cudaMalloc(&sc.map, K * sizeof(uint32_t)));
+    return BISBM_OK;
+}
+
+// the accepted merges of one selection pass: set_e (impacted blocks) and the partition of set_e into accepted sets,
+// kept as "representative = smallest member" per block (src/blockmodel.cc:160-199: a move joins the set that holds its
+// source or target, or opens a new one; a move inside set_e is skipped)
+struct MergeSets {
+    std::vector<int> set_of;                  // block -> set index, -1 outside set_e
+    std::vector<std::vector<uint32_t>> sets;
+    explicit MergeSets(uint32_t K) : set_of(K, -1) {}
+    bool in(uint32_t b) const { return set_of[b] >= 0; }
+    bool accept(uint32_t source, uint32_t target) {   // false: both already impacted (skipped by the reference)
+        if (in(source) && in(target)) return false;
+        if (!in(source) && !in(target)) { sets.push_back({source, target}); set_of[source] = set_of[target] = (int)sets.size() - 1; }
+        else {
+            const int si = in(source) ? set_of[source] : set_of[target];
+            for (uint32_t b : {source, target}) if (!in(b)) { sets[si].push_back(b); set_of[b] = si; }
+        }
+        return true;
+    }
+    std::vector<uint32_t> representatives() const {
+        std::vector<uint32_t> rep(set_of.size());
+        for (uint32_t b = 0; b < rep.size(); ++b) rep[b] = in(b) ? *std::min_element(sets[set_of[b]].begin(), sets[set_of[b]].end()) : b;
+        return rep;
+    }
+};
+
+// agg_split (src/blockmodel.cc:555-611) + apply_split_moves (:433-459): nm random halvings of every block of one type with
+// more than one node, the one with the smallest description-length change becomes a new block.  The shuffles consume
+// `engine` exactly like std::shuffle over the reference's vector<bool>; see split_dS_kernel for what cannot be pinned.
+int agg_split(bisbm_handle* h, uint32_t chain, const ReplaySlot& sl, MergeScratch& sc, bool type_b, uint32_t nm) {
+    const uint32_t ka = h->h_ka[chain], kb = h->h_kb[chain], K = ka + kb, n = h->n;
+    if ((!type_b && ka + 1 > h->KA) || (type_b && kb + 1 > h->KB))
+        return fail(BISBM_ERR_STATE, "agg_split: the pool was created with room for (%u, %u) blocks only", h->KA, h->KB);
+    std::vector<int32_t> lab(n);
+    CU(cudaMemcpy2D(lab.data(), sizeof(int32_t), h->d_labels + chain, (size_t)h->C * sizeof(int32_t), sizeof(int32_t), n, cudaMemcpyDeviceToHost));
+    ReplayState rs;
+    CU(cudaMemcpy(&rs, sl.d_rs, sizeof rs, cudaMemcpyDeviceToHost));
+    const uint32_t b0 = type_b ? ka : 0, nbk = type_b ? kb : ka;
+    std::vector<std::vector<uint32_t>> nodes(nbk);
+    for (uint32_t v = type_b ? h->na : 0; v < (type_b ? n : h->na); ++v) nodes[(uint32_t)lab[v]].push_back(v);
+    std::vector<SplitCand> cands;
+    std::vector<uint32_t> members;
+    std::vector<uint8_t> flags;
+    std::vector<uint32_t> member_off(nbk, 0);
+    for (uint32_t b = 0; b < nbk; ++b) {
+        const uint32_t nr = (uint32_t)nodes[b].size();
+        if (nr <= 1) continue;
+        member_off[b] = (uint32_t)members.size();
+        members.insert(members.end(), nodes[b].begin(), nodes[b].end());
+        std::vector<uint32_t> splitter(nr, 0);
+        for (uint32_t i = nr / 2; i < nr; ++i) splitter[i] = 1;
+        mt_shuffle(splitter.data(), nr, 1, rs.engine);
+        for (uint32_t rep = 0; rep < nm; ++rep) {
+            mt_shuffle(splitter.data(), nr, 1, rs.engine);
+            SplitCand cd; cd.block = b0 + b; cd.first_member = member_off[b]; cd.n_members = nr; cd.first_flag = (uint32_t)flags.size();
+            for (uint32_t i = 0; i < nr; ++i) flags.push_back((uint8_t)splitter[i]);
+            cands.push_back(cd);
+        }
+    }
+    if (cands.empty()) return fail(BISBM_ERR_STATE, "agg_split: no block of type %c has more than one node", type_b ? 'b' : 'a');
+    SplitCand* d_c = nullptr; uint32_t* d_m = nullptr; uint8_t* d_f = nullptr; double* d_o = nullptr;
+    CU(cudaMalloc(&d_c, cands.size() * sizeof(SplitCand)));
+    CU(cudaMalloc(&d_m, members.size() * sizeof(uint32_t)));
+    CU(cudaMalloc(&d_f, flags.size()));
+    CU(cudaMalloc(&d_o, cands.size() * sizeof(double)));
+    CU(cudaMemcpy(d_c, cands.data(), cands.size() * sizeof(SplitCand), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_m, members.data(), members.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_f, flags.data(), flags.size(), cudaMemcpyHostToDevice));
+    MergeCtx x = mctx(h, chain, sl, sc);
+    const uint32_t kopp = type_b ? ka : kb;
+    split_dS_kernel<<<(unsigned)cands.size(), 128, kopp * sizeof(int), h->stream>>>(x, gview(h), d_c, d_m, d_f, d_o);
+    cudaError_t e = cudaGetLastError();
+    std::vector<double> dS(cands.size());
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dS.data(), d_o, dS.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d_c); cudaFree(d_m); cudaFree(d_f); cudaFree(d_o);
+    CU(e);
+    size_t best = cands.size();
+    double ddS = INFINITY;
+    for (size_t i = 0; i < cands.size(); ++i) if (dS[i] < ddS) { ddS = dS[i]; best = i; }
+    if (best == cands.size()) return fail(BISBM_ERR_STATE, "agg_split: every candidate split has an infinite description-length change");
+    const SplitCand& w = cands[best];
+    const int32_t new_local = (int32_t)(type_b ? kb : ka);     // the new block takes the next id of its type
+    for (uint32_t i = 0; i < w.n_members; ++i)
+        if (flags[w.first_flag + i]) lab[members[w.first_member + i]] = new_local;
+    CU(cudaMemcpy2D(h->d_labels + chain, (size_t)h->C * sizeof(int32_t), lab.data(), sizeof(int32_t), sizeof(int32_t), n, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(sl.d_rs, &rs, sizeof rs, cudaMemcpyHostToDevice));
+    wrote_labels32(h);
+    (void)K;
+    return set_chain_k(h, chain, type_b ? ka : ka + 1, type_b ? kb + 1 : kb);
+}
+
+}  // namespace
+
+extern "C" {
+
+int bisbm_replay_agg_merge(bisbm_handle* h, uint32_t chain, int diff_a, int diff_b, uint32_t nm) {
+    ReplaySlot* sl;
+    int rc = need_replay(h, chain, &sl);
+    if (rc) return rc;
+    if (nm == 0) return fail(BISBM_ERR_ARG, "nm must be >= 1");
+    if (diff_a >= (int)h->h_ka[chain] || diff_b >= (int)h->h_kb[chain]) return fail(BISBM_ERR_ARG, "cannot merge away every block of a type");
+    rc = ensure_lgamma_table(h);
+    if (rc) return rc;
+    for (int guard = 0; guard < 1 << 20; ++guard) {      // each round = one (possibly recursive) call of the reference's agg_merge
+        MergeScratch sc;
+        rc = alloc_merge_scratch(h, chain, nm, sc);
+        if (rc) return rc;
+        while (diff_a < 0) { rc = agg_split(h, chain, *sl, sc, false, nm); if (rc) return rc; ++diff_a; }
+        while (diff_b < 0) { rc = agg_split(h, chain, *sl, sc, true, nm); if (rc) return rc; ++diff_b; }
+        if (diff_a + diff_b == 0) return BISBM_OK;       // (also when they cancel: the reference returns here too)
+        const uint32_t ka = h->h_ka[chain], kb = h->h_kb[chain], K = ka + kb;
+        {   // the splits may have grown K: scratch sized for the current K
+            MergeScratch fresh;
+            std::swap(sc.badj, fresh.badj); std::swap(sc.badj_cnt, fresh.badj_cnt); std::swap(sc.cand, fresh.cand); std::swap(sc.cand_dS, fresh.cand_dS);
+            std::swap(sc.n_cand, fresh.n_cand); std::swap(sc.seen, fresh.seen); std::swap(sc.first, fresh.first); std::swap(sc.map, fresh.map);
+        }
+        rc = alloc_merge_scratch(h, chain, nm, sc);
+        if (rc) return rc;
+        uint32_t first_block = 0, n_blocks = K;
+        if (diff_a > 0 && diff_b == 0) n_blocks = ka;
+        else if (diff_a == 0 && diff_b > 0) { first_block = ka; n_blocks = kb; }
+        std::vector<uint32_t> cand;
+        std::vector<double> dS;
+        rc = merge_candidates(h, chain, *sl, sc, first_block, n_blocks, nm, cand, dS);
+        if (rc) return rc;
+        // priority_queue<pair<dS, index>, greater<>>: ascending dS, ties by proposal order
+        std::vector<uint32_t> order(dS.size());
+        std::iota(order.begin(), order.end(), 0u);
+        std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return dS[a] < dS[b] || (dS[a] == dS[b] && a < b); });
+        MergeSets ms(K);
+        bool recursive = false;
+        size_t accepted = 0;
+        for (size_t q = 0; q < order.size() && diff_a + diff_b != 0; ++q) {
+            const uint32_t i = order[q];
+            if (dS[i] == INFINITY) { recursive = true; break; }
+            const uint32_t source = cand[2 * i], target = cand[2 * i + 1];
+            if (source < ka && diff_a != 0) { if (ms.accept(source, target)) { --diff_a; ++accepted; } }
+            else if (source >= ka && diff_b != 0) { if (ms.accept(source, target)) { --diff_b; ++accepted; } }
+        }
+        rc = apply_block_moves(h, chain, *sl, sc, ms.representatives());
+        if (rc) return rc;
+        if (!recursive) return BISBM_OK;
+        if (accepted == 0 && guard > 64)
+            return fail(BISBM_ERR_STATE, "agg_merge: no finite merge candidate left for (%d, %d) more merges", diff_a, diff_b);
+    }
+    return fail(BISBM_ERR_STATE, "agg_merge did not terminate");
+}
+
+int bisbm_replay_agg_merge_total(bisbm_handle* h, uint32_t chain, int diff, uint32_t nm) {
+    ReplaySlot* sl;
+    int rc = need_replay(h, chain, &sl);
+    if (rc) return rc;
+    if (nm == 0) return fail(BISBM_ERR_ARG, "nm must be >= 1");
+    if (diff == 0) return BISBM_OK;
+    if (diff < 0) return fail(BISBM_ERR_ARG, "diff must be >= 0");
+    rc = ensure_lgamma_table(h);
+    if (rc) return rc;
+    const uint32_t ka = h->h_ka[chain], kb = h->h_kb[chain], K = ka + kb;
+    MergeScratch sc;
+    rc = alloc_merge_scratch(h, chain, nm, sc);
+    if (rc) return rc;
+    for (int guard = 0; guard < 4096; ++guard) {
+        std::vector<uint32_t> cand;
+        std::vector<double> dS;
+        rc = merge_candidates(h, chain, *sl, sc, 0, K, nm, cand, dS);
+        if (rc) return rc;
+        std::vector<uint32_t> order(dS.size());
+        std::iota(order.begin(), order.end(), 0u);
+        std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return dS[a] < dS[b] || (dS[a] == dS[b] && a < b); });
+        MergeSets ms(K);
+        int left = diff;
+        bool minS = true;     // the reference starts with minS = true; an empty queue leaves it true (and loops forever)
+        for (size_t q = 0; q < order.size() && left != 0; ++q) {
+            const uint32_t i = order[q];
+            if (ms.accept(cand[2 * i], cand[2 * i + 1])) --left;
+            minS = dS[i] == INFINITY;     // the round is redone when the LAST popped candidate was infinite
+        }
+        if (!minS) return apply_block_moves(h, chain, *sl, sc, ms.representatives());
+    }
+    return fail(BISBM_ERR_STATE, "agg_merge: every round ended on an infinite candidate");
+}
+
+int bisbm_chain_k(bisbm_handle* h, uint32_t chain, uint32_t* ka, uint32_t* kb) {
+    int rc = need_chains(h);
+    if (rc) return rc;
+    if (chain >= h->n_chains) return fail(BISBM_ERR_ARG, "chain %u out of range", chain);
+    if (ka) *ka = h->h_ka[chain];
+    if (kb) *kb = h->h_kb[chain];
+    return BISBM_OK;
+}
+
+}  // extern "C"
+
+extern "C" {
 
 // ---------------------------------------------------------------- parallel mode
 int bisbm_anneal(bisbm_handle* h, int schedule, float p0, float p1, uint64_t duration, uint64_t steps_await,

@@ -158,6 +158,13 @@ template <> struct Ar<double> {
 #endif
     }
     BISBM_HD static double cvt_small(uint32_t x) { return cvt(x); }
+    BISBM_HD static double cvt_small_p1(uint32_t x) {   // x + 1 as a double: the + 1 rides on the constant of the splice
+#if defined(__CUDA_ARCH__) && defined(BISBM_CVT_MAGIC)
+        return __hiloint2double(0x43300000, (int)x) - 4503599627370495.0;
+#else
+        return (double)(x + 1u);
+#endif
+    }
     BISBM_HD static double cvt_s(int x) {
 #if defined(__CUDA_ARCH__) && defined(BISBM_CVT_MAGIC)
         return __hiloint2double(0x43300000, (int)((uint32_t)x ^ 0x80000000u)) - 4503601774854144.0;   // 2^52 + 2^31
@@ -186,6 +193,13 @@ template <> struct Ar<float> {
         return (float)x;
 #endif
     }
+    BISBM_HD static float cvt_small_p1(uint32_t x) {   // x <= 254
+#ifdef __CUDA_ARCH__
+        return __uint_as_float(0x4B000000u | x) - 8388607.0f;
+#else
+        return (float)(x + 1u);
+#endif
+    }
     BISBM_HD static float cvt_s(int x) { return (float)x; }
     BISBM_HD static float rcp(float x) { return f_rcp(x); }
     BISBM_HD static float lg(float x) { return f_lg2(x); }
@@ -209,10 +223,10 @@ template <typename R> struct MAcc { R sA, sB, sC, w, num, den, lg; };
 template <typename R> BISBM_HD void macc_init(MAcc<R>& A) {
     A.sA = (R)0; A.sB = (R)0; A.sC = (R)0; A.w = (R)0; A.num = (R)1; A.den = (R)1; A.lg = (R)0;
 }
-template <typename R> BISBM_HD void macc_edge(MAcc<R>& A, int m_r, int m_s, uint32_t c1, R inv) {
-    const R dC = Ar<R>::cvt_small(c1);
-    const R dA = Ar<R>::cvt((uint32_t)m_r + 1u - c1);
-    const R dB = Ar<R>::cvt((uint32_t)m_s + c1);
+template <typename R> BISBM_HD void macc_edge(MAcc<R>& A, int m_r, int m_s, uint32_t c, R inv) {   // c = c1 - 1: earlier edges with this label
+    const R dC = Ar<R>::cvt_small_p1(c);
+    const R dA = Ar<R>::cvt((uint32_t)m_r - c);
+    const R dB = Ar<R>::cvt((uint32_t)m_s + c + 1u);
     if (Ar<R>::SPLIT) {
         A.sA = fma(dA, inv, A.sA);
         A.sB = fma(dB, inv, A.sB);
@@ -662,6 +676,16 @@ __global__ void __launch_bounds__(NT, 1) sweep2_kernel(const __grid_constant__ S
                 auto issue_next = [&]() {
                     if (nxt < nb) { load_rows(d_n); r_nxt = lab_ld(ninfo.x); }
                 };
+                auto load_q = [&](uint32_t slot) -> LogqExp {   // 48 bytes of this (block, chain); constant during the launch
+                    const uint4* p = reinterpret_cast<const uint4*>(gLQ + slot * 32u + lane);
+                    const uint4 a = __ldg(p), b = __ldg(p + 1), c4 = __ldg(p + 2);
+                    LogqExp q;
+                    q.e0 = (int)a.x; q.n0 = (int)a.y; q.fe = __hiloint2double((int)a.w, (int)a.z);
+                    q.fn = __hiloint2double((int)b.y, (int)b.x);
+                    q.fee = __uint_as_float(b.z); q.fen = __uint_as_float(b.w);
+                    q.fnn = __uint_as_float(c4.x); q.feee = __uint_as_float(c4.y); q.valid = c4.z; q.pad = 0;
+                    return q;
+                };
 
                 // ---- the draw of this move: Philox4x32-10, counter = (vertex, sweep, chain seed), pool-wide key ----
                 u32x4 ctr; ctr.x = v; ctr.y = (uint32_t)P.sweep; ctr.z = key0; ctr.w = key1;
@@ -717,31 +741,35 @@ __global__ void __launch_bounds__(NT, 1) sweep2_kernel(const __grid_constant__ S
                 //      runs it (masked lanes cost the same issue slots); only `eval` lanes may commit. ----
                 MAcc<R> A; macc_init(A);
                 const uint32_t Mr = r * SX, Ms = s * SX;
+                // histogram bin of label t: word t / 4, byte t % 4 -- or, with exactly 8 words (the Ka = Kb = 32 instantiation),
+                // word t % 8, byte t / 8: the byte's shift is then t & 0x18, one instruction less per edge
+                auto h_sh = [&](uint32_t t) -> uint32_t { if constexpr (KF == 32) return t & 0x18u; else return (t & 3u) << 3; };
+                auto h_ad = [&](uint32_t t) -> uint32_t { if constexpr (KF == 32) return hist_base + ((t & 7u) << 7); else return hist_base + ((t >> 2) << 7); };
                 auto edge1 = [&](uint32_t t) {
-                    const uint32_t sh3 = (t & 3u) << 3;
-                    const uint32_t old = sh_atom_add_u32(hist_base + ((t >> 2) << 7), 1u << sh3);
+                    const uint32_t sh3 = h_sh(t);
+                    const uint32_t old = sh_atom_add_u32(h_ad(t), 1u << sh3);
                     const uint32_t off = t * ST;
                     const int m_r = m_ld(Mr + off), m_s = m_ld(Ms + off);
                     const R inv = sh_ld_real<R>(Inv_base + t * IS);
-                    macc_edge(A, m_r, m_s, ((old >> sh3) & 0xffu) + 1u, inv);
+                    macc_edge(A, m_r, m_s, (old >> sh3) & 0xffu, inv);
                 };
                 auto edge4 = [&](uint32_t Lc) {
                     const uint32_t t0 = Lc & 0xffu, t1 = (Lc >> 8) & 0xffu, t2 = (Lc >> 16) & 0xffu, t3 = Lc >> 24;
-                    const uint32_t h0 = (t0 & 3u) << 3, h1 = (t1 & 3u) << 3, h2 = (t2 & 3u) << 3, h3 = (t3 & 3u) << 3;
+                    const uint32_t h0 = h_sh(t0), h1 = h_sh(t1), h2 = h_sh(t2), h3 = h_sh(t3);
                     // the four histogram updates in edge order (a repeated label must see the earlier increment)
-                    const uint32_t o0 = sh_atom_add_u32(hist_base + ((t0 >> 2) << 7), 1u << h0);
-                    const uint32_t o1 = sh_atom_add_u32(hist_base + ((t1 >> 2) << 7), 1u << h1);
-                    const uint32_t o2 = sh_atom_add_u32(hist_base + ((t2 >> 2) << 7), 1u << h2);
-                    const uint32_t o3 = sh_atom_add_u32(hist_base + ((t3 >> 2) << 7), 1u << h3);
+                    const uint32_t o0 = sh_atom_add_u32(h_ad(t0), 1u << h0);
+                    const uint32_t o1 = sh_atom_add_u32(h_ad(t1), 1u << h1);
+                    const uint32_t o2 = sh_atom_add_u32(h_ad(t2), 1u << h2);
+                    const uint32_t o3 = sh_atom_add_u32(h_ad(t3), 1u << h3);
                     const uint32_t f0 = t0 * ST, f1 = t1 * ST, f2 = t2 * ST, f3 = t3 * ST;
                     const int r0 = m_ld(Mr + f0), s0 = m_ld(Ms + f0), r1 = m_ld(Mr + f1), s1 = m_ld(Ms + f1);
                     const int r2 = m_ld(Mr + f2), s2 = m_ld(Ms + f2), r3 = m_ld(Mr + f3), s3 = m_ld(Ms + f3);
                     const R i0 = sh_ld_real<R>(Inv_base + t0 * IS), i1 = sh_ld_real<R>(Inv_base + t1 * IS);
                     const R i2 = sh_ld_real<R>(Inv_base + t2 * IS), i3 = sh_ld_real<R>(Inv_base + t3 * IS);
-                    macc_edge(A, r0, s0, ((o0 >> h0) & 0xffu) + 1u, i0);
-                    macc_edge(A, r1, s1, ((o1 >> h1) & 0xffu) + 1u, i1);
-                    macc_edge(A, r2, s2, ((o2 >> h2) & 0xffu) + 1u, i2);
-                    macc_edge(A, r3, s3, ((o3 >> h3) & 0xffu) + 1u, i3);
+                    macc_edge(A, r0, s0, (o0 >> h0) & 0xffu, i0);
+                    macc_edge(A, r1, s1, (o1 >> h1) & 0xffu, i1);
+                    macc_edge(A, r2, s2, (o2 >> h2) & 0xffu, i2);
+                    macc_edge(A, r3, s3, (o3 >> h3) & 0xffu, i3);
                 };
                 for (uint32_t e0 = 0; e0 < d; e0 += 32u) {
                     const uint32_t nrem = min(32u, d - e0);
@@ -787,16 +815,6 @@ __global__ void __launch_bounds__(NT, 1) sweep2_kernel(const __grid_constant__ S
                 {
                     const int e_r = eo_ld(r), e_s = eo_ld(s);
                     bool ok_b, ok_r, ok_s;
-                    auto load_q = [&](uint32_t slot) -> LogqExp {   // 48 bytes of this (block, chain); constant during the launch
-                        const uint4* p = reinterpret_cast<const uint4*>(gLQ + slot * 32u + lane);
-                        const uint4 a = __ldg(p), b = __ldg(p + 1), c4 = __ldg(p + 2);
-                        LogqExp q;
-                        q.e0 = (int)a.x; q.n0 = (int)a.y; q.fe = __hiloint2double((int)a.w, (int)a.z);
-                        q.fn = __hiloint2double((int)b.y, (int)b.x);
-                        q.fee = __uint_as_float(b.z); q.fen = __uint_as_float(b.w);
-                        q.fnn = __uint_as_float(c4.x); q.feee = __uint_as_float(c4.y); q.valid = c4.z; q.pad = 0;
-                        return q;
-                    };
                     LogqExp q_r = load_q(r), q_s = load_q(s);
                     // (1) shared memory only: the e_r terms, the Hastings factor, the count-ratio product
                     R bdd = bdd_fast<R>(e_r, e_s, (int)d, &ok_b);
@@ -896,7 +914,7 @@ __global__ void __launch_bounds__(NT, 1) sweep2_kernel(const __grid_constant__ S
                         word = go ? word : 0u;
 #pragma unroll
                         for (uint32_t b = 0; b < 4; ++b) {
-                            const uint32_t t = w * 4u + b;
+                            const uint32_t t = (KF == 32) ? w + 8u * b : w * 4u + b;
                             if (t < kopp_max) {
                                 const int kk = (int)((word >> (8u * b)) & 0xffu);
                                 if (STAGED || kk != 0) { m_red(Mr + t * ST, -kk); m_red(Ms + t * ST, kk); }

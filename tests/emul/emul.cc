@@ -207,7 +207,7 @@ static void par2_dS(Emul* s, uint32_t v, uint32_t sg, int use_taylor, double* dS
         uint32_t t = s->labels[(size_t)nb * s->C + s->chain];
         int c = cnt[t]++;
         R inv = (R)(1.0 / ((double)s->e[opp_off + t] + s->eps * (double)(KA + KB)));
-        macc_edge<R>(A, Mr[(size_t)t * st], Ms[(size_t)t * st], (uint32_t)c + 1u, inv);
+        macc_edge<R>(A, Mr[(size_t)t * st], Ms[(size_t)t * st], (uint32_t)c, inv);
         // the kernel folds after every chunk of 4 edges (float) or after every block of 32 (double)
         if (Ar<R>::FOLD < 32 ? ((e & 3u) == 3u || e + 1 == d) : ((e & 31u) == 31u && e + 1 < d)) macc_fold(A);
     }
