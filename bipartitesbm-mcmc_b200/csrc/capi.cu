@@ -126,6 +126,7 @@ struct bisbm_handle {
     int opt_generic = 0;               // 1: never take the Ka = Kb = 32 specialisation
     int opt_vary_k = 0;                // estimate mode: blocks may empty, K-dependent prior terms in dS
     uint32_t opt_warps = 16;           // warps per CTA of the staged sweep2 kernel (experiment builds: 20, 24)
+    uint32_t opt_reserve_ka = 0, opt_reserve_kb = 0;   // minimum strides of the next bisbm_set_chains (room for agg_split)
     std::set<const void*> attr_done;   // kernels whose shared-memory limit is raised on this handle's device
     uint64_t last_sweep_launches = 0, last_marginal_launches = 0;
     uint32_t last_wpc = 0, last_cpg = 0, last_slice = 0;   // launch plan of the last half sweep
@@ -920,6 +921,7 @@ static int alloc_chains(bisbm_handle* h, uint32_t n_chains, const uint32_t* ka, 
         if (ka[c] == 0 || kb[c] == 0) return fail(BISBM_ERR_ARG, "chain %u: ka and kb must be >= 1", c);
         KA = std::max(KA, ka[c]); KB = std::max(KB, kb[c]);
     }
+    KA = std::max(KA, h->opt_reserve_ka); KB = std::max(KB, h->opt_reserve_kb);
     const uint32_t C = (n_chains + 31) / 32 * 32;
     const uint32_t n = h->n;
     const size_t KK = (size_t)KA + KB;
@@ -1775,6 +1777,9 @@ int bisbm_set_option(bisbm_handle* h, const char* name, int64_t value) {
         h->opt_warps = (uint32_t)value;
     } else if (k == "generic") {
         h->opt_generic = value != 0;
+    } else if (k == "reserve_ka" || k == "reserve_kb") {
+        if (value < 0 || value > (1 << 20)) return fail(BISBM_ERR_ARG, "%s out of range", name);
+        (k == "reserve_ka" ? h->opt_reserve_ka : h->opt_reserve_kb) = (uint32_t)value;
     } else {
         return fail(BISBM_ERR_ARG, "unknown option '%s'", name);
     }

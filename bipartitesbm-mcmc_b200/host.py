@@ -64,6 +64,9 @@ SIGNATURES = {
     "bisbm_replay_transition": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, _dp, _dp]),
     "bisbm_replay_get_vlist": (C.c_int, [C.c_void_p, C.c_uint32, _u32p]),
     "bisbm_replay_rng_words": (C.c_int, [C.c_void_p, C.c_uint32, _u64p, _u64p]),
+    "bisbm_replay_agg_merge": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_uint32]),
+    "bisbm_replay_agg_merge_total": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int, C.c_uint32]),
+    "bisbm_chain_k": (C.c_int, [C.c_void_p, C.c_uint32, _u32p, _u32p]),
     "bisbm_anneal": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_uint64, C.c_uint64, _u64p, C.c_uint32,
                                _dp, _u64p]),
     "bisbm_marginalize": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, _u64p, C.c_uint32]),
@@ -163,6 +166,10 @@ class Graph:
         _check(L.bisbm_info(h, None, None, C.byref(md), None))
         self.max_degree = md.value
 
+    def set_option(self, name, value):
+        """handle options that matter before the chains exist ('reserve_ka' / 'reserve_kb', include/bisbm.h)"""
+        _check(self.L.bisbm_set_option(self.h, name.encode(), int(value)))
+
     def close(self):
         if getattr(self, "h", None):
             self.L.bisbm_destroy(self.h)
@@ -223,8 +230,8 @@ class ChainPool:
         labels = np.ascontiguousarray(labels)
         self.n_chains = labels.shape[0]
         assert labels.shape[1] == graph.n
-        self.ka = np.ascontiguousarray(np.broadcast_to(np.asarray(ka, dtype=np.uint32), (self.n_chains,)))
-        self.kb = np.ascontiguousarray(np.broadcast_to(np.asarray(kb, dtype=np.uint32), (self.n_chains,)))
+        self.ka = np.array(np.broadcast_to(np.asarray(ka, dtype=np.uint32), (self.n_chains,)))
+        self.kb = np.array(np.broadcast_to(np.asarray(kb, dtype=np.uint32), (self.n_chains,)))
         self.epsilon = float(epsilon)
         self.set_labels(labels)
 
@@ -358,6 +365,22 @@ class ChainPool:
         _check(self.L.bisbm_replay_rng_words(self.g.h, chain, C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    def chain_k(self, chain):
+        a, b = C.c_uint32(), C.c_uint32()
+        _check(self.L.bisbm_chain_k(self.g.h, chain, C.byref(a), C.byref(b)))
+        self.ka[chain], self.kb[chain] = a.value, b.value
+        return a.value, b.value
+
+    def replay_agg_merge(self, chain, diff_a, diff_b=None, nm=10):
+        """blockmodel_t::agg_merge (src/blockmodel.cc:109-256) on a replay chain: (diff_a, diff_b) blocks fewer per type
+        (negative: agg_split), or -- diff_b None -- diff_a merges of any type (the -u / --nature form).  Returns the new
+        (ka, kb)."""
+        if diff_b is None:
+            _check(self.L.bisbm_replay_agg_merge_total(self.g.h, chain, diff_a, nm))
+        else:
+            _check(self.L.bisbm_replay_agg_merge(self.g.h, chain, diff_a, diff_b, nm))
+        return self.chain_k(chain)
+
     # -- state out
     def labels(self, chain=None, out=None):
         if chain is None:
@@ -484,6 +507,12 @@ class blockmodel_t:
 
     def get_KB(self):
         return self.KB
+
+    def agg_merge(self, engine, diff_a, diff_b=None, nm=10):
+        """src/blockmodel.cc:109-256 (both overloads: agg_merge(engine, diff_a, diff_b, nm) / agg_merge(engine, diff, nm))"""
+        self._bind(engine, False)
+        self.KA, self.KB = self.pool.replay_agg_merge(0, diff_a, diff_b, nm)
+        self.K = self.KA + self.KB
 
     def get_epsilon(self):
         return self.epsilon

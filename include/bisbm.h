@@ -100,6 +100,24 @@ int bisbm_replay_transition(bisbm_handle* h, uint32_t chain, uint32_t v, uint32_
 int bisbm_replay_get_vlist(bisbm_handle* h, uint32_t chain, uint32_t* vlist);
 int bisbm_replay_rng_words(bisbm_handle* h, uint32_t chain, uint64_t* engine_words, uint64_t* gen_words);
 
+/* ---- agglomerative merge / split of a replay chain (the initialiser of the reference's -g / -u paths and of initial labels
+ * whose block counts differ from -z, src/mcmc_main.cc:350-451) ------------------------------
+ * blockmodel_t::agg_merge(engine, diff_a, diff_b, nm) (src/blockmodel.cc:109-204): diff_a (diff_b) type-a (type-b) blocks
+ * fewer; nm block-move proposals per block (single_block_change, :639-669), consumed from the chain's two engines exactly as
+ * the reference does; the proposals with the smallest description-length change (compute_dS, :335-370) are applied
+ * (apply_block_moves, :505-553: blocks renumbered in order of first appearance, counts rebuilt).  A negative diff splits:
+ * agg_split (:555-611), one new block of that type per unit.  Afterwards the chain has bisbm_chain_k blocks; the pool's
+ * strides (the maxima given to bisbm_set_chains) stay, so a split needs a pool created with room for the new block.
+ * Merge path: labels, counts and RNG word counts bit-identical to the reference (tests/test_merge_gpu.py).  Split path:
+ * the reference's compute_dS(mb, split_move) indexes a vector out of bounds (undefined behaviour); this library implements
+ * the evident intent and its parity is property-tested only. */
+int bisbm_replay_agg_merge(bisbm_handle* h, uint32_t chain, int diff_a, int diff_b, uint32_t nm);
+/* blockmodel_t::agg_merge(engine, diff, nm) (src/blockmodel.cc:206-256), the -u / --nature form: diff merges of any type; a
+ * round that ends on an infinite candidate is redone with fresh proposals. */
+int bisbm_replay_agg_merge_total(bisbm_handle* h, uint32_t chain, int diff, uint32_t nm);
+/* blockmodel_t::get_KA / get_KB of one chain (they change under agg_merge) */
+int bisbm_chain_k(bisbm_handle* h, uint32_t chain, uint32_t* ka, uint32_t* kb);
+
 /* ---- parallel mode (all chains per launch) -------------------------------------------
  * anneal for every chain at once.  duration / steps_await as in the reference (steps);
  * seeds[c] keys chain c's counter-based RNG.  max_inflight bounds how many moves of ONE
@@ -129,7 +147,9 @@ int bisbm_set_precision(bisbm_handle* h, int mode);
  *   "vary_k"        1: estimate mode (README "estimation", no code in the reference snapshot): blocks may empty and be
  *                   re-populated by the uniform part of the proposal (no "would empty block r" veto), the K-dependent
  *                   terms of the description length enter dS with the number of OCCUPIED blocks, and bisbm_entropy*
- *                   use the occupied counts too.  ka / kb of bisbm_set_chains are then upper bounds. */
+ *                   use the occupied counts too.  ka / kb of bisbm_set_chains are then upper bounds.
+ *   "reserve_ka" / "reserve_kb"   minimum count-array strides of the NEXT bisbm_set_chains: room for blocks that
+ *                   bisbm_replay_agg_merge with a negative diff (agg_split) adds to a chain */
 int bisbm_set_option(bisbm_handle* h, const char* name, int64_t value);
 /* which sweep kernel the last parallel call launched and how the half sweep was cut:
  * kernel 0 = round-1 sweep_kernel (double, counts in L2: hubs of degree > 255, K > 256 per type); 1 = round-1 staged

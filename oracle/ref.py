@@ -75,6 +75,8 @@ def _load(log_rng):
     L.ref_init_tables.argtypes = [u64]
     L.ref_merge_path.restype = dbl
     L.ref_merge_path.argtypes = [vp, u64, u64, C.c_float, u64, u64]
+    L.ref_agg_merge.argtypes = [vp, C.c_int, C.c_int, C.c_int]
+    L.ref_agg_merge_total.argtypes = [vp, C.c_int, C.c_int]
     L.ref_get_ka.restype = u64
     L.ref_get_ka.argtypes = [vp]
     L.ref_get_kb.restype = u64
@@ -128,6 +130,18 @@ class RefChain:
         self.ka, self.kb = int(self.L.ref_get_ka(self.h)), int(self.L.ref_get_kb(self.h))
         self.K = self.ka + self.kb
         return s
+
+    def _refresh_k(self):
+        self.ka, self.kb = int(self.L.ref_get_ka(self.h)), int(self.L.ref_get_kb(self.h))
+        self.K = self.ka + self.kb
+
+    def agg_merge(self, diff_a, diff_b=None, nm=10):
+        """blockmodel_t::agg_merge, both overloads (src/blockmodel.cc:109-256); diff_b None = the --nature form"""
+        if diff_b is None:
+            self.L.ref_agg_merge_total(self.h, diff_a, nm)
+        else:
+            self.L.ref_agg_merge(self.h, diff_a, diff_b, nm)
+        self._refresh_k()
 
     def anneal_seconds(self):
         return self.L.ref_last_anneal_seconds(self.h)

@@ -133,6 +133,18 @@ double ref_merge_path(void* p, uint64_t KA, uint64_t KB, float p0, uint64_t samp
     h->ka = bm.get_KA(); h->kb = bm.get_KB();
     return bm.entropy();
 }
+// blockmodel_t::agg_merge(engine, diff_a, diff_b, nm) (src/blockmodel.cc:109-204), negative diffs -> agg_split
+void ref_agg_merge(void* p, int diff_a, int diff_b, int nm) {
+    auto* h = static_cast<ref_handle*>(p);
+    h->bm->agg_merge(h->engine, diff_a, diff_b, nm);
+    h->ka = h->bm->get_KA(); h->kb = h->bm->get_KB();
+}
+// blockmodel_t::agg_merge(engine, diff, nm) (src/blockmodel.cc:206-256), the --nature form
+void ref_agg_merge_total(void* p, int diff, int nm) {
+    auto* h = static_cast<ref_handle*>(p);
+    h->bm->agg_merge(h->engine, diff, nm);
+    h->ka = h->bm->get_KA(); h->kb = h->bm->get_KB();
+}
 uint64_t ref_get_ka(void* p) { return static_cast<ref_handle*>(p)->bm->get_KA(); }
 uint64_t ref_get_kb(void* p) { return static_cast<ref_handle*>(p)->bm->get_KB(); }
 
