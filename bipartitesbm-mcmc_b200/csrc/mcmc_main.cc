@@ -12,8 +12,10 @@
 //                          every -f sweeps over --chains chains; prints the arg-max label per node
 //   --estimate             README "estimation" output format for fixed (Ka, Kb): CSV lines
 //                          sweep,Ka,Kb,loglik,labels... of the last 1000 samples
-// The agglomerative merge paths (-g/--merge, -u/--nature, or initial labels that disagree with -z)
-// are outside this build's scope and are rejected with an error.
+//   -g / --merge, -u / --nature, or initial labels whose block counts differ from -z: the agglomerative
+//                          merge / split initialiser (src/mcmc_main.cc:350-451) over bisbm_replay_agg_merge -- the
+//                          geospace ladder, one greedy sweep between rungs, then the abrupt_cool anneal; one replay
+//                          chain, the label line of the reference for the merge paths
 #include <chrono>
 #include <cmath>
 #include <cstdint>
@@ -120,7 +122,8 @@ void usage(const char* argv0) {
                  "  -x [ --steps_await ] arg (=1000)      Stop after x steps without a new entropy minimum.\n"
                  "  -E [ --epsilon ] arg (=1)             epsilon of the smart proposal.\n"
                  "  -r [ --randomize ]                    Randomize initial block state.\n"
-                 "  -g [ --merge ], -u [ --nature ]       Agglomerative paths (not supported by this build).\n"
+                 "  -g [ --merge ]                        Agglomerative merge from singleton blocks down to -z.\n"
+                 "  -u [ --nature ]                       with -g: merge until a type has fewer than sqrt(2E)/2 blocks.\n"
                  "  -d [ --seed ] arg                     Seed of the mt19937 engine.\n"
                  "  -h [ --help ]                         Produce this help message.\n"
                  "  --maximize | --marginalize | --estimate   mode (default: the reference's annealing path)\n"
@@ -130,6 +133,24 @@ void usage(const char* argv0) {
                  "  --gpus arg (=1)                       GPUs of this node: the chains are dealt round-robin to devices\n"
                  "                                        device .. device+gpus-1 (graph replicated); --marginalize sums the\n"
                  "                                        per-node histograms with one NCCL all-reduce\n";
+}
+
+// the ladder of block counts between (start_a, start_b) and (end_a, end_b) (reference src/support/util.hh:99-146): the type
+// with the longer way to go shrinks by the factor `ratio` per rung, the other one follows geometrically with the same number
+// of rungs.  (The reference divides start_b / end_b as integers before taking the root; kept.)
+void geospace(int start_a, int end_a, int start_b, int end_b, double ratio, std::vector<int>& ga, std::vector<int>& gb) {
+    ga.clear(); gb.clear();
+    if (ratio <= 1.) { ga.push_back(0); gb.push_back(0); return; }
+    bool swapped = false;
+    if (start_a - end_a < start_b - end_b) { std::swap(start_a, start_b); std::swap(end_a, end_b); swapped = true; }
+    size_t i = 0;
+    for (int d = start_a; d > end_a; d = (int)std::floor(start_a / std::pow(ratio, (double)i))) { ga.push_back(d); ++i; }
+    ga.push_back(end_a);
+    const size_t rungs = ga.size();
+    const double rb = std::pow((double)(start_b / end_b), 1. / (double)(rungs - 1));
+    for (size_t k = 0; k + 1 < rungs; ++k) gb.push_back((int)std::floor(start_b / std::pow(rb, (double)k)));
+    gb.push_back(end_b);
+    if (swapped) std::swap(ga, gb);
 }
 
 bool check(int rc) {
@@ -203,10 +224,7 @@ int main(int argc, char const* argv[]) {
         }
     }
     bool randomize = o.has("randomize");
-    if (o.has("merge") || o.has("nature")) {
-        std::cerr << "the agglomerative merge paths (-g/--merge, -u/--nature) are not part of this build\n";
-        return 1;
-    }
+    const bool merge = o.has("merge"), nature = o.has("nature");
     if (o.has("seed")) { if (!to_num(o.vals["seed"][0], seed)) { std::cerr << "bad value for --seed\n"; return 1; } }
     else seed = (size_t)std::chrono::high_resolution_clock::now().time_since_epoch().count();  // reference :236-239
     uint32_t gen_seed;
@@ -299,7 +317,9 @@ int main(int argc, char const* argv[]) {
             ea.push_back((uint32_t)a); eb.push_back((uint32_t)b);
         }
     }
-    // ---- the labels must already have (KA, KB) blocks: otherwise the reference takes the merge path (:406-451)
+    // ---- the agglomerative paths (reference src/mcmc_main.cc:350-451): -g starts from singleton blocks; initial labels
+    //      whose block counts differ from -z are merged (or split) to (KA, KB).  One replay chain; every agg_merge and every
+    //      anneal below is the reference's call with the reference's arguments.
     {
         size_t ka = 0, kb = 0;
         for (size_t t = 0; t < NA + NB; ++t) {
@@ -307,10 +327,61 @@ int main(int argc, char const* argv[]) {
             else if (t >= NA && memberships_init[t] > kb) kb = memberships_init[t];
         }
         kb -= ka; ka += 1;
-        if (ka != KA || kb != KB) {
-            std::cerr << "initial memberships have (" << ka << ", " << kb << ") blocks but -z asks for (" << KA << ", " << KB
-                      << "): the agglomerative merge path is not part of this build\n";
-            return 1;
+        if (merge) { for (size_t v = 0; v < N; ++v) memberships_init[v] = (unsigned)v; ka = NA; kb = NB; }
+        int diff_a = (int)ka - (int)KA, diff_b = (int)kb - (int)KB;
+        if (merge || diff_a != 0 || diff_b != 0) {
+            if (chains != 1 || o.has("marginalize") || o.has("estimate")) {
+                std::cerr << "the agglomerative paths run one chain (no --chains / --marginalize / --estimate)\n";
+                return 1;
+            }
+            if ((double)ka * (double)kb * 128.0 > 16e9) { std::cerr << "too many initial blocks for the K x K block matrix\n"; return 1; }
+            bisbm_handle* h = nullptr;
+            if (!check(bisbm_create((uint32_t)NA, (uint32_t)NB, ea.size(), ea.data(), eb.data(), (int)device, &h))) return 1;
+            // room for the blocks a split adds
+            if (!check(bisbm_set_option(h, "reserve_ka", (int64_t)std::max(ka, KA))) || !check(bisbm_set_option(h, "reserve_kb", (int64_t)std::max(kb, KB)))) return 1;
+            const uint32_t ka1 = (uint32_t)ka, kb1 = (uint32_t)kb;
+            std::vector<uint32_t> lab(memberships_init.begin(), memberships_init.end());
+            if (!check(bisbm_set_chains(h, 1, &ka1, &kb1, lab.data(), epsilon))) return 1;
+            if (!check(bisbm_replay_init(h, 0, (uint32_t)seed, gen_seed, 0))) return 1;
+            const double sigma = 1.01;
+            double rate = 0.0;
+            uint64_t sweeps = 0;
+            auto greedy_sweep = [&]() -> int {   // anneal(abrupt_cool, {0}, N, steps_await): one sweep at T = 0
+                if (cooling_schedule != "abrupt_cool") { std::cerr << "Only abrupt cooling annealing is supported."; return 1; }
+                return check(bisbm_replay_anneal(h, 0, BISBM_ABRUPT_COOL, 0.f, 0.f, N, steps_await, &rate, &sweeps)) ? 0 : 1;
+            };
+            uint32_t cka = ka1, ckb = kb1;
+            if (merge && nature) {
+                const size_t ceiling = (size_t)std::ceil(std::sqrt(2.0 * (double)ea.size()) / 2);
+                size_t tKA = NA, tKB = NB, tGroups = NA + NB;
+                while (tKA >= ceiling && tKB >= ceiling) {
+                    if (!check(bisbm_replay_agg_merge_total(h, 0, (int)std::ceil((double)tGroups * (sigma - 1) / sigma), 10))) return 1;
+                    if (!check(bisbm_chain_k(h, 0, &cka, &ckb))) return 1;
+                    tKA = cka; tKB = ckb; tGroups = tKA + tKB;
+                    if (greedy_sweep()) return 1;
+                }
+            } else if (merge || (diff_a >= 0 && diff_b >= 0)) {
+                std::vector<int> ka_s, kb_s;
+                geospace((int)ka, (int)KA, (int)kb, (int)KB, sigma, ka_s, kb_s);
+                if (!merge && ka_s.size() == 1 && !check(bisbm_replay_agg_merge(h, 0, diff_a, diff_b, 10))) return 1;
+                for (size_t i = 0; i + 1 < ka_s.size(); ++i) {
+                    if (!check(bisbm_replay_agg_merge(h, 0, -(ka_s[i + 1] - ka_s[i]), -(kb_s[i + 1] - kb_s[i]), 10))) return 1;
+                    if (i != ka_s.size() - 2 && greedy_sweep()) return 1;
+                }
+            } else {
+                if (!check(bisbm_replay_agg_merge(h, 0, diff_a, diff_b, 100))) return 1;
+            }
+            // the final anneal is always abrupt_cool with the user's schedule arguments (src/mcmc_main.cc:397-398, 446-447)
+            if (!check(bisbm_replay_anneal(h, 0, BISBM_ABRUPT_COOL, kw[0], kw[1], sampling_steps, steps_await, &rate, &sweeps))) return 1;
+            double S = 0.0;
+            std::vector<uint32_t> out(N);
+            if (!check(bisbm_chain_k(h, 0, &cka, &ckb)) || !check(bisbm_entropy(h, 0, &S)) || !check(bisbm_get_labels(h, 0, out.data()))) return 1;
+            std::clog << "(Ka, Kb) = (" << cka << ", " << ckb << ") \n";
+            std::clog << "entropy: " << S << "\n";
+            if (merge && nature) std::cout << cka << " " << ckb << " ";
+            output_vec(out, std::cout);
+            bisbm_destroy(h);
+            return 0;
         }
     }
 

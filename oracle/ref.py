@@ -77,6 +77,8 @@ def _load(log_rng):
     L.ref_merge_path.argtypes = [vp, u64, u64, C.c_float, u64, u64]
     L.ref_agg_merge.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     L.ref_agg_merge_total.argtypes = [vp, C.c_int, C.c_int]
+    L.ref_nature_path.restype = dbl
+    L.ref_nature_path.argtypes = [vp, C.c_float, u64, u64]
     L.ref_get_ka.restype = u64
     L.ref_get_ka.argtypes = [vp]
     L.ref_get_kb.restype = u64
@@ -129,6 +131,12 @@ class RefChain:
         s = self.L.ref_merge_path(self.h, KA, KB, p0, sampling_steps, steps_await)
         self.ka, self.kb = int(self.L.ref_get_ka(self.h)), int(self.L.ref_get_kb(self.h))
         self.K = self.ka + self.kb
+        return s
+
+    def nature_path(self, p0, sampling_steps, steps_await):
+        """reference src/mcmc_main.cc:360-379 + 397-402 (-g -u); the chain must start from singleton blocks"""
+        s = self.L.ref_nature_path(self.h, p0, sampling_steps, steps_await)
+        self._refresh_k()
         return s
 
     def _refresh_k(self):

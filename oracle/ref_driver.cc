@@ -145,6 +145,27 @@ void ref_agg_merge_total(void* p, int diff, int nm) {
     h->bm->agg_merge(h->engine, diff, nm);
     h->ka = h->bm->get_KA(); h->kb = h->bm->get_KB();
 }
+// The reference's -g -u path (src/mcmc_main.cc:360-379, 397-402): from singleton blocks, agg_merge(engine, ceil(K (sigma - 1) /
+// sigma), 10) + one greedy sweep until one type has fewer than ceil(sqrt(2E) / 2) blocks, then the final anneal.
+double ref_nature_path(void* p, float p0, uint64_t sampling_steps, uint64_t steps_await) {
+    auto* h = static_cast<ref_handle*>(p);
+    blockmodel_t& bm = *h->bm;
+    const double sigma = 1.01;
+    float_vec_t agg_kw(1, 0.);
+    size_t tKA = h->na, tKB = h->nb, tGroups = h->na + h->nb;
+    size_t num_edges = bm.get_num_edges();
+    size_t ceiling = ceil(sqrt(2 * num_edges) / 2);
+    while (tKA >= ceiling && tKB >= ceiling) {
+        bm.agg_merge(h->engine, ceil(tGroups * (sigma - 1) / sigma), 10);
+        tKA = bm.get_KA(); tKB = bm.get_KB(); tGroups = tKA + tKB;
+        h->mh.anneal(bm, &abrupt_cool_schedule, agg_kw, (h->na + h->nb) * 1, steps_await, h->engine);
+    }
+    float_vec_t kw(2, 0);
+    kw[0] = p0;
+    h->mh.anneal(bm, &abrupt_cool_schedule, kw, sampling_steps, steps_await, h->engine);
+    h->ka = bm.get_KA(); h->kb = bm.get_KB();
+    return bm.entropy();
+}
 uint64_t ref_get_ka(void* p) { return static_cast<ref_handle*>(p)->bm->get_KA(); }
 uint64_t ref_get_kb(void* p) { return static_cast<ref_handle*>(p)->bm->get_KB(); }
 

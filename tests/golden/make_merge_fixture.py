@@ -82,6 +82,20 @@ out["split_s1_k"] = np.array([ch.ka, ch.kb])
 out["split_s1_words"] = np.array(ch.rng_words(), dtype=np.uint64)
 out["split_s1_n_r"] = ch.n_r()
 
+# ---- the -g path (singletons -> (2, 3)) and the -g -u path of main on southernWomen; the CLI tests print these label lines
+edges, na, nb = graph("c1_seed1")
+n = na + nb
+lab = np.arange(n, dtype=np.uint32)
+ch = ref.RefChain(n, na, nb, edges, lab, na, nb, 1.0, 9, log_rng=True)
+ch.init(False)
+out["swg_args"] = np.array([2, 3, 100.0, 10 * n, 1000], dtype=np.float64)
+out["swg_entropy"] = ch.merge_path(2, 3, 100.0, 10 * n, 1000)
+state(ch, "swg", out)
+ch = ref.RefChain(n, na, nb, edges, lab, na, nb, 1.0, 9, log_rng=True)
+ch.init(False)
+out["swu_entropy"] = ch.nature_path(100.0, 10 * n, 1000)
+state(ch, "swu", out)
+
 np.savez_compressed(os.path.join(OUT, "merge.npz"), **out)
 for k in sorted(out):
     v = np.asarray(out[k])

@@ -55,8 +55,8 @@ def test_usage_and_argument_errors(cli):
     assert rc == 1 and "number of partitions is required (-z flag)" in err
     rc, out, err = run(cli, "-e", "x", "-y", 18, 14, "-n", 10, 10, "-z", 1, 1)
     assert rc == 1 and "Types do not sum to the number of vertices!" in err
-    rc, out, err = run(cli, "-e", "x", "-y", 18, 14, "-n", 18, 14, "-z", 1, 1, "--merge")
-    assert rc == 1 and "not part of this build" in err
+    rc, out, err = run(cli, "-e", "x", "-y", 18, 14, "-n", 18, 14, "-z", 1, 1, "--merge", "--chains", 4)
+    assert rc == 1 and "agglomerative paths run one chain" in err
     rc, out, err = run(cli, "-e", "x", "-y", 18, 14, "-n", 18, 14, "-z", 1, 1, "--bogus")
     assert rc == 1 and "unrecognised option" in err
 
@@ -159,3 +159,40 @@ def test_gpus_mode_shards_chains_and_all_reduces(cli, tmp_path):
     rc3, out3, err3 = run(cli, "-e", path, "-y", 500, 500, "--membership_path", mb, "-c", "abrupt_cool", "-a", 50000, "-t", 100000,
                           "-x", 10 ** 9, "--chains", 16, "--gpus", 2, "--seed", 3)
     assert rc3 == 0 and "entropy:" in err3 and len(out3.split()) == 1000
+
+
+@pytest.mark.gpu
+def test_merge_paths_reproduce_reference_lines(cli, tmp_path):
+    """The agglomerative paths of main (reference src/mcmc_main.cc:350-451) with the engine seeds pinned: -g (singleton
+    blocks merged down the sigma = 1.01 ladder to -z), -g -u (until a type has fewer than sqrt(2E)/2 blocks; prints Ka Kb
+    first) and --mb labels with more blocks than -z.  stdout must be the reference's label line (tests/golden/merge.npz,
+    generated from the unmodified reference build), stderr its two summary lines."""
+    m = load_golden("merge")
+    g = load_golden("c1_seed1")
+    path = write_edges(tmp_path, g)
+    common = ["-e", path, "-y", 18, 14, "-n", 18, 14, "-c", "abrupt_cool", "-a", 100, "-t", 320, "-x", 1000, "-d", 9,
+              "--gen_seed", 12345]
+    rc, out, err = run(cli, *common, "-z", 2, 3, "-g")
+    assert rc == 0, err
+    assert out == " ".join(str(x) for x in m["swg_labels"]) + " \n"
+    assert "(Ka, Kb) = (2, 3) " in err and ("entropy: %s" % float("%.6g" % m["swg_entropy"])) in err
+    rc, out, err = run(cli, *common, "-z", 2, 3, "-g", "-u")
+    assert rc == 0, err
+    ka, kb = (int(x) for x in m["swu_k"])
+    assert out == "%d %d " % (ka, kb) + " ".join(str(x) for x in m["swu_labels"]) + " \n"
+    assert "(Ka, Kb) = (%d, %d) " % (ka, kb) in err
+    # labels with (8, 12) blocks, -z 4 6: the merge path for "more blocks than asked for"
+    g2 = load_golden("c2_const_k46")
+    path2 = write_edges(tmp_path, g2, "b.edgelist")
+    KA, KB, p0, steps, await_ = m["b1000_path_args"]
+    rc, out, err = run(cli, "-e", path2, "-y", 500, 500, "-n", 500, 500, "--mb", *[int(x) for x in m["b1000_labels0"]], "-z", int(KA),
+                       int(KB), "-c", "abrupt_cool", "-a", int(p0), "-t", int(steps), "-x", int(await_), "-d", 11, "--gen_seed", 12345)
+    assert rc == 0, err
+    assert out == " ".join(str(x) for x in m["b1000_path_labels"]) + " \n"
+    assert "(Ka, Kb) = (4, 6) " in err and ("entropy: %s" % float("%.6g" % m["b1000_path_entropy"])) in err
+    # fewer blocks than asked for: the split path (property check only, see include/bisbm.h)
+    rc, out, err = run(cli, "-e", path2, "-y", 500, 500, "-n", 500, 500, "--mb", *[int(x) for x in g2["labels0"]], "-z", 5, 6,
+                       "-c", "abrupt_cool", "-a", 100, "-t", 2000, "-x", 1000, "-d", 2, "--gen_seed", 12345)
+    assert rc == 0, err
+    lab = np.array(out.split(), dtype=np.int64)
+    assert "(Ka, Kb) = (5, 6) " in err and lab.size == 1000 and set(lab[:500]) == set(range(5)) and set(lab[500:]) == set(range(5, 11))
