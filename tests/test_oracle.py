@@ -104,3 +104,36 @@ def test_port_matches_reference_build_on_random_cases():
         assert a.anneal(sched, p0, p1, 12 * n, 50) == b.anneal(sched, p0, p1, 12 * n, 50)
         assert (a.labels() == b.labels()).all() and (a.m() == b.m()).all() and (a.eta() == b.eta()).all()
         assert a.entropy_accum() == b.entropy_accum() and a.entropy() == b.entropy()
+
+
+def test_merge_fixture_is_self_consistent():
+    """tests/golden/merge.npz (reference outputs of agg_merge and of the merge paths of main): every recorded state is a
+    valid bipartite partition with the recorded block counts, and its m_rs / e_r / n_r equal a rebuild from its labels."""
+    from helpers import counts_from_labels
+    g = load_golden("merge")
+    graphs = {"sw": "c1_seed1", "swg": "c1_seed1", "swu": "c1_seed1", "b1000": "c2_const_k46"}
+    tags = sorted(k[:-len("_labels")] for k in g if k.endswith("_labels") and (k[:-len("_labels")] + "_k") in g)
+    assert len(tags) >= 10
+    for tag in tags:
+        gr = load_golden(graphs[tag.split("_")[0]])
+        na, nb = gr["na"], gr["nb"]
+        ka, kb = (int(x) for x in g[tag + "_k"])
+        lab = g[tag + "_labels"]
+        assert set(lab[:na]) == set(range(ka)) and set(lab[na:]) == set(range(ka, ka + kb)), tag
+        m, e, nr, eta = counts_from_labels(gr["edges"], na, nb, lab, ka, kb)
+        assert (g[tag + "_m"] == m).all() and (g[tag + "_m_r"] == e).all() and (g[tag + "_n_r"] == nr).all(), tag
+
+
+@pytest.mark.skipif(not ref.available(), reason="reference build (oracle/_ref) not present")
+def test_merge_fixture_matches_reference_build():
+    """The fixture is what the reference build produces today (first two agg_merge calls of the southernWomen case)."""
+    g = load_golden("merge")
+    gr = load_golden("c1_seed1")
+    na, nb = gr["na"], gr["nb"]
+    n = na + nb
+    ch = ref.RefChain(n, na, nb, gr["edges"], g["sw_labels0"], na, nb, 1.0, 7, log_rng=True)
+    ch.init(False)
+    ch.agg_merge(6, 4, 10)
+    assert (ch.labels() == g["sw_s1_labels"]).all() and tuple(ch.rng_words()) == tuple(int(x) for x in g["sw_s1_words"])
+    ch.agg_merge(5, 0, 10)
+    assert (ch.labels() == g["sw_s2_labels"]).all() and ch.entropy() == g["sw_s2_entropy"]
