@@ -616,7 +616,9 @@ def main():
     acceptance = float(np.mean(accs))
     kern, wpc_, cpg_, slice_ = pool.sweep_info()
     kernel_names = {0: "sweep_kernel<double, counts in L2>", 1: "sweep_kernel<double, staged counts> (round 1)",
-                    2: "sweep2_kernel<float, staged counts>", 3: "sweep2_kernel<double, staged counts>"}
+                    2: "sweep2_kernel<float, staged counts>", 3: "sweep2_kernel<double, staged counts>",
+                    4: "sweep2_kernel<float, counts in L2>", 5: "sweep2_kernel<double, counts in L2>",
+                    6: "sweep2_kernel<float, counts over a cluster>", 7: "sweep2_kernel<double, counts over a cluster>"}
     kernel_name = kernel_names[kern]
     config["sweep_plan"] = {"kernel": kernel_name, "warps_per_cta": wpc_, "ctas_per_chain_group": cpg_,
                             "slice_vertices_per_launch": slice_, "max_inflight": slice_,

@@ -82,6 +82,9 @@ struct SweepParams {
     uint32_t kat_chain, kat_v, kat_s;   //    {dS, log accu_r} to kat_out instead of accepting / committing (bisbm_parallel_transition)
     double* kat_out;
     double beta0;                    // 1 / p0, computed once on the host (constant schedule: 1/T of every step)
+    uint32_t cluster_size;           // sweep2_kernel<.., CLUSTER>: CTAs per cluster (m_rs of the group distributed over their shared memories)
+    uint32_t rows_per_cta;           //   own-type blocks whose m rows one CTA of the cluster holds (ceil(kown_max / cluster_size))
+    uint32_t work_ctas;              //   CTAs per group that take vertices (<= ctas_per_group; the rest only hold their rows of m)
     uint32_t vary_k;                 // estimate mode (README "estimation"): blocks may empty and be re-populated; the K-dependent
                                      // prior terms of the description length enter dS with the OCCUPIED block counts
 };

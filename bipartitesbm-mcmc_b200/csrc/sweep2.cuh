@@ -309,11 +309,12 @@ inline
 #ifdef __CUDACC__
 __host__ __device__
 #endif
-Sweep2Layout sweep2_layout(uint32_t KA, uint32_t KB, uint32_t type, uint32_t warps, uint32_t rsize, bool staged = true) {
+Sweep2Layout sweep2_layout(uint32_t KA, uint32_t KB, uint32_t type, uint32_t warps, uint32_t rsize, bool staged = true,
+                           uint32_t rows_per_cta = 0) {   // rows_per_cta > 0: cluster form, this CTA holds that many own-type rows of m
     const uint32_t kown = type ? KB : KA, kopp = type ? KA : KB;
     Sweep2Layout L;
     uint32_t o = 0;
-    L.oM = o; o += staged ? KA * KB * 128u : 0u;        // counts in L2 (staged = false): only the read-only tables,
+    L.oM = o; o += staged ? (rows_per_cta ? rows_per_cta * kopp : KA * KB) * 128u : 0u;        // counts in L2 (staged = false): only the read-only tables,
     L.oEo = o; o += staged ? kown * 128u : 0u;          // the vertex batch, the histograms and the label tiles
     L.oNo = o; o += staged ? kown * 128u : 0u;
     L.oEp = o; o += kopp * 128u;
@@ -381,6 +382,17 @@ __device__ __forceinline__ void bulk_commit_wait_all() {
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
+// thread-block cluster: rank, address of a shared-memory location in another CTA of the cluster, accesses through it, barrier
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_map(uint32_t saddr, uint32_t rank) {
+    uint32_t a; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(a) : "r"(saddr), "r"(rank)); return a;
+}
+__device__ __forceinline__ int cl_ld(uint32_t a) { int v; asm volatile("ld.shared::cluster.s32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void cl_red(uint32_t a, int v) { asm volatile("red.shared::cluster.add.s32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // counts kept in L2 (STAGED = false): every read goes to L2 (ld.global.cg: other SMs update them with reductions)
 __device__ __forceinline__ int gl_ld(uint64_t base, uint32_t off) {
     int v; asm("{\n\t.reg .u64 a;\n\tcvt.u64.u32 a, %2;\n\tadd.u64 a, a, %1;\n\tld.global.cg.s32 %0, [a];\n\t}" : "=r"(v) : "l"(base), "r"(off)); return v;
@@ -421,9 +433,9 @@ __device__ __noinline__ static double slow2_beta(int schedule, float p0, float p
 __global__ void sweep2_preinit_kernel(const int32_t* __restrict__ m, const int32_t* __restrict__ e, const int32_t* __restrict__ nr,
                                       int32_t* __restrict__ m2, int32_t* __restrict__ e2, int32_t* __restrict__ nr2,
                                       int32_t* __restrict__ nr_live, uint32_t n_m, uint32_t n_e, uint32_t KA, uint32_t KB,
-                                      uint32_t type, uint32_t mult) {
+                                      uint32_t type, uint32_t mult, uint32_t mult_m) {   // mult_m: publishers of m per group - 1 (clusters, or CTAs)
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_m) m2[i] = (int32_t)(0u - mult * (uint32_t)m[i]);
+    if (i < n_m) m2[i] = (int32_t)(0u - mult_m * (uint32_t)m[i]);
     if (i < n_e) {
         const uint32_t slot = (i >> 5) % (KA + KB);
         const bool own = type ? (slot >= KA) : (slot < KA);
@@ -439,7 +451,13 @@ __global__ void sweep2_preinit_kernel(const int32_t* __restrict__ m, const int32
 // histogram bins), K per type <= 256 (u8 labels).
 // STAGED = false: K too large for shared memory -- m_rs / e_r / n_r stay in L2 (loads .cg, commits by global reductions,
 // every CTA sees every committed move at once: no slices, no staging, no publish); the rest of the kernel is the same.
-template <typename R, int KF, int TYPE, bool STAGED = true, int NT = 512>
+// CLUSTER = true (K too large for one CTA's shared memory, up to ~64 + 64): the group's m_rs is DISTRIBUTED over the shared
+// memories of a thread-block cluster -- CTA k of the cluster holds the rows of own-type blocks [k RPC, (k+1) RPC) -- and every
+// CTA reads / reduces all of it through distributed shared memory (ld / red.shared::cluster).  The row of the source block r
+// and of the target s are fixed per vertex, so the pass and the commit address m(r,t), m(s,t) exactly as in the one-CTA form
+// (one multiply-add per edge on a per-vertex base); only the categorical scan walks all CTAs.  The cluster's copy is exact for
+// all its CTAs (no staleness inside a cluster); several clusters per group publish like several CTAs do.
+template <typename R, int KF, int TYPE, bool STAGED = true, int NT = 512, bool CLUSTER = false>
 __global__ void __launch_bounds__(NT, 1) sweep2_kernel(const __grid_constant__ SweepParams P) {
     typedef Ar<R> AR;
     extern __shared__ __align__(128) unsigned char s2_smem[];
@@ -454,8 +472,13 @@ __global__ void __launch_bounds__(NT, 1) sweep2_kernel(const __grid_constant__ S
     const uint32_t type = KF ? (uint32_t)TYPE : P.type;
     const uint32_t C = P.s.C, KB = KF ? (uint32_t)KF : P.s.KB, KA = KF ? (uint32_t)KF : P.s.KA, W = P.s.W, KK = KA + KB;
     const uint32_t kown_max = type ? KB : KA, kopp_max = type ? KA : KB;
-    const uint32_t group = P.group_offset + blockIdx.x % P.n_groups;
-    const uint32_t cta_in_group = blockIdx.x / P.n_groups;
+    static_assert(!CLUSTER || (STAGED && KF == 0), "the cluster form is a staged, generic-stride instantiation");
+    uint32_t crank = 0, csz = 1;
+    if constexpr (CLUSTER) { crank = cluster_ctarank(); csz = P.cluster_size; }
+    const uint32_t unit = CLUSTER ? blockIdx.x / csz : blockIdx.x;       // cluster (or CTA) index: consecutive units -> consecutive groups
+    const uint32_t group = P.group_offset + unit % P.n_groups;
+    const uint32_t cta_in_group = CLUSTER ? (unit / P.n_groups) * csz + crank : unit / P.n_groups;
+    const uint32_t RPC = CLUSTER ? P.rows_per_cta : 0u;
     const uint32_t own_off = type ? KA : 0, opp_off = type ? 0 : KA;
 
     int32_t* const gM = P.s.m + (size_t)group * KA * KB * GROUP;
@@ -473,7 +496,7 @@ __global__ void __launch_bounds__(NT, 1) sweep2_kernel(const __grid_constant__ S
     const R eps = (R)P.s.eps;
     const R epsK32 = (R)(P.s.eps * (double)K * 4294967296.0);   // threshold scale of the uniform-vs-categorical test
 
-    const Sweep2Layout L = sweep2_layout(KA, KB, type, wpc, (uint32_t)sizeof(R), STAGED);
+    const Sweep2Layout L = sweep2_layout(KA, KB, type, wpc, (uint32_t)sizeof(R), STAGED, RPC);
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem_raw);
     int32_t* const sM = reinterpret_cast<int32_t*>(smem_raw + L.oM);
     int32_t* const sEo = reinterpret_cast<int32_t*>(smem_raw + L.oEo);
@@ -494,10 +517,26 @@ __global__ void __launch_bounds__(NT, 1) sweep2_kernel(const __grid_constant__ S
         }
         __syncthreads();
         if (threadIdx.x == 0) {
-            const uint32_t bM = KA * KB * 128u, bO = kown_max * 128u, bP = kopp_max * 128u;
+            const uint32_t bO = kown_max * 128u, bP = kopp_max * 128u;
+            if constexpr (CLUSTER) {
+                // this CTA's rows of m: own-type blocks [x0, x0 + nx).  Type a owns rows of the [KA][KB] array (contiguous);
+                // type b owns columns (one segment per row a), kept as [a][local b]
+                const uint32_t x0 = crank * RPC, nx = (x0 < kown_max) ? min(RPC, kown_max - x0) : 0u;
+                mbar_expect_tx(mbar, nx * kopp_max * 128u + 2u * bO + bP);
+                if (type == 0) {
+                    const uint32_t bM = nx * KB * 128u;
+                    const char* src = reinterpret_cast<const char*>(gM) + (size_t)x0 * KB * 128u;
+                    for (uint32_t off = 0; off < bM; off += 32768u) bulk_g2s(sbase + L.oM + off, src + off, min(32768u, bM - off), mbar);
+                } else if (nx) {
+                    for (uint32_t a = 0; a < KA; ++a)
+                        bulk_g2s(sbase + L.oM + a * RPC * 128u, reinterpret_cast<const char*>(gM) + ((size_t)a * KB + x0) * 128u, nx * 128u, mbar);
+                }
+            } else {
+            const uint32_t bM = KA * KB * 128u;
             mbar_expect_tx(mbar, bM + 2u * bO + bP);
             for (uint32_t off = 0; off < bM; off += 32768u)
                 bulk_g2s(sbase + L.oM + off, reinterpret_cast<const char*>(gM) + off, min(32768u, bM - off), mbar);
+            }
             bulk_g2s(sbase + L.oEo, gE + own_off * 32, bO, mbar);
             bulk_g2s(sbase + L.oNo, gNR + own_off * 32, bO, mbar);
             bulk_g2s(sbase + L.oEp, gE + opp_off * 32, bP, mbar);
@@ -512,9 +551,10 @@ __global__ void __launch_bounds__(NT, 1) sweep2_kernel(const __grid_constant__ S
 
     // ---- the CTA's share of the slice: positions pos_begin + cta + j * ctas_per_group, j < cnt ----
     const uint32_t nv = type ? G.nb : G.na, v0 = type ? G.na : 0;
-    const uint32_t cpg = P.ctas_per_group;
+    const uint32_t cpg = CLUSTER ? P.work_ctas : P.ctas_per_group;      // CTAs of the group that take vertices
     const uint32_t span = P.pos_end - P.pos_begin;
-    const uint32_t cnt = P.kat_mode ? 1u : ((span > cta_in_group) ? (span - cta_in_group + cpg - 1u) / cpg : 0u);
+    const uint32_t cnt = P.kat_mode ? (cta_in_group == 0u ? 1u : 0u)
+                                    : ((cta_in_group < cpg && span > cta_in_group) ? (span - cta_in_group + cpg - 1u) / cpg : 0u);
     const uint64_t pkey = (P.sweep * 2 + type) * 0x9E3779B97F4A7C15ull + (uint64_t)group * 0xD1B54A32D192ED03ull;
     auto prepare = [&](uint32_t j0) -> uint32_t {   // entries j0 .. j0 + nb - 1 into sVtx; all threads
         const uint32_t nb = (cnt > j0) ? min((uint32_t)S2_VB, cnt - j0) : 0u;
@@ -553,6 +593,7 @@ __global__ void __launch_bounds__(NT, 1) sweep2_kernel(const __grid_constant__ S
         }
     }
     __syncthreads();
+    if constexpr (CLUSTER) cluster_sync_all();      // every CTA's rows of m are in place before anybody reads them
 
     // estimate mode: occupied blocks of this lane's chain, per type (own type tracked through this warp's own moves)
     int occ_own = 0, occ_opp = 0;
@@ -575,13 +616,30 @@ __global__ void __launch_bounds__(NT, 1) sweep2_kernel(const __grid_constant__ S
     const uint32_t tile_lane = tile_w + lane * 36u;                               // this chain's labels, edge e at +e
     const uint32_t tile_st = tile_w + (lane & 3u) * 288u + (lane >> 2);            // store base: chains 8 (lane%4) + i, row lane/4 (+ 8 j)
     // m(x_own, t_opp) at byte offset x*SX + t*ST of this lane's view of m_rs
-    const uint32_t SX = (type ? 1u : KB) * 128u, ST = (type ? KB : 1u) * 128u;
+    const uint32_t SX = (type ? 1u : KB) * 128u, ST = (type ? (CLUSTER ? RPC : KB) : 1u) * 128u;
+    // cluster form: this lane's view of CTA k's rows starts at cbase0 + k * cstride in the shared::cluster window
+    uint32_t cbase0 = 0, cstride = 0;
+    if constexpr (CLUSTER) {
+        cbase0 = cluster_map(M_base, 0);
+        cstride = cluster_map(M_base, 1) - cbase0;
+        for (uint32_t k = 2; k < csz; ++k) if (cluster_map(M_base, k) != cbase0 + k * cstride) asm volatile("trap;");
+    }
+    const uint32_t rpc_rcp = CLUSTER ? (65536u + RPC - 1u) / RPC : 0u;      // x / RPC = (x * rpc_rcp) >> 16 for x < 256
+    // handle of own-type block x's row of m: byte offset (one CTA) or shared::cluster address (cluster)
+    auto m_row = [&](uint32_t x) -> uint32_t {
+        if constexpr (CLUSTER) { const uint32_t o = (x * rpc_rcp) >> 16; return cbase0 + o * cstride + (x - o * RPC) * SX; }
+        else return x * SX;
+    };
     // count accessors: shared-memory views (STAGED) or the arrays in L2
     const uint64_t gMl = (uint64_t)__cvta_generic_to_global(gM + lane);
     const uint64_t gEol = (uint64_t)__cvta_generic_to_global(gE + own_off * 32 + lane);
     const uint64_t gNol = (uint64_t)__cvta_generic_to_global(gNR + own_off * 32 + lane);
-    auto m_ld = [&](uint32_t off) -> int { if constexpr (STAGED) return sh_ld(M_base + off); else return gl_ld(gMl, off); };
-    auto m_red = [&](uint32_t off, int v) { if constexpr (STAGED) sh_red_add(M_base + off, v); else gl_red(gMl, off, v); };
+    auto m_ld = [&](uint32_t off) -> int {
+        if constexpr (CLUSTER) return cl_ld(off); else if constexpr (STAGED) return sh_ld(M_base + off); else return gl_ld(gMl, off);
+    };
+    auto m_red = [&](uint32_t off, int v) {
+        if constexpr (CLUSTER) cl_red(off, v); else if constexpr (STAGED) sh_red_add(M_base + off, v); else gl_red(gMl, off, v);
+    };
     auto eo_ld = [&](uint32_t blk) -> int { if constexpr (STAGED) return sh_ld(Eo_base + blk * 128u); else return gl_ld(gEol, blk * 128u); };
     auto eo_red = [&](uint32_t blk, int v) { if constexpr (STAGED) sh_red_add(Eo_base + blk * 128u, v); else gl_red(gEol, blk * 128u, v); };
     auto no_ld = [&](uint32_t blk) -> int { if constexpr (STAGED) return sh_ld(No_base + blk * 128u); else return gl_ld(gNol, blk * 128u); };
@@ -714,7 +772,17 @@ __global__ void __launch_bounds__(NT, 1) sweep2_kernel(const __grid_constant__ S
                 // categorical over row m[t][.]: s = #{x : cum_x <= z}; wz tracks cum - z - 1 (negative while cum <= z)
                 int wz = -(int)mulhi32(rz, (uint32_t)e_t) - 1;
                 uint32_t cnt_le = 0;
-                {
+                if constexpr (CLUSTER) {
+                    for (uint32_t o = 0, x0 = 0; x0 < kown_max; ++o, x0 += RPC) {       // CTA o of the cluster holds blocks x0 ..
+                        uint32_t a = cbase0 + o * cstride + tq * ST;
+                        const uint32_t nx = min(RPC, kown_max - x0);
+#pragma unroll 4
+                        for (uint32_t x = 0; x < nx; ++x, a += SX) {
+                            wz += m_ld(a);
+                            cnt_le += ((uint32_t)wz) >> 31;
+                        }
+                    }
+                } else {
                     uint32_t a = tq * ST;
 #pragma unroll 8
                     for (uint32_t x = 0; x < kown_max; ++x, a += SX) {   // uniform bound; blocks >= kown hold 0
@@ -740,7 +808,7 @@ __global__ void __launch_bounds__(NT, 1) sweep2_kernel(const __grid_constant__ S
                 // ---- one pass over v's neighbours: dS and the Hastings factor (transition_ratio).  Every lane
                 //      runs it (masked lanes cost the same issue slots); only `eval` lanes may commit. ----
                 MAcc<R> A; macc_init(A);
-                const uint32_t Mr = r * SX, Ms = s * SX;
+                const uint32_t Mr = m_row(r), Ms = m_row(s);
                 // histogram bin of label t: word t / 4, byte t % 4 -- or, with exactly 8 words (the Ka = Kb = 32 instantiation),
                 // word t % 8, byte t / 8: the byte's shift is then t & 0x18, one instruction less per edge
                 auto h_sh = [&](uint32_t t) -> uint32_t { if constexpr (KF == 32) return t & 0x18u; else return (t & 3u) << 3; };
@@ -948,9 +1016,37 @@ __global__ void __launch_bounds__(NT, 1) sweep2_kernel(const __grid_constant__ S
     }
 
     // ---- publish the staged counts ----
+    if constexpr (CLUSTER) cluster_sync_all();       // the other CTAs' reductions into this CTA's rows have landed; nobody touches them again
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // shared-memory writes of this thread -> visible to the bulk engine
     __syncthreads();
     if (P.kat_mode || !STAGED) return;
+    if constexpr (CLUSTER) {
+        if (P.exclusive) {     // one working CTA: its e_r / n_r views and the cluster's m are exact -> written back in place
+            const uint32_t x0 = crank * RPC, nx = (x0 < kown_max) ? min(RPC, kown_max - x0) : 0u;
+            if (type == 0) copy_i4(gM + (size_t)x0 * KB * 32, sM, nx * KB * 32);
+            else for (uint32_t a = 0; a < KA; ++a) copy_i4(gM + ((size_t)a * KB + x0) * 32, sM + a * RPC * 32, nx * 32);
+            if (cta_in_group == 0) {
+                copy_i4(gE + own_off * 32, sEo, kown_max * 32);
+                copy_i4(gNR + own_off * 32, sNo, kown_max * 32);
+            }
+            return;
+        }
+        if (threadIdx.x == 0) {
+            const uint32_t x0 = crank * RPC, nx = (x0 < kown_max) ? min(RPC, kown_max - x0) : 0u;
+            char* const nM = reinterpret_cast<char*>(P.m_next + (size_t)group * KA * KB * GROUP);
+            const uint32_t bO = kown_max * 128u;
+            if (type == 0) {
+                const uint32_t bM = nx * KB * 128u;
+                for (uint32_t off = 0; off < bM; off += 32768u) bulk_red_add_s32(nM + (size_t)x0 * KB * 128u + off, sbase + L.oM + off, min(32768u, bM - off));
+            } else if (nx) {
+                for (uint32_t a = 0; a < KA; ++a) bulk_red_add_s32(nM + ((size_t)a * KB + x0) * 128u, sbase + L.oM + a * RPC * 128u, nx * 128u);
+            }
+            bulk_red_add_s32(P.e_next + (size_t)group * KK * GROUP + own_off * 32, sbase + L.oEo, bO);
+            bulk_red_add_s32(P.nr_next + (size_t)group * KK * GROUP + own_off * 32, sbase + L.oNo, bO);
+            bulk_commit_wait_all();
+        }
+        return;
+    }
     if (P.exclusive) {
         copy_i4(gM, sM, KA * KB * 32);
         copy_i4(gE + own_off * 32, sEo, kown_max * 32);

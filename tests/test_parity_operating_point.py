@@ -48,7 +48,7 @@ def _kat_check(pool, chain, kv, ks, kd, ka, lab, precision):
     return worst_ds, worst_la, checked
 
 
-@pytest.mark.parametrize("counts", ["staged", "l2"])
+@pytest.mark.parametrize("counts", ["staged", "l2", "cluster"])
 @pytest.mark.parametrize("precision", ["fp64", "fp32"])
 @pytest.mark.parametrize("name", KAT_GOLDENS)
 def test_parallel_kernel_transition_kats(host, name, precision, counts):
@@ -60,6 +60,8 @@ def test_parallel_kernel_transition_kats(host, name, precision, counts):
     pool.set_precision(precision)
     if counts == "l2":
         pool.set_option("kernel", 5)      # sweep2_kernel<.., STAGED = false>: the large-K form of the same kernel
+    if counts == "cluster":
+        pool.set_option("kernel", 7)      # sweep2_kernel<.., CLUSTER>: m_rs distributed over a thread-block cluster
     w1, w2, n = _kat_check(pool, 33, g["kat_v"], g["kat_s"], g["kat_dS"], g["kat_accu"], g["init_labels"], precision)
     print("%s %s: %d known answers, worst rel dS error %.2e, worst |log accu error| %.2e" % (name, precision, n, w1, w2))
     assert n > 0
