@@ -58,6 +58,18 @@ def planted(na, nb, ka, kb, n_edges, seed, ratio=10.0):
     return np.stack([ea, eb], 1).astype(np.uint32)
 
 
+def planted_chunked(na, nb, ka, kb, n_edges, seed, chunk=50_000_000):
+    """The same generator in pieces of `chunk` edges (one RNG stream per piece), writing into one preallocated uint32 array:
+    bounded host memory for the 10^9-edge graph of BASELINE configs[4]."""
+    out = np.empty((n_edges, 2), dtype=np.uint32)
+    done, k = 0, 0
+    while done < n_edges:
+        m = min(chunk, n_edges - done)
+        out[done:done + m] = planted(na, nb, ka, kb, m, seed * 1000003 + k)
+        done += m; k += 1
+    return out
+
+
 def planted_labels(na, nb, ka, kb):
     return np.concatenate([np.arange(na) * ka // na, ka + np.arange(nb) * kb // nb]).astype(np.uint32)
 
@@ -287,7 +299,7 @@ def bench_c5(args, rank, world, local_rank):
     K = 128
     C = args.c5_chains
     t_gen = time.perf_counter()
-    edges = planted(na, nb, K, K, args.c5_edges, 0)
+    edges = planted(na, nb, K, K, args.c5_edges, 0) if args.c5_edges <= 200_000_000 else planted_chunked(na, nb, K, K, args.c5_edges, 0)
     t_gen = time.perf_counter() - t_gen
     t_build = time.perf_counter()
     graph = host.Graph(edges, na, nb, device=local_rank)

@@ -142,7 +142,7 @@ int bisbm_set_precision(bisbm_handle* h, int mode);
 /* Tuning options of the parallel sweep (no environment variables are read):
  *   "inflight_div"  default in-flight bound of bisbm_anneal(max_inflight = 0) = half sweep / value (default 64)
  *   "kernel"        -1 automatic; 0 / 1 force the round-1 kernels (counts in L2 / staged, double); 5 force sweep2 with
- *                   counts in L2 (A/B runs and tests)
+ *                   counts in L2; 7 sweep2 with m_rs distributed over a thread-block cluster (A/B runs and tests)
  *   "generic"       1: never take the Ka = Kb = 32 compile-time specialisation
  *   "vary_k"        1: estimate mode (README "estimation", no code in the reference snapshot): blocks may empty and be
  *                   re-populated by the uniform part of the proposal (no "would empty block r" veto), the K-dependent
@@ -154,7 +154,8 @@ int bisbm_set_option(bisbm_handle* h, const char* name, int64_t value);
 /* which sweep kernel the last parallel call launched and how the half sweep was cut:
  * kernel 0 = round-1 sweep_kernel (double, counts in L2: hubs of degree > 255, K > 256 per type); 1 = round-1 staged
  * double kernel; 2 / 3 = sweep2_kernel<float / double>, counts staged in shared memory (3 is the default);
- * 4 / 5 = sweep2_kernel<float / double>, counts in L2 (K too large for shared memory);
+ * 4 / 5 = sweep2_kernel<float / double>, counts in L2 (K too large for shared memory); 6 / 7 = sweep2_kernel<float /
+ * double>, m_rs distributed over a thread-block cluster (on request);
  * slice = vertices of the visiting order per launch (the staleness bound between CTAs of one chain group) */
 int bisbm_sweep_info(bisbm_handle* h, int* kernel, uint32_t* warps_per_cta, uint32_t* ctas_per_group, uint32_t* slice);
 /* transition_ratio (src/metropolis_hasting.cc:103-192) for moving v to global block s in chain `chain`, evaluated by the
