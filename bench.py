@@ -596,6 +596,12 @@ def main():
         pool.marginals_clear()
         pool.marginalize(0, 1, 1, seeds)
         pkg.dist.allreduce_marginals(pool)
+    # the labels at the start of the timed region: the end-to-end arm (and the fp32 figure) restart from them, so every arm
+    # times the SAME phase of the chains (throughput follows their state: profiles/r02_experiments.txt)
+    lab_dtype = torch.uint8 if ka + kb <= 256 else torch.int32
+    np_view = (lambda t: t.numpy()) if lab_dtype == torch.uint8 else (lambda t: t.numpy().view(np.uint32))
+    snap_host = torch.empty((C, n), dtype=lab_dtype).pin_memory()
+    pool.labels(out=np_view(snap_host))
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
@@ -638,12 +644,10 @@ def main():
     dtype = "f32+int32 (dS summed in f64)" if kern == 2 else "f64+int32"
 
     # -------- e2e: host buffers in, host buffers out, every step (8-bit labels: K = ka + kb <= 256 here)
-    lab_dtype = torch.uint8 if ka + kb <= 256 else torch.int32
-    np_view = (lambda t: t.numpy()) if lab_dtype == torch.uint8 else (lambda t: t.numpy().view(np.uint32))
     in_host = torch.empty((C, n), dtype=lab_dtype).pin_memory()
     out_host = torch.empty((C, n), dtype=lab_dtype).pin_memory()
-    pool.labels(out=np_view(out_host))
-    in_host.copy_(out_host)
+    in_host.copy_(snap_host)                      # same starting labels as the resident arm's timed region
+    config["e2e_start"] = "labels at the start of the resident arm's timed region (same phase of the chains)"
     # a changed byte per step so the library cannot take its "labels unchanged -> keep the counts" shortcut
     def perturb(t, step):
         a = np_view(t)
@@ -676,6 +680,7 @@ def main():
     # -------- extra: the same pool with fp32 move arithmetic (short run, state resident), for the record
     extra = {}
     if not args.no_fp32_extra and args.precision == "fp64":
+        pool.set_labels(np_view(snap_host))       # same phase of the chains again
         pool.set_precision("fp32")
         pool.anneal("constant", 1.0, 0.0, duration, 10 ** 18, seeds)
         ms32, mv32 = 0.0, 0

@@ -19,6 +19,7 @@
 #include <map>
 #include <set>
 #include <memory>
+#include <mutex>
 #include <numeric>
 #include <string>
 #include <vector>
@@ -26,6 +27,7 @@
 #include "ingest.cuh"
 #include "replay.cuh"
 #include "merge.cuh"
+#include "gltable.h"
 #include "sweep_aux.cuh"
 #include "sweep2.cuh"
 
@@ -89,6 +91,8 @@ struct bisbm_handle {
     double ent_base = 0.0;  // label-independent entropy terms
     // tables
     double* d_qtab = nullptr;
+    GlNode* d_gl = nullptr;             // tabulated g(u), lf(u) of the asymptotic log q (inside d_qtab's allocation)
+    uint32_t gl_n = 0;
     uint32_t qn = 0, qk = 0;
     double* d_lg = nullptr;
     uint64_t lg_n = 0;
@@ -171,11 +175,24 @@ StateView sview(const bisbm_handle* h) {
     return s;
 }
 
+// g(u), lf(u) of log_q_approx (devmath.cuh logq_gl) at u_i = exp(kGlT0 + i / kGlInvH), i < n: computed once per process with
+// the reference's own fixed-point iteration and glibc, uploaded with every graph's exact table.  u = k / sqrt(n) lies in
+// [n^(-1/4), sqrt(n)] for the arguments that reach the asymptotic branch (10001 <= n <= 2^32).
+const double kGlT0 = -2.0, kGlInvH = 1024.0, kGlT1 = 11.6;       // u from 0.135 to 1.1e5 (a block of degree sum e <= 255 n, e >= 10001,
+                                                                 // has u = n / sqrt(e) >= 0.39; smaller u takes the formula itself)
+const std::vector<GlNode>& gl_table() {
+    static std::vector<GlNode> tab;
+    static std::once_flag once;
+    std::call_once(once, []() { build_gl_table(tab, kGlT0, kGlInvH, kGlT1); });
+    return tab;
+}
+
 Tables tview(const bisbm_handle* h, bool with_lgamma) {
     Tables t;
     t.lg = with_lgamma ? h->d_lg : nullptr;
     t.lg_n = with_lgamma ? h->lg_n : 0;
     t.qtab = h->d_qtab; t.qn = h->qn; t.qk = h->qk;
+    t.gl = h->d_gl; t.gl_t0 = kGlT0; t.gl_inv_h = kGlInvH; t.gl_n = h->gl_n;
     return t;
 }
 
@@ -250,8 +267,13 @@ int finish_tables(bisbm_handle* h) {
     {
         std::vector<double> q;
         build_qtab(q, h->qn, h->qk);
-        CU(cudaMalloc(&h->d_qtab, q.size() * sizeof(double)));
+        const std::vector<GlNode>& gl = gl_table();
+        const size_t qpad = (q.size() + 1) / 2 * 2;       // keep the node table 16-byte aligned
+        CU(cudaMalloc(&h->d_qtab, qpad * sizeof(double) + gl.size() * sizeof(GlNode)));
         CU(cudaMemcpy(h->d_qtab, q.data(), q.size() * sizeof(double), cudaMemcpyHostToDevice));
+        h->d_gl = reinterpret_cast<GlNode*>(h->d_qtab + qpad);
+        h->gl_n = (uint32_t)gl.size();
+        CU(cudaMemcpy(h->d_gl, gl.data(), gl.size() * sizeof(GlNode), cudaMemcpyHostToDevice));
     }
     h->gdev = std::make_shared<GraphDev>();
     h->gdev->device = h->device;
@@ -1733,7 +1755,7 @@ int bisbm_share_graph(bisbm_handle* src, bisbm_handle** out) {
     h->device = src->device; h->gdev = src->gdev; h->sm_count = src->sm_count;
     h->n = src->n; h->na = src->na; h->nb = src->nb; h->W = src->W; h->max_degree = src->max_degree; h->n_edges = src->n_edges;
     h->h_row_ptr = src->h_row_ptr; h->h_degvals = src->h_degvals; h->ent_base = src->ent_base;
-    h->d_row_ptr = src->d_row_ptr; h->d_col = src->d_col; h->d_degidx = src->d_degidx; h->d_qtab = src->d_qtab;
+    h->d_row_ptr = src->d_row_ptr; h->d_col = src->d_col; h->d_degidx = src->d_degidx; h->d_qtab = src->d_qtab; h->d_gl = src->d_gl; h->gl_n = src->gl_n;
     h->qn = src->qn; h->qk = src->qk;
     h->precision = src->precision; h->opt_inflight_div = src->opt_inflight_div;
     CU(cudaStreamCreate(&h->stream));

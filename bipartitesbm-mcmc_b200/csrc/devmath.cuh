@@ -179,6 +179,22 @@ struct Tables {
     uint64_t lg_n;
     const double* qtab;  // exact log q(n,k) table, row-major [qn+1][qk+1]     (src/support/int_part.cc:34-51)
     uint32_t qn, qk;
+    // the asymptotic formula of log_q_approx is lf(u) - log(n) + sqrt(n) g(u) with u = k / sqrt(n): g and lf tabulated by
+    // the host (the reference's own iteration, glibc) at u_i = exp(gl_t0 + i / gl_inv_h); see GlNode
+    const struct GlNode* gl;
+    double gl_t0, gl_inv_h;
+    uint32_t gl_n;
+};
+
+// One node of the g(u), lf(u) table.  The reference stops get_v's fixed-point iteration at |v_N - v_(N-1)| <= 1e-8, so its
+// g and lf are smooth only between the values of u where the iteration count N changes (steps of up to ~1e-6 in log q there).
+// The table therefore interpolates inside one RUN of nodes with equal N: [first, last] are the run's node indices, `cross` is
+// the u where the count switches between this node and the next (0 when they are in the same run), `flags` bit 0 marks an
+// interval where the host found the count changing back and forth (the device then iterates like the reference).
+struct GlNode {
+    double g, lf, cross;
+    uint32_t first, last;
+    uint32_t flags, pad;
 };
 
 // lgamma_fast (src/support/cache.hh:82-93): table value when in range, else libm lgamma
@@ -187,6 +203,25 @@ BISBM_HD double lgamma_int(const Tables& tb, int64_t i) {
     if ((uint64_t)i < tb.lg_n) return tb.lg[i];
     return lgamma((double)i);
 }
+
+// the u-dependent part of log_q_approx's large-k branch (src/support/int_part.cc:77-97): v from get_v's fixed-point iteration,
+// then lf (without the - log n) and g; the reference's operation order
+BISBM_HD int logq_gl(double u, double* g_out, double* lf_out) {   // returns the number of iterations get_v took
+    double v = u, delta = 1.0;
+    int guard = 0, iters = 0;
+    while (delta > 1e-8 && guard++ < 10000) {  // get_v (int_part.cc:77-86)
+        double nv = dmul(u, sqrt(spence(exp(-v))));
+        delta = fabs(dsub(nv, v));
+        v = nv;
+        ++iters;
+    }
+    double emv = exp(-v);
+    double t1 = ddiv(log1p(dmul(-emv, dadd(1.0, ddiv(dmul(u, u), 2.0)))), 2.0);
+    *lf_out = dsub(dsub(dsub(dsub(log(v), t1), ddiv(dmul(log(2.0), 3.0), 2.0)), log(u)), log(BISBM_PI));
+    *g_out = dsub(ddiv(dmul(2.0, v), u), dmul(u, log1p(-emv)));
+    return iters;
+}
+
 
 // log_q_approx (src/support/int_part.cc:73-98).  Branch test k < n^(1/4) done in exact
 // integer arithmetic (k^4 < n), which agrees with the reference's pow() for every n < 2^53.
@@ -202,18 +237,58 @@ BISBM_HD double log_q_approx(const Tables& tb, uint64_t n, uint64_t k) {
     }
     double sn = sqrt((double)n);
     double u = ddiv((double)k, sn);
-    double v = u, delta = 1.0;
-    int guard = 0;
-    while (delta > 1e-8 && guard++ < 10000) {  // get_v (int_part.cc:77-86)
-        double nv = dmul(u, sqrt(spence(exp(-v))));
-        delta = fabs(dsub(nv, v));
-        v = nv;
-    }
-    double emv = exp(-v);
-    double t1 = ddiv(log1p(dmul(-emv, dadd(1.0, ddiv(dmul(u, u), 2.0)))), 2.0);
-    double lf = dsub(dsub(dsub(dsub(log(v), t1), ddiv(dmul(log(2.0), 3.0), 2.0)), log(u)), log(BISBM_PI));
-    double g = dsub(ddiv(dmul(2.0, v), u), dmul(u, log1p(-emv)));
+    double g, lf;
+    logq_gl(u, &g, &lf);
     return dadd(dsub(lf, log((double)n)), dmul(sn, g));
+}
+
+// 6-point Lagrange weights for nodes 0 .. 5 and a position p (inside [0, 5], or just outside)
+BISBM_HD void lagrange6(double p, double* w) {
+    const double a = p, b = p - 1.0, c = p - 2.0, d = p - 3.0, e = p - 4.0, g = p - 5.0;
+    w[0] = b * c * d * e * g * (-1.0 / 120.0);
+    w[1] = a * c * d * e * g * (1.0 / 24.0);
+    w[2] = a * b * d * e * g * (-1.0 / 12.0);
+    w[3] = a * b * c * e * g * (1.0 / 12.0);
+    w[4] = a * b * c * d * g * (-1.0 / 24.0);
+    w[5] = a * b * c * d * e * (1.0 / 120.0);
+}
+
+// The same value as log_q_approx's large-k branch from the tabulated g(u), lf(u): 6-point Lagrange in log u (node spacing
+// 2^-10: interpolation error ~1e-17, rounding a few ulp of g) over nodes of ONE run of equal iteration count -- ~80 flops and
+// 6 table rows instead of 2 .. 23 iterations of exp / spence / sqrt.  For the parallel sweep's blocks that have no valid
+// expansion (small, or drifted out of its range).  Outside the table, in runs shorter than the stencil and in the intervals
+// the host flagged, it evaluates the formula itself.
+BISBM_HD double log_q_approx_tab(const Tables& tb, uint64_t n, uint64_t k) {
+    const bool small = (k < 65536ull) && (k * k * k * k < n);
+    if (small || tb.gl == nullptr) return log_q_approx(tb, n, k);
+    const double sn = sqrt((double)n);
+    const double u = ddiv((double)k, sn);
+    const double x = (log(u) - tb.gl_t0) * tb.gl_inv_h;
+    if (!(x >= 0.0) || !(x < (double)tb.gl_n - 1.0)) return log_q_approx(tb, n, k);
+    const uint32_t i = (uint32_t)x;
+    const GlNode a = tb.gl[i];
+    if (a.flags & 1u) return log_q_approx(tb, n, k);
+    uint32_t first = a.first, last = a.last;
+    if (a.cross != 0.0 && !(u < a.cross)) { const GlNode b = tb.gl[i + 1]; first = b.first; last = b.last; }
+    if (last - first < 5u) return log_q_approx(tb, n, k);
+    uint32_t s0 = i >= first + 2u ? i - 2u : first;
+    if (s0 + 5u > last) s0 = last - 5u;
+    double w[6];
+    lagrange6(x - (double)s0, w);
+    const GlNode* p = tb.gl + s0;
+    double g = 0.0, lf = 0.0;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) { g = fma(w[j], p[j].g, g); lf = fma(w[j], p[j].lf, lf); }
+    return (lf - log((double)n)) + sn * g;
+}
+BISBM_HD double log_q_tab(const Tables& tb, int n, int k) {     // log_q with the tabulated asymptotic branch
+    if (n <= 0 || k < 1) return 0.0;
+    if (k > n) k = n;
+    if (n < 10001) {
+        if ((uint32_t)n <= tb.qn && (uint32_t)k <= tb.qk) return tb.qtab[(size_t)n * (tb.qk + 1) + k];
+        return NAN;
+    }
+    return log_q_approx_tab(tb, (uint64_t)n, (uint64_t)k);
 }
 
 // log_q<int> (src/support/int_part.hh:27-37).  qtab is the host-built exact table

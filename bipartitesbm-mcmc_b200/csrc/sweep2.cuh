@@ -406,9 +406,10 @@ __device__ __forceinline__ int gl_atom(uint64_t base, uint32_t off, int v) {
 
 // the rare double-precision completions, out of line (arguments by value)
 __device__ __noinline__ static double slow2_block_degree_delta(int e_r, int e_s, int d) { return block_degree_delta(e_r, e_s, d); }
-__device__ __noinline__ static double slow2_logq_delta(const double* qtab, uint32_t qn, uint32_t qk, int e, int n, int de, int dn) {
-    Tables tb; tb.lg = nullptr; tb.lg_n = 0; tb.qtab = qtab; tb.qn = qn; tb.qk = qk;
-    return logq_delta_exact(tb, e, n, de, dn);
+// log q(e + de, n + dn) - log q(e, n) for a block without a valid expansion (small, or drifted out of its range): the exact
+// table below 10001, else the asymptotic formula from its tabulated g(u), lf(u) -- no fixed-point iteration on the device
+__device__ __noinline__ static double slow2_logq_delta(const Tables tb, int e, int n, int de, int dn) {
+    return log_q_tab(tb, e + de, n + dn) - log_q_tab(tb, e, n);
 }
 // estimate mode: change of the K-dependent terms of entropy() (src/blockmodel.cc:780-782: lbinom(Ka Kb + E - 1, E) +
 // lbinom(na - 1, Ka - 1) + lbinom(nb - 1, Kb - 1)) when the number of occupied blocks of the moving type goes k -> k + dk
@@ -898,8 +899,8 @@ __global__ void __launch_bounds__(NT, 1) sweep2_kernel(const __grid_constant__ S
                     const R lgm = move_lgm<R>(A, ratio, eta_r + z2, eta_s + z2);
                     if (__any_sync(FULL, eval && !(ok_b && ok_r && ok_s))) {
                         if (eval && !ok_b) bdd = (R)slow2_block_degree_delta(e_r, e_s, (int)d);
-                        if (eval && !ok_r) lqr = (R)slow2_logq_delta(P.tb.qtab, P.tb.qn, P.tb.qk, e_r, n_r, -(int)d, -1);
-                        if (eval && !ok_s) lqs = (R)slow2_logq_delta(P.tb.qtab, P.tb.qn, P.tb.qk, e_s, n_s, (int)d, 1);
+                        if (eval && !ok_r) lqr = (R)slow2_logq_delta(P.tb, e_r, n_r, -(int)d, -1);
+                        if (eval && !ok_s) lqs = (R)slow2_logq_delta(P.tb, e_s, n_s, (int)d, 1);
                         __syncwarp();
                     }
                     dS = AR::unit() * lgm + ((d == 0u) ? (R)0 : bdd) + lqr + lqs;

@@ -15,6 +15,7 @@
 #include "../../bipartitesbm-mcmc_b200/csrc/replay.cuh"
 #include "../../bipartitesbm-mcmc_b200/csrc/sweep.cuh"
 #include "../../bipartitesbm-mcmc_b200/csrc/sweep2.cuh"
+#include "../../bipartitesbm-mcmc_b200/csrc/gltable.h"
 
 using namespace bisbm;
 
@@ -270,6 +271,25 @@ double emul_dlog(double x) { return dlog(x); }
 double emul_dexp(double x) { return dexp(x); }
 double emul_block_degree_delta(int e_r, int e_s, int d) { return block_degree_delta(e_r, e_s, d); }
 double emul_log_q_approx(uint64_t n, uint64_t k) { Tables tb; memset(&tb, 0, sizeof tb); return log_q_approx(tb, n, k); }
+// log_q_approx through the tabulated g(u), lf(u) (what the parallel kernel's blocks without an expansion use) next to the formula
+double emul_log_q_approx_tab(uint64_t n, uint64_t k) {
+    static std::vector<GlNode> tab;
+    const double t0 = -2.0, inv_h = 1024.0, t1 = 11.6;
+    if (tab.empty()) build_gl_table(tab, t0, inv_h, t1);
+    Tables tb; memset(&tb, 0, sizeof tb);
+    tb.gl = tab.data(); tb.gl_t0 = t0; tb.gl_inv_h = inv_h; tb.gl_n = (uint32_t)tab.size();
+    return log_q_approx_tab(tb, n, k);
+}
+// how the table is organised: nodes, runs of equal iteration count, flagged intervals
+void emul_gl_table_stats(uint32_t* nodes, uint32_t* runs, uint32_t* short_runs, uint32_t* flagged) {
+    std::vector<GlNode> tab;
+    build_gl_table(tab, -2.0, 1024.0, 11.6);
+    *nodes = (uint32_t)tab.size(); *runs = 0; *short_runs = 0; *flagged = 0;
+    for (size_t i = 0; i < tab.size(); ++i) {
+        if (tab[i].first == i) { ++*runs; if (tab[i].last - tab[i].first < 5) ++*short_runs; }
+        if (tab[i].flags & 1u) ++*flagged;
+    }
+}
 uint32_t emul_feistel(uint32_t i, uint32_t n, uint64_t key) { return feistel_perm(i, n, feistel_half_bits(n), key); }
 
 }  // extern "C"

@@ -22,7 +22,7 @@ pu = C.POINTER(C.c_uint32)
 def emul():
     src = os.path.join(EMUL_DIR, "emul.cc")
     deps = [src] + [os.path.join(ROOT, "bipartitesbm-mcmc_b200", "csrc", f) for f in
-                    ("devmath.cuh", "state.cuh", "replay.cuh", "sweep.cuh", "sweep2.cuh")]
+                    ("devmath.cuh", "state.cuh", "replay.cuh", "sweep.cuh", "sweep2.cuh", "gltable.h")]
     if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-x", "c++",
                                "-o", LIB, src, "-lm"])
@@ -52,6 +52,9 @@ def emul():
     L.emul_block_degree_delta.argtypes = [C.c_int, C.c_int, C.c_int]
     L.emul_log_q_approx.restype = C.c_double
     L.emul_log_q_approx.argtypes = [C.c_uint64, C.c_uint64]
+    L.emul_log_q_approx_tab.restype = C.c_double
+    L.emul_log_q_approx_tab.argtypes = [C.c_uint64, C.c_uint64]
+    L.emul_gl_table_stats.argtypes = [C.c_void_p] * 4
     L.emul_feistel.restype = C.c_uint32
     L.emul_feistel.argtypes = [C.c_uint32, C.c_uint32, C.c_uint64]
     return L
@@ -236,3 +239,38 @@ def test_feistel_is_a_permutation(emul):
     a = np.array([emul.emul_feistel(i, 1000, 1) for i in range(1000)])
     b = np.array([emul.emul_feistel(i, 1000, 2) for i in range(1000)])
     assert (a != b).mean() > 0.9
+
+
+def test_tabulated_asymptotic_log_q(emul):
+    """Blocks without a valid expansion (small or drifted) evaluate the asymptotic log q from the tabulated g(u), lf(u) of
+    u = k / sqrt(n) (devmath.cuh log_q_approx_tab: 6-point Lagrange in log u inside one run of equal iteration count of the
+    reference's get_v) instead of iterating on the device.  Against the formula itself (the reference's int_part.cc:73-98
+    restated, which the oracle pins): 1e-13 relative on the value and 1e-10 absolute on the DIFFERENCES a move needs,
+    log q(e +- d, n +- 1) - log q(e, n), over block shapes from 10^4 to 4 * 10^9 edges ends."""
+    import time
+    rng = np.random.default_rng(5)
+    t0 = time.perf_counter()
+    emul.emul_log_q_approx_tab(20000, 100)          # builds the table (once per process in the library)
+    assert time.perf_counter() - t0 < 5.0
+    st = (C.c_uint32 * 4)()
+    emul.emul_gl_table_stats(C.byref(st, 0), C.byref(st, 4), C.byref(st, 8), C.byref(st, 12))
+    print("g / lf table: %d nodes, %d runs of equal iteration count (%d shorter than the stencil), %d flagged intervals" % tuple(st))
+    assert st[1] < 100 and st[3] < 20
+    worst_v, worst_d = 0.0, 0.0
+    for _ in range(6000):
+        e = int(10 ** rng.uniform(4.01, 9.6))
+        # a block's degree sum is at most 255 n in the kernels that use this path (u8 histogram bins: degree <= 255)
+        n = int(min(e, max(e // 255 + 1, 10 ** rng.uniform(0.3, np.log10(e)))))
+        a, b = emul.emul_log_q_approx_tab(e, n), emul.emul_log_q_approx(e, n)
+        assert abs(a - b) <= 1e-13 * max(1.0, abs(b)), (e, n, a, b)
+        worst_v = max(worst_v, abs(a - b) / max(1.0, abs(b)))
+        d = int(rng.integers(1, 256))
+        if e - d < 10001 or n < 2:
+            continue
+        for de, dn in ((-d, -1), (d, 1)):
+            da = emul.emul_log_q_approx_tab(e + de, n + dn) - a
+            db = emul.emul_log_q_approx(e + de, n + dn) - b
+            tol = 1e-10 if e < 10 ** 7 else 1e-9 * (e / 1e7) ** 0.5      # (sqrt(e) g(u): a few ulp of g times sqrt(e))
+            assert abs(da - db) <= tol, (e, n, de, dn, da, db)
+            worst_d = max(worst_d, abs(da - db))
+    print("tabulated log q: worst relative error of the value %.2e, worst absolute error of a move's difference %.2e" % (worst_v, worst_d))
