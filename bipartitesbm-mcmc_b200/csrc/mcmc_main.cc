@@ -30,6 +30,7 @@
 #include <vector>
 
 #include <thread>
+#include <unistd.h>
 
 #include "bisbm.h"
 
@@ -429,7 +430,15 @@ int main(int argc, char const* argv[]) {
             if (!errs[g].empty()) { std::cerr << "libbisbm (device " << device + g << "): " << errs[g] << "\n"; return 1; }
         std::vector<uint32_t> out(N);
         if (marg) {
-            if (!check(bisbm_marginals_allreduce_local(hs.data(), (int)gpus))) return 1;
+            // stdout carries the label line and nothing else: NCCL prints its version banner on stdout when the environment
+            // sets NCCL_DEBUG (whatever NCCL_DEBUG_FILE says), so file descriptor 1 points at stderr while NCCL initialises
+            std::cout.flush(); fflush(stdout);
+            const int saved_stdout = dup(1);
+            if (saved_stdout >= 0) dup2(2, 1);
+            const bool ar_ok = check(bisbm_marginals_allreduce_local(hs.data(), (int)gpus));
+            fflush(stdout);
+            if (saved_stdout >= 0) { dup2(saved_stdout, 1); close(saved_stdout); }
+            if (!ar_ok) return 1;
             if (!check(bisbm_marginal_argmax(hs[0], out.data()))) return 1;
             output_vec(out, std::cout);
         } else {
