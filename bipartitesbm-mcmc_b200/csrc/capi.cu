@@ -479,6 +479,7 @@ ReplayCtx rctx(bisbm_handle* h, uint32_t chain, const ReplaySlot& sl) {
     x.rs = sl.d_rs;
     x.vlist = sl.d_vlist;
     x.kh = sl.d_kh;
+    x.kt = reinterpret_cast<uint32_t*>(sl.d_kh + std::max(h->KA, h->KB));
     x.eps = h->eps;
     return x;
 }
@@ -1175,8 +1176,9 @@ int bisbm_replay_init(bisbm_handle* h, uint32_t chain, uint32_t engine_seed, uin
     if (!sl.d_rs) {
         CU(cudaMalloc(&sl.d_rs, sizeof(ReplayState)));
         CU(cudaMalloc(&sl.d_vlist, (size_t)h->n * sizeof(uint32_t)));
-        CU(cudaMalloc(&sl.d_kh, (size_t)std::max(h->KA, h->KB) * sizeof(int32_t)));
+        CU(cudaMalloc(&sl.d_kh, ((size_t)std::max(h->KA, h->KB) + 1 + RP_KT_MAX) * sizeof(int32_t)));
     }
+    CU(cudaMemsetAsync(sl.d_kh, 0, ((size_t)std::max(h->KA, h->KB) + 1 + RP_KT_MAX) * sizeof(int32_t), h->stream));   // histogram + its (empty) bin list
     rc = sync_labels32(h);
     if (rc) return rc;
     replay_init_kernel<<<1, 32, 0, h->stream>>>(rctx(h, chain, sl), engine_seed, gen_seed, randomize);
@@ -1496,18 +1498,14 @@ int bisbm_replay_agg_merge(bisbm_handle* h, uint32_t chain, int diff_a, int diff
     rc = ensure_lgamma_table(h);
     if (rc) return rc;
     for (int guard = 0; guard < 1 << 20; ++guard) {      // each round = one (possibly recursive) call of the reference's agg_merge
-        MergeScratch sc;
-        rc = alloc_merge_scratch(h, chain, nm, sc);
-        if (rc) return rc;
-        while (diff_a < 0) { rc = agg_split(h, chain, *sl, sc, false, nm); if (rc) return rc; ++diff_a; }
-        while (diff_b < 0) { rc = agg_split(h, chain, *sl, sc, true, nm); if (rc) return rc; ++diff_b; }
+        {
+            MergeScratch none;       // (agg_split only needs the chain's views)
+            while (diff_a < 0) { rc = agg_split(h, chain, *sl, none, false, nm); if (rc) return rc; ++diff_a; }
+            while (diff_b < 0) { rc = agg_split(h, chain, *sl, none, true, nm); if (rc) return rc; ++diff_b; }
+        }
         if (diff_a + diff_b == 0) return BISBM_OK;       // (also when they cancel: the reference returns here too)
         const uint32_t ka = h->h_ka[chain], kb = h->h_kb[chain], K = ka + kb;
-        {   // the splits may have grown K: scratch sized for the current K
-            MergeScratch fresh;
-            std::swap(sc.badj, fresh.badj); std::swap(sc.badj_cnt, fresh.badj_cnt); std::swap(sc.cand, fresh.cand); std::swap(sc.cand_dS, fresh.cand_dS);
-            std::swap(sc.n_cand, fresh.n_cand); std::swap(sc.seen, fresh.seen); std::swap(sc.first, fresh.first); std::swap(sc.map, fresh.map);
-        }
+        MergeScratch sc;             // sized for the current K (the splits may have grown it)
         rc = alloc_merge_scratch(h, chain, nm, sc);
         if (rc) return rc;
         uint32_t first_block = 0, n_blocks = K;

@@ -92,11 +92,11 @@ __global__ void __launch_bounds__(32) merge_propose_kernel(MergeCtx x, uint32_t 
                 // std::discrete_distribution<size_t>(m_[t].begin(), m_[t].end())(gen) (libstdc++ bits/random.tcc:2657-2714): the
                 // weights are integers, so their sequential double sum is exact and equals the integer sum; the divisions
                 // are independent (all lanes); the partial sums are sequential (lane 0)
-                long long part = 0;
-                for (uint32_t i = lane; i < K; i += 32) part += m_at(c, t, i);
-                for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-                const double sum = (double)part;
-                for (uint32_t i = lane; i < K; i += 32) prob[i] = ddiv((double)m_at(c, t, i), sum);
+                // (row t is zero outside the other type's blocks [lo, hi): see rp_categorical for why walking that range alone
+                //  returns what lower_bound over the full K-long vector returns)
+                const uint32_t lo = t < ka ? ka : 0u, hi = t < ka ? K : ka;
+                const double sum = (double)e_ref(c, slot_of(c, t));
+                for (uint32_t i = lo + lane; i < hi; i += 32) prob[i] = ddiv((double)m_at(c, t, i), sum);
                 __syncwarp();
                 if (lane == 0) {
                     if (K < 2) target = 0;
@@ -104,11 +104,13 @@ __global__ void __launch_bounds__(32) merge_propose_kernel(MergeCtx x, uint32_t 
                         const double u = mt_canon(gen);
                         double acc = 0.0;
                         target = K - 1;
-                        for (uint32_t i = 0; i < K; ++i) {
-                            acc = (i == 0) ? prob[i] : dadd(acc, prob[i]);
-                            const double cp = (i == K - 1) ? 1.0 : acc;
-                            if (!(cp < u)) { target = i; break; }   // lower_bound: first cp >= u
-                        }
+                        if (!(sum > 0.0) || (lo > 0 && !(0.0 < u))) target = 0;
+                        else
+                            for (uint32_t i = lo; i < hi; ++i) {
+                                acc = (i == 0) ? prob[i] : dadd(acc, prob[i]);
+                                const double cp = (i == K - 1) ? 1.0 : acc;
+                                if (!(cp < u)) { target = i; break; }   // lower_bound: first cp >= u
+                            }
                     }
                 }
                 __syncwarp();

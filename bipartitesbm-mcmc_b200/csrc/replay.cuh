@@ -27,13 +27,16 @@ struct ReplayState {
     double last_dS;
 };
 
+enum : uint32_t { RP_KT_MAX = 64u, RP_KT_OVER = 0xffffffffu };
+
 struct ReplayCtx {
     GraphView g;
     ChainRef c;
     Tables tb;
     ReplayState* rs;
     uint32_t* vlist;  // [n], persists across sweeps and anneal calls (src/metropolis_hasting.cc:78)
-    int32_t* kh;      // [max(KA,KB)] neighbour-block histogram scratch
+    int32_t* kh;      // [max(KA,KB)] neighbour-block histogram scratch: zero outside the bins listed in kt
+    uint32_t* kt;     // [1 + RP_KT_MAX]: kt[0] = number of non-zero bins of kh (RP_KT_OVER: too many to list), then the bins, ascending
     double eps;
 };
 
@@ -44,14 +47,33 @@ BISBM_HD uint32_t rp_label(const ReplayCtx& x, uint32_t v) {  // global block id
 
 // neighbour-block histogram of v over the opposite type's blocks (reference k_[v], kept as
 // an N x K matrix there; rebuilt from the adjacency here)
+// The non-zero bins are listed in ascending order (kt), so the loops over "every block t with k_t != 0" of transition_ratio and
+// apply_mcmc_moves cost O(degree) instead of O(K) and still add their terms in the reference's order.
 BISBM_HD void rp_hist(const ReplayCtx& x, uint32_t v) {
-    uint32_t kopp = v < x.g.na ? x.c.kb : x.c.ka;
-    for (uint32_t t = 0; t < kopp; ++t) x.kh[t] = 0;
+    uint32_t n = x.kt[0];
+    if (n == RP_KT_OVER) {
+        uint32_t kmax = x.c.KA > x.c.KB ? x.c.KA : x.c.KB;      // (the strides: K may have changed since the list overflowed)
+        for (uint32_t t = 0; t < kmax; ++t) x.kh[t] = 0;
+    } else {
+        for (uint32_t j = 0; j < n; ++j) x.kh[x.kt[1 + j]] = 0;
+    }
+    n = 0;
+    bool over = false;
     for (uint32_t e = x.g.row_ptr[v]; e < x.g.row_ptr[v + 1]; ++e) {
         uint32_t nb = x.g.col[e];
-        x.kh[x.c.labels[(size_t)nb * x.c.C]]++;
+        uint32_t t = (uint32_t)x.c.labels[(size_t)nb * x.c.C];
+        if (x.kh[t]++ == 0 && !over) {
+            if (n == RP_KT_MAX) { over = true; continue; }
+            uint32_t j = n++;                                   // insert t, keeping the list ascending
+            while (j > 0 && x.kt[j] > t) { x.kt[1 + j] = x.kt[j]; --j; }
+            x.kt[1 + j] = t;
+        }
     }
+    x.kt[0] = over ? RP_KT_OVER : n;
 }
+// the loops below visit bin number j of v's histogram: the j-th listed bin, or simply bin j when the list overflowed
+BISBM_HD uint32_t rp_bins(const ReplayCtx& x, uint32_t kopp) { return x.kt[0] == RP_KT_OVER ? kopp : x.kt[0]; }
+BISBM_HD uint32_t rp_bin(const ReplayCtx& x, uint32_t j) { return x.kt[0] == RP_KT_OVER ? j : x.kt[1 + j]; }
 
 // transition_ratio (src/metropolis_hasting.cc:103-192); kh must hold v's histogram when
 // r != s are of the same type.
@@ -71,7 +93,8 @@ BISBM_HD double rp_transition(const ReplayCtx& x, uint32_t v, uint32_t r, uint32
     double a0 = 0.0, a1 = 0.0, S0 = 0.0, S1 = 0.0;
     bool va = r < ka;
     uint32_t kopp = va ? c.kb : c.ka;
-    for (uint32_t t = 0; t < kopp; ++t) {  // ascending global id of the opposite type
+    for (uint32_t j = 0, nbins = rp_bins(x, kopp); j < nbins; ++j) {  // ascending global id of the opposite type
+        uint32_t t = rp_bin(x, j);
         int kk = x.kh[t];
         if (kk == 0) continue;
         uint32_t gi = va ? ka + t : t;
@@ -107,11 +130,17 @@ BISBM_HD uint32_t rp_categorical(const ReplayCtx& x, uint32_t t) {
     const ChainRef& c = x.c;
     uint32_t K = c.ka + c.kb;
     if (K < 2) return 0;
-    double sum = 0.0;
-    for (uint32_t i = 0; i < K; ++i) sum = dadd(sum, (double)m_at(c, t, i));
+    // the weights are integers: their sequential double sum is exact and equals the row sum m_r_[t] the state carries
+    const double sum = (double)e_ref(c, slot_of(c, t));
     double u = mt_canon(x.rs->gen);
+    // row t is zero outside the other type's blocks [lo, hi): those entries add +0.0 to the running sum.  Leading zeros
+    // have cp = 0 (taken only by u == 0); behind hi the partial sum stays where it is until the forced cp = 1 of the last
+    // entry.  Walking [lo, hi) alone therefore returns what lower_bound over the full K-long vector returns.
+    const uint32_t lo = t < c.ka ? c.ka : 0u, hi = t < c.ka ? K : c.ka;
+    if (!(sum > 0.0)) return 0;              // (0 / 0 weights: every cp is NaN and lower_bound stays at the first entry)
+    if (lo > 0 && !(0.0 < u)) return 0;
     double acc = 0.0;
-    for (uint32_t i = 0; i < K; ++i) {
+    for (uint32_t i = lo; i < hi; ++i) {
         double p = ddiv((double)m_at(c, t, i), sum);
         acc = (i == 0) ? p : dadd(acc, p);
         double cp = (i == K - 1) ? 1.0 : acc;
@@ -149,7 +178,8 @@ BISBM_HD bool rp_apply(const ReplayCtx& x, uint32_t v, uint32_t r, uint32_t s, d
         eta_ref(c, ss, didx)++;
         bool va = r < c.ka;
         uint32_t kopp = va ? c.kb : c.ka;
-        for (uint32_t t = 0; t < kopp; ++t) {
+        for (uint32_t j = 0, nbins = rp_bins(x, kopp); j < nbins; ++j) {
+            uint32_t t = rp_bin(x, j);
             int kk = x.kh[t];
             if (kk == 0) continue;
             uint32_t gi = va ? c.ka + t : t;

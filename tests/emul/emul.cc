@@ -24,6 +24,7 @@ struct Emul {
     uint64_t E;
     std::vector<uint32_t> row_ptr, col, degidx, degvals, vlist;
     std::vector<int32_t> labels, m, e, nr, eta, kh;
+    std::vector<uint32_t> kt;
     std::vector<double> lg, qtab;
     uint32_t qn, qk;
     ReplayState rs;
@@ -73,7 +74,7 @@ static ReplayCtx ctx(Emul* s) {
     x.c.m = s->m.data(); x.c.e = s->e.data(); x.c.nr = s->nr.data(); x.c.eta = s->eta.data();
     x.c.ka = s->ka; x.c.kb = s->kb; x.c.KA = s->ka; x.c.KB = s->kb; x.c.W = s->W; x.c.cs = 1;
     x.tb.lg = s->lg.data(); x.tb.lg_n = s->lg.size(); x.tb.qtab = s->qtab.data(); x.tb.qn = s->qn; x.tb.qk = s->qk;
-    x.rs = &s->rs; x.vlist = s->vlist.data(); x.kh = s->kh.data(); x.eps = s->eps;
+    x.rs = &s->rs; x.vlist = s->vlist.data(); x.kh = s->kh.data(); x.kt = s->kt.data(); x.eps = s->eps;
     return x;
 }
 
@@ -102,7 +103,7 @@ void* emul_create(uint32_t na, uint32_t nb, uint64_t E, const uint32_t* ea, cons
     s->labels.assign((size_t)s->n * s->C, 0);
     for (uint32_t v = 0; v < s->n; ++v) s->labels[(size_t)v * s->C + s->chain] = v < na ? labels[v] : labels[v] - ka;
     s->m.assign((size_t)ka * kb, 0); s->e.assign(ka + kb, 0); s->nr.assign(ka + kb, 0);
-    s->eta.assign((size_t)(ka + kb) * s->W, 0); s->kh.assign(std::max(ka, kb), 0);
+    s->eta.assign((size_t)(ka + kb) * s->W, 0); s->kh.assign(std::max(ka, kb), 0); s->kt.assign(1 + RP_KT_MAX, 0);
     s->vlist.resize(s->n);
     for (uint32_t v = 0; v < s->n; ++v) s->vlist[v] = v;
     s->lg.resize(2 * E + 2 + s->maxdeg);
