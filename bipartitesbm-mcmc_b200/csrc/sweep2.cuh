@@ -10,9 +10,10 @@
 //     into ONE logarithm per vertex, 1/(e_t + eps K) comes from a per-launch table (e_t of the frozen
 //     type cannot change during a half sweep), reciprocals are MUFU.RCP64H + two Newton steps;
 //   * neighbour labels arrive as whole 32-byte rows (lane -> 8 bytes of one row, 8 rows per load
-//     instruction), ONE VERTEX AHEAD, and are transposed through a per-warp tile in shared memory
-//     ([chain][edge], 36-byte pitch: conflict-free both ways) -- the five serial gather round trips of
-//     the round-1 kernel are gone and the proposal's random neighbour label comes from the tile too;
+//     instruction), ONE VERTEX AHEAD, and are parked in a per-warp tile in shared memory as they are
+//     ([edge][chain]: one 8-byte store per lane and block of 8 rows; a lane reads its chain's label of
+//     edge e as one byte, 32 lanes = one 32-byte row, conflict-free) -- the five serial gather round
+//     trips of the round-1 kernel are gone and the proposal's random neighbour label comes from the tile too;
 //   * the warp's u8 neighbour-block histogram is updated with one shared atomic per edge (old value =
 //     c), four edges of a chunk are independent instruction streams;
 //   * the commit walks the edges again (2 shared reductions per edge) instead of all K bins;
@@ -300,10 +301,10 @@ BISBM_HD void move_finish(const MAcc<R>& A, int eta_r, int eta_s, R bdd, R lqr, 
 //   u32   sSmall[ceil(kown/32)][32]   bit b: block b of this lane's chain needs the exact n_r veto
 //   uint4 sVtx[S2_VB]           the CTA's prepared vertices {vertex, CSR row offset, degree, degree index}
 //   u8x4  hist[warps][ceil(kopp/4)][32]
-//   u8    tile[warps][32 lanes][36]   neighbour labels of the warp's vertex, [chain][edge]
+//   u8    tile[warps][32 edges][32]   neighbour labels of the warp's vertex as they arrive, [edge][chain]
 //   ctl   mbarrier (8 bytes) + vertex counter
 struct Sweep2Layout { uint32_t oM, oEo, oNo, oEp, oInv, oSmall, oVtx, oHist, oTile, oCtl, total; };
-enum { S2_VB = 448, S2_TILE = 32 * 36 };
+enum { S2_VB = 448, S2_TILE = 32 * 32 };
 
 inline
 #ifdef __CUDACC__
@@ -614,8 +615,10 @@ __global__ void __launch_bounds__(NT, 1) sweep2_kernel(const __grid_constant__ S
     const uint32_t Small_base = sbase + L.oSmall + lane4;
     const uint32_t hist_base = sbase + L.oHist + warp * hist_words * 128u + lane4;
     const uint32_t tile_w = sbase + L.oTile + warp * (uint32_t)S2_TILE;
-    const uint32_t tile_lane = tile_w + lane * 36u;                               // this chain's labels, edge e at +e
-    const uint32_t tile_st = tile_w + (lane & 3u) * 288u + (lane >> 2);            // store base: chains 8 (lane%4) + i, row lane/4 (+ 8 j)
+    // the tile keeps the rows as they arrive, [edge][chain]: one 8-byte store per lane and block of 8 rows, one byte load per edge
+    const uint32_t tile_lane = tile_w + lane;                                      // this chain's labels, edge e at + 32 e
+    const uint32_t tile_st = tile_w + (lane >> 2) * 32u + (lane & 3u) * 8u;        // store base: row lane/4 (+ 8 j), chains 8 (lane%4) ..
+    constexpr uint32_t TE = 32u;                                                   // bytes between consecutive edges of one chain
     // m(x_own, t_opp) at byte offset x*SX + t*ST of this lane's view of m_rs
     const uint32_t SX = (type ? 1u : KB) * 128u, ST = (type ? (CLUSTER ? RPC : KB) : 1u) * 128u;
     // cluster form: this lane's view of CTA k's rows starts at cbase0 + k * cstride in the shared::cluster window
@@ -682,11 +685,7 @@ __global__ void __launch_bounds__(NT, 1) sweep2_kernel(const __grid_constant__ S
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             if (8u * j < dcnt) {
-                const uint32_t a = tile_st + 8u * j;
-                sh_st_u8(a, rows[j].x);          sh_st_u8(a + 36u, rows[j].x >> 8);
-                sh_st_u8(a + 72u, rows[j].x >> 16);  sh_st_u8(a + 108u, rows[j].x >> 24);
-                sh_st_u8(a + 144u, rows[j].y);       sh_st_u8(a + 180u, rows[j].y >> 8);
-                sh_st_u8(a + 216u, rows[j].y >> 16); sh_st_u8(a + 252u, rows[j].y >> 24);
+                asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(tile_st + 256u * j), "r"(rows[j].x), "r"(rows[j].y) : "memory");
             }
         }
     };
@@ -754,8 +753,8 @@ __global__ void __launch_bounds__(NT, 1) sweep2_kernel(const __grid_constant__ S
                 uint32_t tq = 0;
                 if (d != 0u) {
                     const uint32_t e = mulhi32(ra.x, d);
-                    if (d <= 32u) tq = sh_ld_u8(tile_lane + e);
-                    else tq = (e < 32u) ? sh_ld_u8(tile_lane + e) : lab_ld(__ldcg(G.col + cur.y + e));
+                    if (d <= 32u) tq = sh_ld_u8(tile_lane + e * TE);
+                    else tq = (e < 32u) ? sh_ld_u8(tile_lane + e * TE) : lab_ld(__ldcg(G.col + cur.y + e));
                 }
                 tq = min(tq, kopp_max - 1u);
                 R beta = (R)P.beta0;
@@ -822,8 +821,7 @@ __global__ void __launch_bounds__(NT, 1) sweep2_kernel(const __grid_constant__ S
                     const R inv = sh_ld_real<R>(Inv_base + t * IS);
                     macc_edge(A, m_r, m_s, (old >> sh3) & 0xffu, inv);
                 };
-                auto edge4 = [&](uint32_t Lc) {
-                    const uint32_t t0 = Lc & 0xffu, t1 = (Lc >> 8) & 0xffu, t2 = (Lc >> 16) & 0xffu, t3 = Lc >> 24;
+                auto edge4t = [&](uint32_t t0, uint32_t t1, uint32_t t2, uint32_t t3) {
                     const uint32_t h0 = h_sh(t0), h1 = h_sh(t1), h2 = h_sh(t2), h3 = h_sh(t3);
                     // the four histogram updates in edge order (a repeated label must see the earlier increment)
                     const uint32_t o0 = sh_atom_add_u32(h_ad(t0), 1u << h0);
@@ -856,18 +854,19 @@ __global__ void __launch_bounds__(NT, 1) sweep2_kernel(const __grid_constant__ S
                         if (AR::FOLD >= 32) macc_fold(A);
                     }
                     const uint32_t nfull = nrem >> 2, tail = nrem & 3u;
-                    uint32_t Lw = sh_ld_u32v(tile_lane);
-                    for (uint32_t q = 0; q < nfull; ++q) {
-                        const uint32_t Lc = Lw;
-                        Lw = sh_ld_u32v(tile_lane + 4u * (q + 1u));     // (the row has a pad word: q + 1 <= 8 stays inside)
-                        edge4(Lc);
-                        if (AR::FOLD < 32) macc_fold(A);
-                    }
-                    if (tail) {
-                        edge1(Lw & 0xffu);
-                        if (tail > 1u) edge1((Lw >> 8) & 0xffu);
-                        if (tail > 2u) edge1((Lw >> 16) & 0xffu);
-                        if (AR::FOLD < 32) macc_fold(A);
+                    {
+                        uint32_t ta = tile_lane;
+                        for (uint32_t q = 0; q < nfull; ++q, ta += 128u) {
+                            const uint32_t t0 = sh_ld_u8(ta), t1 = sh_ld_u8(ta + 32u), t2 = sh_ld_u8(ta + 64u), t3 = sh_ld_u8(ta + 96u);
+                            edge4t(t0, t1, t2, t3);
+                            if (AR::FOLD < 32) macc_fold(A);
+                        }
+                        if (tail) {
+                            edge1(sh_ld_u8(ta));
+                            if (tail > 1u) edge1(sh_ld_u8(ta + 32u));
+                            if (tail > 2u) edge1(sh_ld_u8(ta + 64u));
+                            if (AR::FOLD < 32) macc_fold(A);
+                        }
                     }
                 }
                 issue_next();
@@ -963,15 +962,14 @@ __global__ void __launch_bounds__(NT, 1) sweep2_kernel(const __grid_constant__ S
                         auto move1 = [&](uint32_t t) { const uint32_t f = Mr + t * ST; m_red(f, -g1); m_red(f + dMs, g1); };
                         const uint32_t nfull = d >> 2, tail = d & 3u;
                         uint32_t q4 = tile_lane;
-                        for (uint32_t q = 0; q < nfull; ++q, q4 += 4u) {
-                            const uint32_t Lc = sh_ld_u32v(q4);
-                            move1(Lc & 0xffu); move1((Lc >> 8) & 0xffu); move1((Lc >> 16) & 0xffu); move1(Lc >> 24);
+                        for (uint32_t q = 0; q < nfull; ++q, q4 += 128u) {
+                            const uint32_t t0 = sh_ld_u8(q4), t1 = sh_ld_u8(q4 + 32u), t2 = sh_ld_u8(q4 + 64u), t3 = sh_ld_u8(q4 + 96u);
+                            move1(t0); move1(t1); move1(t2); move1(t3);
                         }
                         if (tail) {
-                            const uint32_t Lc = sh_ld_u32v(q4);
-                            move1(Lc & 0xffu);
-                            if (tail > 1u) move1((Lc >> 8) & 0xffu);
-                            if (tail > 2u) move1((Lc >> 16) & 0xffu);
+                            move1(sh_ld_u8(q4));
+                            if (tail > 1u) move1(sh_ld_u8(q4 + 32u));
+                            if (tail > 2u) move1(sh_ld_u8(q4 + 64u));
                         }
                     }
                     for (uint32_t w = 0; w < hist_words; ++w) sh_st_u32v(hist_base + w * 128u, 0u);
