@@ -499,6 +499,7 @@ def main():
                     help="arithmetic of a move: fp64 like the reference's transition_ratio (headline) or fp32")
     ap.add_argument("--inflight-div", type=int, default=0, help="in-flight bound = half sweep / this (0: library default)")
     ap.add_argument("--warps", type=int, default=0, help="experiment builds only: warps per CTA (20, 24)")
+    ap.add_argument("--no-spare-sms", action="store_true", help="A/B: leave the SMs that groups x CTAs do not fill idle")
     ap.add_argument("--no-fp32-extra", action="store_true", help="skip the short fp32 run reported under 'extra'")
     args = ap.parse_args()
 
@@ -574,6 +575,8 @@ def main():
         pool.set_option("inflight_div", args.inflight_div)
     if args.warps:
         pool.set_option("warps", args.warps)
+    if args.no_spare_sms:
+        pool.set_option("spare_sms", 0)
     seeds = pkg.dist.chain_seeds(0, chain_ids)
     pool.randomize(seeds)
     duration = args.sweeps_per_step * n

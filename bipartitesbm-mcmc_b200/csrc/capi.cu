@@ -130,6 +130,7 @@ struct bisbm_handle {
     int opt_generic = 0;               // 1: never take the Ka = Kb = 32 specialisation
     int opt_vary_k = 0;                // estimate mode: blocks may empty, K-dependent prior terms in dS
     uint32_t opt_warps = 16;           // warps per CTA of the staged sweep2 kernel (experiment builds: 20, 24)
+    int opt_spare_sms = 1;             // 1: sliced launches hand the SMs that n_groups x ctas_per_group leaves idle to the groups in turn
     uint32_t opt_reserve_ka = 0, opt_reserve_kb = 0;   // minimum strides of the next bisbm_set_chains (room for agg_split)
     std::set<const void*> attr_done;   // kernels whose shared-memory limit is raised on this handle's device
     uint64_t last_sweep_launches = 0, last_marginal_launches = 0;
@@ -807,13 +808,24 @@ int launch_full_sweep(bisbm_handle* h, int schedule, float p0, float p1, uint64_
         const bool s2 = kern_is_s2(kernel);
         h->last_wpc = lp.wpc; h->last_cpg = lp.ctas_per_group; h->last_slice = lp.slice;
         h->last_kernel = kernel;
-        for (uint32_t pos = 0; pos < nv; pos += lp.slice) {
+        // spare SMs: when the groups' CTAs do not fill the GPU (8 groups x 18 CTAs on 148 SMs), the rest are handed to the groups
+        // in turn, one more CTA (and one more CTA's worth of positions) for `extras` groups per launch
+        uint32_t extras = 0;
+        const uint32_t G = h->C / 32;
+        if (sliced && s2 && !lp.cluster && h->opt_spare_sms && max_inflight == 0 && (uint32_t)h->sm_count > G * lp.ctas_per_group)   // (an explicit in-flight bound is kept to the letter)
+            extras = std::min<uint32_t>((uint32_t)h->sm_count - G * lp.ctas_per_group, G - 1);
+        const uint32_t per_cta = lp.slice / std::max<uint32_t>(1, lp.ctas_per_group);
+        for (uint32_t l = 0;; ++l) {
+            // the group that has been handed the fewest extra slots (the last one) decides when the half sweep is over
+            const uint64_t pos = extras ? ((uint64_t)l * lp.ctas_per_group + ((uint64_t)l * extras) / G) * per_cta : (uint64_t)l * lp.slice;
+            if (pos >= nv) break;
             if (sliced && s2) {
-                // next := -(ctas_per_group - 1) * base: every CTA adds its whole staged copy (sweep2.cuh)
+                // next := -(publishers - 1) * base: every CTA adds its whole staged copy (sweep2.cuh)
                 const uint32_t nmax = std::max(n_m, n_e);
                 sweep2_preinit_kernel<<<(nmax + 255) / 256, 256, 0, h->stream>>>(h->d_m, h->d_e, h->d_nr, h->d_m2, h->d_e2, h->d_nr2,
                                                                                  h->d_nr_live, n_m, n_e, h->KA, h->KB, type, lp.ctas_per_group - 1,
-                                                                                 lp.cluster ? lp.ctas_per_group / lp.cluster - 1 : lp.ctas_per_group - 1);
+                                                                                 lp.cluster ? lp.ctas_per_group / lp.cluster - 1 : lp.ctas_per_group - 1,
+                                                                                 G, extras, l);
                 h->last_launches += 1;
             } else if (sliced) {  // next := base; the launch adds each CTA's (staged - base) into next
                 CU(cudaMemcpyAsync(h->d_m2, h->d_m, (size_t)n_m * sizeof(int32_t), cudaMemcpyDeviceToDevice, h->stream));
@@ -821,13 +833,14 @@ int launch_full_sweep(bisbm_handle* h, int schedule, float p0, float p1, uint64_
             }
             SweepParams P = base_params(h, type);
             P.ctas_per_group = lp.ctas_per_group; P.warps_used = lp.warps_used;
-            P.pos_begin = pos; P.pos_end = (uint32_t)std::min<uint64_t>(nv, (uint64_t)pos + lp.slice);
+            P.pos_begin = (uint32_t)pos; P.pos_end = (uint32_t)std::min<uint64_t>(nv, pos + lp.slice);
             P.exclusive = sliced ? 0 : 1;
             P.sweep = h->sweep_epoch;
             P.step_base = sweep_in_call * (uint64_t)h->n + (type ? h->na : 0);
             P.schedule = schedule; P.p0 = p0; P.p1 = p1; P.beta0 = 1.0 / (double)p0;
             P.cluster_size = lp.cluster; P.rows_per_cta = lp.rows_per_cta; P.work_ctas = lp.work_ctas;
-            const unsigned grid = P.n_groups * lp.ctas_per_group;
+            P.extras = extras; P.launch_idx = l; P.per_cta = per_cta;
+            const unsigned grid = P.n_groups * lp.ctas_per_group + extras;
             rc = dispatch_sweep(h, P, lp, grid);
             if (rc) return rc;
             h->last_launches += 1;
@@ -1866,6 +1879,8 @@ int bisbm_set_option(bisbm_handle* h, const char* name, int64_t value) {
         h->opt_warps = (uint32_t)value;
     } else if (k == "generic") {
         h->opt_generic = value != 0;
+    } else if (k == "spare_sms") {
+        h->opt_spare_sms = value != 0;
     } else if (k == "reserve_ka" || k == "reserve_kb") {
         if (value < 0 || value > (1 << 20)) return fail(BISBM_ERR_ARG, "%s out of range", name);
         (k == "reserve_ka" ? h->opt_reserve_ka : h->opt_reserve_kb) = (uint32_t)value;

@@ -85,6 +85,10 @@ struct SweepParams {
     uint32_t cluster_size;           // sweep2_kernel<.., CLUSTER>: CTAs per cluster (m_rs of the group distributed over their shared memories)
     uint32_t rows_per_cta;           //   own-type blocks whose m rows one CTA of the cluster holds (ceil(kown_max / cluster_size))
     uint32_t work_ctas;              //   CTAs per group that take vertices (<= ctas_per_group; the rest only hold their rows of m)
+    // spare SMs (sliced staged launches whose groups x CTAs do not fill the GPU): `extras` more CTAs per launch, handed to the
+    // groups in turn (extra slot number s of the half sweep goes to group s mod n_groups; launch l hands out slots
+    // [l extras, (l+1) extras)); a group's positions then advance by (ctas_per_group + its extra) x per_cta per launch
+    uint32_t extras, launch_idx, per_cta;
     uint32_t vary_k;                 // estimate mode (README "estimation"): blocks may empty and be re-populated; the K-dependent
                                      // prior terms of the description length enter dS with the OCCUPIED block counts
 };

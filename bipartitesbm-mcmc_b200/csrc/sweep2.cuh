@@ -435,15 +435,22 @@ __device__ __noinline__ static double slow2_beta(int schedule, float p0, float p
 __global__ void sweep2_preinit_kernel(const int32_t* __restrict__ m, const int32_t* __restrict__ e, const int32_t* __restrict__ nr,
                                       int32_t* __restrict__ m2, int32_t* __restrict__ e2, int32_t* __restrict__ nr2,
                                       int32_t* __restrict__ nr_live, uint32_t n_m, uint32_t n_e, uint32_t KA, uint32_t KB,
-                                      uint32_t type, uint32_t mult, uint32_t mult_m) {   // mult_m: publishers of m per group - 1 (clusters, or CTAs)
+                                      uint32_t type, uint32_t mult, uint32_t mult_m,    // mult_m: publishers of m per group - 1 (clusters, or CTAs)
+                                      uint32_t n_groups, uint32_t extras, uint32_t launch_idx) {   // spare-SM CTAs: one more publisher in the groups that have one
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_m) m2[i] = (int32_t)(0u - mult_m * (uint32_t)m[i]);
+    auto extra_of = [&](uint32_t grp) -> uint32_t {
+        if (extras == 0u) return 0u;
+        const uint32_t slot0 = (uint32_t)(((uint64_t)launch_idx * extras) % n_groups);
+        return ((grp + n_groups - slot0) % n_groups < extras) ? 1u : 0u;
+    };
+    if (i < n_m) m2[i] = (int32_t)(0u - (mult_m + extra_of(i / (KA * KB * 32u))) * (uint32_t)m[i]);
     if (i < n_e) {
         const uint32_t slot = (i >> 5) % (KA + KB);
         const bool own = type ? (slot >= KA) : (slot < KA);
         const uint32_t ev = (uint32_t)e[i], nv = (uint32_t)nr[i];
-        e2[i] = (int32_t)(own ? 0u - mult * ev : ev);
-        nr2[i] = (int32_t)(own ? 0u - mult * nv : nv);
+        const uint32_t mg = mult + extra_of(i / ((KA + KB) * 32u));
+        e2[i] = (int32_t)(own ? 0u - mg * ev : ev);
+        nr2[i] = (int32_t)(own ? 0u - mg * nv : nv);
         nr_live[i] = (int32_t)nv;
     }
 }
@@ -478,8 +485,12 @@ __global__ void __launch_bounds__(NT, 1) sweep2_kernel(const __grid_constant__ S
     uint32_t crank = 0, csz = 1;
     if constexpr (CLUSTER) { crank = cluster_ctarank(); csz = P.cluster_size; }
     const uint32_t unit = CLUSTER ? blockIdx.x / csz : blockIdx.x;       // cluster (or CTA) index: consecutive units -> consecutive groups
-    const uint32_t group = P.group_offset + unit % P.n_groups;
-    const uint32_t cta_in_group = CLUSTER ? (unit / P.n_groups) * csz + crank : unit / P.n_groups;
+    // spare-SM CTAs come after the regular ones: extra CTA j of launch l takes slot l extras + j, i.e. group (slot mod n_groups)
+    const bool extra_cta = !CLUSTER && P.extras != 0u && unit >= P.n_groups * P.ctas_per_group;
+    const uint32_t slot0 = (uint32_t)(((uint64_t)P.launch_idx * P.extras) % P.n_groups);
+    const uint32_t grp0 = extra_cta ? (slot0 + (unit - P.n_groups * P.ctas_per_group)) % P.n_groups : unit % P.n_groups;
+    const uint32_t group = P.group_offset + grp0;
+    const uint32_t cta_in_group = CLUSTER ? (unit / P.n_groups) * csz + crank : (extra_cta ? P.ctas_per_group : unit / P.n_groups);
     const uint32_t RPC = CLUSTER ? P.rows_per_cta : 0u;
     const uint32_t own_off = type ? KA : 0, opp_off = type ? 0 : KA;
 
@@ -553,8 +564,19 @@ __global__ void __launch_bounds__(NT, 1) sweep2_kernel(const __grid_constant__ S
 
     // ---- the CTA's share of the slice: positions pos_begin + cta + j * ctas_per_group, j < cnt ----
     const uint32_t nv = type ? G.nb : G.na, v0 = type ? G.na : 0;
-    const uint32_t cpg = CLUSTER ? P.work_ctas : P.ctas_per_group;      // CTAs of the group that take vertices
-    const uint32_t span = P.pos_end - P.pos_begin;
+    uint32_t cpg = CLUSTER ? P.work_ctas : P.ctas_per_group;            // CTAs of the group that take vertices
+    uint32_t pos_begin = P.pos_begin, pos_end = P.pos_end;
+    if (!CLUSTER && P.extras != 0u) {
+        // this group's slice: it has advanced by per_cta x (ctas_per_group per launch + one per extra slot it was handed so far)
+        const uint64_t s0 = (uint64_t)P.launch_idx * P.extras;
+        const uint32_t before = (uint32_t)((s0 + P.n_groups - 1u - grp0) / P.n_groups);
+        const bool has_extra = (grp0 + P.n_groups - slot0) % P.n_groups < P.extras;
+        cpg += has_extra ? 1u : 0u;
+        const uint64_t pb = ((uint64_t)P.launch_idx * P.ctas_per_group + before) * P.per_cta;
+        pos_begin = (uint32_t)min(pb, (uint64_t)nv);
+        pos_end = (uint32_t)min(pb + (uint64_t)cpg * P.per_cta, (uint64_t)nv);
+    }
+    const uint32_t span = pos_end - pos_begin;
     const uint32_t cnt = P.kat_mode ? (cta_in_group == 0u ? 1u : 0u)
                                     : ((cta_in_group < cpg && span > cta_in_group) ? (span - cta_in_group + cpg - 1u) / cpg : 0u);
     const uint64_t pkey = (P.sweep * 2 + type) * 0x9E3779B97F4A7C15ull + (uint64_t)group * 0xD1B54A32D192ED03ull;
@@ -563,7 +585,7 @@ __global__ void __launch_bounds__(NT, 1) sweep2_kernel(const __grid_constant__ S
         for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) {
             uint4 b;
             if (P.kat_mode) b.x = P.kat_v;
-            else b.x = v0 + feistel_perm(P.pos_begin + cta_in_group + (j0 + i) * cpg, nv, P.half_bits, pkey);
+            else b.x = v0 + feistel_perm(pos_begin + cta_in_group + (j0 + i) * cpg, nv, P.half_bits, pkey);
             b.y = __ldcg(G.row_ptr + b.x);          // (.cg: nothing of the graph is reused through L1, which holds the log q expansions)
             b.z = __ldcg(G.row_ptr + b.x + 1) - b.y;
             b.w = __ldcg(G.degidx + b.x);
@@ -758,7 +780,7 @@ __global__ void __launch_bounds__(NT, 1) sweep2_kernel(const __grid_constant__ S
                 }
                 tq = min(tq, kopp_max - 1u);
                 R beta = (R)P.beta0;
-                if (!const_T) beta = (R)slow2_beta(P.schedule, P.p0, P.p1, P.step_base + P.pos_begin + cta_in_group + (uint64_t)pos_index * cpg);
+                if (!const_T) beta = (R)slow2_beta(P.schedule, P.p0, P.p1, P.step_base + pos_begin + cta_in_group + (uint64_t)pos_index * cpg);
                 const bool T_zero = beta < (R)0;
 
                 // ---- proposal (single_vertex_change), branch-free ----

@@ -144,6 +144,8 @@ int bisbm_set_precision(bisbm_handle* h, int mode);
  *   "kernel"        -1 automatic; 0 / 1 force the round-1 kernels (counts in L2 / staged, double); 5 force sweep2 with
  *                   counts in L2; 7 sweep2 with m_rs distributed over a thread-block cluster (A/B runs and tests)
  *   "generic"       1: never take the Ka = Kb = 32 compile-time specialisation
+ *   "spare_sms"     0: do not hand the SMs that n_groups x ctas_per_group leaves idle to the chain groups in turn (default 1;
+ *                   only with max_inflight = 0: a group holding a spare CTA evaluates one more CTA's worth of moves per launch)
  *   "vary_k"        1: estimate mode (README "estimation", no code in the reference snapshot): blocks may empty and be
  *                   re-populated by the uniform part of the proposal (no "would empty block r" veto), the K-dependent
  *                   terms of the description length enter dS with the number of OCCUPIED blocks, and bisbm_entropy*
