@@ -641,9 +641,15 @@ def main():
                     4: "sweep2_kernel<float, counts in L2>", 5: "sweep2_kernel<double, counts in L2>",
                     6: "sweep2_kernel<float, counts over a cluster>", 7: "sweep2_kernel<double, counts over a cluster>"}
     kernel_name = kernel_names[kern]
+    sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+    groups = (C + 31) // 32
+    spare = 0 if args.no_spare_sms or cpg_ <= 1 else max(0, min(sms - groups * cpg_, groups - 1))
+    per_cta = slice_ // max(1, cpg_)
     config["sweep_plan"] = {"kernel": kernel_name, "warps_per_cta": wpc_, "ctas_per_chain_group": cpg_,
-                            "slice_vertices_per_launch": slice_, "max_inflight": slice_,
-                            "inflight_bound": "half sweep / %d" % (args.inflight_div or 64)}
+                            "slice_vertices_per_launch": slice_, "max_inflight": slice_ + (per_cta if spare else 0),
+                            "spare_sm_ctas_per_launch": spare,
+                            "inflight_bound": "half sweep / %d%s" % (args.inflight_div or 64, (
+                                " (+ one CTA's share of %d positions in the launches where a chain group holds one of the %d spare-SM CTAs)" % (per_cta, spare)) if spare else "")}
     dtype = "f32+int32 (dS summed in f64)" if kern == 2 else "f64+int32"
 
     # -------- e2e: host buffers in, host buffers out, every step (8-bit labels: K = ka + kb <= 256 here)
