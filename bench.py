@@ -235,7 +235,7 @@ def bench_c4(args, rank, world, local_rank):
     moves, dev_ms, best = 0.0, 0.0, (float("inf"), None)
     for i in range(args.steps):
         ent, acc, bi, lab, st = step(i + 1)
-        moves += st["moves"]; dev_ms += st["device_ms"]
+        moves += st["moves"]; dev_ms += st["device_ms"]; last_report = st["report"]
         if ent.min() < best[0]:
             best = (float(ent.min()), mine[bi[0]])
     barrier()
@@ -267,11 +267,12 @@ def bench_c4(args, rank, world, local_rank):
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64+int32", "data": "synthetic",
                 "config": {"workload": "C4: (Ka,Kb) in %s^2 x %d restarts = %d chains on the planted SBM %d nodes / %d edges, abrupt_cool (%d hot + %d greedy sweeps per step), bisbm_grid_search, grid points round-robin over %d GPU(s)" % (
                     list(C4_VALUES), restarts, len(points) * restarts, n, args.edges, hot, sweeps - hot, world),
-                    "l2": "inputs larger than L2", "k_buckets": "max(Ka,Kb) padded to 8/16/32 (staged counts) and 64 (counts in L2)"},
+                    "l2": "inputs larger than L2", "k_buckets": "max(Ka,Kb) <= 32: padded to 8/16/32 (staged counts); larger: asymmetric strides that fit shared memory stay staged (64 x 16, 48 x 24 and transposes), the rest (12 of 121 points) padded to 64 x 64 with counts in L2"},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                              "bytes_per_move": bytes_per_move, "note": "per-GPU algorithmic bytes over the slowest rank's device time"},
                 "imbalance": {"device_ms_max": float(t[1]), "device_ms_min": float(tmin[0]), "max_over_min": float(t[1]) / max(float(tmin[0]), 1e-9)},
                 "best": {"entropy": g[0], "ka": int(g[1]), "kb": int(g[2]), "planted": [args.k, args.k]},
+                "buckets_rank0_last_step": last_report,
                 "e2e": {"value": float(tot[0]) / float(t[0]), "unit": "moves/s", "h2d_bytes_per_step": 8 * len(mine), "d2h_bytes_per_step": 8 * len(mine) * restarts * 2 + 4 * n,
                         "api": "bisbm_grid_search: (Ka,Kb) list in, per-chain entropy + best labels out, every step (value is already end to end)"},
                 "gpu_launches": None, "clocks": clocks}

@@ -11,6 +11,7 @@
 #include <nccl.h>     // types and prototypes only: libnccl.so.2 is loaded on first use (dlopen), not linked
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -130,9 +131,11 @@ struct bisbm_handle {
     int opt_generic = 0;               // 1: never take the Ka = Kb = 32 specialisation
     int opt_vary_k = 0;                // estimate mode: blocks may empty, K-dependent prior terms in dS
     uint32_t opt_warps = 16;           // warps per CTA of the staged sweep2 kernel (experiment builds: 20, 24)
+    uint32_t opt_logq_every = 8;       // sliced launches between lazy refreshes of the log q expansions (0x7fffffff: only per half sweep)
     int opt_spare_sms = 1;             // 1: sliced launches hand the SMs that n_groups x ctas_per_group leaves idle to the groups in turn
     uint32_t opt_reserve_ka = 0, opt_reserve_kb = 0;   // minimum strides of the next bisbm_set_chains (room for agg_split)
     std::set<const void*> attr_done;   // kernels whose shared-memory limit is raised on this handle's device
+    std::vector<double> grid_report;   // bisbm_grid_search_report: 8 numbers per K bucket of the last bisbm_grid_search
     uint64_t last_sweep_launches = 0, last_marginal_launches = 0;
     uint32_t last_wpc = 0, last_cpg = 0, last_slice = 0;   // launch plan of the last half sweep
     int last_kernel = -1;                                   // KERN_* of the last parallel call
@@ -801,7 +804,7 @@ int launch_full_sweep(bisbm_handle* h, int schedule, float p0, float p1, uint64_
         if (rc) return rc;
         const uint32_t kmax = type ? h->KB : h->KA;
         const uint32_t tot = h->n_chains * kmax;
-        logq_refresh_kernel<<<(tot + 127) / 128, 128, 0, h->stream>>>(sview(h), tview(h, false), h->d_lq, h->n_chains, type);
+        logq_refresh_kernel<<<(tot * 16 + 127) / 128, 128, 0, h->stream>>>(sview(h), tview(h, false), h->d_lq, h->n_chains, type);
         h->last_launches += 1;
         const uint32_t n_m = h->C * h->KA * h->KB, n_e = h->C * (h->KA + h->KB);
         const bool sliced = lp.smem && lp.work_ctas > 1;
@@ -819,6 +822,11 @@ int launch_full_sweep(bisbm_handle* h, int schedule, float p0, float p1, uint64_
             // the group that has been handed the fewest extra slots (the last one) decides when the half sweep is over
             const uint64_t pos = extras ? ((uint64_t)l * lp.ctas_per_group + ((uint64_t)l * extras) / G) * per_cta : (uint64_t)l * lp.slice;
             if (pos >= nv) break;
+            if (sliced && s2 && l != 0 && l % h->opt_logq_every == 0) {
+                // the blocks whose (e_r, n_r) have left the inner part of their log q expansion's range are expanded again
+                logq_refresh_kernel<<<(tot * 16 + 127) / 128, 128, 0, h->stream>>>(sview(h), tview(h, false), h->d_lq, h->n_chains, type, 1u);
+                h->last_launches += 1;
+            }
             if (sliced && s2) {
                 // next := -(publishers - 1) * base: every CTA adds its whole staged copy (sweep2.cuh)
                 const uint32_t nmax = std::max(n_m, n_e);
@@ -837,7 +845,14 @@ int launch_full_sweep(bisbm_handle* h, int schedule, float p0, float p1, uint64_
             P.exclusive = sliced ? 0 : 1;
             P.sweep = h->sweep_epoch;
             P.step_base = sweep_in_call * (uint64_t)h->n + (type ? h->na : 0);
-            P.schedule = schedule; P.p0 = p0; P.p1 = p1; P.beta0 = 1.0 / (double)p0;
+            P.schedule = schedule; P.p0 = p0; P.p1 = p1; P.beta0 = (p0 == 0.0f) ? -1.0 : 1.0 / (double)p0;     // (beta0 < 0: T == 0)
+            if (schedule == BISBM_ABRUPT_COOL) {
+                // T(t) = 1 for t < p0, else 0 (src/metropolis_hasting.cc:33-37): a half sweep that lies on one side of the
+                // switch runs as constant T (beta0 < 0 means T == 0) -- no per-vertex schedule evaluation
+                const uint64_t lo = P.step_base, hi = P.step_base + nv;      // steps of this half sweep: [lo, hi)
+                if ((float)(hi - 1) < p0) { P.schedule = BISBM_CONSTANT; P.p0 = 1.0f; P.beta0 = 1.0; }
+                else if (!((float)lo < p0)) { P.schedule = BISBM_CONSTANT; P.p0 = 0.0f; P.beta0 = -1.0; }
+            }
             P.cluster_size = lp.cluster; P.rows_per_cta = lp.rows_per_cta; P.work_ctas = lp.work_ctas;
             P.extras = extras; P.launch_idx = l; P.per_cta = per_cta;
             const unsigned grid = P.n_groups * lp.ctas_per_group + extras;
@@ -1768,7 +1783,7 @@ int bisbm_share_graph(bisbm_handle* src, bisbm_handle** out) {
     h->h_row_ptr = src->h_row_ptr; h->h_degvals = src->h_degvals; h->ent_base = src->ent_base;
     h->d_row_ptr = src->d_row_ptr; h->d_col = src->d_col; h->d_degidx = src->d_degidx; h->d_qtab = src->d_qtab; h->d_gl = src->d_gl; h->gl_n = src->gl_n;
     h->qn = src->qn; h->qk = src->qk;
-    h->precision = src->precision; h->opt_inflight_div = src->opt_inflight_div;
+    h->precision = src->precision; h->opt_inflight_div = src->opt_inflight_div; h->opt_logq_every = src->opt_logq_every;
     CU(cudaStreamCreate(&h->stream));
     CU(cudaEventCreate(&h->ev0));
     CU(cudaEventCreate(&h->ev1));
@@ -1791,12 +1806,35 @@ static int set_chains_equal_blocks(bisbm_handle* h, uint32_t n_chains, const uin
     return BISBM_OK;
 }
 
-// K class of a chain: both types padded to the same power of two (>= 8), so that chains of similar K share strides,
-// small-K chains keep the staged kernel and only large-K chains take the counts-in-L2 form
-static uint32_t k_class(uint32_t ka, uint32_t kb) {
+// K class of a chain = the (KA, KB) strides of the pool it runs in.  max(Ka, Kb) <= 32: both types padded to the same
+// power of two (>= 8), so chains of similar K share strides and keep the staged kernel.  Larger: each side is padded on
+// its own ({8, 16, 24, 32, 48, 64, ...}) and the pool stays STAGED whenever the asymmetric m_rs fits shared memory at 16
+// warps (64 x 16, 48 x 24: a det_k_bisbm grid is mostly such points) -- the smaller side is then grown as far as it still
+// fits, so few pools result; only shapes that do not fit take the counts-in-L2 class (both sides padded to the power of two).
+static bool k_fits_staged(uint32_t KA, uint32_t KB, uint32_t rs) {
+    return KA <= 256 && KB <= 256 && sweep2_layout(KA, KB, 0, 16, rs).total <= kSmemMax && sweep2_layout(KA, KB, 1, 16, rs).total <= kSmemMax;
+}
+static uint32_t k_ladder(uint32_t k, bool next = false) {
+    static const uint32_t steps[] = {8, 16, 24, 32, 48, 64, 96, 128, 192, 256};
+    for (uint32_t s : steps) if (next ? s > k : s >= k) return s;
+    return next ? 0u : k;
+}
+static uint64_t k_class(uint32_t ka, uint32_t kb, uint32_t rs) {
     uint32_t k = std::max(ka, kb), c = 8;
     while (c < k) c <<= 1;
-    return c;
+    if (c > 32) {
+        uint32_t pa = k_ladder(ka), pb = k_ladder(kb);
+        if (k_fits_staged(pa, pb, rs)) {
+            uint32_t& small = pa < pb ? pa : pb;
+            for (uint32_t nx = k_ladder(small, true); nx && nx <= 32; nx = k_ladder(small, true)) {
+                const uint32_t keep = small;
+                small = nx;
+                if (!k_fits_staged(pa, pb, rs)) { small = keep; break; }
+            }
+            return ((uint64_t)pa << 32) | pb;
+        }
+    }
+    return ((uint64_t)c << 32) | c;
 }
 
 int bisbm_grid_search(bisbm_handle* g, uint32_t n_points, const uint32_t* ka, const uint32_t* kb, uint32_t restarts, double eps,
@@ -1809,8 +1847,9 @@ int bisbm_grid_search(bisbm_handle* g, uint32_t n_points, const uint32_t* ka, co
     for (uint32_t p = 0; p < n_points; ++p)
         if (ka[p] == 0 || kb[p] == 0 || ka[p] > na || kb[p] > nb)
             return fail(BISBM_ERR_ARG, "point %u: (Ka, Kb) = (%u, %u) needs 1 <= Ka <= na, 1 <= Kb <= nb", p, ka[p], kb[p]);
-    std::map<uint32_t, std::vector<uint32_t>> buckets;      // K class -> points
-    for (uint32_t p = 0; p < n_points; ++p) buckets[k_class(ka[p], kb[p])].push_back(p);
+    std::map<uint64_t, std::vector<uint32_t>> buckets;      // K class -> points
+    const uint32_t rs = g->precision == BISBM_PRECISION_FP32 ? 4u : 8u;
+    for (uint32_t p = 0; p < n_points; ++p) buckets[k_class(ka[p], kb[p], rs)].push_back(p);
     double best = INFINITY;
     uint64_t total_moves = 0;
     double total_ms = 0.0;
@@ -1819,7 +1858,10 @@ int bisbm_grid_search(bisbm_handle* g, uint32_t n_points, const uint32_t* ka, co
     std::vector<uint64_t> seeds;
     std::vector<double> ent, acc;
     std::vector<uint64_t> sw;
+    g->grid_report.clear();
+    auto now_ms = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     for (auto& kv : buckets) {
+        const double t_begin = now_ms();
         const std::vector<uint32_t>& pts = kv.second;
         const uint32_t nc = (uint32_t)pts.size() * restarts;
         bisbm_handle* sub = nullptr;
@@ -1836,7 +1878,10 @@ int bisbm_grid_search(bisbm_handle* g, uint32_t n_points, const uint32_t* ka, co
         rc = set_chains_equal_blocks(sub, nc, cka.data(), ckb.data(), eps);
         if (!rc) rc = bisbm_randomize(sub, seeds.data());
         ent.resize(nc); acc.resize(nc); sw.resize(nc);
+        if (!rc && cudaStreamSynchronize(sub->stream) != cudaSuccess) rc = fail(BISBM_ERR_CUDA, "stream synchronize failed after the pool set-up");
+        const double t_setup = now_ms();
         if (!rc) rc = bisbm_anneal(sub, schedule, p0, p1, duration, steps_await, seeds.data(), max_inflight, acc.data(), sw.data());
+        const double t_anneal = now_ms();
         if (!rc) rc = bisbm_entropy_all(sub, ent.data());
         if (!rc) {
             total_ms += sub->last_ms;
@@ -1855,10 +1900,22 @@ int bisbm_grid_search(bisbm_handle* g, uint32_t n_points, const uint32_t* ka, co
             }
         }
         const std::string err = g_err;
+        const double row[8] = {(double)sub->KA, (double)sub->KB, (double)nc, (double)sub->last_kernel, t_setup - t_begin, sub->last_ms,
+                               t_anneal - t_setup, 0.0};
         bisbm_destroy(sub);
+        g->grid_report.insert(g->grid_report.end(), row, row + 8);
+        g->grid_report.back() = now_ms() - t_anneal;
         if (rc) { g_err = err; return rc; }
     }
     if (stats) { stats[0] = (double)total_moves; stats[1] = total_ms; stats[2] = (double)buckets.size(); stats[3] = best; }
+    return BISBM_OK;
+}
+
+int bisbm_grid_search_report(const bisbm_handle* g, uint32_t max_rows, double* rows, uint32_t* n_rows) {
+    if (!g || !n_rows || (max_rows && !rows)) return fail(BISBM_ERR_ARG, "null argument");
+    const uint32_t have = (uint32_t)(g->grid_report.size() / 8);
+    *n_rows = have;
+    std::copy(g->grid_report.begin(), g->grid_report.begin() + 8 * (size_t)std::min(have, max_rows), rows);
     return BISBM_OK;
 }
 
@@ -1879,6 +1936,9 @@ int bisbm_set_option(bisbm_handle* h, const char* name, int64_t value) {
         h->opt_warps = (uint32_t)value;
     } else if (k == "generic") {
         h->opt_generic = value != 0;
+    } else if (k == "logq_every") {
+        if (value < 1 || value > 0x7fffffff) return fail(BISBM_ERR_ARG, "logq_every must be >= 1");
+        h->opt_logq_every = (uint32_t)value;
     } else if (k == "spare_sms") {
         h->opt_spare_sms = value != 0;
     } else if (k == "reserve_ka" || k == "reserve_kb") {
@@ -1911,7 +1971,7 @@ int bisbm_parallel_transition(bisbm_handle* h, uint32_t chain, uint32_t v, uint3
     if (rc) return rc;
     const uint32_t kmax = type ? h->KB : h->KA;
     const uint32_t tot = h->n_chains * kmax;
-    logq_refresh_kernel<<<(tot + 127) / 128, 128, 0, h->stream>>>(sview(h), tview(h, false), h->d_lq, h->n_chains, type);
+    logq_refresh_kernel<<<(tot * 16 + 127) / 128, 128, 0, h->stream>>>(sview(h), tview(h, false), h->d_lq, h->n_chains, type);
     CU(cudaMemsetAsync(h->d_kat_out, 0xff, 2 * sizeof(double), h->stream));   // NaN: "not written"
     LaunchPlan lp;
     memset(&lp, 0, sizeof lp);

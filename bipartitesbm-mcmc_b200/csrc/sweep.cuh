@@ -191,46 +191,96 @@ __device__ __forceinline__ int cnt_ld(const int32_t* p) {
 // (log_q_approx, src/support/int_part.cc:73-98): first derivatives with a small step (truncation: third derivative
 // times h^2 / 6 times the degree, below 1e-10), second / third derivatives with a larger one (round-off).  Blocks too
 // small for the asymptotic branch, or where the expansion would be poor, get valid = 0 and take the exact routine.
-BISBM_HD LogqExp logq_expand(const Tables& tb, int e0, int n0) {
+// The 15 points of the stencil: 0 centre; 1, 2 (e0 +- h1); 3, 4 (n0 +- k1); 5 .. 8 (e0 + he, - he, + 2 he, - 2 he);
+// 9, 10 (n0 +- hn); 11 .. 14 the corners (+,+), (+,-), (-,+), (-,-) of (he, hn).
+BISBM_HD bool logq_expandable(int e0, int n0) { return e0 >= 16384 && n0 >= 1024 && 2 * (int64_t)n0 <= (int64_t)e0; }
+BISBM_HD void logq_stencil(int e0, int n0, int i, int* e, int* n) {
+    const int h1 = (e0 >> 13) > 1 ? (e0 >> 13) : 1, k1 = (n0 >> 11) > 1 ? (n0 >> 11) : 1;
+    const int he = e0 >> 10, hn = n0 >> 8;
+    int de = 0, dn = 0;
+    switch (i) {
+        case 1: de = h1; break;       case 2: de = -h1; break;
+        case 3: dn = k1; break;       case 4: dn = -k1; break;
+        case 5: de = he; break;       case 6: de = -he; break;
+        case 7: de = 2 * he; break;   case 8: de = -2 * he; break;
+        case 9: dn = hn; break;       case 10: dn = -hn; break;
+        case 11: de = he; dn = hn; break;    case 12: de = he; dn = -hn; break;
+        case 13: de = -he; dn = hn; break;   case 14: de = -he; dn = -hn; break;
+        default: break;
+    }
+    *e = e0 + de; *n = n0 + dn;
+}
+BISBM_HD LogqExp logq_from_stencil(int e0, int n0, const double* f) {
+    LogqExp q;
+    q.e0 = e0; q.n0 = n0; q.pad = 0;
+    const int h1 = (e0 >> 13) > 1 ? (e0 >> 13) : 1, k1 = (n0 >> 11) > 1 ? (n0 >> 11) : 1;
+    const double He = (double)(e0 >> 10), Hn = (double)(n0 >> 8);
+    q.fe = (f[1] - f[2]) / (2.0 * (double)h1);
+    q.fn = (f[3] - f[4]) / (2.0 * (double)k1);
+    q.fee = (float)((f[5] - 2.0 * f[0] + f[6]) / (He * He));
+    q.fnn = (float)((f[9] - 2.0 * f[0] + f[10]) / (Hn * Hn));
+    q.fen = (float)((f[11] - f[12] - f[13] + f[14]) / (4.0 * He * Hn));
+    q.feee = (float)((f[7] - 2.0 * f[5] + 2.0 * f[6] - f[8]) / (2.0 * He * He * He));
+    q.valid = 1;
+    return q;
+}
+BISBM_HD LogqExp logq_invalid(int e0, int n0) {
     LogqExp q;
     q.e0 = e0; q.n0 = n0; q.fe = 0.0; q.fn = 0.0; q.fee = q.fen = q.fnn = q.feee = 0.f; q.valid = 0; q.pad = 0;
-    if (e0 >= 16384 && n0 >= 1024 && 2 * (int64_t)n0 <= (int64_t)e0) {
-        const int h1 = (e0 >> 13) > 1 ? (e0 >> 13) : 1, k1 = (n0 >> 11) > 1 ? (n0 >> 11) : 1;
-        const int he = e0 >> 10, hn = n0 >> 8;
-        const double f00 = log_q_approx(tb, e0, n0);
-        q.fe = (log_q_approx(tb, e0 + h1, n0) - log_q_approx(tb, e0 - h1, n0)) / (2.0 * (double)h1);
-        q.fn = (log_q_approx(tb, e0, n0 + k1) - log_q_approx(tb, e0, n0 - k1)) / (2.0 * (double)k1);
-        const double fp0 = log_q_approx(tb, e0 + he, n0), fm0 = log_q_approx(tb, e0 - he, n0);
-        const double fq0 = log_q_approx(tb, e0 + 2 * he, n0), fn0 = log_q_approx(tb, e0 - 2 * he, n0);
-        const double f0p = log_q_approx(tb, e0, n0 + hn), f0m = log_q_approx(tb, e0, n0 - hn);
-        const double fpp = log_q_approx(tb, e0 + he, n0 + hn), fpm = log_q_approx(tb, e0 + he, n0 - hn);
-        const double fmp = log_q_approx(tb, e0 - he, n0 + hn), fmm = log_q_approx(tb, e0 - he, n0 - hn);
-        const double He = (double)he, Hn = (double)hn;
-        q.fee = (float)((fp0 - 2.0 * f00 + fm0) / (He * He));
-        q.fnn = (float)((f0p - 2.0 * f00 + f0m) / (Hn * Hn));
-        q.fen = (float)((fpp - fpm - fmp + fmm) / (4.0 * He * Hn));
-        q.feee = (float)((fq0 - 2.0 * fp0 + 2.0 * fm0 - fn0) / (2.0 * He * He * He));
-        q.valid = 1;
-    }
     return q;
+}
+BISBM_HD LogqExp logq_expand(const Tables& tb, int e0, int n0) {
+    if (!logq_expandable(e0, n0)) return logq_invalid(e0, n0);
+    double f[15];
+    for (int i = 0; i < 15; ++i) {
+        int e, n;
+        logq_stencil(e0, n0, i, &e, &n);
+        f[i] = log_q_approx(tb, e, n);
+    }
+    return logq_from_stencil(e0, n0, f);
 }
 
 #ifdef __CUDACC__
 // Refresh the log q expansions of the blocks of one type (they only change during that
-// type's half sweep).  One thread per (chain, block).
-__global__ void logq_refresh_kernel(StateView s, Tables tb, LogqExp* lq, uint32_t n_chains, uint32_t type) {
-    uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+// type's half sweep).
+// lazy != 0 (between the slice launches of a half sweep): only the blocks that have drifted more than 1/64 of (e0, n0) from
+// their expansion point -- a quarter of the validity range of logq_fast -- are expanded again; at stationarity that is none
+// and the kernel is a few loads per block, while quenches and burn-in (blocks changing by more than the 6 % range within one
+// half sweep) stop falling onto the out-of-line exact path.
+__global__ void logq_refresh_kernel(StateView s, Tables tb, LogqExp* lq, uint32_t n_chains, uint32_t type, uint32_t lazy = 0) {
+    // 16 lanes per (chain, block): the 15 evaluations of the asymptotic formula run side by side (one thread doing all of them
+    // set the kernel's duration: 123 us whenever a single block needed its expansion)
+    const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t idx = gt >> 4, sub = gt & 15u;
+    const uint32_t seg = (threadIdx.x & 16u), segmask = 0xffffu << seg;
     uint32_t kmax = type ? s.KB : s.KA;
     if (idx >= n_chains * kmax) return;
-    // consecutive threads = consecutive chains of one block slot (coalesced)
+    // consecutive segments = consecutive chains of one block slot
     uint32_t b = idx / n_chains, c = idx % n_chains;
     uint32_t kc = type ? s.kb[c] : s.ka[c];
     uint32_t slot = (type ? s.KA : 0) + b;
     const size_t off = cnt_base(c, (size_t)s.KA + s.KB) + (size_t)slot * GROUP;
-    LogqExp q;
-    q.e0 = 0; q.n0 = 0; q.fe = q.fn = 0.0; q.fee = q.fen = q.fnn = q.feee = 0.f; q.valid = 0; q.pad = 0;
-    if (b < kc) q = logq_expand(tb, s.e[off], s.nr[off]);
-    lq[off] = q;
+    if (b >= kc) {
+        if (!lazy && sub == 0) lq[off] = logq_invalid(0, 0);
+        return;
+    }
+    const int e = s.e[off], n = s.nr[off];
+    if (lazy) {
+        const int e0 = lq[off].e0, n0 = lq[off].n0;
+        const int ax = e > e0 ? e - e0 : e0 - e, ay = n > n0 ? n - n0 : n0 - n;
+        if (lq[off].valid ? (ax <= (e0 >> 6) && ay <= (n0 >> 6)) : (e == e0 && n == n0)) return;
+    }
+    if (!logq_expandable(e, n)) {
+        if (sub == 0) lq[off] = logq_invalid(e, n);
+        return;
+    }
+    int es, ns;
+    logq_stencil(e, n, (int)(sub < 14u ? sub : 14u), &es, &ns);
+    const double fv = log_q_approx(tb, es, ns);
+    double f[15];
+#pragma unroll
+    for (int i = 0; i < 15; ++i) f[i] = __shfl_sync(segmask, fv, (int)seg + i);
+    if (sub == 0) lq[off] = logq_from_stencil(e, n, f);
 }
 
 // shared memory of the SMEM variant, in this order:

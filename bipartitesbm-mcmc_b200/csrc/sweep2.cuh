@@ -395,8 +395,14 @@ __device__ __forceinline__ void cluster_sync_all() {
 }
 
 // counts kept in L2 (STAGED = false): every read goes to L2 (ld.global.cg: other SMs update them with reductions)
-__device__ __forceinline__ int gl_ld(uint64_t base, uint32_t off) {
-    int v; asm("{\n\t.reg .u64 a;\n\tcvt.u64.u32 a, %2;\n\tadd.u64 a, a, %1;\n\tld.global.cg.s32 %0, [a];\n\t}" : "=r"(v) : "l"(base), "r"(off)); return v;
+// `on` == 0 (a padding lane of the last chain group): no request, 0 -- the padding chains' labels are all 0, so their lanes
+// of EVERY warp of the group would otherwise ask one L2 slice for the same few lines (measured: a pool of 80 chains ran 4x
+// slower than one of 96)
+__device__ __forceinline__ int gl_ld(uint64_t base, uint32_t off, uint32_t on) {
+    int v;
+    asm("{\n\t.reg .u64 a;\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\tcvt.u64.u32 a, %2;\n\tadd.u64 a, a, %1;\n\tmov.s32 %0, 0;\n\t@p ld.global.cg.s32 %0, [a];\n\t}"
+        : "=r"(v) : "l"(base), "r"(off), "r"(on));
+    return v;
 }
 __device__ __forceinline__ void gl_red(uint64_t base, uint32_t off, int v) {
     asm volatile("{\n\t.reg .u64 a;\n\tcvt.u64.u32 a, %1;\n\tadd.u64 a, a, %0;\n\tred.global.add.s32 [a], %2;\n\t}" :: "l"(base), "r"(off), "r"(v) : "memory");
@@ -660,15 +666,16 @@ __global__ void __launch_bounds__(NT, 1) sweep2_kernel(const __grid_constant__ S
     const uint64_t gMl = (uint64_t)__cvta_generic_to_global(gM + lane);
     const uint64_t gEol = (uint64_t)__cvta_generic_to_global(gE + own_off * 32 + lane);
     const uint64_t gNol = (uint64_t)__cvta_generic_to_global(gNR + own_off * 32 + lane);
+    const uint32_t live_u = live ? 1u : 0u;
     auto m_ld = [&](uint32_t off) -> int {
-        if constexpr (CLUSTER) return cl_ld(off); else if constexpr (STAGED) return sh_ld(M_base + off); else return gl_ld(gMl, off);
+        if constexpr (CLUSTER) return cl_ld(off); else if constexpr (STAGED) return sh_ld(M_base + off); else return gl_ld(gMl, off, live_u);
     };
     auto m_red = [&](uint32_t off, int v) {
         if constexpr (CLUSTER) cl_red(off, v); else if constexpr (STAGED) sh_red_add(M_base + off, v); else gl_red(gMl, off, v);
     };
-    auto eo_ld = [&](uint32_t blk) -> int { if constexpr (STAGED) return sh_ld(Eo_base + blk * 128u); else return gl_ld(gEol, blk * 128u); };
+    auto eo_ld = [&](uint32_t blk) -> int { if constexpr (STAGED) return sh_ld(Eo_base + blk * 128u); else return gl_ld(gEol, blk * 128u, live_u); };
     auto eo_red = [&](uint32_t blk, int v) { if constexpr (STAGED) sh_red_add(Eo_base + blk * 128u, v); else gl_red(gEol, blk * 128u, v); };
-    auto no_ld = [&](uint32_t blk) -> int { if constexpr (STAGED) return sh_ld(No_base + blk * 128u); else return gl_ld(gNol, blk * 128u); };
+    auto no_ld = [&](uint32_t blk) -> int { if constexpr (STAGED) return sh_ld(No_base + blk * 128u); else return gl_ld(gNol, blk * 128u, live_u); };
     auto no_red = [&](uint32_t blk, int v) { if constexpr (STAGED) sh_red_add(No_base + blk * 128u, v); else gl_red(gNol, blk * 128u, v); };
     constexpr int SAFE_NR = 8192;   // counts in L2: more than any number of concurrently evaluated moves of one chain
     // the group's label rows: chain-minor u8, 32 bytes per vertex and group
@@ -780,7 +787,12 @@ __global__ void __launch_bounds__(NT, 1) sweep2_kernel(const __grid_constant__ S
                 }
                 tq = min(tq, kopp_max - 1u);
                 R beta = (R)P.beta0;
-                if (!const_T) beta = (R)slow2_beta(P.schedule, P.p0, P.p1, P.step_base + pos_begin + cta_in_group + (uint64_t)pos_index * cpg);
+                if (!const_T) {
+                    const uint64_t step = P.step_base + pos_begin + cta_in_group + (uint64_t)pos_index * cpg;
+                    // abrupt_cool in line (a launch that straddles the switch; whole launches on one side arrive as constant T)
+                    if (P.schedule == 4) beta = ((float)step < P.p0) ? (R)1 : (R)-1;
+                    else beta = (R)slow2_beta(P.schedule, P.p0, P.p1, step);
+                }
                 const bool T_zero = beta < (R)0;
 
                 // ---- proposal (single_vertex_change), branch-free ----
@@ -978,7 +990,9 @@ __global__ void __launch_bounds__(NT, 1) sweep2_kernel(const __grid_constant__ S
                 // ---- commit (apply_mcmc_moves) and clear the histogram ----
                 const bool any_go = __any_sync(FULL, go);
                 if (d <= 32u) {
-                    if (any_go) {     // walk the edges again: m(r,t) -= 1, m(s,t) += 1 for the lanes that move
+                    // walk the edges again: m(r,t) -= 1, m(s,t) += 1 for the lanes that move.  Shared-memory counts: every lane
+                    // runs the walk (a reduction of 0 costs nothing extra); counts in L2: only the lanes that move issue reductions
+                    if (any_go && (STAGED || go)) {
                         const int g1 = go ? 1 : 0;
                         const uint32_t dMs = Ms - Mr;          // m(s,t) sits at a fixed distance from m(r,t)
                         auto move1 = [&](uint32_t t) { const uint32_t f = Mr + t * ST; m_red(f, -g1); m_red(f + dMs, g1); };

@@ -54,6 +54,7 @@ SIGNATURES = {
     "bisbm_share_graph": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "bisbm_grid_search": (C.c_int, [C.c_void_p, C.c_uint32, _u32p, _u32p, C.c_uint32, C.c_double, C.c_int, C.c_float, C.c_float,
                                     C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, _dp, _dp, _u32p, _u32p, _dp]),
+    "bisbm_grid_search_report": (C.c_int, [C.c_void_p, C.c_uint32, _dp, _u32p]),
     "bisbm_set_chains": (C.c_int, [C.c_void_p, C.c_uint32, _u32p, _u32p, C.c_void_p, C.c_double]),
     "bisbm_set_chains_u8": (C.c_int, [C.c_void_p, C.c_uint32, _u32p, _u32p, C.c_void_p, C.c_double]),
     "bisbm_randomize": (C.c_int, [C.c_void_p, _u64p]),
@@ -204,8 +205,13 @@ def grid_search(graph, points, restarts, epsilon, schedule, p0, p1, duration, st
     _check(graph.L.bisbm_grid_search(graph.h, len(pts), _p(ka, C.c_uint32), _p(kb, C.c_uint32), restarts, float(epsilon),
                                      schedule, p0, p1, duration, steps_await, seed, max_inflight, _p(ent, C.c_double),
                                      _p(acc, C.c_double), C.byref(best), _p(lab, C.c_uint32), _p(stats, C.c_double)))
+    rows = np.zeros((64, 8), dtype=np.float64)
+    nrows = C.c_uint32()
+    _check(graph.L.bisbm_grid_search_report(graph.h, 64, _p(rows, C.c_double), C.byref(nrows)))
+    report = [{"KA": int(r[0]), "KB": int(r[1]), "chains": int(r[2]), "kernel": int(r[3]), "setup_ms": r[4], "anneal_device_ms": r[5],
+               "anneal_ms": r[6], "score_teardown_ms": r[7]} for r in rows[:min(nrows.value, 64)]]
     return (ent.reshape(len(pts), restarts), acc.reshape(len(pts), restarts), (best.value // restarts, best.value % restarts), lab,
-            {"moves": stats[0], "device_ms": stats[1], "buckets": int(stats[2]), "best_entropy": stats[3]})
+            {"moves": stats[0], "device_ms": stats[1], "buckets": int(stats[2]), "best_entropy": stats[3], "report": report})
 
 
 def edge_to_adj(edge_list, N, na=None, nb=None, device=0):

@@ -174,6 +174,11 @@ int bisbm_grid_search(bisbm_handle* graph, uint32_t n_points, const uint32_t* ka
                       double eps, int schedule, float p0, float p1, uint64_t duration, uint64_t steps_await, uint64_t seed,
                       uint32_t max_inflight, double* entropy, double* accept, uint32_t* best_chain, uint32_t* best_labels,
                       double* stats);
+/* per K bucket (= pool over the shared graph) of the last bisbm_grid_search on this graph handle, in the order they ran:
+ * rows[i][8] = {KA stride, KB stride, chains, kernel id (bisbm_sweep_info), set-up ms (pool, initial partitions, counts,
+ * randomise; host clock), anneal ms (device events), anneal ms (host clock), scoring + teardown ms (host clock)}.
+ * n_rows = buckets of that call (may exceed max_rows; only max_rows rows are written). */
+int bisbm_grid_search_report(const bisbm_handle* graph, uint32_t max_rows, double* rows, uint32_t* n_rows);
 /* ---- multi-GPU: chains are partitioned over GPUs (graph replicated); the only collective is ONE all-reduce (sum, uint32)
  * of the per-node marginal histogram over NVLink.  libnccl.so.2 is loaded on first use (BISBM_ERR_STATE if absent).
  * One process per GPU: rank 0 calls bisbm_nccl_get_unique_id and hands the 128 bytes to the other ranks by any means;

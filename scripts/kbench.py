@@ -22,8 +22,13 @@ for arg in (sys.argv[1:] or ["8", "16", "32", "48", "64"]):
         pool.set_option("kernel", int(os.environ["KERNEL"]))
     seeds = np.arange(C, dtype=np.uint64) + 1
     pool.randomize(seeds)
+    if os.environ.get("INFLIGHT_DIV"):
+        pool.set_option("inflight_div", int(os.environ["INFLIGHT_DIV"]))
     pool.anneal("constant", 1.0, 0.0, 1 * n, 10 ** 18, seeds)
-    acc, _ = pool.anneal("constant", 1.0, 0.0, 2 * n, 10 ** 18, seeds)
+    if os.environ.get("SCHED") == "abrupt":      # one hot + one greedy sweep, as a grid-search step has them
+        acc, _ = pool.anneal("abrupt_cool", 1.0 * n, 0.0, 2 * n, 10 ** 18, seeds)
+    else:
+        acc, _ = pool.anneal("constant", 1.0, 0.0, 2 * n, 10 ** 18, seeds)
     ms, la, mv = pool.last_timing()
     print("K=%s chains=%d kernel/wpc/cpg/slice=%s  %.3e moves/s  acc %.3f  launches %d" % (arg, C, pool.sweep_info(), mv / ms * 1e3, acc.mean(), la), flush=True)
     del pool

@@ -558,16 +558,16 @@ def test_label_arrays_stay_coherent(host):
 
 def test_grid_search_driver_finds_the_planted_k(host):
     """BASELINE configs[3] through the in-process (Ka, Kb) search driver (bisbm_grid_search): a grid around the planted
-    (4, 6) of bisbm-1000 plus two large-K points (a different K class: separate pool over the shared graph), 4 restarts
-    each, abrupt_cool annealing; the description-length minimum must land on or next to the planted point, and the
+    (4, 6) of bisbm-1000 plus large-K points (other K classes: separate pools over the shared graph -- (20, 24) staged at
+    32 + 32, (40, 44) counts in L2, (48, 4) and (3, 64) staged with asymmetric strides), 4 restarts each, abrupt_cool annealing; the description-length minimum must land on or next to the planted point, and the
     returned best partition must score the reported minimum."""
     g = load_golden("c2_const_k46")
     na, nb, edges = g["na"], g["nb"], g["edges"]
     n = na + nb
     graph = host.Graph(edges, na, nb)
-    points = [(a, b) for a in (2, 3, 4, 5, 6, 8) for b in (3, 4, 6, 8, 12)] + [(20, 24), (40, 44)]
+    points = [(a, b) for a in (2, 3, 4, 5, 6, 8) for b in (3, 4, 6, 8, 12)] + [(20, 24), (40, 44), (48, 4), (3, 64)]
     ent, acc, best, lab, stats = host.grid_search(graph, points, 4, 1.0, "abrupt_cool", 60.0 * n, 0.0, 120 * n, 10 ** 9, seed=3)
-    assert ent.shape == (len(points), 4) and np.isfinite(ent).all() and stats["buckets"] == 4
+    assert ent.shape == (len(points), 4) and np.isfinite(ent).all() and stats["buckets"] == 6
     bp = points[best[0]]
     print("grid minimum at", bp, "entropy", ent.min(), "stats", stats)
     assert ent[best] == ent.min() and abs(bp[0] - 4) <= 2 and abs(bp[1] - 6) <= 2
