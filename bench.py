@@ -212,8 +212,9 @@ def bench_c4(args, rank, world, local_rank):
     edges = planted(na, nb, args.k, args.k, args.edges, 0)
     graph = host.Graph(edges, na, nb, device=local_rank)
     points = [(a, b) for a in C4_VALUES for b in C4_VALUES]
-    mine = points[rank::world]
     restarts = 8
+    # whole 32-chain groups of one K bucket per rank, buckets balanced by cost (host.grid_partition)
+    mine = [points[i] for i in host.grid_partition(graph, points, restarts, world)[rank]]
     sweeps = args.sweeps_per_step
     hot = max(1, sweeps // 2)
 
@@ -265,7 +266,7 @@ def bench_c4(args, rank, world, local_rank):
         line = {"metric": "vertex-moves/sec", "value": float(tot[0]) / float(t[0]), "unit": "moves/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(t[0]) / args.steps * 1e3, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64+int32", "data": "synthetic",
-                "config": {"workload": "C4: (Ka,Kb) in %s^2 x %d restarts = %d chains on the planted SBM %d nodes / %d edges, abrupt_cool (%d hot + %d greedy sweeps per step), bisbm_grid_search, grid points round-robin over %d GPU(s)" % (
+                "config": {"workload": "C4: (Ka,Kb) in %s^2 x %d restarts = %d chains on the planted SBM %d nodes / %d edges, abrupt_cool (%d hot + %d greedy sweeps per step), bisbm_grid_search, grid points dealt in whole 32-chain groups per K bucket over %d GPU(s)" % (
                     list(C4_VALUES), restarts, len(points) * restarts, n, args.edges, hot, sweeps - hot, world),
                     "l2": "inputs larger than L2", "k_buckets": "max(Ka,Kb) <= 32: padded to 8/16/32 (staged counts); larger: asymmetric strides that fit shared memory stay staged (64 x 16, 48 x 24 and transposes), the rest (12 of 121 points) padded to 64 x 64 with counts in L2"},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,

@@ -136,6 +136,7 @@ struct bisbm_handle {
     uint32_t opt_reserve_ka = 0, opt_reserve_kb = 0;   // minimum strides of the next bisbm_set_chains (room for agg_split)
     std::set<const void*> attr_done;   // kernels whose shared-memory limit is raised on this handle's device
     std::vector<double> grid_report;   // bisbm_grid_search_report: 8 numbers per K bucket of the last bisbm_grid_search
+    std::map<uint64_t, bisbm_handle*> grid_pools;   // bisbm_grid_search: one pool per K bucket, kept between calls (cudaFree of GBs is slow and erratic)
     uint64_t last_sweep_launches = 0, last_marginal_launches = 0;
     uint32_t last_wpc = 0, last_cpg = 0, last_slice = 0;   // launch plan of the last half sweep
     int last_kernel = -1;                                   // KERN_* of the last parallel call
@@ -1014,6 +1015,8 @@ int bisbm_create(uint32_t na, uint32_t nb, uint64_t n_edges, const uint32_t* ea,
 int bisbm_destroy(bisbm_handle* h) {
     if (!h) return BISBM_OK;
     cudaSetDevice(h->device);
+    for (auto& kv : h->grid_pools) bisbm_destroy(kv.second);
+    h->grid_pools.clear();
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->comm && nccl_api()) { nccl_api()->CommDestroy(h->comm); h->comm = nullptr; }
     free_chains(h);
@@ -1864,9 +1867,15 @@ int bisbm_grid_search(bisbm_handle* g, uint32_t n_points, const uint32_t* ka, co
         const double t_begin = now_ms();
         const std::vector<uint32_t>& pts = kv.second;
         const uint32_t nc = (uint32_t)pts.size() * restarts;
+        // the bucket's pool: kept on the graph handle between calls (same shapes -> alloc_chains reuses every buffer)
         bisbm_handle* sub = nullptr;
-        int rc = bisbm_share_graph(g, &sub);
-        if (rc) return rc;
+        int rc = BISBM_OK;
+        auto cached = g->grid_pools.find(kv.first);
+        if (cached != g->grid_pools.end()) { sub = cached->second; sub->sweep_epoch = 0; sub->precision = g->precision; }
+        else {
+            rc = bisbm_share_graph(g, &sub);
+            if (rc) return rc;
+        }
         // initial labels: equal-size blocks in node order (the reference's `-n` with equal sizes,
         // src/mcmc_main.cc:302-326), then --randomize
         cka.resize(nc); ckb.resize(nc); seeds.resize(nc);
@@ -1902,12 +1911,33 @@ int bisbm_grid_search(bisbm_handle* g, uint32_t n_points, const uint32_t* ka, co
         const std::string err = g_err;
         const double row[8] = {(double)sub->KA, (double)sub->KB, (double)nc, (double)sub->last_kernel, t_setup - t_begin, sub->last_ms,
                                t_anneal - t_setup, 0.0};
-        bisbm_destroy(sub);
+        // keep the pool for the next call unless memory is short (less than a quarter of the device left free) or the call failed
+        size_t mem_free = 0, mem_total = 1;
+        if (rc || cudaMemGetInfo(&mem_free, &mem_total) != cudaSuccess || mem_free < mem_total / 4) {
+            g->grid_pools.erase(kv.first);
+            bisbm_destroy(sub);
+        } else g->grid_pools[kv.first] = sub;
         g->grid_report.insert(g->grid_report.end(), row, row + 8);
         g->grid_report.back() = now_ms() - t_anneal;
         if (rc) { g_err = err; return rc; }
     }
     if (stats) { stats[0] = (double)total_moves; stats[1] = total_ms; stats[2] = (double)buckets.size(); stats[3] = best; }
+    return BISBM_OK;
+}
+
+int bisbm_grid_release(bisbm_handle* g) {
+    if (!g) return fail(BISBM_ERR_ARG, "null handle");
+    for (auto& kv : g->grid_pools) bisbm_destroy(kv.second);
+    g->grid_pools.clear();
+    return BISBM_OK;
+}
+
+int bisbm_grid_k_class(const bisbm_handle* g, uint32_t ka, uint32_t kb, uint32_t* KA, uint32_t* KB, int* staged) {
+    if (!g || !KA || !KB) return fail(BISBM_ERR_ARG, "null argument");
+    const uint32_t rs = g->precision == BISBM_PRECISION_FP32 ? 4u : 8u;
+    const uint64_t c = k_class(ka, kb, rs);
+    *KA = (uint32_t)(c >> 32); *KB = (uint32_t)c;
+    if (staged) *staged = (g->max_degree <= 255u && k_fits_staged(*KA, *KB, rs)) ? 1 : 0;
     return BISBM_OK;
 }
 

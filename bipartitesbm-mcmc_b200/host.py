@@ -54,6 +54,8 @@ SIGNATURES = {
     "bisbm_share_graph": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "bisbm_grid_search": (C.c_int, [C.c_void_p, C.c_uint32, _u32p, _u32p, C.c_uint32, C.c_double, C.c_int, C.c_float, C.c_float,
                                     C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, _dp, _dp, _u32p, _u32p, _dp]),
+    "bisbm_grid_release": (C.c_int, [C.c_void_p]),
+    "bisbm_grid_k_class": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, _u32p, _u32p, C.POINTER(C.c_int)]),
     "bisbm_grid_search_report": (C.c_int, [C.c_void_p, C.c_uint32, _dp, _u32p]),
     "bisbm_set_chains": (C.c_int, [C.c_void_p, C.c_uint32, _u32p, _u32p, C.c_void_p, C.c_double]),
     "bisbm_set_chains_u8": (C.c_int, [C.c_void_p, C.c_uint32, _u32p, _u32p, C.c_void_p, C.c_double]),
@@ -212,6 +214,46 @@ def grid_search(graph, points, restarts, epsilon, schedule, p0, p1, duration, st
                "anneal_ms": r[6], "score_teardown_ms": r[7]} for r in rows[:min(nrows.value, 64)]]
     return (ent.reshape(len(pts), restarts), acc.reshape(len(pts), restarts), (best.value // restarts, best.value % restarts), lab,
             {"moves": stats[0], "device_ms": stats[1], "buckets": int(stats[2]), "best_entropy": stats[3], "report": report})
+
+
+def grid_release(graph):
+    """free the pools bisbm_grid_search keeps on the graph handle between calls"""
+    _check(graph.L.bisbm_grid_release(graph.h))
+
+
+def grid_k_class(graph, ka, kb):
+    """(KA, KB, staged) of the pool bisbm_grid_search runs a (ka, kb) point in."""
+    KA, KB, st = C.c_uint32(), C.c_uint32(), C.c_int()
+    _check(graph.L.bisbm_grid_k_class(graph.h, int(ka), int(kb), C.byref(KA), C.byref(KB), C.byref(st)))
+    return KA.value, KB.value, bool(st.value)
+
+
+def grid_partition(graph, points, restarts, world, l2_cost=6.0, classify=None):
+    """Deal the points of a (Ka, Kb) grid to `world` GPUs: points of one K bucket are kept together in chunks that fill whole
+    32-chain groups (a rank given 2 points x 8 restarts of a bucket would run half-empty warps), and the chunks go to the
+    least-loaded rank in order of decreasing cost (a chain whose counts stay in L2 costs ~l2_cost staged ones).
+    Returns `world` lists of indices into `points`.  `classify(ka, kb) -> (KA, KB, staged)` defaults to the library's own
+    bucketing (bisbm_grid_k_class)."""
+    if classify is None:
+        classify = lambda a, b: grid_k_class(graph, a, b)
+    per_chunk = max(1, -(-32 // restarts))
+    buckets = {}
+    for i, (a, b) in enumerate(points):
+        buckets.setdefault(tuple(classify(a, b)), []).append(i)
+    chunks = []
+    for (KA, KB, staged), idx in sorted(buckets.items()):
+        w = 1.0 if staged else l2_cost
+        for j in range(0, len(idx), per_chunk):
+            part = idx[j:j + per_chunk]
+            chunks.append((w * per_chunk, part))      # a partly filled group costs what a full one does
+    chunks.sort(key=lambda x: (-x[0], x[1][0]))
+    load = [0.0] * world
+    out = [[] for _ in range(world)]
+    for w, part in chunks:
+        r = min(range(world), key=lambda k: (load[k], k))
+        load[r] += w
+        out[r].extend(part)
+    return [sorted(o) for o in out]
 
 
 def edge_to_adj(edge_list, N, na=None, nb=None, device=0):

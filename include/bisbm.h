@@ -169,11 +169,19 @@ int bisbm_parallel_transition(bisbm_handle* h, uint32_t chain, uint32_t v, uint3
  * as parallel chains -- bucketed by K class so that small-K chains keep the staged kernel -- and scored by entropy()
  * (src/blockmodel.cc:753-787).  Initial partitions: equal-size blocks in node order (reference `-n`), then randomised.
  * entropy / accept: [n_points * restarts], chain p * restarts + q; best_chain: index of the minimum; best_labels: [n]
- * global block ids of that chain (may be NULL); stats (may be NULL): {moves attempted, device ms, K buckets, best entropy}. */
+ * global block ids of that chain (may be NULL); stats (may be NULL): {moves attempted, device ms, K buckets, best entropy}.
+ * The buckets' pools (labels, counts) stay allocated on the graph handle for the next call with the same grid -- freeing and
+ * re-allocating gigabytes per call cost more than the annealing -- unless less than a quarter of the device memory would stay
+ * free; bisbm_grid_release (or bisbm_destroy of the graph handle) frees them. */
 int bisbm_grid_search(bisbm_handle* graph, uint32_t n_points, const uint32_t* ka, const uint32_t* kb, uint32_t restarts,
                       double eps, int schedule, float p0, float p1, uint64_t duration, uint64_t steps_await, uint64_t seed,
                       uint32_t max_inflight, double* entropy, double* accept, uint32_t* best_chain, uint32_t* best_labels,
                       double* stats);
+int bisbm_grid_release(bisbm_handle* graph);
+/* the K bucket bisbm_grid_search puts a (ka, kb) point in: the bucket's (KA, KB) strides and whether its counts are staged in
+ * shared memory (1) or stay in L2 (0, several times slower per move) -- what a caller needs to deal the points of a grid to
+ * several GPUs in whole 32-chain groups of equal cost (host.py grid_partition) */
+int bisbm_grid_k_class(const bisbm_handle* graph, uint32_t ka, uint32_t kb, uint32_t* KA, uint32_t* KB, int* staged);
 /* per K bucket (= pool over the shared graph) of the last bisbm_grid_search on this graph handle, in the order they ran:
  * rows[i][8] = {KA stride, KB stride, chains, kernel id (bisbm_sweep_info), set-up ms (pool, initial partitions, counts,
  * randomise; host clock), anneal ms (device events), anneal ms (host clock), scoring + teardown ms (host clock)}.

@@ -66,3 +66,41 @@ def test_two_rank_sharding_and_allreduce(tmp_path):
     allseeds = pkg.dist.chain_seeds(7, np.arange(n_chains))
     for k in range(world):
         assert (r[k]["seeds"] == allseeds[r[k]["ids"]]).all()
+
+
+def test_grid_partition_deals_whole_groups_and_balances_cost():
+    """Host logic of the multi-GPU (Ka, Kb) search (BASELINE configs[3]): every point goes to exactly one rank, the points of
+    one K bucket arrive in chunks that fill 32-chain groups, and the estimated cost (a counts-in-L2 chain ~6 staged ones)
+    is balanced to within one chunk.  The classifier is injected: the library's own (bisbm_grid_k_class) needs a device."""
+    import importlib
+    host = importlib.import_module("bipartitesbm-mcmc_b200").host
+    vals = [2, 3, 4, 6, 8, 12, 16, 24, 32, 48, 64]
+    points = [(a, b) for a in vals for b in vals]
+
+    def classify(a, b):          # the shapes DESIGN.md 3.2 lists
+        k = max(a, b)
+        if k <= 32:
+            c = 8
+            while c < k:
+                c *= 2
+            return c, c, True
+        if a >= 48 and b <= (16 if a == 64 else 24):
+            return (64, 16, True) if a == 64 else (48, 24, True)
+        if b >= 48 and a <= (16 if b == 64 else 24):
+            return (16, 64, True) if b == 64 else (24, 48, True)
+        return 64, 64, False
+
+    for world in (1, 2, 8):
+        parts = host.grid_partition(None, points, 8, world, classify=classify)
+        assert sorted(i for p in parts for i in p) == list(range(len(points)))
+        cost = []
+        for p in parts:
+            by = {}
+            for i in p:
+                by.setdefault(classify(*points[i]), []).append(i)
+            # groups of 32 chains this rank runs (4 points x 8 restarts each), at the bucket's cost per group
+            cost.append(sum((-(-len(v) // 4)) * (1.0 if k[2] else 6.0) for k, v in by.items()))
+        assert max(cost) - min(cost) <= 6.0, cost
+    # fewer points than ranks: some ranks get nothing, nothing is lost
+    parts = host.grid_partition(None, points[:3], 8, 8, classify=classify)
+    assert sorted(i for p in parts for i in p) == [0, 1, 2]

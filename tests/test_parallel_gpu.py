@@ -574,6 +574,23 @@ def test_grid_search_driver_finds_the_planted_k(host):
     pool = host.ChainPool(graph, lab, bp[0], bp[1], 1.0)
     assert abs(pool.entropy(0) - ent.min()) <= 1e-9 * abs(ent.min())
     assert stats["moves"] == len(points) * 4 * 120 * n
+    # a second call runs in the pools the first one left on the graph handle (same streams of random numbers; the order in
+    # which concurrent warps commit is not reproducible, so the numbers agree statistically, not bit for bit)
+    ent2, acc2, best2, lab2, st2 = host.grid_search(graph, points, 4, 1.0, "abrupt_cool", 60.0 * n, 0.0, 120 * n, 10 ** 9, seed=3)
+    bp2 = points[best2[0]]
+    assert np.isfinite(ent2).all() and abs(bp2[0] - 4) <= 2 and abs(bp2[1] - 6) <= 2 and abs(ent2.min() - ent.min()) <= 0.01 * abs(ent.min())
+    assert st2["buckets"] == 6 and st2["moves"] == stats["moves"]
+    assert abs(host.ChainPool(graph, lab2, bp2[0], bp2[1], 1.0).entropy(0) - ent2.min()) <= 1e-9 * abs(ent2.min())
+    host.grid_release(graph)
+    ent3 = host.grid_search(graph, points[:4], 4, 1.0, "abrupt_cool", 60.0 * n, 0.0, 120 * n, 10 ** 9, seed=3)[0]
+    assert np.isfinite(ent3).all()
+    # the buckets behind it (bisbm_grid_k_class) and the per-bucket report
+    assert host.grid_k_class(graph, 5, 7) == (8, 8, True) and host.grid_k_class(graph, 20, 24) == (32, 32, True)
+    assert host.grid_k_class(graph, 64, 2) == (64, 16, True) and host.grid_k_class(graph, 3, 48) == (24, 48, True)
+    assert host.grid_k_class(graph, 40, 44) == (64, 64, False)
+    rep = stats["report"]
+    assert len(rep) == 6 and sum(r["chains"] for r in rep) == 4 * len(points)
+    assert {(r["KA"], r["KB"]): r["kernel"] for r in rep}[(40, 44)] == 5 and all(r["kernel"] in (3, 5) for r in rep)
 
 
 @pytest.mark.parametrize("precision", ["fp64", "fp32"])
