@@ -74,6 +74,31 @@ def planted_labels(na, nb, ka, kb):
     return np.concatenate([np.arange(na) * ka // na, ka + np.arange(nb) * kb // nb]).astype(np.uint32)
 
 
+class stdout_to_stderr:
+    """file descriptor 1 points at stderr inside the block: under NCCL_DEBUG (VERSION / INFO) NCCL prints its banner to
+    stdout while a communicator comes up, and stdout carries exactly ONE JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.keep = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.keep, 1)
+        os.close(self.keep)
+        return False
+
+
+def init_nccl(local_rank):
+    import torch
+    import torch.distributed as dist
+    with stdout_to_stderr():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.barrier()                      # the first collective creates the communicator
+        torch.cuda.synchronize()
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -206,7 +231,7 @@ def bench_c4(args, rank, world, local_rank):
     host = pkg.host
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        init_nccl(local_rank)
     na = nb = args.nodes // 2
     n = na + nb
     edges = planted(na, nb, args.k, args.k, args.edges, 0)
@@ -295,7 +320,7 @@ def bench_c5(args, rank, world, local_rank):
     host = pkg.host
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        init_nccl(local_rank)
     na = nb = args.c5_nodes // 2
     n = na + nb
     K = 128
@@ -311,7 +336,8 @@ def bench_c5(args, rank, world, local_rank):
     seeds = pkg.dist.chain_seeds(0, pkg.dist.shard_chains(C * world, rank, world))
     pool.randomize(seeds)
     if world > 1:
-        pkg.dist.init_pool_comm(pool)
+        with stdout_to_stderr():
+            pkg.dist.init_pool_comm(pool)
     sweeps = args.sweeps_per_step
     for _ in range(args.warmup):
         pool.anneal("constant", 1.0, 0.0, 1 * n, 10 ** 18, seeds)
@@ -403,7 +429,7 @@ def bench_marginalize(args, rank, world, local_rank):
     host = pkg.host
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        init_nccl(local_rank)
     na = nb = args.nodes // 2
     n = na + nb
     ka = kb = args.k
@@ -414,7 +440,8 @@ def bench_marginalize(args, rank, world, local_rank):
     seeds = pkg.dist.chain_seeds(0, pkg.dist.shard_chains(C * world, rank, world))
     every, samples = 10, max(1, args.sweeps_per_step // 2)
     if world > 1:
-        pkg.dist.init_pool_comm(pool)
+        with stdout_to_stderr():
+            pkg.dist.init_pool_comm(pool)
     pool.marginals_clear()
     for _ in range(args.warmup):
         pool.marginalize(0, every, every, seeds)
@@ -563,7 +590,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: libbisbm has no CPU path")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        init_nccl(local_rank)
     edges = planted(na, nb, ka, kb, args.edges, 0)
     graph = host.Graph(edges, na, nb, device=local_rank)
     C = args.chains
@@ -594,7 +621,8 @@ def main():
         pool.anneal("constant", 1.0, 0.0, duration, 10 ** 18, seeds)
     if world > 1:  # warm the one collective of the path too (NCCL communicator set-up is not a sweep cost)
         try:
-            pkg.dist.init_pool_comm(pool)        # the library's own communicator (bisbm_nccl_init)
+            with stdout_to_stderr():
+                pkg.dist.init_pool_comm(pool)        # the library's own communicator (bisbm_nccl_init)
             config["collective"] = "bisbm_marginals_allreduce (ncclAllReduce behind the C ABI)"
         except Exception as ex:                  # no loadable libnccl.so.2: torch.distributed's all-reduce on the same buffer
             config["collective"] = "torch.distributed all_reduce (libbisbm could not set up NCCL: %s)" % str(ex)[:120]
