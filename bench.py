@@ -366,9 +366,12 @@ def bench_c5(args, rank, world, local_rank):
     torch.cuda.synchronize()
     ar_ms = None
     if world > 1:
+        pool.marginals_allreduce()          # warm: the first collective of a communicator sets up its channels
+        torch.cuda.synchronize()
         dist.barrier()
         t1 = time.perf_counter()
         pool.marginals_allreduce()
+        torch.cuda.synchronize()
         ar_ms = (time.perf_counter() - t1) * 1e3
     kern, wpc_, cpg_, slice_ = pool.sweep_info()
     t = torch.tensor([wall, dev_ms, ar_ms or 0.0], dtype=torch.float64, device="cuda")
