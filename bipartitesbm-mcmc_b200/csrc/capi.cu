@@ -323,13 +323,15 @@ int finish_graph(bisbm_handle* h, std::vector<uint32_t>& col) {
 }
 
 // edge list -> CSR ON THE DEVICE (ingest.cuh): edge_to_adj of the reference, src/graph_utilities.cc:36-49
-int ingest_edges_device(bisbm_handle* h, const uint32_t* ea, const uint32_t* eb) {
+// on_device: ea / eb are device arrays (the text parser's output) that this function takes over and frees
+int ingest_edges_device(bisbm_handle* h, const uint32_t* ea, const uint32_t* eb, bool on_device = false) {
     const uint32_t n = h->n;
     const uint64_t E = h->n_edges, E2 = 2 * E;
     CU(cudaSetDevice(h->device));
     uint32_t *d_ea = nullptr, *d_eb = nullptr, *d_keys = nullptr, *d_vals = nullptr, *d_keys2 = nullptr, *d_deg = nullptr, *d_table = nullptr;
     unsigned long long *d_bad = nullptr, *d_pk = nullptr, *d_pk2 = nullptr, *d_mult = nullptr;
     void* d_tmp = nullptr;
+    if (on_device) { d_ea = const_cast<uint32_t*>(ea); d_eb = const_cast<uint32_t*>(eb); }
     auto cleanup = [&]() {
         for (void* p : {(void*)d_ea, (void*)d_eb, (void*)d_keys, (void*)d_vals, (void*)d_keys2, (void*)d_deg, (void*)d_table, (void*)d_bad,
                         (void*)d_pk, (void*)d_pk2, (void*)d_mult, d_tmp})
@@ -345,10 +347,12 @@ int ingest_edges_device(bisbm_handle* h, const uint32_t* ea, const uint32_t* eb)
     CUI(cudaMemset(d_bad, 0xff, sizeof(unsigned long long)));
     std::vector<unsigned long long> mult(INGEST_MULT_BINS, 0);
     if (E) {
-        CUI(cudaMalloc(&d_ea, E * sizeof(uint32_t)));
-        CUI(cudaMalloc(&d_eb, E * sizeof(uint32_t)));
-        CUI(cudaMemcpy(d_ea, ea, E * sizeof(uint32_t), cudaMemcpyHostToDevice));
-        CUI(cudaMemcpy(d_eb, eb, E * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        if (!on_device) {
+            CUI(cudaMalloc(&d_ea, E * sizeof(uint32_t)));
+            CUI(cudaMalloc(&d_eb, E * sizeof(uint32_t)));
+            CUI(cudaMemcpy(d_ea, ea, E * sizeof(uint32_t), cudaMemcpyHostToDevice));
+            CUI(cudaMemcpy(d_eb, eb, E * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        }
         CUI(cudaMalloc(&d_keys, E2 * sizeof(uint32_t)));
         CUI(cudaMalloc(&d_vals, E2 * sizeof(uint32_t)));
         CUI(cudaMalloc(&d_keys2, E2 * sizeof(uint32_t)));
@@ -359,9 +363,12 @@ int ingest_edges_device(bisbm_handle* h, const uint32_t* ea, const uint32_t* eb)
         CUI(cudaMemcpy(&bad, d_bad, sizeof bad, cudaMemcpyDeviceToHost));
         if (bad != ~0ull) {
             const unsigned long long i = bad / 4;
+            if ((bad & 3) == INGEST_BAD_RANGE) { cleanup(); return fail(BISBM_ERR_ARG, "edge %llu: node id out of range", i); }
+            uint32_t xa = 0, xb = 0;
+            if (on_device) { cudaMemcpy(&xa, d_ea + i, 4, cudaMemcpyDeviceToHost); cudaMemcpy(&xb, d_eb + i, 4, cudaMemcpyDeviceToHost); }
+            else { xa = ea[i]; xb = eb[i]; }
             cleanup();
-            if ((bad & 3) == INGEST_BAD_RANGE) return fail(BISBM_ERR_ARG, "edge %llu: node id out of range", i);
-            return fail(BISBM_ERR_ARG, "edge %u-%u joins two nodes of the same type", ea[i], eb[i]);
+            return fail(BISBM_ERR_ARG, "edge %u-%u joins two nodes of the same type", xa, xb);
         }
         // stable sort of the directed entries by source node: rows in file order
         int bits = 1;
@@ -1009,6 +1016,88 @@ int bisbm_create(uint32_t na, uint32_t nb, uint64_t n_edges, const uint32_t* ea,
     int rc = ingest_edges_device(h.get(), ea, eb);
     if (rc) { const std::string err = g_err; bisbm_destroy(h.release()); g_err = err; return rc; }
     *out = h.release();
+    return BISBM_OK;
+}
+
+// load_edge_list on the device: text (host) -> d_ea / d_eb (device, caller frees), E = edge lines in file order
+static int parse_edge_text_device(int device, const char* text, uint64_t bytes, uint32_t** d_ea_out, uint32_t** d_eb_out, uint64_t* E_out) {
+    *d_ea_out = nullptr; *d_eb_out = nullptr; *E_out = 0;
+    if (bytes == 0) return BISBM_OK;
+    CU(cudaSetDevice(device));
+    unsigned char* d_text = nullptr;
+    unsigned long long *d_lines = nullptr, *d_off = nullptr, *d_bad = nullptr;
+    uint32_t *d_ea = nullptr, *d_eb = nullptr;
+    void* d_tmp = nullptr;
+    auto cleanup = [&]() { for (void* p : {(void*)d_text, (void*)d_lines, (void*)d_off, (void*)d_bad, (void*)d_ea, (void*)d_eb, d_tmp}) if (p) cudaFree(p); };
+#define CUP(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return fail(BISBM_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } } while (0)
+    const uint64_t chunks = (bytes + PARSE_CHUNK - 1) / PARSE_CHUNK;
+    if (chunks > 0x7fffffffull) return fail(BISBM_ERR_ARG, "edge list text too large");
+    CUP(cudaMalloc(&d_text, bytes + 16));
+    CUP(cudaMemcpy(d_text, text, bytes, cudaMemcpyHostToDevice));
+    CUP(cudaMalloc(&d_lines, (chunks + 1) * sizeof(unsigned long long)));
+    CUP(cudaMalloc(&d_off, (chunks + 1) * sizeof(unsigned long long)));
+    CUP(cudaMemset(d_lines, 0, (chunks + 1) * sizeof(unsigned long long)));
+    CUP(cudaMalloc(&d_bad, sizeof(unsigned long long)));
+    CUP(cudaMemset(d_bad, 0xff, sizeof(unsigned long long)));
+    parse_edges_kernel<false><<<(unsigned)chunks, PARSE_T>>>(d_text, bytes, d_lines, nullptr, nullptr, d_bad);
+    CUP(cudaGetLastError());
+    size_t tmp_bytes = 0;
+    CUP(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_lines, d_off, (int)(chunks + 1)));
+    CUP(cudaMalloc(&d_tmp, std::max<size_t>(tmp_bytes, 16)));
+    CUP(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_lines, d_off, (int)(chunks + 1)));
+    unsigned long long E = 0;
+    CUP(cudaMemcpy(&E, d_off + chunks, sizeof E, cudaMemcpyDeviceToHost));       // (entry `chunks` of the scan = total)
+    if (E) {
+        CUP(cudaMalloc(&d_ea, E * sizeof(uint32_t)));
+        CUP(cudaMalloc(&d_eb, E * sizeof(uint32_t)));
+        parse_edges_kernel<true><<<(unsigned)chunks, PARSE_T>>>(d_text, bytes, d_off, d_ea, d_eb, d_bad);
+        CUP(cudaGetLastError());
+        unsigned long long bad = 0;
+        CUP(cudaMemcpy(&bad, d_bad, sizeof bad, cudaMemcpyDeviceToHost));
+        if (bad != ~0ull) { cleanup(); return fail(BISBM_ERR_ARG, "edge line %llu: node id does not fit 32 bits", bad); }
+    }
+#undef CUP
+    *d_ea_out = d_ea; *d_eb_out = d_eb; *E_out = E;
+    d_ea = nullptr; d_eb = nullptr;
+    cleanup();
+    return BISBM_OK;
+}
+
+static int check_create_args(uint32_t na, uint32_t nb, int device, bisbm_handle** out) {
+    if (!out) return fail(BISBM_ERR_ARG, "null argument");
+    *out = nullptr;
+    const uint64_t n64 = (uint64_t)na + nb;
+    if (n64 == 0 || n64 > 0xfffffff0ull) return fail(BISBM_ERR_ARG, "bad node count");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(BISBM_ERR_CUDA, "no CUDA device (libbisbm has no CPU path)");
+    if (device < 0 || device >= ndev) return fail(BISBM_ERR_ARG, "device %d out of range (%d devices)", device, ndev);
+    return BISBM_OK;
+}
+
+int bisbm_create_from_text(uint32_t na, uint32_t nb, const char* text, uint64_t n_bytes, int device, bisbm_handle** out) {
+    int rc = check_create_args(na, nb, device, out);
+    if (rc) return rc;
+    if (n_bytes && !text) return fail(BISBM_ERR_ARG, "null text");
+    uint32_t *d_ea = nullptr, *d_eb = nullptr;
+    uint64_t E = 0;
+    rc = parse_edge_text_device(device, text, n_bytes, &d_ea, &d_eb, &E);
+    if (rc) return rc;
+    if (2 * E >= 0xffffffffull) { cudaFree(d_ea); cudaFree(d_eb); return fail(BISBM_ERR_ARG, "too many edges for 32-bit row offsets"); }
+    std::unique_ptr<bisbm_handle> h(new bisbm_handle());
+    h->device = device;
+    h->n = na + nb; h->na = na; h->nb = nb; h->n_edges = E;
+    rc = ingest_edges_device(h.get(), d_ea, d_eb, true);         // (takes the two arrays over)
+    if (rc) { const std::string err = g_err; bisbm_destroy(h.release()); g_err = err; return rc; }
+    *out = h.release();
+    return BISBM_OK;
+}
+
+int bisbm_get_csr(bisbm_handle* h, uint32_t* row_ptr, uint32_t* col_idx) {
+    if (!h || !h->gdev) return fail(BISBM_ERR_ARG, "no graph");
+    CU(cudaSetDevice(h->device));
+    if (row_ptr) std::copy(h->h_row_ptr.begin(), h->h_row_ptr.end(), row_ptr);
+    if (col_idx && h->n_edges) CU(cudaMemcpy(col_idx, h->gdev->col, 2 * h->n_edges * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     return BISBM_OK;
 }
 

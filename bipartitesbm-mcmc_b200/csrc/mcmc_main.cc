@@ -21,6 +21,7 @@
 #include <cstdint>
 #include <cstdlib>
 #include <fstream>
+#include <iterator>
 #include <iostream>
 #include <limits>
 #include <map>
@@ -305,19 +306,16 @@ int main(int argc, char const* argv[]) {
         return 1;
     }
 
-    // ---- graph, reference src/graph_utilities.cc:20-49 (an unreadable file gives an empty graph there too)
-    std::vector<uint32_t> ea, eb;
+    // ---- graph, reference src/graph_utilities.cc:20-49 (an unreadable file gives an empty graph there too): the file's bytes
+    //      go to the library as they are -- parsed on the device (bisbm_create_from_text), no host-side edge vectors
+    std::string edge_text;
     {
-        std::ifstream f(edge_list_path.c_str());
-        std::string line;
-        while (f.is_open() && std::getline(f, line)) {
-            std::stringstream ls(line);
-            size_t a = 0, b = 0;
-            if (!(ls >> a)) continue;  // blank line
-            ls >> b;
-            ea.push_back((uint32_t)a); eb.push_back((uint32_t)b);
-        }
+        std::ifstream f(edge_list_path.c_str(), std::ios::binary);
+        if (f.is_open()) edge_text.assign(std::istreambuf_iterator<char>(f), std::istreambuf_iterator<char>());
     }
+    auto create_graph = [&](int dev, bisbm_handle** out) {
+        return bisbm_create_from_text((uint32_t)NA, (uint32_t)NB, edge_text.data(), edge_text.size(), dev, out);
+    };
     // ---- the agglomerative paths (reference src/mcmc_main.cc:350-451): -g starts from singleton blocks; initial labels
     //      whose block counts differ from -z are merged (or split) to (KA, KB).  One replay chain; every agg_merge and every
     //      anneal below is the reference's call with the reference's arguments.
@@ -337,7 +335,7 @@ int main(int argc, char const* argv[]) {
             }
             if ((double)ka * (double)kb * 128.0 > 16e9) { std::cerr << "too many initial blocks for the K x K block matrix\n"; return 1; }
             bisbm_handle* h = nullptr;
-            if (!check(bisbm_create((uint32_t)NA, (uint32_t)NB, ea.size(), ea.data(), eb.data(), (int)device, &h))) return 1;
+            if (!check(create_graph((int)device, &h))) return 1;
             // room for the blocks a split adds
             if (!check(bisbm_set_option(h, "reserve_ka", (int64_t)std::max(ka, KA))) || !check(bisbm_set_option(h, "reserve_kb", (int64_t)std::max(kb, KB)))) return 1;
             const uint32_t ka1 = (uint32_t)ka, kb1 = (uint32_t)kb;
@@ -353,7 +351,9 @@ int main(int argc, char const* argv[]) {
             };
             uint32_t cka = ka1, ckb = kb1;
             if (merge && nature) {
-                const size_t ceiling = (size_t)std::ceil(std::sqrt(2.0 * (double)ea.size()) / 2);
+                uint64_t n_edges = 0;
+                if (!check(bisbm_info(h, nullptr, &n_edges, nullptr, nullptr))) return 1;
+                const size_t ceiling = (size_t)std::ceil(std::sqrt(2.0 * (double)n_edges) / 2);
                 size_t tKA = NA, tKB = NB, tGroups = NA + NB;
                 while (tKA >= ceiling && tKB >= ceiling) {
                     if (!check(bisbm_replay_agg_merge_total(h, 0, (int)std::ceil((double)tGroups * (sigma - 1) / sigma), 10))) return 1;
@@ -404,7 +404,7 @@ int main(int argc, char const* argv[]) {
         for (size_t g = 0; g < gpus; ++g)
             th.emplace_back([&, g]() {
                 auto ok = [&](int rc) { if (rc != BISBM_OK) { errs[g] = bisbm_last_error(); return false; } return true; };
-                if (!ok(bisbm_create((uint32_t)NA, (uint32_t)NB, ea.size(), ea.data(), eb.data(), (int)(device + g), &hs[g]))) return;
+                if (!ok(create_graph((int)(device + g), &hs[g]))) return;
                 std::vector<size_t> ids;
                 for (size_t c = g; c < chains; c += gpus) ids.push_back(c);
                 const size_t nc = ids.size();
@@ -457,7 +457,7 @@ int main(int argc, char const* argv[]) {
     }
 
     bisbm_handle* h = nullptr;
-    if (!check(bisbm_create((uint32_t)NA, (uint32_t)NB, ea.size(), ea.data(), eb.data(), (int)device, &h))) return 1;
+    if (!check(create_graph((int)device, &h))) return 1;
     std::vector<uint32_t> ka_v(chains, (uint32_t)KA), kb_v(chains, (uint32_t)KB), labels(chains * N);
     for (size_t c = 0; c < chains; ++c)
         for (size_t v = 0; v < N; ++v) labels[c * N + v] = memberships_init[v];

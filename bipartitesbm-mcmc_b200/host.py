@@ -54,6 +54,8 @@ SIGNATURES = {
     "bisbm_share_graph": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "bisbm_grid_search": (C.c_int, [C.c_void_p, C.c_uint32, _u32p, _u32p, C.c_uint32, C.c_double, C.c_int, C.c_float, C.c_float,
                                     C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, _dp, _dp, _u32p, _u32p, _dp]),
+    "bisbm_create_from_text": (C.c_int, [C.c_uint32, C.c_uint32, C.c_char_p, C.c_uint64, C.c_int, C.POINTER(C.c_void_p)]),
+    "bisbm_get_csr": (C.c_int, [C.c_void_p, _u32p, _u32p]),
     "bisbm_grid_release": (C.c_int, [C.c_void_p]),
     "bisbm_grid_k_class": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, _u32p, _u32p, C.POINTER(C.c_int)]),
     "bisbm_grid_search_report": (C.c_int, [C.c_void_p, C.c_uint32, _dp, _u32p]),
@@ -155,19 +157,36 @@ class Graph:
     src/graph_utilities.cc:36-49: both directions pushed in file order, multi-edges kept)."""
 
     def __init__(self, edges, na, nb, device=0):
+        """edges: [E][2] node ids -- or the TEXT of an edge-list file (bytes / str), parsed on the device
+        (bisbm_create_from_text; reference load_edge_list, src/graph_utilities.cc:20-34)."""
         L = load_library()
-        edges = np.ascontiguousarray(edges, dtype=np.uint32).reshape(-1, 2)
-        ea = np.ascontiguousarray(edges[:, 0])
-        eb = np.ascontiguousarray(edges[:, 1])
         h = C.c_void_p()
-        _check(L.bisbm_create(na, nb, len(ea), _p(ea, C.c_uint32), _p(eb, C.c_uint32), device, C.byref(h)))
+        if isinstance(edges, (bytes, bytearray, str)):
+            text = edges.encode() if isinstance(edges, str) else bytes(edges)
+            _check(L.bisbm_create_from_text(na, nb, text, len(text), device, C.byref(h)))
+            ne = C.c_uint64()
+            _check(L.bisbm_info(h, None, C.byref(ne), None, None))
+            n_edges = ne.value
+        else:
+            edges = np.ascontiguousarray(edges, dtype=np.uint32).reshape(-1, 2)
+            ea = np.ascontiguousarray(edges[:, 0])
+            eb = np.ascontiguousarray(edges[:, 1])
+            _check(L.bisbm_create(na, nb, len(ea), _p(ea, C.c_uint32), _p(eb, C.c_uint32), device, C.byref(h)))
+            n_edges = len(ea)
         self.L, self.h = L, h
         self.na, self.nb, self.n = na, nb, na + nb
-        self.n_edges = len(ea)
+        self.n_edges = n_edges
         self.device = device
         md = C.c_uint32()
         _check(L.bisbm_info(h, None, None, C.byref(md), None))
         self.max_degree = md.value
+
+    def csr(self):
+        """(row_ptr [n+1], col_idx [2E]) as the library holds them"""
+        rp = np.zeros(self.n + 1, dtype=np.uint32)
+        col = np.zeros(max(1, 2 * self.n_edges), dtype=np.uint32)
+        _check(self.L.bisbm_get_csr(self.h, _p(rp, C.c_uint32), _p(col, C.c_uint32)))
+        return rp, col[:2 * self.n_edges]
 
     def set_option(self, name, value):
         """handle options that matter before the chains exist ('reserve_ka' / 'reserve_kb', include/bisbm.h)"""

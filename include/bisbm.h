@@ -57,6 +57,13 @@ const char* bisbm_version(void);
  * the adjacency keeps that order and multi-edges, as the reference does. */
 int bisbm_create(uint32_t na, uint32_t nb, uint64_t n_edges, const uint32_t* ea, const uint32_t* eb,
                  int device, bisbm_handle** out);
+/* Same, from the TEXT of an edge-list file (load_edge_list, src/graph_utilities.cc:20-34: one edge per line, two unsigned
+ * integers separated by blanks).  The text is copied to the device once and parsed there (line starts per 4 KB chunk ->
+ * exclusive scan -> parse at the line start), and the edge arrays go straight into the device-side CSR build: no host-side
+ * edge vectors.  Lines whose first token is not a number are skipped; a missing second number reads as 0. */
+int bisbm_create_from_text(uint32_t na, uint32_t nb, const char* text, uint64_t n_bytes, int device, bisbm_handle** out);
+/* the graph as the library holds it: row_ptr[n+1] and col_idx[2E] (either may be NULL), rows in the reference's adjacency order */
+int bisbm_get_csr(bisbm_handle* h, uint32_t* row_ptr, uint32_t* col_idx);
 /* Same, from a ready CSR (row_ptr[n+1], col_idx[2E]) whose rows are already in the
  * reference's adjacency order. */
 int bisbm_create_csr(uint32_t na, uint32_t nb, const uint32_t* row_ptr, const uint32_t* col_idx,

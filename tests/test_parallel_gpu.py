@@ -631,3 +631,40 @@ def test_estimate_mode_variable_k(host, precision):
     lab = pool.labels(5)
     m, e, nr, eta = counts_from_labels(edges, na, nb, lab, 5, 5)
     assert (pool.m(5) == m).all() and (pool.n_r(5) == nr).all() and (nr >= 0).all()
+
+
+def test_edge_list_text_is_parsed_on_the_device(host):
+    """load_edge_list (reference src/graph_utilities.cc:20-34) on the device: the file's text goes in, the CSR that comes
+    out equals the one built from the parsed arrays -- rows in file order, multi-edges kept -- for plain "a b" lines, for
+    tabs / runs of blanks / CRLF / a missing final newline / skipped non-edge lines, and for a text that spans many 4 KB
+    chunks with lines of every length straddling the chunk borders."""
+    g = load_golden("c2_const_k46")
+    na, nb, edges = g["na"], g["nb"], np.asarray(g["edges"], dtype=np.uint32).reshape(-1, 2)
+    ref = host.Graph(edges, na, nb)
+    rp0, col0 = ref.csr()
+    plain = "".join("%d %d\n" % (a, b) for a, b in edges)
+    rng = np.random.default_rng(5)
+    seps = [" ", "\t", "   ", " \t ", "\t\t"]
+    ends = ["\n", "\r\n", " \n", "\t\r\n"]
+    messy = ["# a comment line\n", "\n", "   \n"]
+    for i, (a, b) in enumerate(edges):
+        messy.append("%s%d%s%d%s" % (["", " ", "\t"][i % 3], a, seps[int(rng.integers(len(seps)))], b, ends[int(rng.integers(len(ends)))]))
+        if i % 97 == 0:
+            messy.append(["\n", "nodes follow\n", "\t\n"][i % 3])
+    messy = "".join(messy)
+    messy = messy[:-1] if messy.endswith("\n") else messy          # no newline at the end of the file
+    assert len(plain) > 3 * 4096
+    for text in (plain, messy, messy.encode()):
+        gt = host.Graph(text, na, nb)
+        assert gt.n_edges == len(edges)
+        rp, col = gt.csr()
+        assert (rp == rp0).all() and (col == col0).all()
+    # the same chains on both graphs score the same description length
+    lab = np.tile(g["labels0"], (2, 1))
+    assert (host.ChainPool(host.Graph(messy, na, nb), lab, 4, 6, 1.0).entropy() == host.ChainPool(ref, lab, 4, 6, 1.0).entropy()).all()
+    # a missing second number reads as 0; ids that do not fit 32 bits, out-of-range ids and same-type edges are refused
+    for bad in ("0 99999999999\n", "0 %d\n" % (na + nb), "0 1\n"):
+        with pytest.raises(host.BisbmError):
+            host.Graph(bad, na, nb)
+    empty = host.Graph("", na, nb)
+    assert empty.n_edges == 0
