@@ -1960,7 +1960,10 @@ int bisbm_grid_search(bisbm_handle* g, uint32_t n_points, const uint32_t* ka, co
         bisbm_handle* sub = nullptr;
         int rc = BISBM_OK;
         auto cached = g->grid_pools.find(kv.first);
-        if (cached != g->grid_pools.end()) { sub = cached->second; sub->sweep_epoch = 0; sub->precision = g->precision; }
+        if (cached != g->grid_pools.end()) {
+            sub = cached->second; sub->sweep_epoch = 0;
+            sub->precision = g->precision; sub->opt_inflight_div = g->opt_inflight_div; sub->opt_logq_every = g->opt_logq_every;   // as bisbm_share_graph hands them on
+        }
         else {
             rc = bisbm_share_graph(g, &sub);
             if (rc) return rc;

@@ -677,7 +677,11 @@ __global__ void __launch_bounds__(NT, 1) sweep2_kernel(const __grid_constant__ S
     auto eo_red = [&](uint32_t blk, int v) { if constexpr (STAGED) sh_red_add(Eo_base + blk * 128u, v); else gl_red(gEol, blk * 128u, v); };
     auto no_ld = [&](uint32_t blk) -> int { if constexpr (STAGED) return sh_ld(No_base + blk * 128u); else return gl_ld(gNol, blk * 128u, live_u); };
     auto no_red = [&](uint32_t blk, int v) { if constexpr (STAGED) sh_red_add(No_base + blk * 128u, v); else gl_red(gNol, blk * 128u, v); };
-    constexpr int SAFE_NR = 8192;   // counts in L2: more than any number of concurrently evaluated moves of one chain
+    // counts in L2: a warp evaluates one move of a chain at a time, so about as many moves of one chain are in flight as its
+    // group has warps (round 2 used the constant 8192 = 3.5 x the warps of a whole B200); with a four-fold margin for short
+    // vertices finishing inside a long one's window, a block with more nodes than that cannot empty between the read of n_r and
+    // the commit, and smaller blocks take the exact atomic
+    const int SAFE_NR = (int)(4u * (P.ctas_per_group + 1u) * wpc);
     // the group's label rows: chain-minor u8, 32 bytes per vertex and group
     uint64_t LAB8 = (uint64_t)__cvta_generic_to_global(P.lab8 + (size_t)(group * 32u < C ? group * 32u : 0u));
     asm volatile("" : "+l"(LAB8));
