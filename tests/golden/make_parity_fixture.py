@@ -35,6 +35,8 @@ R = 128
 SWEEPS_EQ = 30      # protocol "eq": planted start, T = 1: samples of the stationary distribution
 SWEEPS_TR = 40      # protocol "tr": randomised start, T = 1: the burn-in transient of the staleness study
 
+HOT_QU, SWEEPS_QU = 10, 20   # protocol "qu": randomised start, abrupt_cool -- 10 sweeps at T = 1, then 10 greedy sweeps (T = 0)
+
 _G = {}
 
 
@@ -50,7 +52,12 @@ def run_chain(args):
     edges, lab = _graph()
     n = NA + NB
     o = port.PortChain(n, NA, NB, edges, lab, KA, KB, 1.0, 7000 + s, 9000 + s)
-    o.init(proto.startswith("tr"))
+    o.init(proto.startswith("tr") or proto.startswith("qu"))
+    if proto.startswith("qu"):      # the quench of the reference's default schedule (src/metropolis_hasting.cc:33-37)
+        acc = o.anneal("abrupt_cool", float(HOT_QU * n), 0.0, SWEEPS_QU * n, 10 ** 18, alternate=proto.endswith("_alt"))
+        out = (o.entropy(), acc, nmi(o.labels(), lab))
+        o.close()
+        return out
     sweeps = SWEEPS_TR if proto.startswith("tr") else SWEEPS_EQ
     # "tr_alt": the same burn-in with the type-alternating visiting order of the GPU's parallel mode (oracle test aid)
     acc = o.anneal("constant", 1.0, 0.0, sweeps * n, 10 ** 18, alternate=proto.endswith("_alt"))
@@ -82,9 +89,19 @@ def main():
         print("tr_alt entropy %.1f +- %.1f  accept %.4f +- %.4f  nmi %.4f" % (res[:, 0].mean(), res[:, 0].std(), res[:, 1].mean(), res[:, 1].std(), res[:, 2].mean()))
         np.savez_compressed(os.path.join(OUT, "parity_mid.npz"), **z)
         return
+    if "--only-quench" in sys.argv:   # add the qu_* / qu_alt_* arrays to an existing fixture
+        z = dict(np.load(os.path.join(OUT, "parity_mid.npz")))
+        with Pool(min(8, os.cpu_count() or 1)) as pool:
+            for proto in ("qu", "qu_alt"):
+                res = np.array(pool.map(run_chain, [(proto, s) for s in range(R)], chunksize=1))
+                z["%s_entropy" % proto], z["%s_accept" % proto], z["%s_nmi" % proto] = res[:, 0], res[:, 1], res[:, 2]
+                print(proto, "entropy %.1f +- %.1f  accept %.4f +- %.4f  nmi %.4f" % (res[:, 0].mean(), res[:, 0].std(), res[:, 1].mean(), res[:, 1].std(), res[:, 2].mean()), flush=True)
+        z["sweeps_qu"], z["hot_qu"] = SWEEPS_QU, HOT_QU
+        np.savez_compressed(os.path.join(OUT, "parity_mid.npz"), **z)
+        return
     edges, lab = _graph()
     n = NA + NB
-    out = dict(na=NA, nb=NB, ka=KA, kb=KB, n_edges=NE, graph_seed=GSEED, R=R, sweeps_eq=SWEEPS_EQ, sweeps_tr=SWEEPS_TR,
+    out = dict(na=NA, nb=NB, ka=KA, kb=KB, n_edges=NE, graph_seed=GSEED, R=R, sweeps_eq=SWEEPS_EQ, sweeps_tr=SWEEPS_TR, sweeps_qu=SWEEPS_QU, hot_qu=HOT_QU,
                edges_sha1=hashlib.sha1(np.ascontiguousarray(edges).tobytes()).hexdigest())
     # transition_ratio known answers on the planted state (RNG-free)
     o = port.PortChain(n, NA, NB, edges, lab, KA, KB, 1.0, 1, 2)
@@ -99,7 +116,7 @@ def main():
                kat_dS=np.array(kd), kat_accu=np.array(ka_), init_entropy=o.entropy())
     o.close()
     with Pool(min(8, os.cpu_count() or 1)) as pool:
-        for proto in ("eq", "tr", "tr_alt"):
+        for proto in ("eq", "tr", "tr_alt", "qu", "qu_alt"):
             res = np.array(pool.map(run_chain, [(proto, s) for s in range(R)], chunksize=1))
             out["%s_entropy" % proto], out["%s_accept" % proto], out["%s_nmi" % proto] = res[:, 0], res[:, 1], res[:, 2]
             print(proto, "entropy %.1f +- %.1f  accept %.4f +- %.4f  nmi %.4f" % (

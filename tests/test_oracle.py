@@ -137,3 +137,23 @@ def test_merge_fixture_matches_reference_build():
     assert (ch.labels() == g["sw_s1_labels"]).all() and tuple(ch.rng_words()) == tuple(int(x) for x in g["sw_s1_words"])
     ch.agg_merge(5, 0, 10)
     assert (ch.labels() == g["sw_s2_labels"]).all() and ch.entropy() == g["sw_s2_entropy"]
+
+
+def test_parity_fixture_quench_chains_come_from_the_oracle():
+    """tests/golden/parity_mid.npz is what tests/golden/make_parity_fixture.py writes: chain 0 of the quench protocol
+    (randomised start, abrupt_cool, 10 hot + 10 greedy sweeps on the 40k + 40k graph), reference visiting order and the
+    type-alternating test aid, recomputed here with the oracle must give the stored numbers bit for bit."""
+    import hashlib
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    fx = load_golden("parity_mid")
+    if "qu_entropy" not in fx:
+        pytest.skip("fixture without the quench protocol")
+    import make_parity_fixture as mk
+    edges, _ = mk._graph()
+    assert hashlib.sha1(np.ascontiguousarray(edges).tobytes()).hexdigest() == str(fx["edges_sha1"])
+    assert int(fx["sweeps_qu"]) == mk.SWEEPS_QU and int(fx["hot_qu"]) == mk.HOT_QU
+    for proto in ("qu", "qu_alt"):
+        ent, acc, nm = mk.run_chain((proto, 0))
+        assert ent == fx["%s_entropy" % proto][0] and acc == fx["%s_accept" % proto][0] and nm == fx["%s_nmi" % proto][0]

@@ -103,10 +103,13 @@ def _run_mid(host, proto, inflight, C, precision="fp64", inflight_div=None):
     if inflight_div:
         pool.set_option("inflight_div", inflight_div)
     seeds = np.arange(C, dtype=np.uint64) + 31337
-    if proto == "tr":
+    if proto in ("tr", "qu"):
         pool.randomize(seeds)
     sweeps = int(fx["sweeps_%s" % proto[:2]])
-    acc, sw = pool.anneal("constant", 1.0, 0.0, sweeps * n, 10 ** 18, seeds, max_inflight=inflight)
+    if proto == "qu":       # abrupt_cool: hot_qu sweeps at T = 1, then greedy sweeps
+        acc, sw = pool.anneal("abrupt_cool", float(int(fx["hot_qu"]) * n), 0.0, sweeps * n, 10 ** 18, seeds, max_inflight=inflight)
+    else:
+        acc, sw = pool.anneal("constant", 1.0, 0.0, sweeps * n, 10 ** 18, seeds, max_inflight=inflight)
     assert (sw == sweeps).all()
     ent = pool.entropy()
     labs = pool.labels()
@@ -189,3 +192,33 @@ def test_parity_with_oracle_burn_in_transient(host):
     assert p_self_acc > 0.01 and p_self_ent > 0.01                                                                   # (ii)
     assert p_ent > 0.01 and p_nmi > 0.01 and q_ent > 0.01 and q_nmi > 0.01                                           # (iii)
     assert _accept_close(fx, "tr", acc) < 1.0 and _accept_close(fx, "tr", acc2) < 1.0
+
+
+def test_parity_with_oracle_quench(host):
+    """Protocol "qu" (randomised start, abrupt_cool: 10 sweeps at T = 1, then 10 greedy sweeps at T = 0 -- the reference's
+    default schedule, src/metropolis_hasting.cc:33-37) at the benchmarked sliced plan.  This is the regime where blocks change
+    by more than the validity range of their log q expansion within one half sweep (lazy refresh between slices, DESIGN.md
+    3.2) and where half sweeps run as constant T = 0.  As for the burn-in transient, the path depends on the visiting order,
+    so: (i) description length, NMI and acceptance agree (KS p > 0.01) with oracle chains run in the type-alternating order
+    (qu_alt_*), for the sliced plan and for strictly sequential chains; (ii) sliced plan vs sequential chains of the same
+    sampler agree; (iii) the mean description length stays within one oracle standard deviation of the reference-order
+    oracle's."""
+    from scipy.stats import ks_2samp
+    if "qu_entropy" not in load_golden("parity_mid"):
+        pytest.skip("fixture without the quench protocol")
+    fx, pool, ent, acc, nm = _run_mid(host, "qu", 0, 256)
+    info = pool.sweep_info()
+    assert info[0] == 3 and info[2] > 1 and info[3] < int(fx["na"])
+    p_ent, p_acc, p_nmi = _report("default_plan", fx, "qu", ent, acc, nm, info)
+    a_ent, a_acc, a_nmi = _report("default_plan", fx, "qu_alt", ent, acc, nm, info)
+    fx2, pool2, ent2, acc2, nm2 = _run_mid(host, "qu", 1, 128)
+    assert pool2.sweep_info()[2] == 1
+    _report("sequential_control", fx, "qu", ent2, acc2, nm2, pool2.sweep_info())
+    b_ent, b_acc, b_nmi = _report("sequential_control", fx, "qu_alt", ent2, acc2, nm2, pool2.sweep_info())
+    p_self_ent, p_self_acc = ks_2samp(ent, ent2).pvalue, ks_2samp(acc, acc2).pvalue
+    off = abs(float(ent.mean()) - float(np.mean(fx["qu_entropy"]))) / float(np.std(fx["qu_entropy"]))
+    print("quench: plan vs sequential chains: KS p description length %.3f, acceptance %.3f; mean description length vs "
+          "reference-order oracle: %.2f sd" % (p_self_ent, p_self_acc, off))
+    assert a_ent > 0.01 and a_nmi > 0.01 and a_acc > 0.01 and b_ent > 0.01 and b_nmi > 0.01 and b_acc > 0.01        # (i)
+    assert p_self_ent > 0.01 and p_self_acc > 0.01                                                                   # (ii)
+    assert off < 1.0                                                                                                 # (iii)
