@@ -247,10 +247,11 @@ def grid_k_class(graph, ka, kb):
     return KA.value, KB.value, bool(st.value)
 
 
-def grid_partition(graph, points, restarts, world, l2_cost=6.0, classify=None):
+def grid_partition(graph, points, restarts, world, l2_cost=4.5, classify=None):
     """Deal the points of a (Ka, Kb) grid to `world` GPUs: points of one K bucket are kept together in chunks that fill whole
     32-chain groups (a rank given 2 points x 8 restarts of a bucket would run half-empty warps), and the chunks go to the
-    least-loaded rank in order of decreasing cost (a chain whose counts stay in L2 costs ~l2_cost staged ones).
+    least-loaded rank in order of decreasing cost (a chain whose counts stay in L2 costs ~l2_cost staged ones: measured
+    1.2e9 against 5.5-6.4e9 moves/s for pools of one or two chain groups, profiles/r02_bench_c4_n8.json).
     Returns `world` lists of indices into `points`.  `classify(ka, kb) -> (KA, KB, staged)` defaults to the library's own
     bucketing (bisbm_grid_k_class)."""
     if classify is None:
@@ -264,7 +265,7 @@ def grid_partition(graph, points, restarts, world, l2_cost=6.0, classify=None):
         w = 1.0 if staged else l2_cost
         for j in range(0, len(idx), per_chunk):
             part = idx[j:j + per_chunk]
-            chunks.append((w * per_chunk, part))      # a partly filled group costs what a full one does
+            chunks.append((w * max(len(part), 0.6 * per_chunk), part))      # (a partly filled group costs most of a full one)
     chunks.sort(key=lambda x: (-x[0], x[1][0]))
     load = [0.0] * world
     out = [[] for _ in range(world)]
