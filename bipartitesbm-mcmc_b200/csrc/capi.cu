@@ -1898,6 +1898,31 @@ static int set_chains_equal_blocks(bisbm_handle* h, uint32_t n_chains, const uin
     return BISBM_OK;
 }
 
+// the grid search's initial partitions in one pass: equal-size blocks in node order, then --randomize with the chain's seed,
+// written straight into the u8 shadow; counts built once.  Same labels as set_chains_equal_blocks + bisbm_randomize.
+static int set_chains_equal_blocks_randomized(bisbm_handle* h, uint32_t n_chains, const uint32_t* ka, const uint32_t* kb, double eps,
+                                              const uint64_t* seeds) {
+    bool same_model = false;
+    int rc = alloc_chains(h, n_chains, ka, kb, eps, &same_model);
+    if (rc) return rc;
+    if (h->KA > 256 || h->KB > 256) {        // labels that do not fit the shadow: the two-step form over the 4-byte array
+        rc = set_chains_equal_blocks(h, n_chains, ka, kb, eps);
+        return rc ? rc : bisbm_randomize(h, seeds);
+    }
+    rc = upload_seeds(h, seeds);
+    if (rc) return rc;
+    const uint64_t tot = (uint64_t)h->n * h->C;
+    equal_blocks_random8_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(gview(h), h->d_lab8, h->C, h->n_chains, h->d_ka, h->d_kb,
+                                                                                      h->d_seeds, feistel_half_bits(h->na), feistel_half_bits(h->nb));
+    CU(cudaGetLastError());
+    wrote_labels8(h);
+    rc = rebuild_counts(h);
+    if (rc) return rc;
+    CU(cudaMemsetAsync(h->d_dS, 0, h->C * sizeof(double), h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return BISBM_OK;
+}
+
 // K class of a chain = the (KA, KB) strides of the pool it runs in.  max(Ka, Kb) <= 32: both types padded to the same
 // power of two (>= 8), so chains of similar K share strides and keep the staged kernel.  Larger: each side is padded on
 // its own ({8, 16, 24, 32, 48, 64, ...}) and the pool stays STAGED whenever the asymmetric m_rs fits shared memory at 16
@@ -1976,8 +2001,7 @@ int bisbm_grid_search(bisbm_handle* g, uint32_t n_points, const uint32_t* ka, co
             cka[i] = ka[p]; ckb[i] = kb[p];
             seeds[i] = seed * 0x9E3779B97F4A7C15ull + ((uint64_t)p << 20) + q + 1;
         }
-        rc = set_chains_equal_blocks(sub, nc, cka.data(), ckb.data(), eps);
-        if (!rc) rc = bisbm_randomize(sub, seeds.data());
+        rc = set_chains_equal_blocks_randomized(sub, nc, cka.data(), ckb.data(), eps, seeds.data());
         ent.resize(nc); acc.resize(nc); sw.resize(nc);
         if (!rc && cudaStreamSynchronize(sub->stream) != cudaSuccess) rc = fail(BISBM_ERR_CUDA, "stream synchronize failed after the pool set-up");
         const double t_setup = now_ms();

@@ -118,6 +118,23 @@ __global__ void randomize_kernel(GraphView G, const int32_t* in, int32_t* out, u
 }
 
 
+// equal_blocks_kernel followed by randomize_kernel in one pass, straight into the u8 label shadow (the grid search's
+// initial partitions: no 4-byte label array written, permuted and narrowed): out[v] = equal-block label of the node the
+// keyed permutation maps v to -- the same labels, chain by chain, as the two kernels give
+__global__ void equal_blocks_random8_kernel(GraphView G, uint8_t* __restrict__ out, uint32_t C, uint32_t n_chains,
+                                            const uint32_t* __restrict__ ka, const uint32_t* __restrict__ kb,
+                                            const uint64_t* __restrict__ seeds, uint32_t hb_a, uint32_t hb_b) {
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (uint64_t)G.n * C) return;
+    const uint32_t v = (uint32_t)(idx / C), c = (uint32_t)(idx % C);
+    if (c >= n_chains) { out[idx] = 0; return; }
+    const bool tb = v >= G.na;
+    const uint32_t nv = tb ? G.nb : G.na;
+    const uint64_t key = seeds[c] * 0x9E3779B97F4A7C15ull + (tb ? 0x632BE59BD9B4E019ull : 0x2545F4914F6CDD1Dull);
+    const uint32_t src = feistel_perm(v - (tb ? G.na : 0), nv, tb ? hb_b : hb_a, key);      // type-local index of the source node
+    out[idx] = (uint8_t)((uint64_t)src * (tb ? kb[c] : ka[c]) / nv);
+}
+
 // ---- label import / export: host layout [chain][node] with GLOBAL block ids  <->  device
 //      layout [node][C] chain-minor, type-local.  32x32 tiles through shared memory so both
 //      sides are coalesced.  `bad` receives 1 + (chain * n + node) of the first invalid label. ----

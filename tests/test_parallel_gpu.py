@@ -668,3 +668,26 @@ def test_edge_list_text_is_parsed_on_the_device(host):
             host.Graph(bad, na, nb)
     empty = host.Graph("", na, nb)
     assert empty.n_edges == 0
+
+
+def test_grid_search_initial_partitions_equal_the_two_step_form(host):
+    """bisbm_grid_search writes its initial partitions (equal-size blocks in node order -- the reference's `-n` with equal
+    sizes -- then --randomize with the chain's seed) in ONE pass straight into the 8-bit label shadow.  With duration 0 the
+    scores it returns are those of the initial partitions: they must be the scores of the same partitions made the long way
+    (labels from the host, ChainPool.randomize with the same seed)."""
+    g = load_golden("c2_const_k46")
+    na, nb, edges = g["na"], g["nb"], g["edges"]
+    graph = host.Graph(edges, na, nb)
+    points, restarts, seed = [(4, 6), (3, 5), (7, 2)], 3, 7
+    ent, acc, best, lab, stats = host.grid_search(graph, points, restarts, 1.0, "abrupt_cool", 0.0, 0.0, 0, 10 ** 9, seed=seed)
+    assert stats["moves"] == 0
+    v = np.arange(na + nb)
+    for p, (a, b) in enumerate(points):
+        lab0 = np.where(v < na, v * a // na, a + (v - na) * b // nb).astype(np.uint32)
+        for q in range(restarts):
+            s = (seed * 0x9E3779B97F4A7C15 + (p << 20) + q + 1) % (1 << 64)
+            pool = host.ChainPool(graph, lab0[None, :], a, b, 1.0)
+            pool.randomize(np.array([s], dtype=np.uint64))
+            assert abs(pool.entropy(0) - ent[p, q]) <= 1e-12 * abs(ent[p, q]), (p, q, pool.entropy(0), ent[p, q])
+            if (p, q) == best:
+                assert (pool.labels(0) == lab).all()
