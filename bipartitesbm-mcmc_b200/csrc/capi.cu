@@ -2318,14 +2318,17 @@ int bisbm_get_labels(bisbm_handle* h, uint32_t chain, uint32_t* labels) {
     if (rc) return rc;
     if (chain >= h->n_chains) return fail(BISBM_ERR_ARG, "chain %u out of range", chain);
     const uint32_t n = h->n;
-    rc = sync_labels32(h);
-    if (rc) return rc;
-    std::vector<int32_t> lab(n);
+    // the chain's column is gathered on the device from whichever label array is current (no refresh of the other one),
+    // then copied as n contiguous words
+    if (!h->d_labels_tmp) CU(cudaMalloc(&h->d_labels_tmp, (size_t)n * h->C * sizeof(int32_t)));
+    uint32_t* const d_col = reinterpret_cast<uint32_t*>(h->d_labels_tmp);
+    if (h->lab32_stale) extract_chain_kernel<uint8_t><<<(n + 255) / 256, 256, 0, h->stream>>>(h->d_lab8, h->C, chain, n, d_col);
+    else extract_chain_kernel<int32_t><<<(n + 255) / 256, 256, 0, h->stream>>>(h->d_labels, h->C, chain, n, d_col);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(labels, d_col, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    CU(cudaMemcpy2D(lab.data(), sizeof(int32_t), h->d_labels + chain, (size_t)h->C * sizeof(int32_t), sizeof(int32_t),
-                    n, cudaMemcpyDeviceToHost));
     const uint32_t ka = h->h_ka[chain];
-    for (uint32_t v = 0; v < n; ++v) labels[v] = v < h->na ? (uint32_t)lab[v] : ka + (uint32_t)lab[v];
+    for (uint32_t v = h->na; v < n; ++v) labels[v] += ka;
     return BISBM_OK;
 }
 

@@ -135,6 +135,14 @@ __global__ void equal_blocks_random8_kernel(GraphView G, uint8_t* __restrict__ o
     out[idx] = (uint8_t)((uint64_t)src * (tb ? kb[c] : ka[c]) / nv);
 }
 
+// one chain's column of a chain-minor label array -> contiguous u32 (bisbm_get_labels: one copy of n words instead of a
+// strided copy of n rows)
+template <typename LabT>
+__global__ void extract_chain_kernel(const LabT* __restrict__ lab, uint32_t C, uint32_t chain, uint32_t n, uint32_t* __restrict__ out) {
+    const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v < n) out[v] = (uint32_t)lab[(size_t)v * C + chain];
+}
+
 // ---- label import / export: host layout [chain][node] with GLOBAL block ids  <->  device
 //      layout [node][C] chain-minor, type-local.  32x32 tiles through shared memory so both
 //      sides are coalesced.  `bad` receives 1 + (chain * n + node) of the first invalid label. ----
