@@ -55,6 +55,9 @@ def test_no_cpu_fallback(lib, host):
     with pytest.raises(host.BisbmError) as ei:
         host.Graph(edges, 2, 2)
     assert ei.value.code == 2 and "no CUDA device" in str(ei.value)
+    with pytest.raises(host.BisbmError) as ei:      # the edge-list text entry has no host-side parser to fall back on either
+        host.Graph("0 2\n1 3\n", 2, 2)
+    assert ei.value.code == 2 and "no CUDA device" in str(ei.value)
 
 
 def test_product_never_imports_the_oracle():
